@@ -1,0 +1,254 @@
+// C ABI of libpolymath_b200.so — standalone kernel entry points (include/polymath_b200.h).
+// Host buffers in, host buffers out; every call stages through device memory owned here.
+#include <mutex>
+#include <vector>
+
+#include "../../include/polymath_b200.h"
+#include "common.cuh"
+#include "field_kernels.cuh"
+#include "fixed_base.cuh"
+#include "msm.cuh"
+#include "ntt.cuh"
+#include "runtime.cuh"
+#include "synth.cuh"
+
+namespace pm {
+
+const std::string& last_error();
+
+Runtime& runtime() {
+    static Runtime rt;
+    return rt;
+}
+
+Runtime::Runtime() {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0)
+        throw CudaError(std::string("no CUDA device available (the product path has no CPU fallback): ") +
+                        cudaGetErrorString(e));
+    PM_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+}
+
+uint64_t Runtime::total_launches() const {
+    return extra_launches + ntt.launches + msm.launches + fixed_base.launches;
+}
+
+// Pack caller-strided affine points into the device layout (96 B, (0,0) = infinity).
+void pack_points_host(const uint8_t* src, size_t stride, size_t n, std::vector<uint8_t>& dst) {
+    dst.resize(n * PM_G1_BYTES);
+    for (size_t i = 0; i < n; i++) {
+        const uint8_t* p = src + i * stride;
+        uint8_t* q = dst.data() + i * PM_G1_BYTES;
+        if (stride >= 104 && p[96] != 0) memset(q, 0, PM_G1_BYTES);
+        else memcpy(q, p, PM_G1_BYTES);
+    }
+}
+
+template <class F>
+int guarded(F&& f) {
+    try {
+        f();
+        return PM_OK;
+    } catch (const StatusError& e) {
+        set_last_error(e.what());
+        return e.code;
+    } catch (const CudaError& e) {
+        set_last_error(e.what());
+        return PM_ERR_CUDA;
+    } catch (const std::exception& e) {
+        set_last_error(e.what());
+        return PM_ERR_CUDA;
+    }
+}
+
+template <class F>
+static int field_batch(FieldOp op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n, bool fq) {
+    return guarded([&] {
+        if (n == 0) return;
+        if (!a || !b || !out) throw StatusError(PM_ERR_ARG, "null buffer");
+        Runtime& rt = runtime();
+        DevBuf da, db, dc;
+        F* pa = da.as<F>(n);
+        F* pb = db.as<F>(n);
+        F* pc = dc.as<F>(n);
+        PM_CUDA(cudaMemcpyAsync(pa, a, n * sizeof(F), cudaMemcpyHostToDevice, rt.stream));
+        PM_CUDA(cudaMemcpyAsync(pb, b, n * sizeof(F), cudaMemcpyHostToDevice, rt.stream));
+        if constexpr (sizeof(F) == sizeof(Fr)) launch_fr_batch(op, (const Fr*)pa, (const Fr*)pb, (Fr*)pc, n, rt.stream);
+        else launch_fq_batch(op, (const Fq*)pa, (const Fq*)pb, (Fq*)pc, n, rt.stream);
+        rt.extra_launches++;
+        PM_CUDA(cudaMemcpyAsync(out, pc, n * sizeof(F), cudaMemcpyDeviceToHost, rt.stream));
+        PM_CUDA(cudaStreamSynchronize(rt.stream));
+        (void)fq;
+    });
+}
+
+}  // namespace pm
+
+using namespace pm;
+
+extern "C" {
+
+const char* pm_last_error(void) { return last_error().c_str(); }
+int pm_abi_version(void) { return 1; }
+int pm_device_count(void) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) return 0;
+    return count;
+}
+uint64_t pm_kernel_launches(void) {
+    uint64_t v = 0;
+    guarded([&] { v = runtime().total_launches(); });
+    return v;
+}
+
+int pm_fr_mul_batch(const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n) { return field_batch<Fr>(FieldOp::Mul, a, b, out, n, false); }
+int pm_fr_add_batch(const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n) { return field_batch<Fr>(FieldOp::Add, a, b, out, n, false); }
+int pm_fr_sub_batch(const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n) { return field_batch<Fr>(FieldOp::Sub, a, b, out, n, false); }
+int pm_fq_mul_batch(const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n) { return field_batch<Fq>(FieldOp::Mul, a, b, out, n, true); }
+
+int pm_ntt_fr(uint8_t* data, unsigned log_n, int inverse, const uint8_t* coset_gen) {
+    return guarded([&] {
+        if (!data || log_n > 32) throw StatusError(PM_ERR_ARG, "bad ntt arguments");
+        Runtime& rt = runtime();
+        const size_t n = (size_t)1 << log_n;
+        DevBuf d, g;
+        Fr* p = d.as<Fr>(n);
+        PM_CUDA(cudaMemcpyAsync(p, data, n * sizeof(Fr), cudaMemcpyHostToDevice, rt.stream));
+        Fr* gd = nullptr;
+        if (coset_gen) {
+            // forward: scale by g^i then transform; inverse: transform then scale by g^-i (caller passes g; we invert on device)
+            gd = g.as<Fr>(2);
+            PM_CUDA(cudaMemcpyAsync(gd, coset_gen, sizeof(Fr), cudaMemcpyHostToDevice, rt.stream));
+        }
+        if (coset_gen && !inverse) { launch_scale_by_powers(p, n, gd, rt.stream); rt.extra_launches++; }
+        rt.ntt.run(p, (int)log_n, inverse != 0, rt.stream);
+        if (coset_gen && inverse) {
+            launch_fr_inverse(gd, gd + 1, rt.stream);
+            launch_scale_by_powers(p, n, gd + 1, rt.stream);
+            rt.extra_launches += 2;
+        }
+        PM_CUDA(cudaMemcpyAsync(data, p, n * sizeof(Fr), cudaMemcpyDeviceToHost, rt.stream));
+        PM_CUDA(cudaStreamSynchronize(rt.stream));
+    });
+}
+
+int pm_msm_g1_window(const uint8_t* bases, size_t base_stride, const uint8_t* scalars, size_t n, int window_bits,
+                     int heavy_threshold, uint8_t out[PM_G1_BYTES]) {
+    return guarded([&] {
+        if (!out || (n && (!bases || !scalars)) || base_stride < PM_G1_BYTES) throw StatusError(PM_ERR_ARG, "bad msm arguments");
+        Runtime& rt = runtime();
+        std::vector<uint8_t> packed;
+        const uint8_t* src = bases;
+        if (base_stride != PM_G1_BYTES) { pack_points_host(bases, base_stride, n, packed); src = packed.data(); }
+        DevBuf db, ds, dres;
+        G1Affine* pb = db.as<G1Affine>(n ? n : 1);
+        Fr* ps = ds.as<Fr>(n ? n : 1);
+        G1XYZZ* acc = dres.as<G1XYZZ>(2);
+        G1Affine* res = reinterpret_cast<G1Affine*>(acc + 1);
+        PM_CUDA(cudaMemcpyAsync(pb, src, n * sizeof(G1Affine), cudaMemcpyHostToDevice, rt.stream));
+        PM_CUDA(cudaMemcpyAsync(ps, scalars, n * sizeof(Fr), cudaMemcpyHostToDevice, rt.stream));
+        MsmConfig cfg;
+        cfg.c = window_bits;
+        cfg.heavy = heavy_threshold;
+        rt.msm.run(pb, ps, n, acc, rt.stream, cfg);
+        launch_xyzz_sum_to_affine(acc, 1, res, rt.stream);
+        rt.extra_launches++;
+        PM_CUDA(cudaMemcpyAsync(out, res, sizeof(G1Affine), cudaMemcpyDeviceToHost, rt.stream));
+        PM_CUDA(cudaStreamSynchronize(rt.stream));
+    });
+}
+
+int pm_msm_g1(const uint8_t* bases, size_t base_stride, const uint8_t* scalars, size_t n, uint8_t out[PM_G1_BYTES]) {
+    return pm_msm_g1_window(bases, base_stride, scalars, n, 0, 0, out);
+}
+
+int pm_fixed_base_mul(const uint8_t* scalars, size_t n, uint8_t* out) {
+    return guarded([&] {
+        if (n == 0) return;
+        if (!scalars || !out) throw StatusError(PM_ERR_ARG, "null buffer");
+        Runtime& rt = runtime();
+        DevBuf ds, dout;
+        Fr* ps = ds.as<Fr>(n);
+        G1Affine* po = dout.as<G1Affine>(n);
+        PM_CUDA(cudaMemcpyAsync(ps, scalars, n * sizeof(Fr), cudaMemcpyHostToDevice, rt.stream));
+        rt.fixed_base.run(ps, n, po, rt.stream);
+        PM_CUDA(cudaMemcpyAsync(out, po, n * sizeof(G1Affine), cudaMemcpyDeviceToHost, rt.stream));
+        PM_CUDA(cudaStreamSynchronize(rt.stream));
+    });
+}
+
+int pm_bench_imad_peak(double* mads_per_s) {
+    return guarded([&] { runtime(); *mads_per_s = measure_imad_peak(2000); });
+}
+
+int pm_bench_field_mul(int field, double* muls_per_s) {
+    return guarded([&] { runtime(); *muls_per_s = field ? measure_fq_mul_rate(2000) : measure_fr_mul_rate(4000); });
+}
+
+int pm_bench_ntt(unsigned log_n, int inverse, int iters, double* ms_avg) {
+    return guarded([&] {
+        if (log_n > 30 || iters <= 0 || !ms_avg) throw StatusError(PM_ERR_ARG, "bad bench arguments");
+        Runtime& rt = runtime();
+        const size_t n = (size_t)1 << log_n;
+        DevBuf d;
+        Fr* p = d.as<Fr>(n);
+        launch_fill_fr(p, n, 0x1234 + log_n, rt.stream);
+        rt.ntt.run(p, (int)log_n, inverse != 0, rt.stream);  // warm-up (builds twiddle tables)
+        cudaEvent_t e0, e1;
+        PM_CUDA(cudaEventCreate(&e0));
+        PM_CUDA(cudaEventCreate(&e1));
+        PM_CUDA(cudaStreamSynchronize(rt.stream));
+        PM_CUDA(cudaEventRecord(e0, rt.stream));
+        for (int i = 0; i < iters; i++) rt.ntt.run(p, (int)log_n, inverse != 0, rt.stream);
+        PM_CUDA(cudaEventRecord(e1, rt.stream));
+        PM_CUDA(cudaEventSynchronize(e1));
+        float ms = 0;
+        PM_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        *ms_avg = ms / iters;
+    });
+}
+
+int pm_bench_msm(size_t n, int window_bits, int iters, double* ms_avg, double* ms_accumulate) {
+    return guarded([&] {
+        if (n == 0 || iters <= 0 || !ms_avg) throw StatusError(PM_ERR_ARG, "bad bench arguments");
+        Runtime& rt = runtime();
+        DevBuf db, ds, dres;
+        G1Affine* pb = db.as<G1Affine>(n);
+        Fr* ps = ds.as<Fr>(n);
+        G1XYZZ* acc = dres.as<G1XYZZ>(1);
+        launch_fill_fr(ps, n, 0xabcdef, rt.stream);
+        rt.fixed_base.run(ps, n, pb, rt.stream);       // bases = [s_i]G for pseudo-random s_i
+        launch_fill_fr(ps, n, 0x5eed, rt.stream);      // uniform scalars
+        MsmConfig cfg;
+        cfg.c = window_bits;
+        rt.msm.time_accumulate = true;
+        rt.msm.run(pb, ps, n, acc, rt.stream, cfg);    // warm-up
+        cudaEvent_t e0, e1;
+        PM_CUDA(cudaEventCreate(&e0));
+        PM_CUDA(cudaEventCreate(&e1));
+        PM_CUDA(cudaStreamSynchronize(rt.stream));
+        double acc_ms = 0;
+        float total = 0;
+        for (int i = 0; i < iters; i++) {
+            PM_CUDA(cudaEventRecord(e0, rt.stream));
+            rt.msm.run(pb, ps, n, acc, rt.stream, cfg);
+            PM_CUDA(cudaEventRecord(e1, rt.stream));
+            PM_CUDA(cudaEventSynchronize(e1));
+            float ms = 0, ams = 0;
+            PM_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+            PM_CUDA(cudaEventElapsedTime(&ams, rt.msm.ev_acc_begin, rt.msm.ev_acc_end));
+            total += ms;
+            acc_ms += ams;
+        }
+        rt.msm.time_accumulate = false;
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        *ms_avg = total / iters;
+        if (ms_accumulate) *ms_accumulate = acc_ms / iters;
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,136 @@
+// BLS12-381 G1 on the device: affine bases (96 B, Montgomery limbs, (0,0) = infinity) and
+// XYZZ accumulators (x = X/ZZ, y = Y/ZZZ, ZZ^3 = ZZZ^2; ZZ == 0 is infinity).
+//
+// Replaces ark-ec's `Projective<g1::Config>` arithmetic used inside
+// `VariableBaseMSM::msm_unchecked` (/root/reference/src/prover.rs:380-384) and `g * scalar`
+// (/root/reference/src/generator.rs:169-177).  Only the affine image leaves the device, so
+// the coordinate system is free; XYZZ gives the cheapest mixed addition (8M + 2S).
+#pragma once
+#include "field.cuh"
+
+namespace pm {
+
+struct alignas(16) G1Affine {
+    Fq x, y;
+    __device__ __forceinline__ bool is_inf() const { return x.is_zero() && y.is_zero(); }
+    __device__ __forceinline__ static G1Affine inf() { return {Fq::zero(), Fq::zero()}; }
+};
+
+struct alignas(16) G1XYZZ {
+    Fq x, y, zz, zzz;
+    __device__ __forceinline__ bool is_inf() const { return zz.is_zero(); }
+    __device__ __forceinline__ static G1XYZZ inf() { return {Fq::zero(), Fq::zero(), Fq::zero(), Fq::zero()}; }
+    __device__ __forceinline__ static G1XYZZ from_affine(const G1Affine& p) {
+        if (p.is_inf()) return inf();
+        return {p.x, p.y, Fq::one(), Fq::one()};
+    }
+};
+
+// acc = 2 * p (p affine, not infinity)   EFD mdbl-2008-s-1
+static __device__ __noinline__ G1XYZZ xyzz_dbl_affine(const G1Affine& p) {
+    G1XYZZ r;
+    Fq u = p.y.dbl();
+    Fq v = u.sqr();
+    Fq w = u * v;
+    Fq s = p.x * v;
+    Fq xx = p.x.sqr();
+    Fq m = xx.dbl() + xx;
+    r.x = m.sqr() - s.dbl();
+    r.y = m * (s - r.x) - w * p.y;
+    r.zz = v;
+    r.zzz = w;
+    return r;
+}
+
+// acc = 2 * acc   EFD dbl-2008-s-1 (a = 0)
+static __device__ __noinline__ void xyzz_dbl(G1XYZZ& a) {
+    if (a.is_inf()) return;
+    Fq u = a.y.dbl();
+    Fq v = u.sqr();
+    Fq w = u * v;
+    Fq s = a.x * v;
+    Fq xx = a.x.sqr();
+    Fq m = xx.dbl() + xx;
+    Fq x3 = m.sqr() - s.dbl();
+    a.y = m * (s - x3) - w * a.y;
+    a.x = x3;
+    a.zz = v * a.zz;
+    a.zzz = w * a.zzz;
+}
+
+// acc += p (p affine; `neg` adds -p)   EFD madd-2008-s
+__device__ __forceinline__ void xyzz_madd(G1XYZZ& a, const G1Affine& p_in, bool neg = false) {
+    if (p_in.is_inf()) return;
+    Fq py = neg ? p_in.y.neg() : p_in.y;
+    if (a.is_inf()) {
+        a.x = p_in.x; a.y = py; a.zz = Fq::one(); a.zzz = Fq::one();
+        return;
+    }
+    Fq u2 = p_in.x * a.zz;
+    Fq s2 = py * a.zzz;
+    Fq p = u2 - a.x;
+    Fq r = s2 - a.y;
+    if (p.is_zero()) {
+        if (r.is_zero()) {
+            G1Affine q{p_in.x, py};
+            a = xyzz_dbl_affine(q);
+        } else {
+            a = G1XYZZ::inf();
+        }
+        return;
+    }
+    Fq pp = p.sqr();
+    Fq ppp = p * pp;
+    Fq q = a.x * pp;
+    Fq x3 = r.sqr() - ppp - q.dbl();
+    a.y = r * (q - x3) - a.y * ppp;
+    a.x = x3;
+    a.zz = a.zz * pp;
+    a.zzz = a.zzz * ppp;
+}
+
+// acc += b   EFD add-2008-s
+static __device__ __noinline__ void xyzz_add(G1XYZZ& a, const G1XYZZ& b) {
+    if (b.is_inf()) return;
+    if (a.is_inf()) { a = b; return; }
+    Fq u1 = a.x * b.zz;
+    Fq u2 = b.x * a.zz;
+    Fq s1 = a.y * b.zzz;
+    Fq s2 = b.y * a.zzz;
+    Fq p = u2 - u1;
+    Fq r = s2 - s1;
+    if (p.is_zero()) {
+        if (r.is_zero()) xyzz_dbl(a);
+        else a = G1XYZZ::inf();
+        return;
+    }
+    Fq pp = p.sqr();
+    Fq ppp = p * pp;
+    Fq q = u1 * pp;
+    Fq x3 = r.sqr() - ppp - q.dbl();
+    a.y = r * (q - x3) - s1 * ppp;
+    a.x = x3;
+    a.zz = a.zz * b.zz * pp;
+    a.zzz = a.zzz * b.zzz * ppp;
+}
+
+// canonical affine image: x = X/ZZ, y = Y/ZZZ with 1/ZZ = (ZZ/ZZZ)^2
+static __device__ __noinline__ G1Affine xyzz_to_affine(const G1XYZZ& a) {
+    if (a.is_inf()) return G1Affine::inf();
+    Fq izzz = a.zzz.inv();
+    Fq t = a.zz * izzz;
+    Fq izz = t.sqr();
+    return {a.x * izz, a.y * izzz};
+}
+
+// acc = k * acc for a small unsigned k (double-and-add, MSB first)
+static __device__ __noinline__ G1XYZZ xyzz_mul_small(const G1XYZZ& p, uint32_t k) {
+    G1XYZZ r = G1XYZZ::inf();
+    for (int bit = 31 - __clz(k | 1); bit >= 0; bit--) {
+        xyzz_dbl(r);
+        if ((k >> bit) & 1) xyzz_add(r, p);
+    }
+    return r;
+}
+
+}  // namespace pm

@@ -1,0 +1,338 @@
+// K4 — G1 Pippenger MSM for sm_100a.
+//
+// Replaces `VariableBaseMSM::msm_unchecked` as called from /root/reference/src/prover.rs:380-384
+// (callers :114-121, :229, :330-357).  Pipeline (all on one stream, no host sync):
+//   1. k_digits<COUNT>   scalar -> canonical -> signed c-bit digits; histogram of (window, bucket)
+//   2. k_scan            exclusive prefix of the histogram -> bucket offsets
+//   3. k_digits<SCATTER> counting-sort scatter of (point index | sign) by (window, bucket)
+//                        (order inside a bucket is irrelevant: group addition commutes)
+//   4. k_accumulate      one thread per bucket, XYZZ mixed additions over its sorted run;
+//                        buckets longer than a threshold are deferred to
+//      k_accumulate_heavy (one CTA per heavy bucket, shared-memory tree) so skewed scalar
+//                        distributions (SURVEY.md §7 "hard parts") do not serialise
+//   5. k_reduce_segments running-sum over K-bucket segments + small scalar mul by the segment base
+//      k_reduce_windows  per-window tree sum of the segment partials
+//      k_combine_windows Horner over windows (c doublings each) -> one XYZZ point
+// Points at infinity ((0,0)) and zero scalars are skipped in step 1/3.
+#include "msm.cuh"
+
+namespace pm {
+
+namespace {
+
+constexpr int kMaxWindows = 64;
+constexpr int kSegBuckets = 16;     // buckets per reduce segment
+
+__device__ __forceinline__ uint32_t window_bits(const uint32_t* s, int pos, int c) {
+    int limb = pos >> 5, off = pos & 31;
+    if (limb >= 8) return 0;
+    uint64_t v = s[limb];
+    if (limb + 1 < 8) v |= (uint64_t)s[limb + 1] << 32;
+    return (uint32_t)(v >> off) & ((1u << c) - 1u);
+}
+
+template <bool SCATTER>
+__global__ void __launch_bounds__(256) k_digits(const G1Affine* __restrict__ bases, const Fr* __restrict__ scalars,
+                                                size_t n, int c, int nwin, uint32_t nb,
+                                                uint32_t* __restrict__ counters, uint32_t* __restrict__ sorted) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fr s = scalars[i];
+    if (s.is_zero()) return;
+    // infinity bases carry no weight: test the first limbs cheaply, full test only if they vanish
+    {
+        const uint4* bp = reinterpret_cast<const uint4*>(bases + i);
+        uint4 q = __ldg(bp);
+        if ((q.x | q.y | q.z | q.w) == 0) {
+            G1Affine b = bases[i];
+            if (b.is_inf()) return;
+        }
+    }
+    s = s.from_mont();
+    uint32_t limbs[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) limbs[k] = s.v[k];
+    const uint32_t half = 1u << (c - 1);
+    uint32_t carry = 0;
+    for (int w = 0; w < nwin; w++) {
+        uint32_t d = window_bits(limbs, w * c, c) + carry;
+        uint32_t neg = 0;
+        if (d > half) { d = (1u << c) - d; neg = 1; carry = 1; } else { carry = 0; }
+        if (d == 0) continue;
+        uint32_t slot = (uint32_t)w * nb + (d - 1);
+        if (SCATTER) {
+            uint32_t pos = atomicAdd(&counters[slot], 1u);
+            sorted[pos] = (uint32_t)i | (neg << 31);
+        } else {
+            atomicAdd(&counters[slot], 1u);
+        }
+    }
+}
+
+// Single-CTA exclusive scan of `total` counters; writes offsets[0..total] and a copy into cursors[0..total).
+__global__ void __launch_bounds__(1024) k_scan(const uint32_t* __restrict__ counts, uint32_t total,
+                                               uint32_t* __restrict__ offsets, uint32_t* __restrict__ cursors) {
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t carry_s;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) carry_s = 0;
+    __syncthreads();
+    // process in tiles of 1024*4 for coalesced access
+    for (uint32_t base = 0; base < total; base += 4096) {
+        uint32_t idx = base + tid * 4;
+        uint32_t v[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) v[k] = (idx + k < total) ? counts[idx + k] : 0;
+        uint32_t local = v[0] + v[1] + v[2] + v[3];
+        uint32_t incl = local;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        if (lane == 31) warp_sums[wid] = incl;
+        __syncthreads();
+        if (wid == 0) {
+            uint32_t ws = warp_sums[lane];
+            uint32_t wi = ws;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                uint32_t t = __shfl_up_sync(0xffffffffu, wi, d);
+                if (lane >= d) wi += t;
+            }
+            warp_sums[lane] = wi - ws;  // exclusive
+        }
+        __syncthreads();
+        uint32_t excl = carry_s + warp_sums[wid] + incl - local;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (idx + k < total) { offsets[idx + k] = excl; cursors[idx + k] = excl; }
+            excl += v[k];
+        }
+        __syncthreads();
+        if (tid == 1023) carry_s = excl;
+        __syncthreads();
+    }
+    if (tid == 0) offsets[total] = carry_s;
+}
+
+__device__ __forceinline__ G1Affine load_point(const G1Affine* __restrict__ bases, uint32_t idx) {
+    G1Affine p;
+    const uint4* src = reinterpret_cast<const uint4*>(bases + idx);
+    uint4* dst = reinterpret_cast<uint4*>(&p);
+#pragma unroll
+    for (int k = 0; k < 6; k++) dst[k] = __ldg(src + k);
+    return p;
+}
+
+__global__ void __launch_bounds__(128) k_accumulate(const G1Affine* __restrict__ bases, const uint32_t* __restrict__ sorted,
+                                                    const uint32_t* __restrict__ offsets, G1XYZZ* __restrict__ buckets,
+                                                    uint32_t total_buckets, uint32_t heavy_thr,
+                                                    uint32_t* __restrict__ heavy_list, uint32_t* __restrict__ heavy_count) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total_buckets) return;
+    uint32_t beg = offsets[t], end = offsets[t + 1];
+    if (end - beg > heavy_thr) {
+        uint32_t slot = atomicAdd(heavy_count, 1u);
+        heavy_list[slot] = t;
+        return;
+    }
+    G1XYZZ acc = G1XYZZ::inf();
+    if (beg < end) {
+        uint32_t e = sorted[beg];
+        G1Affine p = load_point(bases, e & 0x7fffffffu);
+        for (uint32_t k = beg; k < end; k++) {
+            uint32_t e_next = 0;
+            G1Affine p_next;
+            if (k + 1 < end) {
+                e_next = sorted[k + 1];
+                p_next = load_point(bases, e_next & 0x7fffffffu);
+            }
+            xyzz_madd(acc, p, (e >> 31) != 0);
+            p = p_next;
+            e = e_next;
+        }
+    }
+    buckets[t] = acc;
+}
+
+// One CTA per heavy bucket: strided per-thread sums, then a shared-memory tree.
+__global__ void __launch_bounds__(256) k_accumulate_heavy(const G1Affine* __restrict__ bases, const uint32_t* __restrict__ sorted,
+                                                          const uint32_t* __restrict__ offsets, G1XYZZ* __restrict__ buckets,
+                                                          const uint32_t* __restrict__ heavy_list,
+                                                          const uint32_t* __restrict__ heavy_count) {
+    extern __shared__ uint4 smem_raw[];
+    G1XYZZ* sh = reinterpret_cast<G1XYZZ*>(smem_raw);
+    const uint32_t nheavy = *heavy_count;
+    for (uint32_t h = blockIdx.x; h < nheavy; h += gridDim.x) {
+        uint32_t t = heavy_list[h];
+        uint32_t beg = offsets[t], end = offsets[t + 1];
+        G1XYZZ acc = G1XYZZ::inf();
+        for (uint32_t k = beg + threadIdx.x; k < end; k += blockDim.x) {
+            uint32_t e = sorted[k];
+            G1Affine p = load_point(bases, e & 0x7fffffffu);
+            xyzz_madd(acc, p, (e >> 31) != 0);
+        }
+        sh[threadIdx.x] = acc;
+        __syncthreads();
+        for (uint32_t stride = blockDim.x / 2; stride > 0; stride >>= 1) {
+            if (threadIdx.x < stride) {
+                G1XYZZ a = sh[threadIdx.x];
+                xyzz_add(a, sh[threadIdx.x + stride]);
+                sh[threadIdx.x] = a;
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) buckets[t] = sh[0];
+        __syncthreads();
+    }
+}
+
+// Segment s of window w covers buckets [s*K, (s+1)*K); bucket b has weight b+1.
+// partial = sum_{b in seg} (b - lo + 1) * B[b] + lo * sum_{b in seg} B[b]
+__global__ void __launch_bounds__(128) k_reduce_segments(const G1XYZZ* __restrict__ buckets, uint32_t nb, uint32_t nseg,
+                                                         uint32_t total_segs, G1XYZZ* __restrict__ segs) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total_segs) return;
+    uint32_t w = t / nseg, s = t % nseg;
+    uint32_t lo = s * kSegBuckets;
+    uint32_t hi = min(lo + kSegBuckets, nb);
+    const G1XYZZ* wb = buckets + (size_t)w * nb;
+    G1XYZZ running = G1XYZZ::inf(), acc = G1XYZZ::inf();
+    for (uint32_t b = hi; b-- > lo;) {
+        xyzz_add(running, wb[b]);
+        xyzz_add(acc, running);
+    }
+    if (lo != 0 && !running.is_inf()) {
+        G1XYZZ scaled = xyzz_mul_small(running, lo);
+        xyzz_add(acc, scaled);
+    }
+    segs[t] = acc;
+}
+
+// One CTA per window: sum its nseg partials.
+__global__ void __launch_bounds__(128) k_reduce_windows(const G1XYZZ* __restrict__ segs, uint32_t nseg, G1XYZZ* __restrict__ winsums) {
+    __shared__ uint4 smem_raw[128 * sizeof(G1XYZZ) / sizeof(uint4)];
+    G1XYZZ* sh = reinterpret_cast<G1XYZZ*>(smem_raw);
+    const G1XYZZ* ws = segs + (size_t)blockIdx.x * nseg;
+    G1XYZZ acc = G1XYZZ::inf();
+    for (uint32_t k = threadIdx.x; k < nseg; k += blockDim.x) xyzz_add(acc, ws[k]);
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (uint32_t stride = blockDim.x / 2; stride > 0; stride >>= 1) {
+        if (threadIdx.x < stride) {
+            G1XYZZ a = sh[threadIdx.x];
+            xyzz_add(a, sh[threadIdx.x + stride]);
+            sh[threadIdx.x] = a;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) winsums[blockIdx.x] = sh[0];
+}
+
+__global__ void k_combine_windows(const G1XYZZ* __restrict__ winsums, int nwin, int c, G1XYZZ* __restrict__ out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    G1XYZZ acc = G1XYZZ::inf();
+    for (int w = nwin - 1; w >= 0; w--) {
+        for (int k = 0; k < c; k++) xyzz_dbl(acc);
+        xyzz_add(acc, winsums[w]);
+    }
+    out[0] = acc;
+}
+
+__global__ void k_xyzz_sum_to_affine(const G1XYZZ* __restrict__ parts, int k, G1Affine* __restrict__ out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    G1XYZZ acc = G1XYZZ::inf();
+    for (int i = 0; i < k; i++) xyzz_add(acc, parts[i]);
+    out[0] = xyzz_to_affine(acc);
+}
+
+}  // namespace
+
+int MsmEngine::choose_window(size_t n) {
+    // balance n*ceil(256/c) bucket additions against 2^(c-1)*ceil(256/c) bucket reductions,
+    // keeping >= ~32k bucket threads in flight for the 148-SM part
+    int lg = 0;
+    while (((size_t)1 << (lg + 1)) <= n) lg++;
+    int c = lg - 4;
+    if (c < 10) c = 10;
+    if (c > 16) c = 16;
+    if (n < 1024) c = 8;
+    if (n < 64) c = 4;
+    return c;
+}
+
+MsmEngine::~MsmEngine() {
+    if (ev_acc_begin) cudaEventDestroy(ev_acc_begin);
+    if (ev_acc_end) cudaEventDestroy(ev_acc_end);
+}
+
+void MsmEngine::run(const G1Affine* bases, const Fr* scalars, size_t n, G1XYZZ* out_xyzz, cudaStream_t stream,
+                    MsmConfig cfg) {
+    if (n == 0) {
+        PM_CUDA(cudaMemsetAsync(out_xyzz, 0, sizeof(G1XYZZ), stream));
+        return;
+    }
+    if (n >= ((size_t)1 << 31)) throw CudaError("msm: n must be < 2^31");
+    const int c = cfg.c ? cfg.c : choose_window(n);
+    const int nwin = (256 + c - 1) / c;
+    if (nwin > kMaxWindows) throw CudaError("msm: too many windows");
+    const uint32_t nb = 1u << (c - 1);
+    const uint32_t total = (uint32_t)nwin * nb;
+    const uint32_t nseg = (nb + kSegBuckets - 1) / kSegBuckets;
+    const uint32_t total_segs = nseg * (uint32_t)nwin;
+    size_t avg = (n + nb - 1) / nb;
+    uint32_t heavy_thr = cfg.heavy ? (uint32_t)cfg.heavy : (uint32_t)(avg * 8 > 2048 ? avg * 8 : 2048);
+
+    uint32_t* counts = counts_.as<uint32_t>(total + 1);
+    uint32_t* offsets = offsets_.as<uint32_t>(total + 1);
+    uint32_t* cursors = cursors_.as<uint32_t>(total + 1);
+    uint32_t* sorted = sorted_.as<uint32_t>(n * (size_t)nwin);
+    G1XYZZ* buckets = buckets_.as<G1XYZZ>(total);
+    G1XYZZ* segs = segs_.as<G1XYZZ>(total_segs);
+    G1XYZZ* winsums = winsums_.as<G1XYZZ>(nwin);
+    uint32_t* heavy_list = heavy_list_.as<uint32_t>(total);
+    uint32_t* heavy_count = heavy_count_.as<uint32_t>(1);
+
+    PM_CUDA(cudaMemsetAsync(counts, 0, (total + 1) * sizeof(uint32_t), stream));
+    PM_CUDA(cudaMemsetAsync(heavy_count, 0, sizeof(uint32_t), stream));
+    const unsigned dgrid = ceil_div(n, 256);
+    k_digits<false><<<dgrid, 256, 0, stream>>>(bases, scalars, n, c, nwin, nb, counts, nullptr);
+    PM_LAUNCH_CHECK();
+    k_scan<<<1, 1024, 0, stream>>>(counts, total, offsets, cursors);
+    PM_LAUNCH_CHECK();
+    k_digits<true><<<dgrid, 256, 0, stream>>>(bases, scalars, n, c, nwin, nb, cursors, sorted);
+    PM_LAUNCH_CHECK();
+    if (time_accumulate) {
+        if (!ev_acc_begin) { PM_CUDA(cudaEventCreate(&ev_acc_begin)); PM_CUDA(cudaEventCreate(&ev_acc_end)); }
+        PM_CUDA(cudaEventRecord(ev_acc_begin, stream));
+    }
+    k_accumulate<<<ceil_div(total, 128), 128, 0, stream>>>(bases, sorted, offsets, buckets, total, heavy_thr,
+                                                          heavy_list, heavy_count);
+    PM_LAUNCH_CHECK();
+    if (time_accumulate) PM_CUDA(cudaEventRecord(ev_acc_end, stream));
+    {
+        static bool attr_set = false;
+        const int smem = 256 * (int)sizeof(G1XYZZ);
+        if (!attr_set) {
+            PM_CUDA(cudaFuncSetAttribute(k_accumulate_heavy, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            attr_set = true;
+        }
+        k_accumulate_heavy<<<2 * sm_count(), 256, smem, stream>>>(bases, sorted, offsets, buckets, heavy_list, heavy_count);
+        PM_LAUNCH_CHECK();
+    }
+    k_reduce_segments<<<ceil_div(total_segs, 128), 128, 0, stream>>>(buckets, nb, nseg, total_segs, segs);
+    PM_LAUNCH_CHECK();
+    k_reduce_windows<<<nwin, 128, 0, stream>>>(segs, nseg, winsums);
+    PM_LAUNCH_CHECK();
+    k_combine_windows<<<1, 32, 0, stream>>>(winsums, nwin, c, out_xyzz);
+    PM_LAUNCH_CHECK();
+    launches += 8;
+}
+
+void launch_xyzz_sum_to_affine(const G1XYZZ* parts, int k, G1Affine* out_affine, cudaStream_t stream) {
+    k_xyzz_sum_to_affine<<<1, 32, 0, stream>>>(parts, k, out_affine);
+    PM_LAUNCH_CHECK();
+}
+
+}  // namespace pm

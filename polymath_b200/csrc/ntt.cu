@@ -1,0 +1,371 @@
+// K3 — Fr NTT / iNTT for sm_100a (shared-memory staged, four-step layout).
+//
+// Replaces `Radix2EvaluationDomain::{fft, ifft_in_place}` as called from
+// /root/reference/src/prover.rs:239-243 (poly_coeffs) and :315-328 (square_polynomial).
+// Natural order in and out; w_N is arkworks' `group_gen` (TWO_ADIC_ROOT squared 32-log_n times).
+//
+// N = 2^k is split into up to three digits N = N1*N2*N3 (each 2^6..2^11):
+//   column pass(es): for every residue of the lower digits, an M-point sub-NTT over a
+//       strided digit, done entirely in shared memory by one CTA for a batch of B adjacent
+//       columns (B*32-byte contiguous chunks in HBM), then the inter-digit twiddle
+//       w^(low*k) is applied on the way out.  In place.
+//   row pass: contiguous M-point sub-NTTs; the store performs the digit-reversal transpose
+//       (B adjacent outputs per k), so the result lands in natural order.  Out of place.
+// Inside a CTA: 2048 elements, 256 threads, 8 elements per thread; radix-8 register rounds
+// (three butterfly stages between shared-memory exchanges), limb-plane layout padded one
+// slot per eight so strided rounds are bank-conflict free; the sub-NTT twiddles stay
+// resident in shared memory.
+#include "ntt.cuh"
+
+namespace pm {
+
+namespace {
+
+constexpr int kCoreBits = 11;
+constexpr int kElemsPerCta = 2048;
+constexpr int kThreads = 256;
+constexpr int kTwBits = 11;
+constexpr int kPlane = kElemsPerCta + kElemsPerCta / 8;  // padded slots per plane
+
+// 2^32-th primitive root of unity of Fr (7^((r-1)/2^32)) and its inverse, Montgomery form
+__device__ __constant__ uint32_t ROOT32[8] = {0x5f0e466au, 0xb9b58d8cu, 0x1819d7ecu, 0x5b1b4c80u,
+                                             0x52a31e64u, 0x0af53ae3u, 0x19e9b27bu, 0x5bf3addau};
+__device__ __constant__ uint32_t ROOT32_INV[8] = {0xdcf3219au, 0x4256481au, 0x96b6cad3u, 0x45f37b7fu,
+                                                 0x5f7a3b27u, 0xf9c3f1d7u, 0x658afd43u, 0x2d2fc049u};
+
+__device__ __forceinline__ Fr root_of_unity(int log_size, bool inverse) {
+    Fr w;
+#pragma unroll
+    for (int i = 0; i < 8; i++) w.v[i] = inverse ? ROOT32_INV[i] : ROOT32[i];
+    for (int i = log_size; i < 32; i++) w = w.sqr();
+    return w;
+}
+
+// table[k] = base^k for k < count, base = w_{2^log_size}^(2^shift)
+__global__ void k_build_table(Fr* table, int count, int log_size, int shift, bool inverse) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    Fr base = root_of_unity(log_size, inverse);
+    for (int i = 0; i < shift; i++) base = base.sqr();
+    table[k] = base.pow_u64((uint64_t)k);
+}
+
+__global__ void k_build_ninv(Fr* out, int log_n) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    // n^-1 = (2^-1)^log_n
+    Fr two = Fr::one() + Fr::one();
+    Fr half = two.inv();
+    out[0] = half.pow_u64((uint64_t)log_n);
+}
+
+struct PassArgs {
+    const Fr* in;
+    Fr* out;
+    int m;        // log2 of the sub-transform size M
+    int log_n;    // log2 of the full transform
+    int log_s;    // column pass: log2 stride between sub-transform points
+    int log_n1;   // row pass: bits of the most significant digit of the row index
+    const Fr* core;
+    const Fr* tw0;
+    const Fr* tw1;
+    const Fr* tw2;
+    const Fr* scale;  // row pass: optional n^-1
+};
+
+__device__ __forceinline__ int phys(int i) { return i + (i >> 3); }
+
+__device__ __forceinline__ Fr sm_load(const uint4* lo, const uint4* hi, int slot) {
+    Fr r;
+    uint4 a = lo[slot], b = hi[slot];
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+    r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    return r;
+}
+__device__ __forceinline__ void sm_store(uint4* lo, uint4* hi, int slot, const Fr& r) {
+    lo[slot] = make_uint4(r.v[0], r.v[1], r.v[2], r.v[3]);
+    hi[slot] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
+}
+
+// In-place M-point DIT butterflies on bit-reversed data for every sub-transform of the CTA.
+// Thread t owns 8 slots per round; a round covers up to three stages (s, s+1, s+2).
+__device__ __forceinline__ void core_ntt(uint4* lo, uint4* hi, const Fr* tw, int m, int tid) {
+    const int M = 1 << m;
+    const int mpad = M + (M >> 3);
+    const int per_sub = M >> 3;          // threads per sub-transform
+    const int b = tid / per_sub;
+    const int tt = tid - b * per_sub;
+    uint4* blo = lo + b * mpad;
+    uint4* bhi = hi + b * mpad;
+    for (int s = 0; s < m; s += 3) {
+        const int r = (m - s) < 3 ? (m - s) : 3;
+        int pos[8];
+        Fr x[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            int vt = (tt << (3 - r)) + (j >> r);
+            int jb = j & ((1 << r) - 1);
+            pos[j] = ((vt >> s) << (s + r)) | (jb << s) | (vt & ((1 << s) - 1));
+            x[j] = sm_load(blo, bhi, phys(pos[j]));
+        }
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+            if (q < r) {
+                const int hb = s + q;  // half-size = 2^hb
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    if ((j >> q) & 1) continue;
+                    const int jj = j | (1 << q);
+                    int e = (pos[j] & ((1 << hb) - 1)) << (m - hb - 1);
+                    Fr v = (e == 0) ? x[jj] : x[jj] * tw[e];
+                    x[jj] = x[j] - v;
+                    x[j] = x[j] + v;
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++) sm_store(blo, bhi, phys(pos[j]), x[j]);
+        __syncthreads();
+    }
+}
+
+__device__ __forceinline__ Fr interpass_twiddle(const PassArgs& a, uint64_t e) {
+    Fr t = a.tw0[e & ((1u << kTwBits) - 1)];
+    if (a.log_n > kTwBits) t = t * a.tw1[(e >> kTwBits) & ((1u << kTwBits) - 1)];
+    if (a.log_n > 2 * kTwBits) t = t * a.tw2[e >> (2 * kTwBits)];
+    return t;
+}
+
+__device__ __forceinline__ void load_core_twiddles(Fr* tw, const Fr* core, int m, int tid, int nthreads) {
+    const int half = 1 << (m - 1);
+    for (int k = tid; k < half; k += nthreads) tw[k] = core[(size_t)k << (kCoreBits - m)];
+}
+
+// ---- column pass ----------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) k_ntt_columns(PassArgs a) {
+    extern __shared__ uint4 smem[];
+    uint4* lo = smem;
+    uint4* hi = smem + kPlane;
+    Fr* tw = reinterpret_cast<Fr*>(smem + 2 * kPlane);
+    const int tid = threadIdx.x;
+    const int m = a.m, M = 1 << m;
+    const int log_b = 11 - m;            // B = 2048 / M columns per CTA
+    const int B = 1 << log_b;
+    const int mpad = M + (M >> 3);
+    const uint64_t blocks_per_outer = (uint64_t)1 << (a.log_s - log_b);
+    const uint64_t outer = blockIdx.x / blocks_per_outer;
+    const uint64_t low0 = (blockIdx.x % blocks_per_outer) << log_b;
+
+    load_core_twiddles(tw, a.core, m, tid, kThreads);
+    const uint4* in4 = reinterpret_cast<const uint4*>(a.in);
+    for (int u = tid; u < 2 * kElemsPerCta; u += kThreads) {
+        int el = u >> 1, half = u & 1;
+        int c = el & (B - 1);
+        int n1 = el >> log_b;
+        uint64_t gi = ((((outer << m) + (uint64_t)n1) << a.log_s) + low0 + (uint64_t)c);
+        uint4 val = in4[gi * 2 + half];
+        int slot = c * mpad + phys((int)(__brev((unsigned)n1) >> (32 - m)));
+        (half ? hi : lo)[slot] = val;
+    }
+    __syncthreads();
+    core_ntt(lo, hi, tw, m, tid);
+    // twiddle by w_{M*S}^(low*k1) = w_N^(low*k1 * N/(M*S)) and store in place
+    const int tw_shift = a.log_n - m - a.log_s;
+    for (int el = tid; el < kElemsPerCta; el += kThreads) {
+        int c = el & (B - 1);
+        int k1 = el >> log_b;
+        Fr v = sm_load(lo, hi, c * mpad + phys(k1));
+        uint64_t low = low0 + (uint64_t)c;
+        uint64_t e = (low * (uint64_t)k1) << tw_shift;
+        if (e != 0) v = v * interpass_twiddle(a, e);
+        uint64_t gi = ((((outer << m) + (uint64_t)k1) << a.log_s) + low);
+        a.out[gi] = v;
+    }
+}
+
+// ---- row pass (final; digit-reversal transpose on store) --------------------------------
+__global__ void __launch_bounds__(kThreads) k_ntt_rows(PassArgs a) {
+    extern __shared__ uint4 smem[];
+    uint4* lo = smem;
+    uint4* hi = smem + kPlane;
+    Fr* tw = reinterpret_cast<Fr*>(smem + 2 * kPlane);
+    const int tid = threadIdx.x;
+    const int nthreads = blockDim.x;
+    const int m = a.m, M = 1 << m;
+    const int log_rows = a.log_n - m;
+    int log_b = 11 - m;
+    if (log_b > log_rows) log_b = log_rows;
+    const int B = 1 << log_b;
+    const int mpad = M + (M >> 3);
+    const int elems = B << m;
+    // rows handled: k1 = k1_0 + b (most significant digit), rest = lower digits
+    const int log_rest = log_rows - a.log_n1;
+    const uint64_t blocks_per_rest = (uint64_t)1 << (a.log_n1 - log_b);
+    const uint64_t rest = blockIdx.x / blocks_per_rest;
+    const uint64_t k1_0 = (blockIdx.x % blocks_per_rest) << log_b;
+
+    load_core_twiddles(tw, a.core, m, tid, nthreads);
+    const uint4* in4 = reinterpret_cast<const uint4*>(a.in);
+    for (int u = tid; u < 2 * elems; u += nthreads) {
+        int el = u >> 1, half = u & 1;
+        int n = el & (M - 1);
+        int b = el >> m;
+        uint64_t row = ((k1_0 + (uint64_t)b) << log_rest) + rest;
+        uint4 val = in4[((row << m) + (uint64_t)n) * 2 + half];
+        int slot = b * mpad + phys((int)(__brev((unsigned)n) >> (32 - m)));
+        (half ? hi : lo)[slot] = val;
+    }
+    __syncthreads();
+    core_ntt(lo, hi, tw, m, tid);
+    Fr scale;
+    const bool do_scale = a.scale != nullptr;
+    if (do_scale) scale = a.scale[0];
+    for (int el = tid; el < elems; el += nthreads) {
+        int b = el & (B - 1);
+        int k = el >> log_b;
+        Fr v = sm_load(lo, hi, b * mpad + phys(k));
+        if (do_scale) v = v * scale;
+        uint64_t out_base = (k1_0 + (uint64_t)b) + (rest << a.log_n1);
+        a.out[out_base + ((uint64_t)k << log_rows)] = v;
+    }
+}
+
+// N <= 4: direct evaluation by one thread
+__global__ void k_ntt_tiny(Fr* data, int log_n, bool inverse) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int n = 1 << log_n;
+    Fr w = root_of_unity(log_n, inverse);
+    Fr in[4], out[4];
+    for (int i = 0; i < n; i++) in[i] = data[i];
+    Fr wi = Fr::one();
+    for (int i = 0; i < n; i++) {
+        Fr acc = Fr::zero(), p = Fr::one();
+        for (int j = 0; j < n; j++) { acc = acc + in[j] * p; p = p * wi; }
+        out[i] = acc;
+        wi = wi * w;
+    }
+    Fr scale = Fr::one();
+    if (inverse) {
+        Fr two = Fr::one() + Fr::one();
+        scale = two.inv().pow_u64((uint64_t)log_n);
+    }
+    for (int i = 0; i < n; i++) data[i] = out[i] * scale;
+}
+
+__global__ void k_scale_by_powers(Fr* data, size_t n, const Fr* g) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fr gi = g[0].pow_u64((uint64_t)i);
+    data[i] = data[i] * gi;
+}
+
+constexpr int kSmemBytes = 2 * kPlane * (int)sizeof(uint4) + (1 << (kCoreBits - 1)) * (int)sizeof(Fr);
+
+}  // namespace
+
+NttEngine::~NttEngine() {
+    if (ev_begin) cudaEventDestroy(ev_begin);
+    if (ev_end) cudaEventDestroy(ev_end);
+}
+
+const NttEngine::Tables& NttEngine::tables(int log_n, cudaStream_t stream) {
+    auto it = tables_.find(log_n);
+    if (it != tables_.end()) return *it->second;
+    auto t = std::make_unique<Tables>();
+    const int core_n = 1 << (kCoreBits - 1);
+    k_build_table<<<ceil_div(core_n, 128), 128, 0, stream>>>(t->core_fwd.as<Fr>(core_n), core_n, kCoreBits, 0, false);
+    k_build_table<<<ceil_div(core_n, 128), 128, 0, stream>>>(t->core_inv.as<Fr>(core_n), core_n, kCoreBits, 0, true);
+    PM_LAUNCH_CHECK();
+    const int tw_n = 1 << kTwBits;
+    for (int level = 0; level < 3; level++) {
+        if (level * kTwBits >= log_n && level > 0) break;
+        k_build_table<<<ceil_div(tw_n, 128), 128, 0, stream>>>(t->tw_fwd[level].as<Fr>(tw_n), tw_n, log_n, level * kTwBits, false);
+        k_build_table<<<ceil_div(tw_n, 128), 128, 0, stream>>>(t->tw_inv[level].as<Fr>(tw_n), tw_n, log_n, level * kTwBits, true);
+        PM_LAUNCH_CHECK();
+    }
+    k_build_ninv<<<1, 32, 0, stream>>>(t->n_inv.as<Fr>(1), log_n);
+    PM_LAUNCH_CHECK();
+    auto& ref = *t;
+    tables_[log_n] = std::move(t);
+    return ref;
+}
+
+void NttEngine::run(Fr* data, int log_n, bool inverse, cudaStream_t stream) {
+    if (log_n < 0 || log_n > 32) throw CudaError("ntt: log_n out of range");
+    if (log_n == 0) return;
+    if (log_n <= 2) {
+        k_ntt_tiny<<<1, 32, 0, stream>>>(data, log_n, inverse);
+        PM_LAUNCH_CHECK();
+        launches++;
+        return;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        PM_CUDA(cudaFuncSetAttribute(k_ntt_columns, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        PM_CUDA(cudaFuncSetAttribute(k_ntt_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        attr_set = true;
+    }
+    const Tables& t = tables(log_n, stream);
+    const size_t n = (size_t)1 << log_n;
+    Fr* scratch = scratch_.as<Fr>(n);
+
+    // digit split: 1 pass up to 2^11, 2 passes up to 2^22, else 3; most significant digit first
+    int npass = log_n <= kCoreBits ? 1 : (log_n <= 2 * kCoreBits ? 2 : 3);
+    int digits[3] = {0, 0, 0};
+    {
+        int rem = log_n;
+        for (int p = 0; p < npass; p++) {
+            digits[p] = (rem + (npass - p) - 1) / (npass - p);
+            rem -= digits[p];
+        }
+    }
+    PassArgs a{};
+    a.log_n = log_n;
+    a.core = (inverse ? t.core_inv : t.core_fwd).get<Fr>();
+    a.tw0 = (inverse ? t.tw_inv[0] : t.tw_fwd[0]).get<Fr>();
+    a.tw1 = (inverse ? t.tw_inv[1] : t.tw_fwd[1]).get<Fr>();
+    a.tw2 = (inverse ? t.tw_inv[2] : t.tw_fwd[2]).get<Fr>();
+    if (time_passes) {
+        if (!ev_begin) { PM_CUDA(cudaEventCreate(&ev_begin)); PM_CUDA(cudaEventCreate(&ev_end)); }
+        PM_CUDA(cudaEventRecord(ev_begin, stream));
+    }
+    int consumed = 0;
+    for (int p = 0; p < npass - 1; p++) {
+        a.in = data;
+        a.out = data;
+        a.m = digits[p];
+        a.log_s = log_n - consumed - digits[p];
+        a.scale = nullptr;
+        // sub-problem of size 2^(log_n - consumed): twiddle exponent scaled by 2^consumed via log_n - m - log_s
+        PassArgs c = a;
+        c.log_n = log_n;
+        k_ntt_columns<<<(unsigned)(n / kElemsPerCta), kThreads, kSmemBytes, stream>>>(c);
+        PM_LAUNCH_CHECK();
+        launches++;
+        consumed += digits[p];
+    }
+    a.in = data;
+    a.out = scratch;
+    a.m = digits[npass - 1];
+    a.log_s = 0;
+    a.log_n1 = npass == 1 ? 0 : digits[0];
+    a.scale = inverse ? t.n_inv.get<Fr>() : nullptr;
+    {
+        const int log_rows = log_n - a.m;
+        int log_b = 11 - a.m;
+        if (log_b > log_rows) log_b = log_rows;
+        const unsigned ctas = (unsigned)((size_t)1 << (log_rows - log_b));
+        const int threads = ((1 << log_b) << a.m) / 8;
+        k_ntt_rows<<<ctas, threads, kSmemBytes, stream>>>(a);
+        PM_LAUNCH_CHECK();
+        launches++;
+    }
+    PM_CUDA(cudaMemcpyAsync(data, scratch, n * sizeof(Fr), cudaMemcpyDeviceToDevice, stream));
+    if (time_passes) PM_CUDA(cudaEventRecord(ev_end, stream));
+}
+
+void launch_scale_by_powers(Fr* data, size_t n, const Fr* g_dev, cudaStream_t stream) {
+    k_scale_by_powers<<<ceil_div(n, 256), 256, 0, stream>>>(data, n, g_dev);
+    PM_LAUNCH_CHECK();
+}
+
+}  // namespace pm

@@ -1,0 +1,37 @@
+// K3 — Fr NTT engine (interface).  See ntt.cu.
+#pragma once
+#include <map>
+#include <memory>
+#include "common.cuh"
+#include "field.cuh"
+
+namespace pm {
+
+class NttEngine {
+public:
+    // In-place transform of data[0 .. 2^log_n), natural order in and out, on `stream`.
+    //   forward: out[i] = sum_j in[j] * w^(i*j), w = Radix2EvaluationDomain::group_gen
+    //   inverse: out = n^-1 * (transform with w^-1)
+    void run(Fr* data, int log_n, bool inverse, cudaStream_t stream);
+    size_t launches = 0;
+    // CUDA events around the passes of the last run (bench.py roofline)
+    bool time_passes = false;
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    ~NttEngine();
+
+    struct Tables {
+        DevBuf core_fwd, core_inv;     // w_{2^11}^k and its inverse, k < 2^10
+        DevBuf tw_fwd[3], tw_inv[3];   // w_N^(k * 2^(11*level)), k < 2^11 per level
+        DevBuf n_inv;                  // n^-1
+    };
+
+private:
+    const Tables& tables(int log_n, cudaStream_t stream);
+    std::map<int, std::unique_ptr<Tables>> tables_;
+    DevBuf scratch_;
+};
+
+// data[i] *= g^i (coset shift) — elementwise helper used by pm_ntt_fr's coset variant
+void launch_scale_by_powers(Fr* data, size_t n, const Fr* g_dev, cudaStream_t stream);
+
+}  // namespace pm

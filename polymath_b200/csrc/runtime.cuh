@@ -1,0 +1,37 @@
+// Process-wide device runtime shared by the C-ABI entry points: one stream, one instance of
+// each engine (grow-only workspaces).  One process drives one GPU (the CUDA device current
+// at first use).
+#pragma once
+#include <string>
+#include <vector>
+#include "common.cuh"
+#include "fixed_base.cuh"
+#include "msm.cuh"
+#include "ntt.cuh"
+
+namespace pm {
+
+struct StatusError : std::runtime_error {
+    int code;
+    StatusError(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+struct Runtime {
+    Runtime();
+    cudaStream_t stream = nullptr;
+    NttEngine ntt;
+    MsmEngine msm;
+    FixedBaseEngine fixed_base;
+    uint64_t extra_launches = 0;
+    uint64_t total_launches() const;
+};
+
+Runtime& runtime();
+
+template <class F> int guarded(F&& f);
+void pack_points_host(const uint8_t* src, size_t stride, size_t n, std::vector<uint8_t>& dst);
+
+// out[0] = in[0]^-1 (single thread)
+void launch_fr_inverse(const Fr* in, Fr* out, cudaStream_t stream);
+
+}  // namespace pm

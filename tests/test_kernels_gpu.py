@@ -1,0 +1,144 @@
+"""Parity of the standalone CUDA kernels (through the C ABI) against the oracle.  Bit-exact."""
+import random
+
+import pytest
+
+from oracle.fields import R_MOD, Q_MOD
+from oracle import curve, poly
+
+pytestmark = pytest.mark.gpu
+
+EDGE_FR = [0, 1, 2, R_MOD - 1, R_MOD - 2, (1 << 256) % R_MOD, (1 << 255) % R_MOD, 0xFFFFFFFF, 1 << 32, (1 << 64) - 1]
+EDGE_FQ = [0, 1, 2, Q_MOD - 1, Q_MOD - 2, (1 << 384) % Q_MOD, 0xFFFFFFFF, 1 << 32, (1 << 380)]
+
+
+def test_fr_field_ops(pmlib):
+    from polymath_b200 import kernels
+    rnd = random.Random(1)
+    a = [x for x in EDGE_FR for _ in EDGE_FR] + [rnd.randrange(R_MOD) for _ in range(20000)]
+    b = [y for _ in EDGE_FR for y in EDGE_FR] + [rnd.randrange(R_MOD) for _ in range(20000)]
+    assert kernels.fr_mul_batch(a, b) == [x * y % R_MOD for x, y in zip(a, b)]
+    assert kernels.fr_add_batch(a, b) == [(x + y) % R_MOD for x, y in zip(a, b)]
+    assert kernels.fr_sub_batch(a, b) == [(x - y) % R_MOD for x, y in zip(a, b)]
+
+
+def test_fq_mul(pmlib):
+    from polymath_b200 import kernels
+    rnd = random.Random(2)
+    a = [x for x in EDGE_FQ for _ in EDGE_FQ] + [rnd.randrange(Q_MOD) for _ in range(20000)]
+    b = [y for _ in EDGE_FQ for y in EDGE_FQ] + [rnd.randrange(Q_MOD) for _ in range(20000)]
+    assert kernels.fq_mul_batch(a, b) == [x * y % Q_MOD for x, y in zip(a, b)]
+
+
+@pytest.mark.parametrize("log_n", list(range(0, 15)))
+def test_ntt_matches_oracle(pmlib, log_n):
+    from polymath_b200 import kernels
+    rnd = random.Random(100 + log_n)
+    n = 1 << log_n
+    vals = [rnd.randrange(R_MOD) for _ in range(n)]
+    dom = poly.Domain(n)
+    fwd = kernels.ntt_fr(vals)
+    assert fwd == dom.fft(vals)
+    assert kernels.ntt_fr(vals, inverse=True) == dom.ifft(vals)
+    if log_n <= 6:
+        assert fwd == poly.naive_dft(vals, dom.group_gen)
+
+
+@pytest.mark.parametrize("log_n", [16, 20, 21, 23])
+def test_ntt_roundtrip_and_linearity_large(pmlib, log_n):
+    """Size-independent properties at sizes the Python oracle cannot reach."""
+    from polymath_b200 import kernels
+    rnd = random.Random(7 + log_n)
+    n = 1 << log_n
+    seeds = [rnd.randrange(R_MOD) for _ in range(64)]
+    vals = [seeds[i % 64] * (i + 1) % R_MOD for i in range(n)]
+    fwd = kernels.ntt_fr(vals)
+    assert kernels.ntt_fr(fwd, inverse=True) == vals
+    # spot-check evaluations by Horner at a few domain points
+    dom = poly.Domain(n)
+    for idx in (0, 1, n // 2 + 3, n - 1):
+        assert fwd[idx] == poly.poly_eval(vals, pow(dom.group_gen, idx, R_MOD))
+
+
+def test_ntt_coset(pmlib):
+    from polymath_b200 import kernels
+    rnd = random.Random(5)
+    n = 1 << 10
+    g = 7
+    vals = [rnd.randrange(R_MOD) for _ in range(n)]
+    dom = poly.Domain(n)
+    shifted = [v * pow(g, i, R_MOD) % R_MOD for i, v in enumerate(vals)]
+    ev = kernels.ntt_fr(vals, coset_gen=g)
+    assert ev == dom.fft(shifted)
+    assert kernels.ntt_fr(ev, inverse=True, coset_gen=g) == vals
+
+
+def _bases(k, rnd):
+    tbl = curve.FixedBaseTable(curve.G1_GEN, window=8)
+    return tbl.mul_many([rnd.randrange(1, R_MOD) for _ in range(k)])
+
+
+def test_fixed_base_mul(pmlib):
+    from polymath_b200 import kernels
+    rnd = random.Random(11)
+    scalars = [0, 1, 2, R_MOD - 1, (1 << 255) % R_MOD] + [rnd.randrange(R_MOD) for _ in range(300)]
+    got = kernels.fixed_base_mul(scalars)
+    tbl = curve.FixedBaseTable(curve.G1_GEN, window=8)
+    assert got == tbl.mul_many(scalars)
+    assert got[0] is None and got[1] == curve.G1_GEN
+
+
+@pytest.mark.parametrize("n,c", [(1, 0), (2, 0), (7, 0), (33, 0), (300, 0), (300, 4), (1500, 0), (1500, 13), (4096, 0)])
+def test_msm_matches_oracle(pmlib, n, c):
+    from polymath_b200 import kernels
+    rnd = random.Random(1000 + n + c)
+    bases = _bases(n, rnd)
+    scalars = [rnd.randrange(R_MOD) for _ in range(n)]
+    want = poly.msm_pippenger(scalars, bases)
+    assert kernels.msm_g1(bases, scalars, window_bits=c) == want
+    if n <= 33:
+        assert want == poly.msm_naive(scalars, bases)
+
+
+def test_msm_edge_cases(pmlib):
+    """Infinity bases, zero scalars, repeated points, +/- pairs, skewed scalars, heavy buckets, 104-byte stride."""
+    from polymath_b200 import kernels
+    rnd = random.Random(77)
+    n = 600
+    bases = _bases(n, rnd)
+    for i in range(0, n, 7):
+        bases[i] = None
+    for i in range(3, n, 50):
+        bases[i] = bases[i - 1]                     # duplicate points
+    bases[11] = curve.g1_neg(bases[10])             # P and -P
+    hot = rnd.randrange(R_MOD)
+    scalars = [hot if i % 3 else rnd.randrange(R_MOD) for i in range(n)]
+    for i in range(0, n, 13):
+        scalars[i] = 0
+    scalars[10] = scalars[11] = 5
+    scalars[20] = R_MOD - 1
+    scalars[21] = (1 << 255) % R_MOD
+    want = poly.msm_pippenger(scalars, bases)
+    assert kernels.msm_g1(bases, scalars) == want
+    assert kernels.msm_g1(bases, scalars, window_bits=8, heavy_threshold=16) == want   # force the heavy-bucket path
+    assert kernels.msm_g1(bases, scalars, stride=104) == want
+    # everything cancels / empty
+    assert kernels.msm_g1([bases[1], curve.g1_neg(bases[1])], [9, 9]) is None
+    assert kernels.msm_g1([], []) is None
+    assert kernels.msm_g1(bases[:5], [0] * 5) is None
+    # msm_unchecked truncates to the shorter input (prover.rs:380-384 asserts scalars <= bases)
+    assert kernels.msm_g1(bases, scalars[:100]) == poly.msm_pippenger(scalars[:100], bases[:100])
+
+
+def test_msm_linearity_large(pmlib):
+    """2^18 points: MSM(k*s) == k*MSM(s) and MSM(s) + MSM(t) == MSM(s+t), bases generated on the device."""
+    from polymath_b200 import kernels
+    rnd = random.Random(5)
+    n = 1 << 18
+    seeds = [rnd.randrange(R_MOD) for _ in range(97)]
+    base_scalars = [seeds[i % 97] * (i + 1) % R_MOD for i in range(n)]
+    bases = kernels.fixed_base_mul(base_scalars)
+    s = [seeds[(i * 7) % 97] * (i + 3) % R_MOD for i in range(n)]
+    # sum_i s_i * (b_i * G) = (sum_i s_i * b_i) * G
+    dot = sum(x * y for x, y in zip(s, base_scalars)) % R_MOD
+    assert kernels.msm_g1(bases, s) == curve.g1_mul(curve.G1_GEN, dot)

@@ -1,0 +1,46 @@
+"""Standalone kernel sweep (BASELINE.json configs[4]): IMAD peak, field-mul rates, Fr NTT and G1 MSM
+throughput on resident synthetic data.  Prints one JSON object per line."""
+import argparse
+import ctypes as C
+import json
+import sys
+import os
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from polymath_b200.lib import require_device, check  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--ntt", default="16,18,20,21,22,24")
+    ap.add_argument("--msm", default="16,18,20,22")
+    ap.add_argument("--windows", default="0")
+    ap.add_argument("--iters", type=int, default=3)
+    a = ap.parse_args()
+    lib = require_device()
+    d = C.c_double()
+    check(lib.pm_bench_imad_peak(C.byref(d)))
+    imad = d.value
+    print(json.dumps({"kernel": "imad_wide_peak", "mads_per_s": imad}), flush=True)
+    for f, name, cost in ((0, "fr_mul", 136), (1, "fq_mul", 300)):
+        check(lib.pm_bench_field_mul(f, C.byref(d)))
+        print(json.dumps({"kernel": name, "muls_per_s": d.value, "imad_equiv_per_s": d.value * cost,
+                          "frac_of_imad_peak": d.value * cost / imad}), flush=True)
+    for lg in [int(x) for x in a.ntt.split(",") if x]:
+        for inv in (0, 1):
+            check(lib.pm_bench_ntt(lg, inv, a.iters, C.byref(d)))
+            n = 1 << lg
+            print(json.dumps({"kernel": "ntt_fr", "log_n": lg, "inverse": inv, "ms": d.value,
+                              "gelem_per_s": n / d.value / 1e6, "algo_gb_per_s": 64 * n / d.value / 1e6,
+                              "butterfly_muls_per_s": (n / 2) * lg / (d.value * 1e-3)}), flush=True)
+    acc = C.c_double()
+    for lg in [int(x) for x in a.msm.split(",") if x]:
+        for w in [int(x) for x in a.windows.split(",")]:
+            n = 1 << lg
+            check(lib.pm_bench_msm(n, w, a.iters, C.byref(d), C.byref(acc)))
+            print(json.dumps({"kernel": "msm_g1", "log_n": lg, "window": w, "ms": d.value, "ms_accumulate": acc.value,
+                              "mpts_per_s": n / d.value / 1e3}), flush=True)
+
+
+if __name__ == "__main__":
+    main()
