@@ -79,6 +79,102 @@ int pm_msm_g1_window(const uint8_t* bases, size_t base_stride, const uint8_t* sc
  * Replaces `generate()` (src/generator.rs:169-177). */
 int pm_fixed_base_mul(const uint8_t* scalars, size_t n, uint8_t* out);
 
+/* ---- prover context: proving key resident on the device, one call per protocol phase ---- */
+
+/* R1CS matrices as produced by `cs.to_matrices()` (src/generator.rs:46-54), flattened to CSR:
+ * row r of matrix M holds entries [row_ptr[r], row_ptr[r+1]) of (col, val); columns follow
+ * arkworks (0 = the constant one, 1..m0-1 = instance, m0.. = witness).  Duplicate columns in a
+ * row keep first-match semantics like `m_at` (src/common.rs:100-105). */
+typedef struct {
+    uint64_t num_instance_variables;      /* m0, includes the leading 1 (SAPMatrices, src/common.rs:113-127) */
+    uint64_t num_r1cs_witness_variables;  /* mw */
+    uint64_t num_r1cs_constraints;        /* nr */
+    const uint64_t* a_row_ptr; const uint32_t* a_col; const uint8_t* a_val;
+    const uint64_t* b_row_ptr; const uint32_t* b_col; const uint8_t* b_val;
+    const uint64_t* c_row_ptr; const uint32_t* c_col; const uint8_t* c_val;
+} pm_r1cs_view;
+
+/* Borrowed view of a `ProvingKey` (src/data_structures.rs:56-73).  All point arrays share `point_stride`. */
+typedef struct {
+    pm_r1cs_view r1cs;                    /* pk.sap_matrices */
+    uint64_t n;                           /* pk.vk.n  (domain size) */
+    uint64_t sigma;                       /* pk.vk.sigma = n + 3 */
+    size_t point_stride;
+    const uint8_t* x_powers_g1;               uint64_t x_powers_g1_len;               /* n + 1 */
+    const uint8_t* x_powers_y_alpha_g1;       uint64_t x_powers_y_alpha_g1_len;       /* 3 */
+    const uint8_t* x_powers_zh_by_y_alpha_g1; uint64_t x_powers_zh_by_y_alpha_g1_len; /* n - 1 */
+    const uint8_t* x_powers_y_gamma_g1;       uint64_t x_powers_y_gamma_g1_len;       /* 2 */
+    const uint8_t* x_powers_y_gamma_z_g1;     uint64_t x_powers_y_gamma_z_g1_len;     /* 10n + 23 */
+    const uint8_t* uj_wj_lcs_by_y_alpha_g1;   uint64_t uj_wj_lcs_by_y_alpha_g1_len;   /* cols - m0 */
+} pm_pk_view;
+
+typedef struct pm_ctx pm_ctx;
+
+/* Upload (and repack) a proving key once; later `prove` calls reuse the device copy
+ * (`prove(&pk, ..)` borrows the key on every call, src/lib.rs:72-78). */
+int pm_ctx_create(const pm_pk_view* pk, pm_ctx** out);
+void pm_ctx_destroy(pm_ctx* ctx);
+
+/* Setup on the device: the six G1 vectors of `generate_proving_key` (src/generator.rs:81-137)
+ * from the trapdoors x, z (32 B each, Montgomery), kept resident in a new context.  Also
+ * writes [x]_2 and [z]_2 (src/generator.rs:144-145) as 2 x 192 bytes (x.c0, x.c1, y.c0, y.c1; Montgomery). */
+int pm_setup(const pm_r1cs_view* r1cs, const uint8_t x[PM_FR_BYTES], const uint8_t z[PM_FR_BYTES], pm_ctx** out,
+             uint8_t x_g2[192], uint8_t z_g2[192]);
+/* Sizes (n, sigma, columns) of the context's key. */
+int pm_ctx_dims(const pm_ctx* ctx, uint64_t* n, uint64_t* sigma, uint64_t* num_columns);
+/* Copy one of the key's vectors back to the host (to build/serialise a ProvingKey).
+ * which: 0 x_powers_g1, 1 x_powers_y_alpha_g1, 2 x_powers_zh_by_y_alpha_g1, 3 x_powers_y_gamma_g1,
+ *        4 x_powers_y_gamma_z_g1, 5 uj_wj_lcs_by_y_alpha_g1.  `out` receives len*stride bytes
+ * (stride 96: packed; >= 104: arkworks layout with the infinity flag byte at offset 96). */
+int pm_ctx_key_len(const pm_ctx* ctx, int which, uint64_t* len);
+int pm_ctx_export_key(const pm_ctx* ctx, int which, uint8_t* out, size_t stride);
+
+/* Phase 1 (src/prover.rs:73-123): witness -> y vector -> U.z, W.z -> u, w, h -> [a]_1, [c]_1.
+ * x: m0 instance values (x[0] = 1), w: mw witness values, r_a: the two blinding coefficients
+ * drawn by the caller's RNG (src/prover.rs:110, coefficient 0 first). */
+int pm_prove_phase1(pm_ctx* ctx, const uint8_t* x, const uint8_t* w, const uint8_t r_a[2 * PM_FR_BYTES],
+                    uint8_t a_out[PM_G1_BYTES], uint8_t c_out[PM_G1_BYTES]);
+/* Same, split so the assignment upload can be kept out of a timed region. */
+int pm_ctx_set_assignment(pm_ctx* ctx, const uint8_t* x, const uint8_t* w);
+int pm_prove_phase1_resident(pm_ctx* ctx, const uint8_t r_a[2 * PM_FR_BYTES], uint8_t a_out[PM_G1_BYTES],
+                             uint8_t c_out[PM_G1_BYTES]);
+/* Phase 2 (src/prover.rs:128-132): a(x1) = u(x1) + r_a(x1) * y1^alpha. */
+int pm_prove_phase2(pm_ctx* ctx, const uint8_t x1[PM_FR_BYTES], const uint8_t y1_alpha[PM_FR_BYTES],
+                    uint8_t a_at_x1_out[PM_FR_BYTES]);
+/* Phase 3 (src/prover.rs:142-229): opening quotient by (X - x1) and [d]_1. */
+int pm_prove_phase3(pm_ctx* ctx, const uint8_t x2[PM_FR_BYTES], const uint8_t c_at_x1[PM_FR_BYTES],
+                    uint8_t d_out[PM_G1_BYTES]);
+/* Test hook: copy an intermediate of the last proof to the host.
+ * which: 0 u coeffs (n), 1 w coeffs (n), 2 witness-u coeffs (n), 3 u^2 coeffs (2n), 4 [x|w|y] (cols - m0),
+ *        5 phase-1 c-side scalars, 6 opening quotient D (10n + 22).  Returns the element count in *len. */
+int pm_ctx_debug_read(pm_ctx* ctx, int which, uint8_t* out, uint64_t capacity_elems, uint64_t* len);
+/* Milliseconds spent on the device by the last phase-1 / phase-2 / phase-3 call (CUDA events). */
+int pm_ctx_phase_ms(const pm_ctx* ctx, double ms[3]);
+
+/* ---- host mirror of Polymath::setup / prove (C++; the reference's Rust host flow restated) ---- */
+
+/* rand 0.8 `StdRng` (ChaCha12) as used by the reference's tests and bench (benches/bench.rs:65). */
+typedef struct pm_rng pm_rng;
+pm_rng* pm_rng_seed_from_u64(uint64_t seed);
+pm_rng* pm_rng_from_seed(const uint8_t seed[32]);
+void pm_rng_free(pm_rng* rng);
+uint64_t pm_rng_next_u64(pm_rng* rng);
+/* ark-ff `Fr::rand(rng)`; writes the Montgomery form. */
+void pm_rng_fr_rand(pm_rng* rng, uint8_t out[PM_FR_BYTES]);
+/* merlin known-answer vector ("test protocol" / "some label" / "some data" / "challenge"). */
+int pm_merlin_test_vector(uint8_t out[32]);
+
+/* `Polymath::setup` / `generate_proving_key` (src/generator.rs:24-167) for already-synthesised
+ * R1CS matrices: samples the trapdoors x, z from `rng` exactly like the reference, builds the key
+ * on the device (kept resident in *ctx_out) and writes the compressed VerifyingKey (392 bytes,
+ * src/data_structures.rs:25-50). */
+int pm_polymath_setup(const pm_r1cs_view* r1cs, pm_rng* rng, pm_ctx** ctx_out, uint8_t vk_out[392]);
+/* `create_proof_with_assignment` (src/prover.rs:66-237): instance = m0 values (leading 1 first),
+ * witness = mw values, both Montgomery; draws r_a from `rng`; runs the Merlin transcript
+ * (src/common.rs:21-37) on the host between the device phases; writes the compressed Proof
+ * (176 bytes, src/data_structures.rs:10-19). */
+int pm_polymath_prove(pm_ctx* ctx, const uint8_t* instance, const uint8_t* witness, pm_rng* rng, uint8_t proof_out[176]);
+
 /* ---- measurement hooks (bench.py; synthetic device-resident inputs, CUDA-event timing) ---- */
 
 /* Issue rate of dependency-free IMAD.WIDE.U32 (32x32+64 multiply-adds per second, whole GPU):

@@ -46,23 +46,6 @@ void pack_points_host(const uint8_t* src, size_t stride, size_t n, std::vector<u
 }
 
 template <class F>
-int guarded(F&& f) {
-    try {
-        f();
-        return PM_OK;
-    } catch (const StatusError& e) {
-        set_last_error(e.what());
-        return e.code;
-    } catch (const CudaError& e) {
-        set_last_error(e.what());
-        return PM_ERR_CUDA;
-    } catch (const std::exception& e) {
-        set_last_error(e.what());
-        return PM_ERR_CUDA;
-    }
-}
-
-template <class F>
 static int field_batch(FieldOp op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n, bool fq) {
     return guarded([&] {
         if (n == 0) return;

@@ -248,9 +248,10 @@ struct alignas(16) Fp {
     // Fermat inverse a^(p-2); inverse of zero is zero
     __device__ Fp inv() const {
         uint32_t e[N];
+        e[0] = ptx::sub_cc(P::mod()[0], 2u);
 #pragma unroll
-        for (int i = 0; i < N; i++) e[i] = P::mod()[i];
-        e[0] -= 2;  // both moduli end in ...01 / ...ab: no borrow
+        for (int i = 1; i < N - 1; i++) e[i] = ptx::subc_cc(P::mod()[i], 0u);
+        e[N - 1] = ptx::subc(P::mod()[N - 1], 0u);
         return pow(e, N);
     }
 };

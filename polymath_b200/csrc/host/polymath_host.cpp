@@ -1,0 +1,199 @@
+// C++ host mirror of `Polymath::<Bls12_381, MerlinFieldTranscript<Fr>>::setup / prove`
+// (/root/reference/src/lib.rs:52-91) above the phase C-ABI.  The reference's own toolchain
+// (cargo/rustc) is absent from this image, so the Rust host side of INTEGRATION.md is
+// mirrored here: same flow, same RNG consumption, same transcript bytes, same errors.
+//
+//   pm_polymath_setup  = generate_proving_key           (src/generator.rs:24-167)
+//   pm_polymath_prove  = create_proof_with_assignment   (src/prover.rs:66-237)
+//
+// Circuit synthesis (src/prover.rs:33-52) stays with the caller: these entry points take the
+// R1CS matrices / the instance and witness assignments it produces.
+#include <memory>
+#include <vector>
+
+#include "../../../include/polymath_b200.h"
+#include "../common.cuh"
+#include "transcript_host.hpp"
+
+using namespace pm::host;
+
+struct pm_rng {
+    StdRng rng;
+    explicit pm_rng(StdRng r) : rng(r) {}
+};
+
+namespace {
+
+const char* B_POLYMATH = "polymath";   // common.rs:8
+constexpr uint64_t MINUS_ALPHA = 3;     // common.rs:11
+constexpr uint64_t MINUS_GAMMA = 5;     // common.rs:14
+
+FrH neg_power(const FrH& y, uint64_t minus_exp) { return y.inv().pow_u64(minus_exp); }   // common.rs:45-47
+
+// common.rs:77-97
+FrH z_tilde_i(const std::vector<FrH>& pub, size_t i) {
+    const size_t m0 = pub.size();
+    FrH one = FrH::one();
+    if (i == 0) return one + one;
+    if (i < m0) return one + pub[i];
+    if (i == m0) return FrH::zero();
+    return one - pub[i - m0];
+}
+
+// common.rs:49-71
+FrH compute_pi_at_x1(uint64_t n, const FrH& omega, const std::vector<FrH>& pub, const FrH& x1, const FrH& y1_gamma) {
+    FrH sum = FrH::zero();
+    FrH num = (x1.pow_u64(n) - FrH::one()) * FrH::from_u64(n).inv();
+    FrH omega_i = FrH::one();
+    for (size_t i = 0; i < 2 * pub.size(); i++) {
+        FrH lagrange = num * (x1 - omega_i).inv();
+        sum = sum + z_tilde_i(pub, i) * lagrange;
+        num = num * omega;
+        omega_i = omega_i * omega;
+    }
+    return sum * y1_gamma;
+}
+
+int log2_u64(uint64_t n) { int l = 0; while (((uint64_t)1 << l) < n) l++; return l; }
+
+}  // namespace
+
+extern "C" {
+
+pm_rng* pm_rng_seed_from_u64(uint64_t seed) { return new pm_rng(StdRng::seed_from_u64(seed)); }
+pm_rng* pm_rng_from_seed(const uint8_t seed[32]) { return new pm_rng(StdRng(seed)); }
+void pm_rng_free(pm_rng* r) { delete r; }
+uint64_t pm_rng_next_u64(pm_rng* r) { return r->rng.next_u64(); }
+void pm_rng_fr_rand(pm_rng* r, uint8_t out[PM_FR_BYTES]) { r->rng.fr_rand().to_wire(out); }
+
+int pm_merlin_test_vector(uint8_t out[32]) {
+    // merlin's "equivalence_simple" transcript: new("test protocol"), append("some label","some data"), challenge("challenge")
+    MerlinTranscript t("test protocol");
+    const char* data = "some data";
+    t.append_message("some label", reinterpret_cast<const uint8_t*>(data), 9);
+    t.challenge_bytes("challenge", out, 32);
+    return PM_OK;
+}
+
+int pm_polymath_setup(const pm_r1cs_view* r1cs, pm_rng* rng, pm_ctx** ctx_out, uint8_t vk_out[392]) {
+    if (!r1cs || !rng || !ctx_out || !vk_out) { pm::set_last_error("null argument"); return PM_ERR_ARG; }
+    const uint64_t m0 = r1cs->num_instance_variables, nr = r1cs->num_r1cs_constraints;
+    uint64_t rows = 2 * (m0 + nr), n = 1;
+    while (n < rows) n <<= 1;
+    const int log_n = log2_u64(n);
+    // sample_element_outside_domain: x (generator.rs:72) then z (generator.rs:77)
+    auto sample = [&]() {
+        for (;;) {
+            FrH t = rng->rng.fr_rand();
+            if (!(t.pow_u64(n) == FrH::one())) return t;
+        }
+    };
+    FrH x = sample();
+    FrH z = sample();
+    uint8_t xb[32], zb[32], x_g2[192], z_g2[192];
+    x.to_wire(xb);
+    z.to_wire(zb);
+    int rc = pm_setup(r1cs, xb, zb, ctx_out, x_g2, z_g2);
+    if (rc != PM_OK) return rc;
+    // VerifyingKey, compressed (data_structures.rs:25-50): e.one_g1, e.one_g2, e.x_g2, e.z_g2, n, m0, sigma, omega
+    std::vector<uint8_t> vk;
+    static const uint8_t G1_GEN_COMPRESSED[48] = {
+        0x97, 0xf1, 0xd3, 0xa7, 0x31, 0x97, 0xd7, 0x94, 0x26, 0x95, 0x63, 0x8c, 0x4f, 0xa9, 0xac, 0x0f, 0xc3, 0x68, 0x8c, 0x4f, 0x97, 0x74, 0xb9, 0x05,
+        0xa1, 0x4e, 0x3a, 0x3f, 0x17, 0x1b, 0xac, 0x58, 0x6c, 0x55, 0xe8, 0x3f, 0xf9, 0x7a, 0x1a, 0xef, 0xfb, 0x3a, 0xf0, 0x0a, 0xdb, 0x22, 0xc6, 0xbb};
+    static const uint8_t G2_GEN_COMPRESSED[96] = {
+        0x93, 0xe0, 0x2b, 0x60, 0x52, 0x71, 0x9f, 0x60, 0x7d, 0xac, 0xd3, 0xa0, 0x88, 0x27, 0x4f, 0x65, 0x59, 0x6b, 0xd0, 0xd0, 0x99, 0x20, 0xb6, 0x1a,
+        0xb5, 0xda, 0x61, 0xbb, 0xdc, 0x7f, 0x50, 0x49, 0x33, 0x4c, 0xf1, 0x12, 0x13, 0x94, 0x5d, 0x57, 0xe5, 0xac, 0x7d, 0x05, 0x5d, 0x04, 0x2b, 0x7e,
+        0x02, 0x4a, 0xa2, 0xb2, 0xf0, 0x8f, 0x0a, 0x91, 0x26, 0x08, 0x05, 0x27, 0x2d, 0xc5, 0x10, 0x51, 0xc6, 0xe4, 0x7a, 0xd4, 0xfa, 0x40, 0x3b, 0x02,
+        0xb4, 0x51, 0x0b, 0x64, 0x7a, 0xe3, 0xd1, 0x77, 0x0b, 0xac, 0x03, 0x26, 0xa8, 0x05, 0xbb, 0xef, 0xd4, 0x80, 0x56, 0xc8, 0xc1, 0x21, 0xbd, 0xb8};
+    vk.insert(vk.end(), G1_GEN_COMPRESSED, G1_GEN_COMPRESSED + 48);
+    vk.insert(vk.end(), G2_GEN_COMPRESSED, G2_GEN_COMPRESSED + 96);
+    ser_g2_compressed(vk, x_g2);
+    ser_g2_compressed(vk, z_g2);
+    ser_u64(vk, n);
+    ser_u64(vk, m0);
+    ser_u64(vk, n + 3);
+    ser_fr(vk, fr_group_gen(log_n));
+    memcpy(vk_out, vk.data(), 392);
+    return PM_OK;
+}
+
+int pm_polymath_prove(pm_ctx* ctx, const uint8_t* instance, const uint8_t* witness, pm_rng* rng, uint8_t proof_out[176]) {
+    if (!ctx || !instance || !rng || !proof_out) { pm::set_last_error("null argument"); return PM_ERR_ARG; }
+    uint64_t n = 0, sigma = 0, cols = 0;
+    int rc = pm_ctx_dims(ctx, &n, &sigma, &cols);
+    if (rc != PM_OK) return rc;
+    uint64_t m0 = 0;
+    {
+        uint64_t lcs_len = 0;
+        rc = pm_ctx_key_len(ctx, 5, &lcs_len);
+        if (rc != PM_OK) return rc;
+        m0 = cols - lcs_len;
+    }
+    // the device work of phase 1 needs r_a, which the reference draws after the polynomial
+    // work (prover.rs:110) — nothing else consumes the RNG in between, so the stream is identical.
+    rc = pm_ctx_set_assignment(ctx, instance, witness);
+    if (rc != PM_OK) return rc;
+    uint8_t ra[64], a_g1[96], c_g1[96];
+    rng->rng.fr_rand().to_wire(ra);         // r_a coefficient 0
+    rng->rng.fr_rand().to_wire(ra + 32);    // r_a coefficient 1
+    rc = pm_prove_phase1_resident(ctx, ra, a_g1, c_g1);
+    if (rc != PM_OK) return rc;
+
+    std::vector<FrH> pub(m0);
+    for (uint64_t i = 0; i < m0; i++) pub[i] = FrH::from_wire(instance + 32 * i);
+
+    // compute_x1, common.rs:21-30
+    MerlinFieldTranscript t(B_POLYMATH);
+    std::vector<uint8_t> msg;
+    ser_u64(msg, m0);
+    for (auto& v : pub) ser_fr(msg, v);
+    t.append_message("public_inputs", msg);
+    msg.clear();
+    ser_u64(msg, 2);
+    ser_g1_compressed(msg, a_g1);
+    ser_g1_compressed(msg, c_g1);
+    t.append_message("commitments", msg);
+    FrH x1 = t.challenge("x1");
+
+    FrH y1 = x1.pow_u64(sigma);                         // compute_y1, common.rs:40-42
+    FrH y1_alpha = neg_power(y1, MINUS_ALPHA);
+    uint8_t x1b[32], y1ab[32], a_at_x1b[32];
+    x1.to_wire(x1b);
+    y1_alpha.to_wire(y1ab);
+    rc = pm_prove_phase2(ctx, x1b, y1ab, a_at_x1b);      // prover.rs:132
+    if (rc != PM_OK) return rc;
+    FrH a_at_x1 = FrH::from_wire(a_at_x1b);
+
+    FrH y1_gamma = neg_power(y1, MINUS_GAMMA);
+    FrH omega = fr_group_gen(log2_u64(n));
+    FrH pi_at_x1 = compute_pi_at_x1(n, omega, pub, x1, y1_gamma);
+    FrH c_at_x1 = ((a_at_x1 + y1_gamma) * a_at_x1 - pi_at_x1) * y1_alpha.inv();   // common.rs:73-75
+
+    // compute_x2, common.rs:32-37
+    msg.clear();
+    ser_fr(msg, x1);
+    t.append_message("x1", msg);
+    msg.clear();
+    ser_u64(msg, 2);
+    ser_fr(msg, a_at_x1);
+    ser_fr(msg, c_at_x1);
+    t.append_message("values", msg);
+    FrH x2 = t.challenge("x2");
+
+    uint8_t x2b[32], cb[32], d_g1[96];
+    x2.to_wire(x2b);
+    c_at_x1.to_wire(cb);
+    rc = pm_prove_phase3(ctx, x2b, cb, d_g1);            // prover.rs:142-229
+    if (rc != PM_OK) return rc;
+
+    // Proof, compressed (data_structures.rs:10-19): a_g1, c_g1, a_at_x1, d_g1
+    std::vector<uint8_t> proof;
+    ser_g1_compressed(proof, a_g1);
+    ser_g1_compressed(proof, c_g1);
+    ser_fr(proof, a_at_x1);
+    ser_g1_compressed(proof, d_g1);
+    memcpy(proof_out, proof.data(), 176);
+    return PM_OK;
+}
+
+}  // extern "C"

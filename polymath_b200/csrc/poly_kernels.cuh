@@ -1,0 +1,77 @@
+// K2 / K6 — SAP evaluation (CSR SpMV + closed-form rows), Hadamard/quotient helpers, chunked
+// Horner evaluation and the (X - x1) linear-recurrence division (interface).  See poly_kernels.cu.
+#pragma once
+#include "common.cuh"
+#include "field.cuh"
+
+namespace pm {
+
+// R1CS matrix in CSR form on the device (duplicates removed on the host with first-match
+// semantics, mirroring `m_at`, /root/reference/src/common.rs:100-105).
+struct DevCsr {
+    const uint32_t* row_ptr = nullptr;  // [rows + 1]
+    const uint32_t* col = nullptr;      // [nnz]
+    const Fr* val = nullptr;            // [nnz], Montgomery
+};
+
+struct SapDims {
+    uint32_t m0, mw, nr;   // instance vars (incl. the leading 1), witness vars, R1CS constraints
+    uint64_t n;            // domain size
+};
+
+// status bits written by the device checks (read back once per phase)
+enum : uint32_t {
+    ST_REMAINDER_NONZERO = 1u,   // (u^2 - w) mod Z_H != 0          -> PM_ERR_UNSATISFIED
+    ST_H_ZERO = 2u,              // h == 0                            -> PM_ERR_DEGENERATE
+    ST_H_DEGREE = 4u,            // deg h > n - 2                     -> PM_ERR_DEGENERATE
+    ST_OPENING_REMAINDER = 8u,   // numerator(x1) != 0                -> PM_ERR_REMAINDER
+};
+
+// ztail = [x | w | y]; on entry x and w are filled, on exit y (m0 + nr entries) too.
+// u_ev / w_ev / wu_ev (n entries each) receive U.z, W.z and the witness-column part of U.z.
+void launch_sap_evals(const SapDims& d, const DevCsr& A, const DevCsr& B, const DevCsr& C, Fr* ztail,
+                      Fr* u_ev, Fr* w_ev, Fr* wu_ev, cudaStream_t stream);
+
+// data[i] = data[i]^2
+void launch_square(Fr* data, size_t n, cudaStream_t stream);
+
+// Checks on u2 (2n coeffs) against w (n coeffs): remainder zero, h = u2[n..2n) non-zero, u2[2n-1] == 0.
+void launch_quotient_checks(const Fr* u2, const Fr* w, uint64_t n, uint32_t* status, cudaStream_t stream);
+
+// ra_ext[0..2) = r_a, ra_ext[2..5) = r_a^2 coefficients (single thread)
+void launch_ra_square(Fr* ra_ext, cudaStream_t stream);
+
+// scal_a = [u (n) | 0 | r0 r1 0]; scal_c = [2 r_a u (n+1) | r_a^2 (3) | r_a (2) | h (n-1) | ztail (tail)]
+void launch_assemble_phase1_scalars(const Fr* u, const Fr* u2, const Fr* ztail, uint64_t tail, const Fr* ra_ext,
+                                    uint64_t n, Fr* scal_a, Fr* scal_c, cudaStream_t stream);
+
+// ---- chunked polynomial machinery ------------------------------------------------------
+// A polynomial is described by a "source": either a plain coefficient array or the virtual
+// opening numerator of prover.rs:142-209 assembled on the fly from its five blocks.
+struct NumeratorSrc {
+    const Fr* u;        // n
+    const Fr* wu;       // n
+    const Fr* u2;       // 2n  (= witness_w + h_numerator)
+    const Fr* ra_ext;   // r_a (2) | r_a^2 (3)
+    const Fr* consts;   // [0] = x2, [1] = a(x1) + x2*c(x1)
+    uint64_t n, sigma, len;  // len = 8*sigma + 2n - 1
+};
+
+constexpr int kChunk = 4096;  // coefficients per CTA in the chunked kernels
+
+// chunk_vals[c] = sum_{k in chunk c} p_k * x^(k - c*kChunk)
+void launch_chunk_eval_plain(const Fr* coeffs, uint64_t len, const Fr* x, Fr* chunk_vals, cudaStream_t stream);
+void launch_chunk_eval_numerator(const NumeratorSrc& src, const Fr* x, Fr* chunk_vals, cudaStream_t stream);
+// out[0] = sum_c chunk_vals[c] * x^(c*kChunk)   (+ addend[0] * addend[1]... see launch_a_at_x1)
+void launch_combine_chunks(const Fr* chunk_vals, uint64_t nchunks, const Fr* x, Fr* out, cudaStream_t stream);
+// a_at_x1 = u(x1) + (r0 + r1*x1) * y1_alpha ; inputs: u_at_x1 (device), ra_ext, consts2 = [x1, y1_alpha]
+void launch_a_at_x1(const Fr* u_at_x1, const Fr* ra_ext, const Fr* x1_y1a, Fr* out, cudaStream_t stream);
+// carries[c] = quotient coefficient entering chunk c from above; sets ST_OPENING_REMAINDER if p(x) != 0
+void launch_chunk_carries(const Fr* chunk_vals, uint64_t nchunks, const Fr* x, Fr* carries, uint32_t* status,
+                          cudaStream_t stream);
+// q[k-1] = p_k + x * q_k for the virtual numerator; q has len-1 entries
+void launch_divide_numerator(const NumeratorSrc& src, const Fr* x, const Fr* carries, Fr* q, cudaStream_t stream);
+// materialise the virtual numerator (tests / debugging)
+void launch_materialize_numerator(const NumeratorSrc& src, Fr* out, cudaStream_t stream);
+
+}  // namespace pm

@@ -1,0 +1,483 @@
+// Prover context and the three proving phases on the device.
+//
+// Follows `create_proof_with_assignment` (/root/reference/src/prover.rs:66-237).  Control
+// crosses the host boundary only where the reference needs a Fiat-Shamir challenge:
+//   phase 1  prover.rs:73-123   -> ([a]_1, [c]_1)
+//   host     x1 = H(public inputs, a, c)            (common.rs:21-30)
+//   phase 2  prover.rs:128-132  -> a(x1)
+//   host     pi(x1), c(x1), x2 = H(x1, a(x1), c(x1)) (common.rs:32-75)
+//   phase 3  prover.rs:142-229  -> [d]_1
+#include "prover.cuh"
+
+#include <algorithm>
+
+#include "msm.cuh"
+#include "ntt.cuh"
+
+namespace pm {
+
+namespace {
+
+enum SmallSlot { S_RA = 0, S_X1 = 5, S_Y1A = 6, S_U_AT_X1 = 7, S_A_AT_X1 = 8, S_X2 = 9, S_EVAL = 10, S_C_AT_X1 = 11, S_COUNT = 16 };
+
+__global__ void k_phase3_consts(Fr* small) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    // consts[1] = a(x1) + x2 * c(x1)    (prover.rs:191-209)
+    small[S_EVAL] = small[S_A_AT_X1] + small[S_X2] * small[S_C_AT_X1];
+}
+
+int log2_exact(uint64_t v) {
+    int l = 0;
+    while (((uint64_t)1 << l) < v) l++;
+    if (((uint64_t)1 << l) != v) throw StatusError(PM_ERR_ARG, "domain size is not a power of two");
+    return l;
+}
+
+}  // namespace
+
+ProverCtx::~ProverCtx() {
+    if (host_stage) cudaFreeHost(host_stage);
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+}
+
+void ProverCtx::upload_matrix(DevMatrix& dst, const uint64_t* row_ptr, const uint32_t* col, const uint8_t* val, bool want_csc) {
+    Runtime& rt = runtime();
+    const uint64_t ncols = m0 + mw;
+    std::vector<uint32_t> rp(nr + 1, 0), cc;
+    std::vector<uint8_t> vv;
+    if (nr && (!row_ptr || (row_ptr[nr] && (!col || !val)))) throw StatusError(PM_ERR_ARG, "null R1CS matrix arrays");
+    const uint64_t nnz_in = nr ? row_ptr[nr] : 0;
+    cc.reserve(nnz_in);
+    vv.reserve(nnz_in * PM_FR_BYTES);
+    std::vector<uint32_t> seen;
+    for (uint64_t r = 0; r < nr; r++) {
+        rp[r] = (uint32_t)cc.size();
+        seen.clear();
+        for (uint64_t k = row_ptr[r]; k < row_ptr[r + 1]; k++) {
+            uint32_t j = col[k];
+            if (j >= ncols) throw StatusError(PM_ERR_ARG, "R1CS column index out of range");
+            // m_at (common.rs:100-105) returns the first entry of a column: later duplicates are dead
+            if (std::find(seen.begin(), seen.end(), j) != seen.end()) continue;
+            seen.push_back(j);
+            cc.push_back(j);
+            vv.insert(vv.end(), val + k * PM_FR_BYTES, val + (k + 1) * PM_FR_BYTES);
+        }
+    }
+    rp[nr] = (uint32_t)cc.size();
+    if (cc.size() >= ((uint64_t)1 << 32)) throw StatusError(PM_ERR_ARG, "R1CS matrix too large");
+    dst.nnz = cc.size();
+    PM_CUDA(cudaMemcpyAsync(dst.row_ptr.as<uint32_t>(nr + 1), rp.data(), (nr + 1) * 4, cudaMemcpyHostToDevice, rt.stream));
+    PM_CUDA(cudaMemcpyAsync(dst.col.as<uint32_t>(dst.nnz + 1), cc.data(), dst.nnz * 4, cudaMemcpyHostToDevice, rt.stream));
+    PM_CUDA(cudaMemcpyAsync(dst.val.as<Fr>(dst.nnz + 1), vv.data(), dst.nnz * PM_FR_BYTES, cudaMemcpyHostToDevice, rt.stream));
+    if (want_csc) {
+        std::vector<uint32_t> cp(ncols + 1, 0), rows(dst.nnz);
+        std::vector<uint8_t> cv(dst.nnz * PM_FR_BYTES);
+        for (uint32_t j : cc) cp[j + 1]++;
+        for (uint64_t j = 0; j < ncols; j++) cp[j + 1] += cp[j];
+        std::vector<uint32_t> cur(cp.begin(), cp.end() - 1);
+        for (uint64_t r = 0; r < nr; r++)
+            for (uint32_t k = rp[r]; k < rp[r + 1]; k++) {
+                uint32_t pos = cur[cc[k]]++;
+                rows[pos] = (uint32_t)r;
+                memcpy(cv.data() + (size_t)pos * PM_FR_BYTES, vv.data() + (size_t)k * PM_FR_BYTES, PM_FR_BYTES);
+            }
+        PM_CUDA(cudaMemcpyAsync(dst.col_ptr.as<uint32_t>(ncols + 1), cp.data(), (ncols + 1) * 4, cudaMemcpyHostToDevice, rt.stream));
+        PM_CUDA(cudaMemcpyAsync(dst.row.as<uint32_t>(dst.nnz + 1), rows.data(), dst.nnz * 4, cudaMemcpyHostToDevice, rt.stream));
+        PM_CUDA(cudaMemcpyAsync(dst.cval.as<Fr>(dst.nnz + 1), cv.data(), dst.nnz * PM_FR_BYTES, cudaMemcpyHostToDevice, rt.stream));
+    }
+    PM_CUDA(cudaStreamSynchronize(rt.stream));  // host vectors die here
+}
+
+void ProverCtx::allocate_work() {
+    log_n = log2_exact(n);
+    if (sigma != n + 3) throw StatusError(PM_ERR_ARG, "sigma != n + 3 (generator.rs:70)");
+    if (2 * (m0 + nr) > n) throw StatusError(PM_ERR_ARG, "SAP rows exceed the domain size");
+    if (m0 < 1) throw StatusError(PM_ERR_ARG, "instance must contain the leading 1");
+    ztail.as<Fr>(cols - m0);
+    u.as<Fr>(n); w.as<Fr>(n); wu.as<Fr>(n);
+    u2.as<Fr>(2 * n);
+    scal_a.as<Fr>(n + 4);
+    scal_c.as<Fr>(len_c());
+    q.as<Fr>(len_d());
+    const uint64_t nchunks = (len_d() + kChunk - 1) / kChunk;
+    chunk_vals.as<Fr>(nchunks + 1);
+    carries.as<Fr>(nchunks + 1);
+    small.as<Fr>(S_COUNT);
+    status.as<uint32_t>(4);
+    acc.as<G1XYZZ>(4);
+    result.as<G1Affine>(4);
+    PM_CUDA(cudaMallocHost(&host_stage, 1024));
+    PM_CUDA(cudaEventCreate(&ev0));
+    PM_CUDA(cudaEventCreate(&ev1));
+}
+
+void ProverCtx::set_assignment(const uint8_t* x, const uint8_t* wv) {
+    Runtime& rt = runtime();
+    if (!x || (mw && !wv)) throw StatusError(PM_ERR_ARG, "null assignment");
+    Fr* zt = ztail.get<Fr>();
+    PM_CUDA(cudaMemcpyAsync(zt, x, m0 * sizeof(Fr), cudaMemcpyHostToDevice, rt.stream));
+    if (mw) PM_CUDA(cudaMemcpyAsync(zt + m0, wv, mw * sizeof(Fr), cudaMemcpyHostToDevice, rt.stream));
+    assignment_set = true;
+    phase = 0;
+}
+
+static void check_status(uint32_t st) {
+    if (st & ST_REMAINDER_NONZERO)
+        throw StatusError(PM_ERR_UNSATISFIED, "(u^2 - w) is not divisible by Z_H: witness does not satisfy the SAP (prover.rs:108)");
+    if (st & (ST_H_ZERO | ST_H_DEGREE)) throw StatusError(PM_ERR_DEGENERATE, "h is zero or deg h > n-2 (prover.rs:107)");
+    if (st & ST_OPENING_REMAINDER) throw StatusError(PM_ERR_REMAINDER, "opening numerator does not vanish at x1 (prover.rs:221)");
+}
+
+void ProverCtx::phase1(const uint8_t* ra, uint8_t* a_out, uint8_t* c_out) {
+    Runtime& rt = runtime();
+    cudaStream_t s = rt.stream;
+    if (!assignment_set) throw StatusError(PM_ERR_STATE, "phase 1 needs an assignment");
+    if (!ra || !a_out || !c_out) throw StatusError(PM_ERR_ARG, "null phase-1 argument");
+    phase = 0;
+    Fr* sm = small.get<Fr>();
+    uint32_t* st = status.get<uint32_t>();
+    PM_CUDA(cudaEventRecord(ev0, s));
+    PM_CUDA(cudaMemcpyAsync(sm + S_RA, ra, 2 * sizeof(Fr), cudaMemcpyHostToDevice, s));
+    PM_CUDA(cudaMemsetAsync(st, 0, 4 * sizeof(uint32_t), s));
+    launch_ra_square(sm + S_RA, s);
+    SapDims d{(uint32_t)m0, (uint32_t)mw, (uint32_t)nr, n};
+    Fr *pu = u.get<Fr>(), *pw = w.get<Fr>(), *pwu = wu.get<Fr>(), *pu2 = u2.get<Fr>();
+    launch_sap_evals(d, A.csr(), B.csr(), C.csr(), ztail.get<Fr>(), pu, pw, pwu, s);
+    rt.ntt.run(pu, log_n, true, s);    // poly_coeffs, prover.rs:94
+    rt.ntt.run(pw, log_n, true, s);    // prover.rs:96
+    rt.ntt.run(pwu, log_n, true, s);   // prover.rs:161 (witness_w == w: prover.rs:165 is not recomputed)
+    // square_polynomial, prover.rs:315-328
+    PM_CUDA(cudaMemcpyAsync(pu2, pu, n * sizeof(Fr), cudaMemcpyDeviceToDevice, s));
+    PM_CUDA(cudaMemsetAsync(pu2 + n, 0, n * sizeof(Fr), s));
+    rt.ntt.run(pu2, log_n + 1, false, s);
+    launch_square(pu2, 2 * n, s);
+    rt.ntt.run(pu2, log_n + 1, true, s);
+    launch_quotient_checks(pu2, pw, n, st, s);   // prover.rs:104-108
+    launch_assemble_phase1_scalars(pu, pu2, ztail.get<Fr>(), cols - m0, sm + S_RA, n, scal_a.get<Fr>(), scal_c.get<Fr>(), s);
+    rt.extra_launches += 9;
+    G1XYZZ* ac = acc.get<G1XYZZ>();
+    const G1Affine* bc = bases_c.get<G1Affine>();
+    rt.msm.run(bc, scal_a.get<Fr>(), n + 4, ac + 0, s);          // compute_a_g1, prover.rs:330-338
+    rt.msm.run(bc, scal_c.get<Fr>(), len_c(), ac + 1, s);        // c_g1, prover.rs:116-123
+    G1Affine* res = result.get<G1Affine>();
+    launch_xyzz_sum_to_affine(ac + 0, 1, res + 0, s);
+    launch_xyzz_sum_to_affine(ac + 1, 1, res + 1, s);
+    rt.extra_launches += 2;
+    uint8_t* hs = static_cast<uint8_t*>(host_stage);
+    PM_CUDA(cudaMemcpyAsync(hs, res, 2 * sizeof(G1Affine), cudaMemcpyDeviceToHost, s));
+    PM_CUDA(cudaMemcpyAsync(hs + 256, st, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    PM_CUDA(cudaEventRecord(ev1, s));
+    PM_CUDA(cudaStreamSynchronize(s));
+    float ms = 0;
+    PM_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+    phase_ms[0] = ms;
+    uint32_t stv;
+    memcpy(&stv, hs + 256, 4);
+    check_status(stv);
+    memcpy(a_out, hs, PM_G1_BYTES);
+    memcpy(c_out, hs + PM_G1_BYTES, PM_G1_BYTES);
+    phase = 1;
+}
+
+void ProverCtx::phase2(const uint8_t* x1, const uint8_t* y1_alpha, uint8_t* a_at_x1_out) {
+    Runtime& rt = runtime();
+    cudaStream_t s = rt.stream;
+    if (phase != 1) throw StatusError(PM_ERR_STATE, "phase 2 must follow phase 1");
+    if (!x1 || !y1_alpha || !a_at_x1_out) throw StatusError(PM_ERR_ARG, "null phase-2 argument");
+    Fr* sm = small.get<Fr>();
+    PM_CUDA(cudaEventRecord(ev0, s));
+    PM_CUDA(cudaMemcpyAsync(sm + S_X1, x1, sizeof(Fr), cudaMemcpyHostToDevice, s));
+    PM_CUDA(cudaMemcpyAsync(sm + S_Y1A, y1_alpha, sizeof(Fr), cudaMemcpyHostToDevice, s));
+    const uint64_t nchunks = (n + kChunk - 1) / kChunk;
+    launch_chunk_eval_plain(u.get<Fr>(), n, sm + S_X1, chunk_vals.get<Fr>(), s);      // u_poly.evaluate(&x1), prover.rs:132
+    launch_combine_chunks(chunk_vals.get<Fr>(), nchunks, sm + S_X1, sm + S_U_AT_X1, s);
+    launch_a_at_x1(sm + S_U_AT_X1, sm + S_RA, sm + S_X1, sm + S_A_AT_X1, s);
+    rt.extra_launches += 3;
+    uint8_t* hs = static_cast<uint8_t*>(host_stage);
+    PM_CUDA(cudaMemcpyAsync(hs, sm + S_A_AT_X1, sizeof(Fr), cudaMemcpyDeviceToHost, s));
+    PM_CUDA(cudaEventRecord(ev1, s));
+    PM_CUDA(cudaStreamSynchronize(s));
+    float ms = 0;
+    PM_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+    phase_ms[1] = ms;
+    memcpy(a_at_x1_out, hs, PM_FR_BYTES);
+    phase = 2;
+}
+
+NumeratorSrc ProverCtx::numerator_src() const {
+    NumeratorSrc src;
+    const Fr* sm = small.get<Fr>();
+    src.u = u.get<Fr>();
+    src.wu = wu.get<Fr>();
+    src.u2 = u2.get<Fr>();
+    src.ra_ext = sm + S_RA;
+    src.consts = sm + S_X2;
+    src.n = n;
+    src.sigma = sigma;
+    src.len = len_d();
+    return src;
+}
+
+void ProverCtx::phase3(const uint8_t* x2, const uint8_t* c_at_x1, uint8_t* d_out) {
+    Runtime& rt = runtime();
+    cudaStream_t s = rt.stream;
+    if (phase != 2) throw StatusError(PM_ERR_STATE, "phase 3 must follow phase 2");
+    if (!x2 || !c_at_x1 || !d_out) throw StatusError(PM_ERR_ARG, "null phase-3 argument");
+    Fr* sm = small.get<Fr>();
+    uint32_t* st = status.get<uint32_t>();
+    PM_CUDA(cudaEventRecord(ev0, s));
+    PM_CUDA(cudaMemcpyAsync(sm + S_X2, x2, sizeof(Fr), cudaMemcpyHostToDevice, s));
+    PM_CUDA(cudaMemcpyAsync(sm + S_C_AT_X1, c_at_x1, sizeof(Fr), cudaMemcpyHostToDevice, s));
+    k_phase3_consts<<<1, 32, 0, s>>>(sm);
+    PM_LAUNCH_CHECK();
+    NumeratorSrc src = numerator_src();
+    const uint64_t nchunks = (src.len + kChunk - 1) / kChunk;
+    launch_chunk_eval_numerator(src, sm + S_X1, chunk_vals.get<Fr>(), s);
+    launch_chunk_carries(chunk_vals.get<Fr>(), nchunks, sm + S_X1, carries.get<Fr>(), st, s);
+    launch_divide_numerator(src, sm + S_X1, carries.get<Fr>(), q.get<Fr>(), s);       // prover.rs:211-225
+    rt.extra_launches += 4;
+    G1XYZZ* ac = acc.get<G1XYZZ>();
+    rt.msm.run(bases_d.get<G1Affine>(), q.get<Fr>(), src.len - 1, ac + 2, s);         // prover.rs:229
+    G1Affine* res = result.get<G1Affine>();
+    launch_xyzz_sum_to_affine(ac + 2, 1, res + 2, s);
+    rt.extra_launches += 1;
+    uint8_t* hs = static_cast<uint8_t*>(host_stage);
+    PM_CUDA(cudaMemcpyAsync(hs, res + 2, sizeof(G1Affine), cudaMemcpyDeviceToHost, s));
+    PM_CUDA(cudaMemcpyAsync(hs + 256, st, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    PM_CUDA(cudaEventRecord(ev1, s));
+    PM_CUDA(cudaStreamSynchronize(s));
+    float ms = 0;
+    PM_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+    phase_ms[2] = ms;
+    uint32_t stv;
+    memcpy(&stv, hs + 256, 4);
+    check_status(stv);
+    memcpy(d_out, hs, PM_G1_BYTES);
+    phase = 0;
+}
+
+}  // namespace pm
+
+// ---------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------
+using namespace pm;
+
+struct pm_ctx {
+    ProverCtx impl;
+};
+
+namespace {
+
+void init_dims(ProverCtx& c, const pm_r1cs_view& r) {
+    c.m0 = r.num_instance_variables;
+    c.mw = r.num_r1cs_witness_variables;
+    c.nr = r.num_r1cs_constraints;
+    if (c.m0 + c.mw >= ((uint64_t)1 << 32) || c.nr >= ((uint64_t)1 << 31)) throw StatusError(PM_ERR_ARG, "R1CS too large");
+    c.cols = 3 * c.m0 + c.mw + c.nr;   // SAPMatrices::size, common.rs:131-135
+}
+
+void upload_points(G1Affine* dst, const uint8_t* src, size_t stride, uint64_t len, uint64_t expect, const char* name) {
+    if (len != expect) throw StatusError(PM_ERR_ARG, std::string("unexpected length of ") + name);
+    if (len && !src) throw StatusError(PM_ERR_ARG, std::string("null ") + name);
+    Runtime& rt = runtime();
+    if (stride == PM_G1_BYTES) {
+        PM_CUDA(cudaMemcpyAsync(dst, src, len * sizeof(G1Affine), cudaMemcpyHostToDevice, rt.stream));
+        PM_CUDA(cudaStreamSynchronize(rt.stream));
+    } else {
+        std::vector<uint8_t> packed;
+        pack_points_host(src, stride, len, packed);
+        PM_CUDA(cudaMemcpyAsync(dst, packed.data(), len * sizeof(G1Affine), cudaMemcpyHostToDevice, rt.stream));
+        PM_CUDA(cudaStreamSynchronize(rt.stream));
+    }
+}
+
+struct KeySlice { uint64_t off, len; bool in_d; };
+KeySlice key_slice(const ProverCtx& c, int which) {
+    const uint64_t n = c.n;
+    switch (which) {
+        case 0: return {0, n + 1, false};
+        case 1: return {n + 1, 3, false};
+        case 2: return {n + 6, n - 1, false};
+        case 3: return {n + 4, 2, false};
+        case 4: return {0, c.len_d(), true};
+        case 5: return {n + 6 + (n - 1), c.cols - c.m0, false};
+        default: throw StatusError(PM_ERR_ARG, "bad key vector index");
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int pm_ctx_create(const pm_pk_view* pk, pm_ctx** out) {
+    return guarded([&] {
+        if (!pk || !out) throw StatusError(PM_ERR_ARG, "null argument");
+        if (pk->point_stride < PM_G1_BYTES) throw StatusError(PM_ERR_ARG, "point stride < 96");
+        runtime();
+        std::unique_ptr<pm_ctx> h(new pm_ctx());
+        ProverCtx& c = h->impl;
+        init_dims(c, pk->r1cs);
+        c.n = pk->n;
+        c.sigma = pk->sigma;
+        c.allocate_work();
+        c.upload_matrix(c.A, pk->r1cs.a_row_ptr, pk->r1cs.a_col, pk->r1cs.a_val, false);
+        c.upload_matrix(c.B, pk->r1cs.b_row_ptr, pk->r1cs.b_col, pk->r1cs.b_val, false);
+        c.upload_matrix(c.C, pk->r1cs.c_row_ptr, pk->r1cs.c_col, pk->r1cs.c_val, false);
+        G1Affine* bc = c.bases_c.as<G1Affine>(c.len_c());
+        G1Affine* bd = c.bases_d.as<G1Affine>(c.len_d());
+        const size_t st = pk->point_stride;
+        const uint64_t n = c.n;
+        upload_points(bc, pk->x_powers_g1, st, pk->x_powers_g1_len, n + 1, "x_powers_g1");
+        upload_points(bc + n + 1, pk->x_powers_y_alpha_g1, st, pk->x_powers_y_alpha_g1_len, 3, "x_powers_y_alpha_g1");
+        upload_points(bc + n + 4, pk->x_powers_y_gamma_g1, st, pk->x_powers_y_gamma_g1_len, 2, "x_powers_y_gamma_g1");
+        upload_points(bc + n + 6, pk->x_powers_zh_by_y_alpha_g1, st, pk->x_powers_zh_by_y_alpha_g1_len, n - 1, "x_powers_zh_by_y_alpha_g1");
+        upload_points(bc + n + 6 + (n - 1), pk->uj_wj_lcs_by_y_alpha_g1, st, pk->uj_wj_lcs_by_y_alpha_g1_len, c.cols - c.m0, "uj_wj_lcs_by_y_alpha_g1");
+        upload_points(bd, pk->x_powers_y_gamma_z_g1, st, pk->x_powers_y_gamma_z_g1_len, c.len_d(), "x_powers_y_gamma_z_g1");
+        *out = h.release();
+    });
+}
+
+void pm_ctx_destroy(pm_ctx* ctx) {
+    if (!ctx) return;
+    cudaDeviceSynchronize();
+    delete ctx;
+}
+
+int pm_setup(const pm_r1cs_view* r1cs, const uint8_t x[PM_FR_BYTES], const uint8_t z[PM_FR_BYTES], pm_ctx** out,
+             uint8_t x_g2[192], uint8_t z_g2[192]) {
+    return guarded([&] {
+        if (!r1cs || !x || !z || !out || !x_g2 || !z_g2) throw StatusError(PM_ERR_ARG, "null argument");
+        runtime();
+        std::unique_ptr<pm_ctx> h(new pm_ctx());
+        ProverCtx& c = h->impl;
+        init_dims(c, *r1cs);
+        uint64_t rows = 2 * (c.m0 + c.nr);           // Radix2EvaluationDomain::new(rows), generator.rs:60-66
+        uint64_t n = 1;
+        while (n < rows) n <<= 1;
+        c.n = n;
+        c.sigma = n + 3;                              // generator.rs:70
+        c.allocate_work();
+        c.upload_matrix(c.A, r1cs->a_row_ptr, r1cs->a_col, r1cs->a_val, true);
+        c.upload_matrix(c.B, r1cs->b_row_ptr, r1cs->b_col, r1cs->b_val, true);
+        c.upload_matrix(c.C, r1cs->c_row_ptr, r1cs->c_col, r1cs->c_val, true);
+        c.bases_c.as<G1Affine>(c.len_c());
+        c.bases_d.as<G1Affine>(c.len_d());
+        run_setup(c, x, z, x_g2, z_g2);
+        *out = h.release();
+    });
+}
+
+int pm_ctx_dims(const pm_ctx* ctx, uint64_t* n, uint64_t* sigma, uint64_t* num_columns) {
+    return guarded([&] {
+        if (!ctx) throw StatusError(PM_ERR_ARG, "null context");
+        if (n) *n = ctx->impl.n;
+        if (sigma) *sigma = ctx->impl.sigma;
+        if (num_columns) *num_columns = ctx->impl.cols;
+    });
+}
+
+int pm_ctx_key_len(const pm_ctx* ctx, int which, uint64_t* len) {
+    return guarded([&] {
+        if (!ctx || !len) throw StatusError(PM_ERR_ARG, "null argument");
+        *len = key_slice(ctx->impl, which).len;
+    });
+}
+
+int pm_ctx_export_key(const pm_ctx* ctx, int which, uint8_t* out, size_t stride) {
+    return guarded([&] {
+        if (!ctx || !out || stride < PM_G1_BYTES) throw StatusError(PM_ERR_ARG, "bad export arguments");
+        const ProverCtx& c = ctx->impl;
+        KeySlice ks = key_slice(c, which);
+        const G1Affine* src = (ks.in_d ? c.bases_d.get<G1Affine>() : c.bases_c.get<G1Affine>()) + ks.off;
+        Runtime& rt = runtime();
+        if (stride == PM_G1_BYTES) {
+            PM_CUDA(cudaMemcpyAsync(out, src, ks.len * sizeof(G1Affine), cudaMemcpyDeviceToHost, rt.stream));
+            PM_CUDA(cudaStreamSynchronize(rt.stream));
+            return;
+        }
+        std::vector<uint8_t> tmp(ks.len * PM_G1_BYTES);
+        PM_CUDA(cudaMemcpyAsync(tmp.data(), src, tmp.size(), cudaMemcpyDeviceToHost, rt.stream));
+        PM_CUDA(cudaStreamSynchronize(rt.stream));
+        static const uint8_t zero96[PM_G1_BYTES] = {0};
+        for (uint64_t i = 0; i < ks.len; i++) {
+            uint8_t* q = out + i * stride;
+            memset(q, 0, stride);
+            memcpy(q, tmp.data() + i * PM_G1_BYTES, PM_G1_BYTES);
+            if (stride >= 104 && memcmp(q, zero96, PM_G1_BYTES) == 0) q[96] = 1;
+        }
+    });
+}
+
+int pm_ctx_set_assignment(pm_ctx* ctx, const uint8_t* x, const uint8_t* w) {
+    return guarded([&] {
+        if (!ctx) throw StatusError(PM_ERR_ARG, "null context");
+        ctx->impl.set_assignment(x, w);
+        PM_CUDA(cudaStreamSynchronize(runtime().stream));
+    });
+}
+
+int pm_prove_phase1_resident(pm_ctx* ctx, const uint8_t r_a[2 * PM_FR_BYTES], uint8_t a_out[PM_G1_BYTES], uint8_t c_out[PM_G1_BYTES]) {
+    return guarded([&] {
+        if (!ctx) throw StatusError(PM_ERR_ARG, "null context");
+        ctx->impl.phase1(r_a, a_out, c_out);
+    });
+}
+
+int pm_prove_phase1(pm_ctx* ctx, const uint8_t* x, const uint8_t* w, const uint8_t r_a[2 * PM_FR_BYTES],
+                    uint8_t a_out[PM_G1_BYTES], uint8_t c_out[PM_G1_BYTES]) {
+    return guarded([&] {
+        if (!ctx) throw StatusError(PM_ERR_ARG, "null context");
+        ctx->impl.set_assignment(x, w);
+        ctx->impl.phase1(r_a, a_out, c_out);
+    });
+}
+
+int pm_prove_phase2(pm_ctx* ctx, const uint8_t x1[PM_FR_BYTES], const uint8_t y1_alpha[PM_FR_BYTES], uint8_t a_at_x1_out[PM_FR_BYTES]) {
+    return guarded([&] {
+        if (!ctx) throw StatusError(PM_ERR_ARG, "null context");
+        ctx->impl.phase2(x1, y1_alpha, a_at_x1_out);
+    });
+}
+
+int pm_prove_phase3(pm_ctx* ctx, const uint8_t x2[PM_FR_BYTES], const uint8_t c_at_x1[PM_FR_BYTES], uint8_t d_out[PM_G1_BYTES]) {
+    return guarded([&] {
+        if (!ctx) throw StatusError(PM_ERR_ARG, "null context");
+        ctx->impl.phase3(x2, c_at_x1, d_out);
+    });
+}
+
+int pm_ctx_debug_read(pm_ctx* ctx, int which, uint8_t* out, uint64_t capacity_elems, uint64_t* len) {
+    return guarded([&] {
+        if (!ctx || !len) throw StatusError(PM_ERR_ARG, "null argument");
+        ProverCtx& c = ctx->impl;
+        const Fr* src = nullptr;
+        uint64_t cnt = 0;
+        switch (which) {
+            case 0: src = c.u.get<Fr>(); cnt = c.n; break;
+            case 1: src = c.w.get<Fr>(); cnt = c.n; break;
+            case 2: src = c.wu.get<Fr>(); cnt = c.n; break;
+            case 3: src = c.u2.get<Fr>(); cnt = 2 * c.n; break;
+            case 4: src = c.ztail.get<Fr>(); cnt = c.cols - c.m0; break;
+            case 5: src = c.scal_c.get<Fr>(); cnt = c.len_c(); break;
+            case 6: src = c.q.get<Fr>(); cnt = c.len_d() - 1; break;
+            default: throw StatusError(PM_ERR_ARG, "bad debug selector");
+        }
+        *len = cnt;
+        if (!out) return;
+        if (capacity_elems < cnt) throw StatusError(PM_ERR_ARG, "debug buffer too small");
+        Runtime& rt = runtime();
+        PM_CUDA(cudaMemcpyAsync(out, src, cnt * sizeof(Fr), cudaMemcpyDeviceToHost, rt.stream));
+        PM_CUDA(cudaStreamSynchronize(rt.stream));
+    });
+}
+
+int pm_ctx_phase_ms(const pm_ctx* ctx, double ms[3]) {
+    return guarded([&] {
+        if (!ctx || !ms) throw StatusError(PM_ERR_ARG, "null argument");
+        for (int i = 0; i < 3; i++) ms[i] = ctx->impl.phase_ms[i];
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,51 @@
+// Device-resident prover context: proving key + per-proof work buffers + the three phases.
+#pragma once
+#include <vector>
+#include "common.cuh"
+#include "ec.cuh"
+#include "poly_kernels.cuh"
+#include "runtime.cuh"
+
+namespace pm {
+
+// CSR (and optionally CSC) of one R1CS matrix, deduplicated on the host, resident on the device.
+struct DevMatrix {
+    DevBuf row_ptr, col, val;          // CSR
+    DevBuf col_ptr, row, cval;         // CSC (setup only)
+    uint64_t nnz = 0;
+    DevCsr csr() const { return {row_ptr.get<uint32_t>(), col.get<uint32_t>(), val.get<Fr>()}; }
+};
+
+struct ProverCtx {
+    // dimensions
+    uint64_t m0 = 0, mw = 0, nr = 0, n = 0, sigma = 0, cols = 0;
+    int log_n = 0;
+    // key
+    DevMatrix A, B, C;
+    DevBuf bases_c;   // [x_powers (n+1) | x_powers_y_alpha (3) | x_powers_y_gamma (2) | zh (n-1) | lcs (cols-m0)]
+    DevBuf bases_d;   // x_powers_y_gamma_z (10n + 23)
+    uint64_t len_c() const { return (n + 1) + 3 + 2 + (n - 1) + (cols - m0); }
+    uint64_t len_d() const { return 2 * (n - 1) + 8 * sigma + 1; }
+    // per-proof buffers
+    DevBuf ztail, u, w, wu, u2, scal_a, scal_c, q, chunk_vals, carries, small;
+    DevBuf status, acc, result;
+    void* host_stage = nullptr;   // pinned staging for results
+    int phase = 0;                // 0 idle, 1 after phase 1, 2 after phase 2
+    bool assignment_set = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double phase_ms[3] = {0, 0, 0};
+
+    ~ProverCtx();
+    void allocate_work();
+    void upload_matrix(DevMatrix& dst, const uint64_t* row_ptr, const uint32_t* col, const uint8_t* val, bool want_csc);
+    void set_assignment(const uint8_t* x, const uint8_t* w);
+    void phase1(const uint8_t* ra, uint8_t* a_out, uint8_t* c_out);
+    void phase2(const uint8_t* x1, const uint8_t* y1_alpha, uint8_t* a_at_x1_out);
+    void phase3(const uint8_t* x2, const uint8_t* c_at_x1, uint8_t* d_out);
+    NumeratorSrc numerator_src() const;
+};
+
+// setup.cu: fill bases_c / bases_d of a context whose matrices are uploaded (with CSC), and the G2 images.
+void run_setup(ProverCtx& ctx, const uint8_t* x, const uint8_t* z, uint8_t* x_g2, uint8_t* z_g2);
+
+}  // namespace pm

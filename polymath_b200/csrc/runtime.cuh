@@ -28,7 +28,23 @@ struct Runtime {
 
 Runtime& runtime();
 
-template <class F> int guarded(F&& f);
+template <class F>
+int guarded(F&& f) {
+    try {
+        f();
+        return PM_OK;
+    } catch (const StatusError& e) {
+        set_last_error(e.what());
+        return e.code;
+    } catch (const CudaError& e) {
+        set_last_error(e.what());
+        return PM_ERR_CUDA;
+    } catch (const std::exception& e) {
+        set_last_error(e.what());
+        return PM_ERR_CUDA;
+    }
+}
+
 void pack_points_host(const uint8_t* src, size_t stride, size_t n, std::vector<uint8_t>& dst);
 
 // out[0] = in[0]^-1 (single thread)
