@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""bench.py — Polymath prove latency on synthetic SAP circuits (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--log-n 20]
+
+One "step" = one `Polymath::prove` of the S-mimc(2^log_n) circuit with the proving
+key resident on the device.  `value` times K proves whose witness is already resident in HBM
+(CUDA events on the library's stream, host transcript round-trips included); `e2e` times the same K
+proves through the public host-buffer call (`pm_polymath_prove`: H2D of instance+witness from
+pinned memory, D2H of the proof pieces, inside the timed region).  One JSON line on stdout.
+
+`--impl reference` times the CPU restatement of the reference's arkworks path (oracle/cpu_ref.cpp,
+OpenMP on all host cores) on a bounded sample of the same workload, scaled to the metric's unit.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import random
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC_FMT = "prove_ms_2p{log_n}_sap_constraints"
+
+
+# --------------------------------------------------------------------------------------------
+# CPU baseline (oracle port) — bounded sample, scaled
+# --------------------------------------------------------------------------------------------
+def ark_window(n):
+    if n < 32:
+        return 3
+    return ((n - 1).bit_length()) * 69 // 100 + 2
+
+
+def cpu_baseline(log_n, msm_log=16, ntt_log=18):
+    """Time the C++/OpenMP port on a bounded sample and scale to one prove at n = 2^log_n.
+
+    prove(n) = MSMs over ~14n + 29 points + 3 iNTT(n) + NTT(2n) + iNTT(2n).
+    MSM cost is scaled by points x windows (arkworks window rule at each size); NTT by (N/2) log2 N.
+    """
+    from oracle import cpp
+    n = 1 << log_n
+    m = 1 << msm_log
+    rnd = random.Random(7)
+    bases = cpp.make_bases_wire(m)
+    scalars = b"".join(rnd.getrandbits(254).to_bytes(32, "little") for _ in range(m))
+    cpp.msm_wire(bases[:96 * 1024], scalars[:32 * 1024], 1024)   # warm up threads
+    t0 = time.perf_counter()
+    cpp.msm_wire(bases, scalars, m)
+    t_msm = time.perf_counter() - t0
+    buf = bytearray(os.urandom(32 << ntt_log))
+    for i in range(31, len(buf), 32):
+        buf[i] &= 0x3F
+    t0 = time.perf_counter()
+    cpp.ntt_wire(buf, ntt_log, False)
+    t_ntt = time.perf_counter() - t0
+
+    def msm_work(pts):
+        c = ark_window(pts)
+        return pts * ((255 + c - 1) // c)
+
+    sizes = [n + 4, 3 * n + 5, 10 * n + 22]     # the three MSM launches of one prove (a, c, d)
+    msm_s = sum(msm_work(s) for s in sizes) / msm_work(m) * t_msm
+
+    def ntt_work(lg):
+        return (1 << lg) // 2 * lg
+
+    ntt_s = (3 * ntt_work(log_n) + 2 * ntt_work(log_n + 1)) / ntt_work(ntt_log) * t_ntt
+    total_ms = (msm_s + ntt_s) * 1e3
+    return {
+        "value": total_ms, "unit": "ms", "cores": cpp.num_threads(), "kind": "port",
+        "sample": "oracle/cpu_ref.cpp (OpenMP): one G1 MSM of 2^%d points (%.2f s) and one Fr NTT of 2^%d (%.3f s), "
+                  "scaled by points*windows resp. (N/2)log2N to one prove at n=2^%d (MSMs of n+4, 3n+5, 10n+22 points; "
+                  "3 iNTT(n) + NTT(2n) + iNTT(2n)); SpMV/scan terms omitted" % (msm_log, t_msm, ntt_log, t_ntt, log_n),
+        "msm_mpts_per_s": m / t_msm / 1e6, "ntt_gelem_per_s": (1 << ntt_log) / t_ntt / 1e9,
+    }
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals = []
+    last = None
+    for _ in range(args.warmup):
+        cpu_baseline(args.log_n, msm_log=14, ntt_log=16)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        last = cpu_baseline(args.log_n)
+        vals.append(last["value"])
+    wall = time.perf_counter() - t0
+    value = sum(vals) / len(vals)
+    last["value"] = value
+    out = {
+        "impl": "reference", "metric": METRIC_FMT.format(log_n=args.log_n), "value": value, "unit": "ms",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3,
+        "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": "S-mimc(2^%d) prove, CPU port of the arkworks primitives on a bounded sample (see cpu_baseline.sample)" % args.log_n,
+                   "log_n": args.log_n},
+        "cpu_baseline": last,
+        "e2e": {"value": value, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+# clocks sampling
+# --------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.stop_flag = threading.Event()
+        self.thread = None
+
+    def _run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def start(self):
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+
+    def stop(self):
+        self.stop_flag.set()
+        if self.thread:
+            self.thread.join(timeout=6)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for s in self.samples for i in range(4) if s[2 + i].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl")
+
+    from polymath_b200 import circuits
+    from polymath_b200.api import Polymath, StdRng, _lib
+    from polymath_b200 import codec
+    from polymath_b200.lib import check
+    lib = _lib()
+
+    log_n = args.log_n
+    n = 1 << log_n
+    r1cs, instance, witness, rng = circuits.synthetic_mimc(n, seed=1)
+    t0 = time.perf_counter()
+    if world > 1:
+        from polymath_b200 import sharded
+        prover = sharded.ShardedProver(r1cs, rng, rank, world)
+    else:
+        pk, vk_bytes = Polymath.setup(r1cs, rng)
+        prover = None
+    setup_s = time.perf_counter() - t0
+
+    inst_wire = codec.frs_to_wire(instance)
+    wit_wire = codec.frs_to_wire(witness)
+    # pinned host buffers for the e2e leg
+    pin_inst = torch.empty(len(inst_wire), dtype=torch.uint8).pin_memory()
+    pin_wit = torch.empty(len(wit_wire), dtype=torch.uint8).pin_memory()
+    pin_inst.copy_(torch.frombuffer(bytearray(inst_wire), dtype=torch.uint8))
+    pin_wit.copy_(torch.frombuffer(bytearray(wit_wire), dtype=torch.uint8))
+    p_inst = C.c_char_p(pin_inst.data_ptr())
+    p_wit = C.c_char_p(pin_wit.data_ptr())
+    proof = C.create_string_buffer(176)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def prove_resident():
+        if prover is not None:
+            return prover.prove_resident(inst_wire, rng)
+        check(lib.pm_polymath_prove_resident(pk._h, p_inst, rng._h, proof))
+        return proof.raw
+
+    def prove_e2e():
+        if prover is not None:
+            return prover.prove(inst_wire, p_wit, rng)
+        check(lib.pm_polymath_prove(pk._h, p_inst, p_wit, rng._h, proof))
+        return proof.raw
+
+    # resident leg ------------------------------------------------------------------------
+    if prover is not None:
+        prover.set_assignment(p_inst, p_wit)
+    else:
+        check(lib.pm_ctx_set_assignment(pk._h, p_inst, p_wit))
+    for _ in range(args.warmup):
+        prove_resident()
+    check(lib.pm_bench_set_kernel_timing(1))
+    launches0 = lib.pm_kernel_launches()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    check(lib.pm_timer_start())
+    wall0 = time.perf_counter()
+    acc_ms = []
+    for _ in range(args.steps):
+        last_proof = prove_resident()
+        km = (C.c_double * 2)()
+        check(lib.pm_bench_last_kernel_ms(km))
+        acc_ms.append(km[0])
+    ms = C.c_double()
+    check(lib.pm_timer_stop(C.byref(ms)))
+    barrier()
+    wall_resident = (time.perf_counter() - wall0) * 1e3
+    clocks = sampler.stop()
+    launches = lib.pm_kernel_launches() - launches0
+    check(lib.pm_bench_set_kernel_timing(0))
+    dev_ms = ms.value
+    if world > 1:
+        t = torch.tensor([dev_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms = float(t.item())
+    value = dev_ms / args.steps
+    phase_ms = pk.phase_ms() if prover is None else prover.phase_ms()
+
+    # e2e leg -----------------------------------------------------------------------------
+    prove_e2e()
+    barrier()
+    check(lib.pm_timer_start())
+    for _ in range(args.steps):
+        prove_e2e()
+    check(lib.pm_timer_stop(C.byref(ms)))
+    barrier()
+    e2e_ms = ms.value
+    if world > 1:
+        t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_value = e2e_ms / args.steps
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # roofline of the dominant kernel: bucket accumulation of the [d]_1 MSM (10n + 22 points) -----
+    d = C.c_double()
+    check(lib.pm_bench_imad_peak(C.byref(d)))
+    imad_peak = d.value
+    d_points = (10 * n + 22) // world
+    c_ark = ark_window(10 * n + 22)
+    w_ark = (255 + c_ark - 1) // c_ark
+    algo_imad = d_points * w_ark * 10 * 300          # N*W madds x 10 Fq-modmul x 300 IMAD
+    acc = sorted(acc_ms)[len(acc_ms) // 2] if acc_ms else 0.0
+    achieved = algo_imad / (acc * 1e-3) / 1e12 if acc > 0 else None
+    roofline = {
+        "kernel": "k_accumulate (bucket accumulation of the [d]_1 MSM)", "bound": "imad",
+        "achieved": achieved, "peak": imad_peak / 1e12, "unit": "TIMAD/s",
+        "frac": (achieved / (imad_peak / 1e12)) if achieved else None,
+        "traffic": None, "kernel_ms": acc, "kernel_share_of_step": acc / value if value else None,
+        "peak_source": "measured live: dependency-free IMAD.WIDE.U32 issue rate (pm_bench_imad_peak); "
+                       "north_star names the INT32 IMAD pipe as the roofline for MSM / field multiplication",
+        "algorithmic": "%d points x %d windows (arkworks window rule c=%d) x 10 Fq-modmul x 300 IMAD" % (d_points, w_ark, c_ark),
+    }
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    check(lib.pm_bench_ntt(log_n + 1, 0, 5, C.byref(d)))
+    ntt_ms = d.value
+    ntt_gbs = 64.0 * (2 * n) / (ntt_ms * 1e-3) / 1e9
+    roofline_hbm = {"kernel": "Fr NTT 2^%d (column + row pass)" % (log_n + 1), "bound": "hbm", "achieved": ntt_gbs,
+                    "peak": hbm_peak, "unit": "GB/s", "frac": ntt_gbs / hbm_peak, "traffic": None,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
+                    "gelem_per_s": (2 * n) / (ntt_ms * 1e-3) / 1e9}
+    acc_d = C.c_double()
+    check(lib.pm_bench_msm(1 << 22, 0, 2, C.byref(d), C.byref(acc_d)))
+    msm_mpts = (1 << 22) / (d.value * 1e-3) / 1e6
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        try:
+            cpu = cpu_baseline(log_n)
+        except Exception as e:  # the oracle library is optional on the product path
+            cpu = {"value": None, "unit": "ms", "cores": 0, "kind": "port", "sample": "unavailable: %r" % (e,)}
+
+    h2d = len(inst_wire) + len(wit_wire) + 64 + 64 + 64
+    d2h = 2 * 96 + 4 + 32 + 96 + 4
+    out = {
+        "metric": METRIC_FMT.format(log_n=log_n), "value": value, "unit": "ms", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": value, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
+        "dtype": "u32", "data": "synthetic",
+        "config": {"workload": "S-mimc(2^%d): MiMC chain of tests/mimc.rs with %d rounds (SURVEY.md 8d), "
+                               "Polymath prove, proving key resident on the device" % (log_n, n // 4 - 1),
+                   "log_n": log_n, "msm_points_per_prove": 14 * n + 31,
+                   "l2": "inputs larger than L2: key %.2f GB, MSM workspace > 0.7 GB per launch" % ((14 * n + 29) * 96 / 1e9),
+                   "parallelism": "1 GPU" if world == 1 else "MSM split by point range over %d GPUs, all-gather of partial sums" % world},
+        "e2e": {"value": e2e_value, "unit": "ms", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": int(launches), "clocks": clocks,
+        "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu,
+        "phase_ms": {"phase1": phase_ms[0], "phase2": phase_ms[1], "phase3": phase_ms[2]},
+        "wall_ms_per_step": wall_resident / args.steps, "setup_s": setup_s,
+        "kernel_sweep": {"g1_msm_mpts_per_s_2p22": msm_mpts, "fr_ntt_gelem_per_s_2p%d" % (log_n + 1): roofline_hbm["gelem_per_s"]},
+        "proof_hex": last_proof.hex(),
+    }
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--log-n", type=int, default=20)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -175,6 +175,10 @@ int pm_polymath_setup(const pm_r1cs_view* r1cs, pm_rng* rng, pm_ctx** ctx_out, u
  * (176 bytes, src/data_structures.rs:10-19). */
 int pm_polymath_prove(pm_ctx* ctx, const uint8_t* instance, const uint8_t* witness, pm_rng* rng, uint8_t proof_out[176]);
 
+/* Same as pm_polymath_prove but uses the assignment already resident from pm_ctx_set_assignment
+ * (bench.py's device-resident timing leg); `instance` is still needed for the transcript. */
+int pm_polymath_prove_resident(pm_ctx* ctx, const uint8_t* instance, pm_rng* rng, uint8_t proof_out[176]);
+
 /* ---- measurement hooks (bench.py; synthetic device-resident inputs, CUDA-event timing) ---- */
 
 /* Issue rate of dependency-free IMAD.WIDE.U32 (32x32+64 multiply-adds per second, whole GPU):
@@ -187,6 +191,15 @@ int pm_bench_ntt(unsigned log_n, int inverse, int iters, double* ms_avg);
 /* Average milliseconds of `iters` n-point MSMs on resident synthetic bases/scalars (after one warm-up);
  * ms_accumulate (nullable) receives the average time of the bucket-accumulation kernel alone. */
 int pm_bench_msm(size_t n, int window_bits, int iters, double* ms_avg, double* ms_accumulate);
+
+/* CUDA-event stopwatch on the library's stream: start records an event, stop records another,
+ * synchronises it and returns the elapsed device-timeline milliseconds. */
+int pm_timer_start(void);
+int pm_timer_stop(double* ms);
+/* Enable/disable per-kernel event timing inside the MSM and NTT engines, and read the last values:
+ * ms[0] = bucket-accumulation kernel of the last MSM, ms[1] = passes of the last NTT. */
+int pm_bench_set_kernel_timing(int enable);
+int pm_bench_last_kernel_ms(double ms[2]);
 
 #ifdef __cplusplus
 }

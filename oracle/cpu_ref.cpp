@@ -1,0 +1,305 @@
+// CPU restatement (C++/OpenMP) of the two heavy primitives of the Polymath proving path.
+// TEST INFRASTRUCTURE / CPU BASELINE ONLY — never linked into libpolymath_b200.so.
+//
+// What it restates (un-vendored arkworks 0.4.x dependencies of /root/reference):
+//   orc_ntt  — ark-poly `Radix2EvaluationDomain::{fft, ifft}` (reference call sites
+//              src/prover.rs:241,319,325): in-order radix-2, natural order in/out, n^-1 on inverse;
+//   orc_msm  — ark-ec `VariableBaseMSM::msm_unchecked` (src/prover.rs:380-384): window rule
+//              c = 3 if n < 32 else ceil(log2 n)*69/100 + 2, signed digits, one bucket set per
+//              window, windows processed in parallel (rayon in arkworks, OpenMP here), running-sum
+//              bucket reduction, Horner combine.  Output is the canonical affine point.
+// Data forms are those of the device ABI (Montgomery little-endian limbs), so the same buffers feed
+// both sides.  PARITY UNPINNED against real arkworks; pinned against oracle/*.py in tests/test_oracle_cpp.py.
+#include <cstdint>
+#include <cstring>
+#include <vector>
+#include <omp.h>
+
+typedef unsigned __int128 u128;
+
+template <int N>
+struct Mod {
+    uint64_t p[N], r2[N], one[N], ninv;
+};
+
+static const Mod<4> FR = {
+    {0xffffffff00000001ull, 0x53bda402fffe5bfeull, 0x3339d80809a1d805ull, 0x73eda753299d7d48ull},
+    {0xc999e990f3f29c6dull, 0x2b6cedcb87925c23ull, 0x05d314967254398full, 0x0748d9d99f59ff11ull},
+    {0x00000001fffffffeull, 0x5884b7fa00034802ull, 0x998c4fefecbc4ff5ull, 0x1824b159acc5056full},
+    0xfffffffeffffffffull};
+static const Mod<6> FQ = {
+    {0xb9feffffffffaaabull, 0x1eabfffeb153ffffull, 0x6730d2a0f6b0f624ull, 0x64774b84f38512bfull, 0x4b1ba7b6434bacd7ull, 0x1a0111ea397fe69aull},
+    {0xf4df1f341c341746ull, 0x0a76e6a609d104f1ull, 0x8de5476c4c95b6d5ull, 0x67eb88a9939d83c0ull, 0x9a793e85b519952dull, 0x11988fe592cae3aaull},
+    {0x760900000002fffdull, 0xebf4000bc40c0002ull, 0x5f48985753c758baull, 0x77ce585370525745ull, 0x5c071a97a256ec6dull, 0x15f65ec3fa80e493ull},
+    0x89f3fffcfffcfffdull};
+
+template <int N, const Mod<N>& M>
+struct El {
+    uint64_t l[N];
+    static El zero() { El e; memset(e.l, 0, sizeof e.l); return e; }
+    static El one() { El e; memcpy(e.l, M.one, sizeof e.l); return e; }
+    bool is_zero() const { uint64_t o = 0; for (int i = 0; i < N; i++) o |= l[i]; return !o; }
+    bool eq(const El& b) const { return !memcmp(l, b.l, sizeof l); }
+    static bool ge_p(const uint64_t* a) {
+        for (int i = N - 1; i >= 0; i--) if (a[i] != M.p[i]) return a[i] > M.p[i];
+        return true;
+    }
+    static void sub_p(uint64_t* a) {
+        uint64_t br = 0;
+        for (int i = 0; i < N; i++) { u128 t = (u128)a[i] - M.p[i] - br; a[i] = (uint64_t)t; br = (uint64_t)(t >> 64) & 1; }
+    }
+    El add(const El& b) const {
+        El r; uint64_t c = 0;
+        for (int i = 0; i < N; i++) { u128 t = (u128)l[i] + b.l[i] + c; r.l[i] = (uint64_t)t; c = (uint64_t)(t >> 64); }
+        if (c || ge_p(r.l)) sub_p(r.l);
+        return r;
+    }
+    El sub(const El& b) const {
+        El r; uint64_t br = 0;
+        for (int i = 0; i < N; i++) { u128 t = (u128)l[i] - b.l[i] - br; r.l[i] = (uint64_t)t; br = (uint64_t)(t >> 64) & 1; }
+        if (br) { uint64_t c = 0; for (int i = 0; i < N; i++) { u128 t = (u128)r.l[i] + M.p[i] + c; r.l[i] = (uint64_t)t; c = (uint64_t)(t >> 64); } }
+        return r;
+    }
+    El neg() const { return zero().sub(*this); }
+    El dbl() const { return add(*this); }
+    // separated product + Montgomery reduction (SOS form)
+    El mul(const El& b) const {
+        uint64_t t[2 * N + 1];
+        memset(t, 0, sizeof t);
+        for (int i = 0; i < N; i++) {
+            uint64_t c = 0;
+            for (int j = 0; j < N; j++) { u128 s = (u128)l[i] * b.l[j] + t[i + j] + c; t[i + j] = (uint64_t)s; c = (uint64_t)(s >> 64); }
+            t[i + N] = c;
+        }
+        for (int i = 0; i < N; i++) {
+            uint64_t m = t[i] * M.ninv, c = 0;
+            for (int j = 0; j < N; j++) { u128 s = (u128)m * M.p[j] + t[i + j] + c; t[i + j] = (uint64_t)s; c = (uint64_t)(s >> 64); }
+            for (int k = i + N; c && k <= 2 * N; k++) { u128 s = (u128)t[k] + c; t[k] = (uint64_t)s; c = (uint64_t)(s >> 64); }
+        }
+        El r; memcpy(r.l, t + N, sizeof r.l);
+        if (t[2 * N] || ge_p(r.l)) sub_p(r.l);
+        return r;
+    }
+    El sqr() const { return mul(*this); }
+    El from_mont() const { El o = zero(); o.l[0] = 1; return mul(o); }
+    El to_mont() const { El r; memcpy(r.l, M.r2, sizeof r.l); return mul(r); }
+    El pow(const uint64_t* e, int words) const {
+        El acc = one();
+        for (int w = words - 1; w >= 0; w--)
+            for (int b = 63; b >= 0; b--) { acc = acc.sqr(); if ((e[w] >> b) & 1) acc = acc.mul(*this); }
+        return acc;
+    }
+    El inv() const {
+        uint64_t e[N]; memcpy(e, M.p, sizeof e);
+        uint64_t br = 2;
+        for (int i = 0; i < N && br; i++) { u128 t = (u128)e[i] - br; e[i] = (uint64_t)t; br = (uint64_t)(t >> 64) & 1; }
+        return pow(e, N);
+    }
+};
+typedef El<4, FR> Fr;
+typedef El<6, FQ> Fq;
+
+// ------------------------------------------------------------------------------------------
+// NTT
+// ------------------------------------------------------------------------------------------
+static Fr fr_root(int log_n, bool inverse) {
+    // 7^((r-1)/2^32) in Montgomery form, squared down to order 2^log_n
+    Fr w;
+    const uint64_t root[4] = {0xb9b58d8c5f0e466aull, 0x5b1b4c801819d7ecull, 0x0af53ae352a31e64ull, 0x5bf3adda19e9b27bull};
+    memcpy(w.l, root, sizeof root);
+    for (int i = log_n; i < 32; i++) w = w.sqr();
+    return inverse ? w.inv() : w;
+}
+
+extern "C" int orc_ntt(uint64_t* data, int log_n, int inverse) {
+    const size_t n = (size_t)1 << log_n;
+    Fr* a = reinterpret_cast<Fr*>(data);
+    // bit reversal
+    for (size_t i = 1, j = 0; i < n; i++) {
+        size_t bit = n >> 1;
+        for (; j & bit; bit >>= 1) j ^= bit;
+        j |= bit;
+        if (i < j) { Fr t = a[i]; a[i] = a[j]; a[j] = t; }
+    }
+    Fr w_n = fr_root(log_n, inverse != 0);
+    std::vector<Fr> tw(n / 2 ? n / 2 : 1);
+    tw[0] = Fr::one();
+    for (size_t k = 1; k < n / 2; k++) tw[k] = tw[k - 1].mul(w_n);
+    for (size_t len = 2; len <= n; len <<= 1) {
+        const size_t half = len >> 1, step = n / len;
+        if (len <= 1024 || n / len >= 8) {
+#pragma omp parallel for schedule(static)
+            for (size_t start = 0; start < n; start += len)
+                for (size_t k = 0; k < half; k++) {
+                    Fr u = a[start + k], v = a[start + k + half].mul(tw[k * step]);
+                    a[start + k] = u.add(v);
+                    a[start + k + half] = u.sub(v);
+                }
+        } else {
+            for (size_t start = 0; start < n; start += len) {
+#pragma omp parallel for schedule(static)
+                for (size_t k = 0; k < half; k++) {
+                    Fr u = a[start + k], v = a[start + k + half].mul(tw[k * step]);
+                    a[start + k] = u.add(v);
+                    a[start + k + half] = u.sub(v);
+                }
+            }
+        }
+    }
+    if (inverse) {
+        uint64_t nn[4] = {n, 0, 0, 0};
+        Fr nf; memcpy(nf.l, nn, sizeof nn);
+        Fr ninv = nf.to_mont().inv();
+#pragma omp parallel for schedule(static)
+        for (size_t i = 0; i < n; i++) a[i] = a[i].mul(ninv);
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// G1 (Jacobian) and MSM
+// ------------------------------------------------------------------------------------------
+struct Aff { Fq x, y; bool inf() const { return x.is_zero() && y.is_zero(); } };
+struct Jac { Fq x, y, z; bool inf() const { return z.is_zero(); } };
+static Jac jac_inf() { return {Fq::one(), Fq::one(), Fq::zero()}; }
+
+static Jac jac_dbl(const Jac& p) {
+    if (p.inf()) return p;
+    Fq a = p.x.sqr(), b = p.y.sqr(), c = b.sqr();
+    Fq d = p.x.add(b).sqr().sub(a).sub(c).dbl();
+    Fq e = a.dbl().add(a), f = e.sqr();
+    Jac r;
+    r.x = f.sub(d.dbl());
+    r.y = e.mul(d.sub(r.x)).sub(c.dbl().dbl().dbl());
+    r.z = p.y.mul(p.z).dbl();
+    return r;
+}
+static Jac jac_add(const Jac& p, const Jac& q) {
+    if (p.inf()) return q;
+    if (q.inf()) return p;
+    Fq z1z1 = p.z.sqr(), z2z2 = q.z.sqr();
+    Fq u1 = p.x.mul(z2z2), u2 = q.x.mul(z1z1);
+    Fq s1 = p.y.mul(q.z).mul(z2z2), s2 = q.y.mul(p.z).mul(z1z1);
+    if (u1.eq(u2)) return s1.eq(s2) ? jac_dbl(p) : jac_inf();
+    Fq h = u2.sub(u1), rr = s2.sub(s1);
+    Fq hh = h.sqr(), hhh = h.mul(hh), v = u1.mul(hh);
+    Jac r;
+    r.x = rr.sqr().sub(hhh).sub(v.dbl());
+    r.y = rr.mul(v.sub(r.x)).sub(s1.mul(hhh));
+    r.z = p.z.mul(q.z).mul(h);
+    return r;
+}
+static Jac jac_madd(const Jac& p, const Aff& q, bool neg) {
+    if (q.inf()) return p;
+    Fq qy = neg ? q.y.neg() : q.y;
+    if (p.inf()) return {q.x, qy, Fq::one()};
+    Fq z1z1 = p.z.sqr();
+    Fq u2 = q.x.mul(z1z1), s2 = qy.mul(p.z).mul(z1z1);
+    if (u2.eq(p.x)) return s2.eq(p.y) ? jac_dbl(p) : jac_inf();
+    Fq h = u2.sub(p.x), rr = s2.sub(p.y);
+    Fq hh = h.sqr(), hhh = h.mul(hh), v = p.x.mul(hh);
+    Jac r;
+    r.x = rr.sqr().sub(hhh).sub(v.dbl());
+    r.y = rr.mul(v.sub(r.x)).sub(p.y.mul(hhh));
+    r.z = p.z.mul(h);
+    return r;
+}
+
+static int ark_window(size_t n) {
+    if (n < 32) return 3;
+    int lg = 0;
+    while (((size_t)1 << lg) < n) lg++;
+    return lg * 69 / 100 + 2;
+}
+
+extern "C" int orc_msm_window_bits(size_t n) { return ark_window(n); }
+
+extern "C" int orc_msm(const uint64_t* bases_raw, const uint64_t* scalars_raw, size_t n, uint64_t* out_affine) {
+    const Aff* bases = reinterpret_cast<const Aff*>(bases_raw);
+    const Fr* sc = reinterpret_cast<const Fr*>(scalars_raw);
+    const int c = ark_window(n);
+    const int nwin = (255 + c - 1) / c + 1;   // one extra window absorbs the last signed-digit carry
+    const size_t nb = (size_t)1 << (c - 1);
+    // signed digits
+    std::vector<int32_t> digits((size_t)nwin * n);
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < n; i++) {
+        Fr s = sc[i].from_mont();
+        int carry = 0;
+        for (int w = 0; w < nwin; w++) {
+            int pos = w * c, limb = pos >> 6, off = pos & 63;
+            uint64_t v = limb < 4 ? s.l[limb] >> off : 0;
+            if (off + c > 64 && limb + 1 < 4) v |= s.l[limb + 1] << (64 - off);
+            int d = (int)(v & (((uint64_t)1 << c) - 1)) + carry;
+            if (d > (int)nb) { d -= 1 << c; carry = 1; } else carry = 0;
+            digits[(size_t)w * n + i] = d;
+        }
+    }
+    std::vector<Jac> wsum(nwin);
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int w = 0; w < nwin; w++) {
+        std::vector<Jac> buckets(nb, jac_inf());
+        const int32_t* dw = &digits[(size_t)w * n];
+        for (size_t i = 0; i < n; i++) {
+            int d = dw[i];
+            if (d > 0) buckets[d - 1] = jac_madd(buckets[d - 1], bases[i], false);
+            else if (d < 0) buckets[-d - 1] = jac_madd(buckets[-d - 1], bases[i], true);
+        }
+        Jac running = jac_inf(), acc = jac_inf();
+        for (size_t b = nb; b-- > 0;) { running = jac_add(running, buckets[b]); acc = jac_add(acc, running); }
+        wsum[w] = acc;
+    }
+    Jac total = jac_inf();
+    for (int w = nwin - 1; w >= 0; w--) {
+        for (int k = 0; k < c; k++) total = jac_dbl(total);
+        total = jac_add(total, wsum[w]);
+    }
+    Aff* out = reinterpret_cast<Aff*>(out_affine);
+    if (total.inf()) { out->x = Fq::zero(); out->y = Fq::zero(); return 0; }
+    Fq zi = total.z.inv(), zi2 = zi.sqr();
+    out->x = total.x.mul(zi2);
+    out->y = total.y.mul(zi2).mul(zi);
+    return 0;
+}
+
+// Synthetic bases for the CPU baseline: out[i] = (i+1)*G, canonical affine (chain of mixed additions,
+// one batched inversion).  Any valid points do for a throughput sample.
+extern "C" int orc_make_bases(size_t n, uint64_t* out_affine) {
+    static const uint64_t gx[6] = {0x5cb38790fd530c16ull, 0x7817fc679976fff5ull, 0x154f95c7143ba1c1ull, 0xf0ae6acdf3d0e747ull, 0xedce6ecc21dbf440ull, 0x120177419e0bfb75ull};
+    static const uint64_t gy[6] = {0xbaac93d50ce72271ull, 0x8c22631a7918fd8eull, 0xdd595f13570725ceull, 0x51ac582950405194ull, 0x0e1c8c3fad0059c0ull, 0x0bbc3efc5008a26aull};
+    Aff g;
+    memcpy(g.x.l, gx, sizeof gx);
+    memcpy(g.y.l, gy, sizeof gy);
+    std::vector<Jac> pts(n);
+    Jac cur = jac_inf();
+    for (size_t i = 0; i < n; i++) { cur = jac_madd(cur, g, false); pts[i] = cur; }
+    std::vector<Fq> prefix(n);
+    Fq acc = Fq::one();
+    for (size_t i = 0; i < n; i++) { prefix[i] = acc; acc = acc.mul(pts[i].z); }
+    Fq inv = acc.inv();
+    Aff* out = reinterpret_cast<Aff*>(out_affine);
+    for (size_t i = n; i-- > 0;) {
+        Fq zi = inv.mul(prefix[i]);
+        inv = inv.mul(pts[i].z);
+        Fq zi2 = zi.sqr();
+        out[i].x = pts[i].x.mul(zi2);
+        out[i].y = pts[i].y.mul(zi2).mul(zi);
+    }
+    return 0;
+}
+
+extern "C" int orc_fr_mul(const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n) {
+    const Fr* x = reinterpret_cast<const Fr*>(a);
+    const Fr* y = reinterpret_cast<const Fr*>(b);
+    Fr* o = reinterpret_cast<Fr*>(out);
+    for (size_t i = 0; i < n; i++) o[i] = x[i].mul(y[i]);
+    return 0;
+}
+extern "C" int orc_fq_mul(const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n) {
+    const Fq* x = reinterpret_cast<const Fq*>(a);
+    const Fq* y = reinterpret_cast<const Fq*>(b);
+    Fq* o = reinterpret_cast<Fq*>(out);
+    for (size_t i = 0; i < n; i++) o[i] = x[i].mul(y[i]);
+    return 0;
+}
+extern "C" int orc_num_threads(void) { return omp_get_max_threads(); }

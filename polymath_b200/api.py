@@ -72,6 +72,11 @@ def _bind(lib):
     lib.pm_ctx_phase_ms.argtypes = [vp, C.POINTER(C.c_double)]
     lib.pm_polymath_setup.argtypes = [C.POINTER(R1CSView), vp, C.POINTER(vp), u8p]
     lib.pm_polymath_prove.argtypes = [vp, u8p, u8p, vp, u8p]
+    lib.pm_polymath_prove_resident.argtypes = [vp, u8p, vp, u8p]
+    lib.pm_timer_start.argtypes = []
+    lib.pm_timer_stop.argtypes = [C.POINTER(C.c_double)]
+    lib.pm_bench_set_kernel_timing.argtypes = [C.c_int]
+    lib.pm_bench_last_kernel_ms.argtypes = [C.POINTER(C.c_double)]
     lib._api_bound = True
 
 
@@ -130,11 +135,17 @@ class R1CS:
         col = (C.c_uint32 * max(nnz, 1))()
         val = bytearray()
         k = 0
+        cache = {}
         for i, row in enumerate(mat):
             row_ptr[i] = k
             for coeff, j in row:
                 col[k] = j
-                val += codec.fr_to_wire(coeff)
+                w = cache.get(coeff)
+                if w is None:
+                    w = codec.fr_to_wire(coeff)
+                    if len(cache) < 4096:
+                        cache[coeff] = w
+                val += w
                 k += 1
         row_ptr[self.nr] = k
         vbuf = C.create_string_buffer(bytes(val), max(len(val), 1))

@@ -161,6 +161,45 @@ int pm_fixed_base_mul(const uint8_t* scalars, size_t n, uint8_t* out) {
     });
 }
 
+static cudaEvent_t g_t0 = nullptr, g_t1 = nullptr;
+int pm_timer_start(void) {
+    return guarded([&] {
+        Runtime& rt = runtime();
+        if (!g_t0) { PM_CUDA(cudaEventCreate(&g_t0)); PM_CUDA(cudaEventCreate(&g_t1)); }
+        PM_CUDA(cudaStreamSynchronize(rt.stream));
+        PM_CUDA(cudaEventRecord(g_t0, rt.stream));
+    });
+}
+int pm_timer_stop(double* ms) {
+    return guarded([&] {
+        Runtime& rt = runtime();
+        if (!g_t0 || !ms) throw StatusError(PM_ERR_STATE, "timer not started");
+        PM_CUDA(cudaEventRecord(g_t1, rt.stream));
+        PM_CUDA(cudaEventSynchronize(g_t1));
+        float f = 0;
+        PM_CUDA(cudaEventElapsedTime(&f, g_t0, g_t1));
+        *ms = f;
+    });
+}
+int pm_bench_set_kernel_timing(int enable) {
+    return guarded([&] {
+        Runtime& rt = runtime();
+        rt.msm.time_accumulate = enable != 0;
+        rt.ntt.time_passes = enable != 0;
+    });
+}
+int pm_bench_last_kernel_ms(double ms[2]) {
+    return guarded([&] {
+        Runtime& rt = runtime();
+        ms[0] = ms[1] = 0;
+        PM_CUDA(cudaStreamSynchronize(rt.stream));
+        float f = 0;
+        if (rt.msm.ev_acc_begin && cudaEventElapsedTime(&f, rt.msm.ev_acc_begin, rt.msm.ev_acc_end) == cudaSuccess) ms[0] = f;
+        if (rt.ntt.ev_begin && cudaEventElapsedTime(&f, rt.ntt.ev_begin, rt.ntt.ev_end) == cudaSuccess) ms[1] = f;
+        cudaGetLastError();
+    });
+}
+
 int pm_bench_imad_peak(double* mads_per_s) {
     return guarded([&] { runtime(); *mads_per_s = measure_imad_peak(2000); });
 }

@@ -117,7 +117,16 @@ int pm_polymath_setup(const pm_r1cs_view* r1cs, pm_rng* rng, pm_ctx** ctx_out, u
     return PM_OK;
 }
 
+static int prove_impl(pm_ctx* ctx, const uint8_t* instance, const uint8_t* witness, bool upload, pm_rng* rng, uint8_t proof_out[176]);
+
 int pm_polymath_prove(pm_ctx* ctx, const uint8_t* instance, const uint8_t* witness, pm_rng* rng, uint8_t proof_out[176]) {
+    return prove_impl(ctx, instance, witness, true, rng, proof_out);
+}
+int pm_polymath_prove_resident(pm_ctx* ctx, const uint8_t* instance, pm_rng* rng, uint8_t proof_out[176]) {
+    return prove_impl(ctx, instance, nullptr, false, rng, proof_out);
+}
+
+static int prove_impl(pm_ctx* ctx, const uint8_t* instance, const uint8_t* witness, bool upload, pm_rng* rng, uint8_t proof_out[176]) {
     if (!ctx || !instance || !rng || !proof_out) { pm::set_last_error("null argument"); return PM_ERR_ARG; }
     uint64_t n = 0, sigma = 0, cols = 0;
     int rc = pm_ctx_dims(ctx, &n, &sigma, &cols);
@@ -131,8 +140,10 @@ int pm_polymath_prove(pm_ctx* ctx, const uint8_t* instance, const uint8_t* witne
     }
     // the device work of phase 1 needs r_a, which the reference draws after the polynomial
     // work (prover.rs:110) — nothing else consumes the RNG in between, so the stream is identical.
-    rc = pm_ctx_set_assignment(ctx, instance, witness);
-    if (rc != PM_OK) return rc;
+    if (upload) {
+        rc = pm_ctx_set_assignment(ctx, instance, witness);
+        if (rc != PM_OK) return rc;
+    }
     uint8_t ra[64], a_g1[96], c_g1[96];
     rng->rng.fr_rand().to_wire(ra);         // r_a coefficient 0
     rng->rng.fr_rand().to_wire(ra + 32);    // r_a coefficient 1
