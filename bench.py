@@ -204,13 +204,13 @@ def run_ours(args):
 
     def prove_resident():
         if prover is not None:
-            return prover.prove_resident(inst_wire, rng)
+            return prover.prove_resident(p_inst, rng)
         check(lib.pm_polymath_prove_resident(pk._h, p_inst, rng._h, proof))
         return proof.raw
 
     def prove_e2e():
         if prover is not None:
-            return prover.prove(inst_wire, p_wit, rng)
+            return prover.prove(p_inst, p_wit, rng)
         check(lib.pm_polymath_prove(pk._h, p_inst, p_wit, rng._h, proof))
         return proof.raw
 

@@ -43,6 +43,7 @@ enum {
 #define PM_FR_BYTES 32
 #define PM_FQ_BYTES 48
 #define PM_G1_BYTES 96
+#define PM_XYZZ_BYTES 192 /* (X, Y, ZZ, ZZZ) partial sum of a sharded MSM; x = X/ZZ, y = Y/ZZZ */
 
 const char* pm_last_error(void);
 /* ABI version of this header; bumped on any incompatible change. */
@@ -144,6 +145,26 @@ int pm_prove_phase2(pm_ctx* ctx, const uint8_t x1[PM_FR_BYTES], const uint8_t y1
 /* Phase 3 (src/prover.rs:142-229): opening quotient by (X - x1) and [d]_1. */
 int pm_prove_phase3(pm_ctx* ctx, const uint8_t x2[PM_FR_BYTES], const uint8_t c_at_x1[PM_FR_BYTES],
                     uint8_t d_out[PM_G1_BYTES]);
+/* ---- multi-GPU: one process per GPU, MSMs split by point range ----
+ * A sharded context holds the points g = k*world + rank of every key vector (interleaved split, so
+ * the a-, c- and d-side MSMs are all balanced).  The polynomial work is replicated on every rank.
+ * Each MSM phase is split in two: *_partial runs the device work and returns this rank's XYZZ sum(s);
+ * the caller all-gathers them (e.g. ncclAllGather of world * 384 / 192 bytes) and every rank calls
+ * *_finish on the gathered buffer, which adds the partials on the host and returns the same affine
+ * point everywhere.  Group addition is not an NCCL reduction, hence all-gather + local add. */
+int pm_setup_sharded(const pm_r1cs_view* r1cs, const uint8_t x[PM_FR_BYTES], const uint8_t z[PM_FR_BYTES], int rank,
+                     int world, pm_ctx** out, uint8_t x_g2[192], uint8_t z_g2[192]);
+int pm_ctx_create_sharded(const pm_pk_view* pk, int rank, int world, pm_ctx** out);
+int pm_ctx_shard(const pm_ctx* ctx, int* rank, int* world);
+int pm_prove_phase1_partial(pm_ctx* ctx, const uint8_t r_a[2 * PM_FR_BYTES], uint8_t partials_out[2 * PM_XYZZ_BYTES]);
+int pm_prove_phase1_finish(pm_ctx* ctx, const uint8_t* gathered, int count, uint8_t a_out[PM_G1_BYTES],
+                           uint8_t c_out[PM_G1_BYTES]);
+int pm_prove_phase3_partial(pm_ctx* ctx, const uint8_t x2[PM_FR_BYTES], const uint8_t c_at_x1[PM_FR_BYTES],
+                            uint8_t partial_out[PM_XYZZ_BYTES]);
+int pm_prove_phase3_finish(pm_ctx* ctx, const uint8_t* gathered, int count, uint8_t d_out[PM_G1_BYTES]);
+/* Host-only helper (no device needed): canonical affine sum of `count` XYZZ records spaced `stride` bytes. */
+int pm_host_sum_partials(const uint8_t* parts, int count, size_t stride, uint8_t out[PM_G1_BYTES]);
+
 /* Test hook: copy an intermediate of the last proof to the host.
  * which: 0 u coeffs (n), 1 w coeffs (n), 2 witness-u coeffs (n), 3 u^2 coeffs (2n), 4 [x|w|y] (cols - m0),
  *        5 phase-1 c-side scalars, 6 opening quotient D (10n + 22).  Returns the element count in *len. */
@@ -174,6 +195,18 @@ int pm_polymath_setup(const pm_r1cs_view* r1cs, pm_rng* rng, pm_ctx** ctx_out, u
  * (src/common.rs:21-37) on the host between the device phases; writes the compressed Proof
  * (176 bytes, src/data_structures.rs:10-19). */
 int pm_polymath_prove(pm_ctx* ctx, const uint8_t* instance, const uint8_t* witness, pm_rng* rng, uint8_t proof_out[176]);
+
+/* Collective supplied by the caller for the sharded flow: gather `bytes` from every rank into
+ * recv (world * bytes, rank order).  Returns 0 on success. */
+typedef int (*pm_allgather_fn)(void* user, const uint8_t* send, size_t bytes, uint8_t* recv);
+/* Sharded variants: every rank calls them with the same arguments and its own sharded context; all
+ * ranks obtain identical vk / proof bytes.  `upload` = 0 reuses the resident assignment. */
+int pm_polymath_setup_sharded(const pm_r1cs_view* r1cs, pm_rng* rng, int rank, int world, pm_ctx** ctx_out,
+                              uint8_t vk_out[392]);
+int pm_polymath_prove_sharded(pm_ctx* ctx, const uint8_t* instance, const uint8_t* witness, int upload, pm_rng* rng,
+                              pm_allgather_fn allgather, void* user, uint8_t proof_out[176]);
+/* Calls `allgather` with a rank-tagged payload and verifies the result (plumbing self-test). */
+int pm_allgather_selftest(pm_allgather_fn allgather, void* user, int rank, int world);
 
 /* Same as pm_polymath_prove but uses the assignment already resident from pm_ctx_set_assignment
  * (bench.py's device-resident timing leg); `instance` is still needed for the transcript. */

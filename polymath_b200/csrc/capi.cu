@@ -11,6 +11,7 @@
 #include "ntt.cuh"
 #include "runtime.cuh"
 #include "synth.cuh"
+#include "host/g1_host.hpp"
 
 namespace pm {
 
@@ -127,18 +128,17 @@ int pm_msm_g1_window(const uint8_t* bases, size_t base_stride, const uint8_t* sc
         DevBuf db, ds, dres;
         G1Affine* pb = db.as<G1Affine>(n ? n : 1);
         Fr* ps = ds.as<Fr>(n ? n : 1);
-        G1XYZZ* acc = dres.as<G1XYZZ>(2);
-        G1Affine* res = reinterpret_cast<G1Affine*>(acc + 1);
+        G1XYZZ* wins = dres.as<G1XYZZ>(kMaxMsmWindows);
         PM_CUDA(cudaMemcpyAsync(pb, src, n * sizeof(G1Affine), cudaMemcpyHostToDevice, rt.stream));
         PM_CUDA(cudaMemcpyAsync(ps, scalars, n * sizeof(Fr), cudaMemcpyHostToDevice, rt.stream));
         MsmConfig cfg;
         cfg.c = window_bits;
         cfg.heavy = heavy_threshold;
-        rt.msm.run(pb, ps, n, acc, rt.stream, cfg);
-        launch_xyzz_sum_to_affine(acc, 1, res, rt.stream);
-        rt.extra_launches++;
-        PM_CUDA(cudaMemcpyAsync(out, res, sizeof(G1Affine), cudaMemcpyDeviceToHost, rt.stream));
+        MsmEngine::Shape sh = rt.msm.run(pb, ps, n, wins, rt.stream, cfg);
+        std::vector<uint8_t> hw((size_t)sh.nwin * sizeof(G1XYZZ));
+        PM_CUDA(cudaMemcpyAsync(hw.data(), wins, hw.size(), cudaMemcpyDeviceToHost, rt.stream));
         PM_CUDA(cudaStreamSynchronize(rt.stream));
+        host::xyzz_to_affine_wire(host::combine_windows(hw.data(), sh.nwin, sh.c), out);
     });
 }
 
@@ -240,7 +240,7 @@ int pm_bench_msm(size_t n, int window_bits, int iters, double* ms_avg, double* m
         DevBuf db, ds, dres;
         G1Affine* pb = db.as<G1Affine>(n);
         Fr* ps = ds.as<Fr>(n);
-        G1XYZZ* acc = dres.as<G1XYZZ>(1);
+        G1XYZZ* acc = dres.as<G1XYZZ>(kMaxMsmWindows);
         launch_fill_fr(ps, n, 0xabcdef, rt.stream);
         rt.fixed_base.run(ps, n, pb, rt.stream);       // bases = [s_i]G for pseudo-random s_i
         launch_fill_fr(ps, n, 0x5eed, rt.stream);      // uniform scalars

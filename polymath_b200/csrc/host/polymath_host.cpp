@@ -76,6 +76,22 @@ int pm_merlin_test_vector(uint8_t out[32]) {
 }
 
 int pm_polymath_setup(const pm_r1cs_view* r1cs, pm_rng* rng, pm_ctx** ctx_out, uint8_t vk_out[392]) {
+    return pm_polymath_setup_sharded(r1cs, rng, 0, 1, ctx_out, vk_out);
+}
+
+int pm_allgather_selftest(pm_allgather_fn allgather, void* user, int rank, int world) {
+    if (!allgather || world < 1 || rank < 0 || rank >= world) { pm::set_last_error("bad argument"); return PM_ERR_ARG; }
+    const size_t bytes = 192;
+    std::vector<uint8_t> send(bytes), recv(bytes * world, 0xee);
+    for (size_t i = 0; i < bytes; i++) send[i] = (uint8_t)(rank * 31 + i);
+    if (allgather(user, send.data(), bytes, recv.data()) != 0) { pm::set_last_error("allgather callback failed"); return PM_ERR_STATE; }
+    for (int r = 0; r < world; r++)
+        for (size_t i = 0; i < bytes; i++)
+            if (recv[r * bytes + i] != (uint8_t)(r * 31 + i)) { pm::set_last_error("allgather returned wrong data"); return PM_ERR_STATE; }
+    return PM_OK;
+}
+
+int pm_polymath_setup_sharded(const pm_r1cs_view* r1cs, pm_rng* rng, int rank, int world, pm_ctx** ctx_out, uint8_t vk_out[392]) {
     if (!r1cs || !rng || !ctx_out || !vk_out) { pm::set_last_error("null argument"); return PM_ERR_ARG; }
     const uint64_t m0 = r1cs->num_instance_variables, nr = r1cs->num_r1cs_constraints;
     uint64_t rows = 2 * (m0 + nr), n = 1;
@@ -93,7 +109,7 @@ int pm_polymath_setup(const pm_r1cs_view* r1cs, pm_rng* rng, pm_ctx** ctx_out, u
     uint8_t xb[32], zb[32], x_g2[192], z_g2[192];
     x.to_wire(xb);
     z.to_wire(zb);
-    int rc = pm_setup(r1cs, xb, zb, ctx_out, x_g2, z_g2);
+    int rc = pm_setup_sharded(r1cs, xb, zb, rank, world, ctx_out, x_g2, z_g2);
     if (rc != PM_OK) return rc;
     // VerifyingKey, compressed (data_structures.rs:25-50): e.one_g1, e.one_g2, e.x_g2, e.z_g2, n, m0, sigma, omega
     std::vector<uint8_t> vk;
@@ -117,17 +133,34 @@ int pm_polymath_setup(const pm_r1cs_view* r1cs, pm_rng* rng, pm_ctx** ctx_out, u
     return PM_OK;
 }
 
-static int prove_impl(pm_ctx* ctx, const uint8_t* instance, const uint8_t* witness, bool upload, pm_rng* rng, uint8_t proof_out[176]);
+static int prove_impl(pm_ctx* ctx, const uint8_t* instance, const uint8_t* witness, bool upload, pm_rng* rng,
+                      pm_allgather_fn allgather, void* user, uint8_t proof_out[176]);
 
 int pm_polymath_prove(pm_ctx* ctx, const uint8_t* instance, const uint8_t* witness, pm_rng* rng, uint8_t proof_out[176]) {
-    return prove_impl(ctx, instance, witness, true, rng, proof_out);
+    return prove_impl(ctx, instance, witness, true, rng, nullptr, nullptr, proof_out);
 }
 int pm_polymath_prove_resident(pm_ctx* ctx, const uint8_t* instance, pm_rng* rng, uint8_t proof_out[176]) {
-    return prove_impl(ctx, instance, nullptr, false, rng, proof_out);
+    return prove_impl(ctx, instance, nullptr, false, rng, nullptr, nullptr, proof_out);
+}
+int pm_polymath_prove_sharded(pm_ctx* ctx, const uint8_t* instance, const uint8_t* witness, int upload, pm_rng* rng,
+                              pm_allgather_fn allgather, void* user, uint8_t proof_out[176]) {
+    return prove_impl(ctx, instance, witness, upload != 0, rng, allgather, user, proof_out);
 }
 
-static int prove_impl(pm_ctx* ctx, const uint8_t* instance, const uint8_t* witness, bool upload, pm_rng* rng, uint8_t proof_out[176]) {
+static int prove_impl(pm_ctx* ctx, const uint8_t* instance, const uint8_t* witness, bool upload, pm_rng* rng,
+                      pm_allgather_fn allgather, void* user, uint8_t proof_out[176]) {
     if (!ctx || !instance || !rng || !proof_out) { pm::set_last_error("null argument"); return PM_ERR_ARG; }
+    int rank = 0, world = 1;
+    if (pm_ctx_shard(ctx, &rank, &world) != PM_OK) return PM_ERR_ARG;
+    if (world > 1 && !allgather) { pm::set_last_error("sharded context needs an all-gather callback"); return PM_ERR_ARG; }
+    // gather `bytes` from every rank (identity when unsharded)
+    auto gather = [&](const uint8_t* send, size_t bytes, std::vector<uint8_t>& recv) -> int {
+        recv.resize(bytes * world);
+        if (world == 1) { memcpy(recv.data(), send, bytes); return PM_OK; }
+        if (allgather(user, send, bytes, recv.data()) != 0) { pm::set_last_error("all-gather callback failed"); return PM_ERR_STATE; }
+        return PM_OK;
+    };
+    std::vector<uint8_t> gathered;
     uint64_t n = 0, sigma = 0, cols = 0;
     int rc = pm_ctx_dims(ctx, &n, &sigma, &cols);
     if (rc != PM_OK) return rc;
@@ -138,6 +171,7 @@ static int prove_impl(pm_ctx* ctx, const uint8_t* instance, const uint8_t* witne
         if (rc != PM_OK) return rc;
         m0 = cols - lcs_len;
     }
+    (void)rank;
     // the device work of phase 1 needs r_a, which the reference draws after the polynomial
     // work (prover.rs:110) — nothing else consumes the RNG in between, so the stream is identical.
     if (upload) {
@@ -147,7 +181,12 @@ static int prove_impl(pm_ctx* ctx, const uint8_t* instance, const uint8_t* witne
     uint8_t ra[64], a_g1[96], c_g1[96];
     rng->rng.fr_rand().to_wire(ra);         // r_a coefficient 0
     rng->rng.fr_rand().to_wire(ra + 32);    // r_a coefficient 1
-    rc = pm_prove_phase1_resident(ctx, ra, a_g1, c_g1);
+    uint8_t part1[2 * PM_XYZZ_BYTES];
+    rc = pm_prove_phase1_partial(ctx, ra, part1);
+    if (rc != PM_OK) return rc;
+    rc = gather(part1, sizeof part1, gathered);
+    if (rc != PM_OK) return rc;
+    rc = pm_prove_phase1_finish(ctx, gathered.data(), world, a_g1, c_g1);
     if (rc != PM_OK) return rc;
 
     std::vector<FrH> pub(m0);
@@ -194,7 +233,12 @@ static int prove_impl(pm_ctx* ctx, const uint8_t* instance, const uint8_t* witne
     uint8_t x2b[32], cb[32], d_g1[96];
     x2.to_wire(x2b);
     c_at_x1.to_wire(cb);
-    rc = pm_prove_phase3(ctx, x2b, cb, d_g1);            // prover.rs:142-229
+    uint8_t part3[PM_XYZZ_BYTES];
+    rc = pm_prove_phase3_partial(ctx, x2b, cb, part3);   // prover.rs:142-229
+    if (rc != PM_OK) return rc;
+    rc = gather(part3, sizeof part3, gathered);
+    if (rc != PM_OK) return rc;
+    rc = pm_prove_phase3_finish(ctx, gathered.data(), world, d_g1);
     if (rc != PM_OK) return rc;
 
     // Proof, compressed (data_structures.rs:10-19): a_g1, c_g1, a_at_x1, d_g1

@@ -12,15 +12,18 @@
 //                        distributions (SURVEY.md §7 "hard parts") do not serialise
 //   5. k_reduce_segments running-sum over K-bucket segments + small scalar mul by the segment base
 //      k_reduce_windows  per-window tree sum of the segment partials
-//      k_combine_windows Horner over windows (c doublings each) -> one XYZZ point
+//   6. host: Horner over the <= 32 window sums (c doublings each) and the affine normalisation
+//      (host/g1_host.hpp) — a serial chain of ~255 doublings that costs a GPU thread milliseconds
 // Points at infinity ((0,0)) and zero scalars are skipped in step 1/3.
 #include "msm.cuh"
+
+#include <cstdlib>
 
 namespace pm {
 
 namespace {
 
-constexpr int kMaxWindows = 64;
+constexpr int kMaxWindows = kMaxMsmWindows;
 constexpr int kSegBuckets = 16;     // buckets per reduce segment
 
 __device__ __forceinline__ uint32_t window_bits(const uint32_t* s, int pos, int c) {
@@ -33,11 +36,11 @@ __device__ __forceinline__ uint32_t window_bits(const uint32_t* s, int pos, int 
 
 template <bool SCATTER>
 __global__ void __launch_bounds__(256) k_digits(const G1Affine* __restrict__ bases, const Fr* __restrict__ scalars,
-                                                size_t n, int c, int nwin, uint32_t nb,
+                                                size_t n, size_t sc_stride, size_t sc_offset, int c, int nwin, uint32_t nb,
                                                 uint32_t* __restrict__ counters, uint32_t* __restrict__ sorted) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    Fr s = scalars[i];
+    Fr s = scalars[i * sc_stride + sc_offset];
     if (s.is_zero()) return;
     // infinity bases carry no weight: test the first limbs cheaply, full test only if they vanish
     {
@@ -125,7 +128,10 @@ __device__ __forceinline__ G1Affine load_point(const G1Affine* __restrict__ base
     return p;
 }
 
-__global__ void __launch_bounds__(128) k_accumulate(const G1Affine* __restrict__ bases, const uint32_t* __restrict__ sorted,
+// Variant selection (tuning hook): PM_ACC_VARIANT = <minBlocks> for the register-prefetch kernel,
+// or 10 + <minBlocks> for the shared-memory staged kernel (cp.async double buffer).
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) k_accumulate(const G1Affine* __restrict__ bases, const uint32_t* __restrict__ sorted,
                                                     const uint32_t* __restrict__ offsets, G1XYZZ* __restrict__ buckets,
                                                     uint32_t total_buckets, uint32_t heavy_thr,
                                                     uint32_t* __restrict__ heavy_list, uint32_t* __restrict__ heavy_count) {
@@ -151,6 +157,64 @@ __global__ void __launch_bounds__(128) k_accumulate(const G1Affine* __restrict__
             xyzz_madd(acc, p, (e >> 31) != 0);
             p = p_next;
             e = e_next;
+        }
+    }
+    buckets[t] = acc;
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Same walk, but the next point is staged into shared memory with cp.async (per-thread private
+// slots, [buffer][16-byte chunk][thread] so a warp's accesses are conflict free): no registers are
+// spent on the prefetch and the point's limbs are read from shared memory where they are consumed.
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) k_accumulate_smem(const G1Affine* __restrict__ bases, const uint32_t* __restrict__ sorted,
+                                                         const uint32_t* __restrict__ offsets, G1XYZZ* __restrict__ buckets,
+                                                         uint32_t total_buckets, uint32_t heavy_thr,
+                                                         uint32_t* __restrict__ heavy_list, uint32_t* __restrict__ heavy_count) {
+    __shared__ uint4 stage[2][6][128];
+    const uint32_t tid = threadIdx.x;
+    uint32_t t = blockIdx.x * blockDim.x + tid;
+    if (t >= total_buckets) return;
+    uint32_t beg = offsets[t], end = offsets[t + 1];
+    if (end - beg > heavy_thr) {
+        uint32_t slot = atomicAdd(heavy_count, 1u);
+        heavy_list[slot] = t;
+        return;
+    }
+    G1XYZZ acc = G1XYZZ::inf();
+    if (beg < end) {
+        uint32_t e = sorted[beg];
+        {
+            const uint4* src = reinterpret_cast<const uint4*>(bases + (e & 0x7fffffffu));
+#pragma unroll
+            for (int c = 0; c < 6; c++) cp_async16(&stage[0][c][tid], src + c);
+            cp_async_commit();
+        }
+        uint32_t buf = 0;
+        for (uint32_t k = beg; k < end; k++) {
+            uint32_t e_next = 0;
+            if (k + 1 < end) {
+                e_next = sorted[k + 1];
+                const uint4* src = reinterpret_cast<const uint4*>(bases + (e_next & 0x7fffffffu));
+#pragma unroll
+                for (int c = 0; c < 6; c++) cp_async16(&stage[buf ^ 1][c][tid], src + c);
+            }
+            cp_async_commit();
+            cp_async_wait<1>();
+            G1Affine p;
+            uint4* dst = reinterpret_cast<uint4*>(&p);
+#pragma unroll
+            for (int c = 0; c < 6; c++) dst[c] = stage[buf][c][tid];
+            xyzz_madd(acc, p, (e >> 31) != 0);
+            e = e_next;
+            buf ^= 1;
         }
     }
     buckets[t] = acc;
@@ -230,23 +294,6 @@ __global__ void __launch_bounds__(128) k_reduce_windows(const G1XYZZ* __restrict
     if (threadIdx.x == 0) winsums[blockIdx.x] = sh[0];
 }
 
-__global__ void k_combine_windows(const G1XYZZ* __restrict__ winsums, int nwin, int c, G1XYZZ* __restrict__ out) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    G1XYZZ acc = G1XYZZ::inf();
-    for (int w = nwin - 1; w >= 0; w--) {
-        for (int k = 0; k < c; k++) xyzz_dbl(acc);
-        xyzz_add(acc, winsums[w]);
-    }
-    out[0] = acc;
-}
-
-__global__ void k_xyzz_sum_to_affine(const G1XYZZ* __restrict__ parts, int k, G1Affine* __restrict__ out) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    G1XYZZ acc = G1XYZZ::inf();
-    for (int i = 0; i < k; i++) xyzz_add(acc, parts[i]);
-    out[0] = xyzz_to_affine(acc);
-}
-
 }  // namespace
 
 int MsmEngine::choose_window(size_t n) {
@@ -267,11 +314,11 @@ MsmEngine::~MsmEngine() {
     if (ev_acc_end) cudaEventDestroy(ev_acc_end);
 }
 
-void MsmEngine::run(const G1Affine* bases, const Fr* scalars, size_t n, G1XYZZ* out_xyzz, cudaStream_t stream,
-                    MsmConfig cfg) {
+MsmEngine::Shape MsmEngine::run(const G1Affine* bases, const Fr* scalars, size_t n, G1XYZZ* winsums, cudaStream_t stream,
+                                MsmConfig cfg, size_t scalar_stride, size_t scalar_offset) {
     if (n == 0) {
-        PM_CUDA(cudaMemsetAsync(out_xyzz, 0, sizeof(G1XYZZ), stream));
-        return;
+        PM_CUDA(cudaMemsetAsync(winsums, 0, sizeof(G1XYZZ), stream));
+        return {1, 1};
     }
     if (n >= ((size_t)1 << 31)) throw CudaError("msm: n must be < 2^31");
     const int c = cfg.c ? cfg.c : choose_window(n);
@@ -290,26 +337,41 @@ void MsmEngine::run(const G1Affine* bases, const Fr* scalars, size_t n, G1XYZZ* 
     uint32_t* sorted = sorted_.as<uint32_t>(n * (size_t)nwin);
     G1XYZZ* buckets = buckets_.as<G1XYZZ>(total);
     G1XYZZ* segs = segs_.as<G1XYZZ>(total_segs);
-    G1XYZZ* winsums = winsums_.as<G1XYZZ>(nwin);
     uint32_t* heavy_list = heavy_list_.as<uint32_t>(total);
     uint32_t* heavy_count = heavy_count_.as<uint32_t>(1);
 
     PM_CUDA(cudaMemsetAsync(counts, 0, (total + 1) * sizeof(uint32_t), stream));
     PM_CUDA(cudaMemsetAsync(heavy_count, 0, sizeof(uint32_t), stream));
     const unsigned dgrid = ceil_div(n, 256);
-    k_digits<false><<<dgrid, 256, 0, stream>>>(bases, scalars, n, c, nwin, nb, counts, nullptr);
+    k_digits<false><<<dgrid, 256, 0, stream>>>(bases, scalars, n, scalar_stride, scalar_offset, c, nwin, nb, counts, nullptr);
     PM_LAUNCH_CHECK();
     k_scan<<<1, 1024, 0, stream>>>(counts, total, offsets, cursors);
     PM_LAUNCH_CHECK();
-    k_digits<true><<<dgrid, 256, 0, stream>>>(bases, scalars, n, c, nwin, nb, cursors, sorted);
+    k_digits<true><<<dgrid, 256, 0, stream>>>(bases, scalars, n, scalar_stride, scalar_offset, c, nwin, nb, cursors, sorted);
     PM_LAUNCH_CHECK();
     if (time_accumulate) {
         if (!ev_acc_begin) { PM_CUDA(cudaEventCreate(&ev_acc_begin)); PM_CUDA(cudaEventCreate(&ev_acc_end)); }
         PM_CUDA(cudaEventRecord(ev_acc_begin, stream));
     }
-    k_accumulate<<<ceil_div(total, 128), 128, 0, stream>>>(bases, sorted, offsets, buckets, total, heavy_thr,
-                                                          heavy_list, heavy_count);
-    PM_LAUNCH_CHECK();
+    {
+        static int variant = -1;
+        if (variant < 0) {
+            const char* v = getenv("PM_ACC_VARIANT");
+            variant = v ? atoi(v) : 3;
+        }
+        const unsigned g = ceil_div(total, 128);
+#define PM_ACC_ARGS bases, sorted, offsets, buckets, total, heavy_thr, heavy_list, heavy_count
+        switch (variant) {
+            case 3: k_accumulate<3><<<g, 128, 0, stream>>>(PM_ACC_ARGS); break;
+            case 4: k_accumulate<4><<<g, 128, 0, stream>>>(PM_ACC_ARGS); break;
+            case 12: k_accumulate_smem<2><<<g, 128, 0, stream>>>(PM_ACC_ARGS); break;
+            case 13: k_accumulate_smem<3><<<g, 128, 0, stream>>>(PM_ACC_ARGS); break;
+            case 14: k_accumulate_smem<4><<<g, 128, 0, stream>>>(PM_ACC_ARGS); break;
+            default: k_accumulate<2><<<g, 128, 0, stream>>>(PM_ACC_ARGS); break;
+        }
+#undef PM_ACC_ARGS
+        PM_LAUNCH_CHECK();
+    }
     if (time_accumulate) PM_CUDA(cudaEventRecord(ev_acc_end, stream));
     {
         static bool attr_set = false;
@@ -325,14 +387,8 @@ void MsmEngine::run(const G1Affine* bases, const Fr* scalars, size_t n, G1XYZZ* 
     PM_LAUNCH_CHECK();
     k_reduce_windows<<<nwin, 128, 0, stream>>>(segs, nseg, winsums);
     PM_LAUNCH_CHECK();
-    k_combine_windows<<<1, 32, 0, stream>>>(winsums, nwin, c, out_xyzz);
-    PM_LAUNCH_CHECK();
-    launches += 8;
-}
-
-void launch_xyzz_sum_to_affine(const G1XYZZ* parts, int k, G1Affine* out_affine, cudaStream_t stream) {
-    k_xyzz_sum_to_affine<<<1, 32, 0, stream>>>(parts, k, out_affine);
-    PM_LAUNCH_CHECK();
+    launches += 7;
+    return {c, nwin};
 }
 
 }  // namespace pm

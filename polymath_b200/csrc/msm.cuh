@@ -13,12 +13,15 @@ struct MsmConfig {
 // Reusable workspace + launch sequence.  One engine per context / stream.
 class MsmEngine {
 public:
-    // out_xyzz[0] = sum_{i<n} scalars[i] * bases[i].
+    // Enqueues sum_{i<n} scalars[i*scalar_stride + scalar_offset] * bases[i] up to the per-window sums:
+    // on completion winsums_out[w] (device, >= kMaxMsmWindows entries) holds W_w and the result is
+    // sum_w 2^(c*w) * W_w, finished on the host (host/g1_host.hpp: combine_windows).
     //  bases   : device, 96-byte affine points, Montgomery limbs, (0,0) = infinity
     //  scalars : device, Fr in Montgomery form (arkworks in-memory form)
     // All work is enqueued on `stream`; nothing is synchronised.
-    void run(const G1Affine* bases, const Fr* scalars, size_t n, G1XYZZ* out_xyzz, cudaStream_t stream,
-             MsmConfig cfg = {});
+    struct Shape { int c; int nwin; };
+    Shape run(const G1Affine* bases, const Fr* scalars, size_t n, G1XYZZ* winsums_out, cudaStream_t stream,
+              MsmConfig cfg = {}, size_t scalar_stride = 1, size_t scalar_offset = 0);
     static int choose_window(size_t n);
     size_t launches = 0;   // kernels launched so far (bench accounting)
     // timing hook for bench.py's roofline: CUDA events around the bucket-accumulation kernel of the last run
@@ -27,10 +30,9 @@ public:
     ~MsmEngine();
 
 private:
-    DevBuf counts_, offsets_, cursors_, sorted_, buckets_, segs_, winsums_, heavy_list_, heavy_count_;
+    DevBuf counts_, offsets_, cursors_, sorted_, buckets_, segs_, heavy_list_, heavy_count_;
 };
 
-// out_affine = canonical affine image of sum of `k` XYZZ partials (k small); single-thread kernel.
-void launch_xyzz_sum_to_affine(const G1XYZZ* parts, int k, G1Affine* out_affine, cudaStream_t stream);
+constexpr int kMaxMsmWindows = 64;
 
 }  // namespace pm

@@ -11,6 +11,7 @@
 
 #include <algorithm>
 
+#include "host/g1_host.hpp"
 #include "msm.cuh"
 #include "ntt.cuh"
 
@@ -25,6 +26,10 @@ __global__ void k_phase3_consts(Fr* small) {
     // consts[1] = a(x1) + x2 * c(x1)    (prover.rs:191-209)
     small[S_EVAL] = small[S_A_AT_X1] + small[S_X2] * small[S_C_AT_X1];
 }
+
+constexpr size_t kStageWin = (size_t)kMaxMsmWindows * sizeof(G1XYZZ);   // one MSM's window sums
+constexpr size_t kStageBytes = 3 * kStageWin + 256;
+constexpr size_t kStageStatus = 3 * kStageWin;
 
 int log2_exact(uint64_t v) {
     int l = 0;
@@ -105,9 +110,8 @@ void ProverCtx::allocate_work() {
     carries.as<Fr>(nchunks + 1);
     small.as<Fr>(S_COUNT);
     status.as<uint32_t>(4);
-    acc.as<G1XYZZ>(4);
-    result.as<G1Affine>(4);
-    PM_CUDA(cudaMallocHost(&host_stage, 1024));
+    acc.as<G1XYZZ>(3 * kMaxMsmWindows);
+    PM_CUDA(cudaMallocHost(&host_stage, kStageBytes));
     PM_CUDA(cudaEventCreate(&ev0));
     PM_CUDA(cudaEventCreate(&ev1));
 }
@@ -129,11 +133,11 @@ static void check_status(uint32_t st) {
     if (st & ST_OPENING_REMAINDER) throw StatusError(PM_ERR_REMAINDER, "opening numerator does not vanish at x1 (prover.rs:221)");
 }
 
-void ProverCtx::phase1(const uint8_t* ra, uint8_t* a_out, uint8_t* c_out) {
+void ProverCtx::phase1_partial(const uint8_t* ra, uint8_t* partials_out) {
     Runtime& rt = runtime();
     cudaStream_t s = rt.stream;
     if (!assignment_set) throw StatusError(PM_ERR_STATE, "phase 1 needs an assignment");
-    if (!ra || !a_out || !c_out) throw StatusError(PM_ERR_ARG, "null phase-1 argument");
+    if (!ra || !partials_out) throw StatusError(PM_ERR_ARG, "null phase-1 argument");
     phase = 0;
     Fr* sm = small.get<Fr>();
     uint32_t* st = status.get<uint32_t>();
@@ -158,25 +162,32 @@ void ProverCtx::phase1(const uint8_t* ra, uint8_t* a_out, uint8_t* c_out) {
     rt.extra_launches += 9;
     G1XYZZ* ac = acc.get<G1XYZZ>();
     const G1Affine* bc = bases_c.get<G1Affine>();
-    rt.msm.run(bc, scal_a.get<Fr>(), n + 4, ac + 0, s);          // compute_a_g1, prover.rs:330-338
-    rt.msm.run(bc, scal_c.get<Fr>(), len_c(), ac + 1, s);        // c_g1, prover.rs:116-123
-    G1Affine* res = result.get<G1Affine>();
-    launch_xyzz_sum_to_affine(ac + 0, 1, res + 0, s);
-    launch_xyzz_sum_to_affine(ac + 1, 1, res + 1, s);
-    rt.extra_launches += 2;
+    // compute_a_g1 (prover.rs:330-338) and c_g1 (prover.rs:116-123) over this rank's share of the bases
+    MsmEngine::Shape sa = rt.msm.run(bc, scal_a.get<Fr>(), local_count(n + 4), ac, s, {}, world, rank);
+    MsmEngine::Shape sc = rt.msm.run(bc, scal_c.get<Fr>(), local_count(len_c()), ac + kMaxMsmWindows, s, {}, world, rank);
     uint8_t* hs = static_cast<uint8_t*>(host_stage);
-    PM_CUDA(cudaMemcpyAsync(hs, res, 2 * sizeof(G1Affine), cudaMemcpyDeviceToHost, s));
-    PM_CUDA(cudaMemcpyAsync(hs + 256, st, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    PM_CUDA(cudaMemcpyAsync(hs, ac, sa.nwin * sizeof(G1XYZZ), cudaMemcpyDeviceToHost, s));
+    PM_CUDA(cudaMemcpyAsync(hs + kStageWin, ac + kMaxMsmWindows, sc.nwin * sizeof(G1XYZZ), cudaMemcpyDeviceToHost, s));
+    PM_CUDA(cudaMemcpyAsync(hs + kStageStatus, st, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     PM_CUDA(cudaEventRecord(ev1, s));
     PM_CUDA(cudaStreamSynchronize(s));
     float ms = 0;
     PM_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
     phase_ms[0] = ms;
     uint32_t stv;
-    memcpy(&stv, hs + 256, 4);
+    memcpy(&stv, hs + kStageStatus, 4);
     check_status(stv);
-    memcpy(a_out, hs, PM_G1_BYTES);
-    memcpy(c_out, hs + PM_G1_BYTES, PM_G1_BYTES);
+    host::combine_windows(hs, sa.nwin, sa.c).to_wire(partials_out);
+    host::combine_windows(hs + kStageWin, sc.nwin, sc.c).to_wire(partials_out + sizeof(G1XYZZ));
+    phase = 10;   // partial done, waiting for finish
+}
+
+void ProverCtx::phase1_finish(const uint8_t* gathered, int count, uint8_t* a_out, uint8_t* c_out) {
+    if (phase != 10) throw StatusError(PM_ERR_STATE, "phase-1 finish must follow phase-1 partial");
+    if (!gathered || count < 1 || !a_out || !c_out) throw StatusError(PM_ERR_ARG, "bad phase-1 finish argument");
+    // gathered = count records of [a-partial (192 B) | c-partial (192 B)]
+    host::xyzz_to_affine_wire(host::sum_partials(gathered, count, 2 * sizeof(G1XYZZ)), a_out);
+    host::xyzz_to_affine_wire(host::sum_partials(gathered + sizeof(G1XYZZ), count, 2 * sizeof(G1XYZZ)), c_out);
     phase = 1;
 }
 
@@ -219,11 +230,11 @@ NumeratorSrc ProverCtx::numerator_src() const {
     return src;
 }
 
-void ProverCtx::phase3(const uint8_t* x2, const uint8_t* c_at_x1, uint8_t* d_out) {
+void ProverCtx::phase3_partial(const uint8_t* x2, const uint8_t* c_at_x1, uint8_t* partial_out) {
     Runtime& rt = runtime();
     cudaStream_t s = rt.stream;
     if (phase != 2) throw StatusError(PM_ERR_STATE, "phase 3 must follow phase 2");
-    if (!x2 || !c_at_x1 || !d_out) throw StatusError(PM_ERR_ARG, "null phase-3 argument");
+    if (!x2 || !c_at_x1 || !partial_out) throw StatusError(PM_ERR_ARG, "null phase-3 argument");
     Fr* sm = small.get<Fr>();
     uint32_t* st = status.get<uint32_t>();
     PM_CUDA(cudaEventRecord(ev0, s));
@@ -237,23 +248,27 @@ void ProverCtx::phase3(const uint8_t* x2, const uint8_t* c_at_x1, uint8_t* d_out
     launch_chunk_carries(chunk_vals.get<Fr>(), nchunks, sm + S_X1, carries.get<Fr>(), st, s);
     launch_divide_numerator(src, sm + S_X1, carries.get<Fr>(), q.get<Fr>(), s);       // prover.rs:211-225
     rt.extra_launches += 4;
-    G1XYZZ* ac = acc.get<G1XYZZ>();
-    rt.msm.run(bases_d.get<G1Affine>(), q.get<Fr>(), src.len - 1, ac + 2, s);         // prover.rs:229
-    G1Affine* res = result.get<G1Affine>();
-    launch_xyzz_sum_to_affine(ac + 2, 1, res + 2, s);
-    rt.extra_launches += 1;
+    G1XYZZ* ac = acc.get<G1XYZZ>() + 2 * kMaxMsmWindows;
+    MsmEngine::Shape sd = rt.msm.run(bases_d.get<G1Affine>(), q.get<Fr>(), local_count(src.len - 1), ac, s, {}, world, rank);  // prover.rs:229
     uint8_t* hs = static_cast<uint8_t*>(host_stage);
-    PM_CUDA(cudaMemcpyAsync(hs, res + 2, sizeof(G1Affine), cudaMemcpyDeviceToHost, s));
-    PM_CUDA(cudaMemcpyAsync(hs + 256, st, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    PM_CUDA(cudaMemcpyAsync(hs, ac, sd.nwin * sizeof(G1XYZZ), cudaMemcpyDeviceToHost, s));
+    PM_CUDA(cudaMemcpyAsync(hs + kStageStatus, st, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     PM_CUDA(cudaEventRecord(ev1, s));
     PM_CUDA(cudaStreamSynchronize(s));
     float ms = 0;
     PM_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
     phase_ms[2] = ms;
     uint32_t stv;
-    memcpy(&stv, hs + 256, 4);
+    memcpy(&stv, hs + kStageStatus, 4);
     check_status(stv);
-    memcpy(d_out, hs, PM_G1_BYTES);
+    host::combine_windows(hs, sd.nwin, sd.c).to_wire(partial_out);
+    phase = 30;
+}
+
+void ProverCtx::phase3_finish(const uint8_t* gathered, int count, uint8_t* d_out) {
+    if (phase != 30) throw StatusError(PM_ERR_STATE, "phase-3 finish must follow phase-3 partial");
+    if (!gathered || count < 1 || !d_out) throw StatusError(PM_ERR_ARG, "bad phase-3 finish argument");
+    host::xyzz_to_affine_wire(host::sum_partials(gathered, count), d_out);
     phase = 0;
 }
 
@@ -278,17 +293,29 @@ void init_dims(ProverCtx& c, const pm_r1cs_view& r) {
     c.cols = 3 * c.m0 + c.mw + c.nr;   // SAPMatrices::size, common.rs:131-135
 }
 
-void upload_points(G1Affine* dst, const uint8_t* src, size_t stride, uint64_t len, uint64_t expect, const char* name) {
+// Upload the points of one key vector that belong to this rank.  `global_off` is the vector's offset
+// inside the concatenated base array; the rank keeps global indices g with g % world == rank, stored
+// compactly at local index g / world.
+void upload_points(const ProverCtx& c, G1Affine* dst_base, uint64_t global_off, const uint8_t* src, size_t stride,
+                   uint64_t len, uint64_t expect, const char* name) {
     if (len != expect) throw StatusError(PM_ERR_ARG, std::string("unexpected length of ") + name);
     if (len && !src) throw StatusError(PM_ERR_ARG, std::string("null ") + name);
     Runtime& rt = runtime();
-    if (stride == PM_G1_BYTES) {
-        PM_CUDA(cudaMemcpyAsync(dst, src, len * sizeof(G1Affine), cudaMemcpyHostToDevice, rt.stream));
+    if (c.world == 1 && stride == PM_G1_BYTES) {
+        PM_CUDA(cudaMemcpyAsync(dst_base + global_off, src, len * sizeof(G1Affine), cudaMemcpyHostToDevice, rt.stream));
         PM_CUDA(cudaStreamSynchronize(rt.stream));
-    } else {
-        std::vector<uint8_t> packed;
-        pack_points_host(src, stride, len, packed);
-        PM_CUDA(cudaMemcpyAsync(dst, packed.data(), len * sizeof(G1Affine), cudaMemcpyHostToDevice, rt.stream));
+        return;
+    }
+    // first global index >= global_off owned by this rank
+    uint64_t g0 = global_off + ((uint64_t)c.rank + c.world - global_off % c.world) % c.world;
+    std::vector<uint8_t> packed;
+    for (uint64_t g = g0; g < global_off + len; g += c.world) {
+        const uint8_t* p = src + (g - global_off) * stride;
+        if (stride >= 104 && p[96] != 0) packed.insert(packed.end(), PM_G1_BYTES, 0);
+        else packed.insert(packed.end(), p, p + PM_G1_BYTES);
+    }
+    if (!packed.empty()) {
+        PM_CUDA(cudaMemcpyAsync(dst_base + g0 / c.world, packed.data(), packed.size(), cudaMemcpyHostToDevice, rt.stream));
         PM_CUDA(cudaStreamSynchronize(rt.stream));
     }
 }
@@ -311,13 +338,18 @@ KeySlice key_slice(const ProverCtx& c, int which) {
 
 extern "C" {
 
-int pm_ctx_create(const pm_pk_view* pk, pm_ctx** out) {
+int pm_ctx_create(const pm_pk_view* pk, pm_ctx** out) { return pm_ctx_create_sharded(pk, 0, 1, out); }
+
+int pm_ctx_create_sharded(const pm_pk_view* pk, int rank, int world, pm_ctx** out) {
     return guarded([&] {
         if (!pk || !out) throw StatusError(PM_ERR_ARG, "null argument");
         if (pk->point_stride < PM_G1_BYTES) throw StatusError(PM_ERR_ARG, "point stride < 96");
+        if (world < 1 || rank < 0 || rank >= world) throw StatusError(PM_ERR_ARG, "bad rank/world");
         runtime();
         std::unique_ptr<pm_ctx> h(new pm_ctx());
         ProverCtx& c = h->impl;
+        c.rank = rank;
+        c.world = world;
         init_dims(c, pk->r1cs);
         c.n = pk->n;
         c.sigma = pk->sigma;
@@ -325,16 +357,16 @@ int pm_ctx_create(const pm_pk_view* pk, pm_ctx** out) {
         c.upload_matrix(c.A, pk->r1cs.a_row_ptr, pk->r1cs.a_col, pk->r1cs.a_val, false);
         c.upload_matrix(c.B, pk->r1cs.b_row_ptr, pk->r1cs.b_col, pk->r1cs.b_val, false);
         c.upload_matrix(c.C, pk->r1cs.c_row_ptr, pk->r1cs.c_col, pk->r1cs.c_val, false);
-        G1Affine* bc = c.bases_c.as<G1Affine>(c.len_c());
-        G1Affine* bd = c.bases_d.as<G1Affine>(c.len_d());
+        G1Affine* bc = c.bases_c.as<G1Affine>(c.local_count(c.len_c()) + 1);
+        G1Affine* bd = c.bases_d.as<G1Affine>(c.local_count(c.len_d()) + 1);
         const size_t st = pk->point_stride;
         const uint64_t n = c.n;
-        upload_points(bc, pk->x_powers_g1, st, pk->x_powers_g1_len, n + 1, "x_powers_g1");
-        upload_points(bc + n + 1, pk->x_powers_y_alpha_g1, st, pk->x_powers_y_alpha_g1_len, 3, "x_powers_y_alpha_g1");
-        upload_points(bc + n + 4, pk->x_powers_y_gamma_g1, st, pk->x_powers_y_gamma_g1_len, 2, "x_powers_y_gamma_g1");
-        upload_points(bc + n + 6, pk->x_powers_zh_by_y_alpha_g1, st, pk->x_powers_zh_by_y_alpha_g1_len, n - 1, "x_powers_zh_by_y_alpha_g1");
-        upload_points(bc + n + 6 + (n - 1), pk->uj_wj_lcs_by_y_alpha_g1, st, pk->uj_wj_lcs_by_y_alpha_g1_len, c.cols - c.m0, "uj_wj_lcs_by_y_alpha_g1");
-        upload_points(bd, pk->x_powers_y_gamma_z_g1, st, pk->x_powers_y_gamma_z_g1_len, c.len_d(), "x_powers_y_gamma_z_g1");
+        upload_points(c, bc, 0, pk->x_powers_g1, st, pk->x_powers_g1_len, n + 1, "x_powers_g1");
+        upload_points(c, bc, n + 1, pk->x_powers_y_alpha_g1, st, pk->x_powers_y_alpha_g1_len, 3, "x_powers_y_alpha_g1");
+        upload_points(c, bc, n + 4, pk->x_powers_y_gamma_g1, st, pk->x_powers_y_gamma_g1_len, 2, "x_powers_y_gamma_g1");
+        upload_points(c, bc, n + 6, pk->x_powers_zh_by_y_alpha_g1, st, pk->x_powers_zh_by_y_alpha_g1_len, n - 1, "x_powers_zh_by_y_alpha_g1");
+        upload_points(c, bc, n + 6 + (n - 1), pk->uj_wj_lcs_by_y_alpha_g1, st, pk->uj_wj_lcs_by_y_alpha_g1_len, c.cols - c.m0, "uj_wj_lcs_by_y_alpha_g1");
+        upload_points(c, bd, 0, pk->x_powers_y_gamma_z_g1, st, pk->x_powers_y_gamma_z_g1_len, c.len_d(), "x_powers_y_gamma_z_g1");
         *out = h.release();
     });
 }
@@ -347,11 +379,26 @@ void pm_ctx_destroy(pm_ctx* ctx) {
 
 int pm_setup(const pm_r1cs_view* r1cs, const uint8_t x[PM_FR_BYTES], const uint8_t z[PM_FR_BYTES], pm_ctx** out,
              uint8_t x_g2[192], uint8_t z_g2[192]) {
+    return pm_setup_sharded(r1cs, x, z, 0, 1, out, x_g2, z_g2);
+}
+
+int pm_host_sum_partials(const uint8_t* parts, int count, size_t stride, uint8_t out[PM_G1_BYTES]) {
+    return guarded([&] {
+        if (!parts || count < 0 || stride < sizeof(G1XYZZ) || !out) throw StatusError(PM_ERR_ARG, "bad argument");
+        host::xyzz_to_affine_wire(host::sum_partials(parts, count, stride), out);
+    });
+}
+
+int pm_setup_sharded(const pm_r1cs_view* r1cs, const uint8_t x[PM_FR_BYTES], const uint8_t z[PM_FR_BYTES], int rank, int world,
+                     pm_ctx** out, uint8_t x_g2[192], uint8_t z_g2[192]) {
     return guarded([&] {
         if (!r1cs || !x || !z || !out || !x_g2 || !z_g2) throw StatusError(PM_ERR_ARG, "null argument");
+        if (world < 1 || rank < 0 || rank >= world) throw StatusError(PM_ERR_ARG, "bad rank/world");
         runtime();
         std::unique_ptr<pm_ctx> h(new pm_ctx());
         ProverCtx& c = h->impl;
+        c.rank = rank;
+        c.world = world;
         init_dims(c, *r1cs);
         uint64_t rows = 2 * (c.m0 + c.nr);           // Radix2EvaluationDomain::new(rows), generator.rs:60-66
         uint64_t n = 1;
@@ -362,8 +409,8 @@ int pm_setup(const pm_r1cs_view* r1cs, const uint8_t x[PM_FR_BYTES], const uint8
         c.upload_matrix(c.A, r1cs->a_row_ptr, r1cs->a_col, r1cs->a_val, true);
         c.upload_matrix(c.B, r1cs->b_row_ptr, r1cs->b_col, r1cs->b_val, true);
         c.upload_matrix(c.C, r1cs->c_row_ptr, r1cs->c_col, r1cs->c_val, true);
-        c.bases_c.as<G1Affine>(c.len_c());
-        c.bases_d.as<G1Affine>(c.len_d());
+        c.bases_c.as<G1Affine>(c.local_count(c.len_c()) + 1);
+        c.bases_d.as<G1Affine>(c.local_count(c.len_d()) + 1);
         run_setup(c, x, z, x_g2, z_g2);
         *out = h.release();
     });
@@ -389,6 +436,7 @@ int pm_ctx_export_key(const pm_ctx* ctx, int which, uint8_t* out, size_t stride)
     return guarded([&] {
         if (!ctx || !out || stride < PM_G1_BYTES) throw StatusError(PM_ERR_ARG, "bad export arguments");
         const ProverCtx& c = ctx->impl;
+        if (c.world != 1) throw StatusError(PM_ERR_STATE, "key export needs an unsharded context");
         KeySlice ks = key_slice(c, which);
         const G1Affine* src = (ks.in_d ? c.bases_d.get<G1Affine>() : c.bases_c.get<G1Affine>()) + ks.off;
         Runtime& rt = runtime();
@@ -418,10 +466,49 @@ int pm_ctx_set_assignment(pm_ctx* ctx, const uint8_t* x, const uint8_t* w) {
     });
 }
 
+static void require_unsharded(const ProverCtx& c) {
+    if (c.world != 1) throw StatusError(PM_ERR_STATE, "sharded context: use the *_partial / *_finish entry points");
+}
+
 int pm_prove_phase1_resident(pm_ctx* ctx, const uint8_t r_a[2 * PM_FR_BYTES], uint8_t a_out[PM_G1_BYTES], uint8_t c_out[PM_G1_BYTES]) {
     return guarded([&] {
         if (!ctx) throw StatusError(PM_ERR_ARG, "null context");
-        ctx->impl.phase1(r_a, a_out, c_out);
+        require_unsharded(ctx->impl);
+        uint8_t part[2 * sizeof(G1XYZZ)];
+        ctx->impl.phase1_partial(r_a, part);
+        ctx->impl.phase1_finish(part, 1, a_out, c_out);
+    });
+}
+
+int pm_prove_phase1_partial(pm_ctx* ctx, const uint8_t r_a[2 * PM_FR_BYTES], uint8_t partials_out[2 * PM_XYZZ_BYTES]) {
+    return guarded([&] {
+        if (!ctx) throw StatusError(PM_ERR_ARG, "null context");
+        ctx->impl.phase1_partial(r_a, partials_out);
+    });
+}
+int pm_prove_phase1_finish(pm_ctx* ctx, const uint8_t* gathered, int count, uint8_t a_out[PM_G1_BYTES], uint8_t c_out[PM_G1_BYTES]) {
+    return guarded([&] {
+        if (!ctx) throw StatusError(PM_ERR_ARG, "null context");
+        ctx->impl.phase1_finish(gathered, count, a_out, c_out);
+    });
+}
+int pm_prove_phase3_partial(pm_ctx* ctx, const uint8_t x2[PM_FR_BYTES], const uint8_t c_at_x1[PM_FR_BYTES], uint8_t partial_out[PM_XYZZ_BYTES]) {
+    return guarded([&] {
+        if (!ctx) throw StatusError(PM_ERR_ARG, "null context");
+        ctx->impl.phase3_partial(x2, c_at_x1, partial_out);
+    });
+}
+int pm_prove_phase3_finish(pm_ctx* ctx, const uint8_t* gathered, int count, uint8_t d_out[PM_G1_BYTES]) {
+    return guarded([&] {
+        if (!ctx) throw StatusError(PM_ERR_ARG, "null context");
+        ctx->impl.phase3_finish(gathered, count, d_out);
+    });
+}
+int pm_ctx_shard(const pm_ctx* ctx, int* rank, int* world) {
+    return guarded([&] {
+        if (!ctx) throw StatusError(PM_ERR_ARG, "null context");
+        if (rank) *rank = ctx->impl.rank;
+        if (world) *world = ctx->impl.world;
     });
 }
 
@@ -429,8 +516,11 @@ int pm_prove_phase1(pm_ctx* ctx, const uint8_t* x, const uint8_t* w, const uint8
                     uint8_t a_out[PM_G1_BYTES], uint8_t c_out[PM_G1_BYTES]) {
     return guarded([&] {
         if (!ctx) throw StatusError(PM_ERR_ARG, "null context");
+        require_unsharded(ctx->impl);
         ctx->impl.set_assignment(x, w);
-        ctx->impl.phase1(r_a, a_out, c_out);
+        uint8_t part[2 * sizeof(G1XYZZ)];
+        ctx->impl.phase1_partial(r_a, part);
+        ctx->impl.phase1_finish(part, 1, a_out, c_out);
     });
 }
 
@@ -444,7 +534,10 @@ int pm_prove_phase2(pm_ctx* ctx, const uint8_t x1[PM_FR_BYTES], const uint8_t y1
 int pm_prove_phase3(pm_ctx* ctx, const uint8_t x2[PM_FR_BYTES], const uint8_t c_at_x1[PM_FR_BYTES], uint8_t d_out[PM_G1_BYTES]) {
     return guarded([&] {
         if (!ctx) throw StatusError(PM_ERR_ARG, "null context");
-        ctx->impl.phase3(x2, c_at_x1, d_out);
+        require_unsharded(ctx->impl);
+        uint8_t part[sizeof(G1XYZZ)];
+        ctx->impl.phase3_partial(x2, c_at_x1, part);
+        ctx->impl.phase3_finish(part, 1, d_out);
     });
 }
 

@@ -20,6 +20,10 @@ struct ProverCtx {
     // dimensions
     uint64_t m0 = 0, mw = 0, nr = 0, n = 0, sigma = 0, cols = 0;
     int log_n = 0;
+    // MSM sharding: this process holds the points g = k*world + rank of both base
+    // arrays; the polynomial work is replicated.  world == 1: the whole key.
+    int rank = 0, world = 1;
+    uint64_t local_count(uint64_t total) const { return total > (uint64_t)rank ? (total - rank + world - 1) / world : 0; }
     // key
     DevMatrix A, B, C;
     DevBuf bases_c;   // [x_powers (n+1) | x_powers_y_alpha (3) | x_powers_y_gamma (2) | zh (n-1) | lcs (cols-m0)]
@@ -28,7 +32,7 @@ struct ProverCtx {
     uint64_t len_d() const { return 2 * (n - 1) + 8 * sigma + 1; }
     // per-proof buffers
     DevBuf ztail, u, w, wu, u2, scal_a, scal_c, q, chunk_vals, carries, small;
-    DevBuf status, acc, result;
+    DevBuf status, acc;
     void* host_stage = nullptr;   // pinned staging for results
     int phase = 0;                // 0 idle, 1 after phase 1, 2 after phase 2
     bool assignment_set = false;
@@ -39,9 +43,12 @@ struct ProverCtx {
     void allocate_work();
     void upload_matrix(DevMatrix& dst, const uint64_t* row_ptr, const uint32_t* col, const uint8_t* val, bool want_csc);
     void set_assignment(const uint8_t* x, const uint8_t* w);
-    void phase1(const uint8_t* ra, uint8_t* a_out, uint8_t* c_out);
+    // partial = this rank's XYZZ sums (192 B each): [a-side, c-side] for phase 1, [d] for phase 3
+    void phase1_partial(const uint8_t* ra, uint8_t* partials_out);
+    void phase1_finish(const uint8_t* gathered, int count, uint8_t* a_out, uint8_t* c_out);
     void phase2(const uint8_t* x1, const uint8_t* y1_alpha, uint8_t* a_at_x1_out);
-    void phase3(const uint8_t* x2, const uint8_t* c_at_x1, uint8_t* d_out);
+    void phase3_partial(const uint8_t* x2, const uint8_t* c_at_x1, uint8_t* partial_out);
+    void phase3_finish(const uint8_t* gathered, int count, uint8_t* d_out);
     NumeratorSrc numerator_src() const;
 };
 

@@ -125,6 +125,12 @@ __global__ void __launch_bounds__(128) k_lcs_scalars(DevCsc A, DevCsc B, DevCsc 
     }
 }
 
+// dst[k] = src[k * stride + offset] for k < count   (this rank's share of a scalar vector)
+__global__ void k_gather_strided(const Fr* __restrict__ src, uint64_t stride, uint64_t offset, uint64_t count, Fr* __restrict__ dst) {
+    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < count) dst[k] = src[k * stride + offset];
+}
+
 // ---- G2 = E'(Fq2): y^2 = x^3 + 4(1 + u), Jacobian coordinates, a = 0 --------------------
 struct Fq2 {
     Fq c0, c1;
@@ -251,10 +257,23 @@ void run_setup(ProverCtx& ctx, const uint8_t* x, const uint8_t* z, uint8_t* x_g2
         PM_LAUNCH_CHECK();
         rt.extra_launches += 3;
     }
-    rt.fixed_base.run(sc, len_c, ctx.bases_c.get<G1Affine>(), s);
+    // the expensive part — one fixed-base multiplication per point — runs only on this rank's share
+    DevBuf share_b;
+    auto run_share = [&](uint64_t total, G1Affine* out) {
+        if (ctx.world == 1) { rt.fixed_base.run(sc, total, out, s); return; }
+        const uint64_t cnt = ctx.local_count(total);
+        Fr* share = share_b.as<Fr>(cnt + 1);
+        if (cnt) {
+            k_gather_strided<<<ceil_div(cnt, 256), 256, 0, s>>>(sc, (uint64_t)ctx.world, (uint64_t)ctx.rank, cnt, share);
+            PM_LAUNCH_CHECK();
+            rt.extra_launches++;
+        }
+        rt.fixed_base.run(share, cnt, out, s);
+    };
+    run_share(len_c, ctx.bases_c.get<G1Affine>());
     // d-side
     powers(sc, len_d, C_Y_GAMMA_Z);
-    rt.fixed_base.run(sc, len_d, ctx.bases_d.get<G1Affine>(), s);
+    run_share(len_d, ctx.bases_d.get<G1Affine>());
     // vk: [x]_2, [z]_2
     Fq* g2 = g2_b.as<Fq>(8);
     k_g2_mul<<<1, 32, 0, s>>>(c + C_X, 2, g2);

@@ -1,0 +1,107 @@
+"""Multi-GPU proving: one process per GPU, MSMs split by point range.
+
+Every rank holds the points g = k*world + rank of the proving key, runs the (small) polynomial work
+redundantly and its share of each MSM; the per-rank XYZZ partial sums (2 x 192 B in phase 1, 192 B in
+phase 3) are exchanged with one `all_gather` each — NCCL over NVLink when the process group is NCCL,
+gloo in the CPU tests — and added on the host by every rank (group addition is not an NCCL reduction).
+The protocol flow itself stays in the C++ host mirror (`pm_polymath_prove_sharded`); this module only
+supplies the collective as a callback.
+"""
+import ctypes as C
+
+from . import codec
+from .api import _lib, R1CS, StdRng, ProvingKey
+from .lib import check, load
+
+ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)
+
+
+def shard_indices(total: int, rank: int, world: int):
+    """Global indices owned by `rank` under the interleaved split (mirrors ProverCtx::local_count)."""
+    return range(rank, total, world)
+
+
+def make_allgather(group=None, device=None):
+    """Build the `pm_allgather_fn` callback on top of torch.distributed."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+
+    def _cb(_user, send, nbytes, recv):
+        try:
+            src = (C.c_ubyte * nbytes).from_address(send)
+            t = torch.frombuffer(bytearray(src), dtype=torch.uint8).to(device)
+            out = torch.empty(world * nbytes, dtype=torch.uint8, device=device)
+            dist.all_gather_into_tensor(out, t, group=group)
+            host = out.cpu().numpy().tobytes()
+            C.memmove(recv, host, len(host))
+            return 0
+        except Exception:  # the C side turns a non-zero return into PM_ERR_STATE
+            import traceback
+            traceback.print_exc()
+            return 1
+
+    return ALLGATHER_FN(_cb)
+
+
+def bind(lib):
+    if getattr(lib, "_sharded_bound", False):
+        return
+    vp, u8p = C.c_void_p, C.c_char_p
+    from .api import R1CSView, PKView
+    lib.pm_polymath_setup_sharded.argtypes = [C.POINTER(R1CSView), vp, C.c_int, C.c_int, C.POINTER(vp), u8p]
+    lib.pm_polymath_prove_sharded.argtypes = [vp, u8p, u8p, C.c_int, vp, ALLGATHER_FN, vp, u8p]
+    lib.pm_allgather_selftest.argtypes = [ALLGATHER_FN, vp, C.c_int, C.c_int]
+    lib.pm_setup_sharded.argtypes = [C.POINTER(R1CSView), u8p, u8p, C.c_int, C.c_int, C.POINTER(vp), u8p, u8p]
+    lib.pm_ctx_create_sharded.argtypes = [C.POINTER(PKView), C.c_int, C.c_int, C.POINTER(vp)]
+    lib.pm_prove_phase1_partial.argtypes = [vp, u8p, u8p]
+    lib.pm_prove_phase1_finish.argtypes = [vp, u8p, C.c_int, u8p, u8p]
+    lib.pm_prove_phase3_partial.argtypes = [vp, u8p, u8p, u8p]
+    lib.pm_prove_phase3_finish.argtypes = [vp, u8p, C.c_int, u8p]
+    lib.pm_host_sum_partials.argtypes = [u8p, C.c_int, C.c_size_t, u8p]
+    lib._sharded_bound = True
+
+
+def host_sum_partials(parts: bytes, count: int, stride: int = 192):
+    """Host-only: canonical affine sum of XYZZ partial records (no GPU needed)."""
+    lib = load()
+    bind(lib)
+    out = C.create_string_buffer(96)
+    check(lib.pm_host_sum_partials(parts, count, stride, out))
+    return codec.g1_from_wire(out.raw)
+
+
+class ShardedProver:
+    """`Polymath::setup` + `prove` across `world` processes (one GPU each)."""
+
+    def __init__(self, r1cs: R1CS, rng: StdRng, rank: int, world: int, group=None):
+        self.lib = _lib()
+        bind(self.lib)
+        self.rank, self.world = rank, world
+        self._cb = make_allgather(group) if world > 1 else ALLGATHER_FN(lambda *_: 1)
+        h = C.c_void_p()
+        vk = C.create_string_buffer(392)
+        check(self.lib.pm_polymath_setup_sharded(C.byref(r1cs.view), rng._h, rank, world, C.byref(h), vk))
+        self.pk = ProvingKey(h, vk.raw)
+        self.pk._r1cs = r1cs
+        self.vk_bytes = vk.raw
+        self._proof = C.create_string_buffer(176)
+
+    def set_assignment(self, instance_ptr, witness_ptr):
+        check(self.lib.pm_ctx_set_assignment(self.pk._h, instance_ptr, witness_ptr))
+
+    def prove(self, instance_wire, witness_ptr, rng: StdRng) -> bytes:
+        check(self.lib.pm_polymath_prove_sharded(self.pk._h, instance_wire, witness_ptr, 1, rng._h, self._cb, None, self._proof))
+        return self._proof.raw
+
+    def prove_resident(self, instance_wire, rng: StdRng) -> bytes:
+        check(self.lib.pm_polymath_prove_sharded(self.pk._h, instance_wire, None, 0, rng._h, self._cb, None, self._proof))
+        return self._proof.raw
+
+    def phase_ms(self):
+        return self.pk.phase_ms()
+
+    def close(self):
+        self.pk.close()

@@ -1,0 +1,70 @@
+"""Sharded MSM path on a single GPU: `world` sharded contexts in one process stand in for `world`
+ranks; their partial sums are concatenated in rank order (what the all-gather delivers) and every
+"rank" must finish to the oracle's proof.  Bit-exact."""
+import ctypes as C
+
+import pytest
+
+from oracle import polymath as opm, r1cs as orc
+from oracle.fields import R_MOD
+from oracle.merlin import MerlinFieldTranscript
+from oracle.rng import StdRng as ORng, fr_rand
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_virtual_ranks_reproduce_the_oracle_proof(pmlib, world):
+    from polymath_b200 import codec, sharded
+    from polymath_b200.api import R1CS, _lib
+    from polymath_b200.lib import check
+    lib = _lib()
+    sharded.bind(lib)
+    consts = [11, 22, 33, 44, 55, 66, 77]
+    circ = orc.MiMCDemo(None, None, consts)
+    cs = orc.synthesize(circ, setup_mode=True)
+    a, b, c = cs.to_matrices()
+    orng = ORng.seed_from_u64(77)
+    pk_or = opm.generate_proving_key(circ, orng)
+    x, z = pk_or.trapdoor["x"], pk_or.trapdoor["z"]
+    r1cs = R1CS(cs.num_instance_variables, cs.num_witness_variables, a, b, c)
+    ctxs = []
+    for rank in range(world):
+        h = C.c_void_p()
+        xg2, zg2 = C.create_string_buffer(192), C.create_string_buffer(192)
+        check(lib.pm_setup_sharded(C.byref(r1cs.view), codec.fr_to_wire(x), codec.fr_to_wire(z), rank, world, C.byref(h), xg2, zg2))
+        ctxs.append(h)
+    pcs = orc.synthesize(orc.MiMCDemo(5, 6, consts), setup_mode=False)
+    inst, wit = pcs.instance_assignment, pcs.witness_assignment
+    trace = {}
+    want = opm.create_proof_with_assignment(pk_or, inst, wit, orng, trace=trace)
+    ra = codec.frs_to_wire(trace["ra"])
+    # phase 1
+    parts = b""
+    for h in ctxs:
+        check(lib.pm_ctx_set_assignment(h, codec.frs_to_wire(inst), codec.frs_to_wire(wit)))
+        out = C.create_string_buffer(384)
+        check(lib.pm_prove_phase1_partial(h, ra, out))
+        parts += out.raw
+    for h in ctxs:
+        ao, co = C.create_string_buffer(96), C.create_string_buffer(96)
+        check(lib.pm_prove_phase1_finish(h, parts, world, ao, co))
+        assert codec.g1_from_wire(ao.raw) == want.a_g1 and codec.g1_from_wire(co.raw) == want.c_g1
+    # phase 2 (replicated)
+    for h in ctxs:
+        ev = C.create_string_buffer(32)
+        check(lib.pm_prove_phase2(h, codec.fr_to_wire(trace["x1"]), codec.fr_to_wire(trace["y1_alpha"]), ev))
+        assert codec.fr_from_wire(ev.raw) == want.a_at_x1
+    # phase 3
+    parts = b""
+    for h in ctxs:
+        out = C.create_string_buffer(192)
+        check(lib.pm_prove_phase3_partial(h, codec.fr_to_wire(trace["x2"]), codec.fr_to_wire(trace["c_at_x1"]), out))
+        parts += out.raw
+    for h in ctxs:
+        do = C.create_string_buffer(96)
+        check(lib.pm_prove_phase3_finish(h, parts, world, do))
+        assert codec.g1_from_wire(do.raw) == want.d_g1
+    assert opm.verify_proof(pk_or.vk, want, inst[1:])
+    for h in ctxs:
+        lib.pm_ctx_destroy(h)
