@@ -58,6 +58,48 @@ static __device__ __noinline__ void xyzz_dbl(G1XYZZ& a) {
     a.zzz = w * a.zzz;
 }
 
+// Multiplication policies for the hot loop: fully inlined products, or one shared out-of-line copy
+// of the Fq product (keeps the loop body inside the instruction caches).
+struct MulInline {
+    static __device__ __forceinline__ Fq mul(const Fq& a, const Fq& b) { return a * b; }
+};
+static __device__ __noinline__ Fq fq_mul_call(Fq a, Fq b) { return a * b; }
+struct MulCall {
+    static __device__ __forceinline__ Fq mul(const Fq& a, const Fq& b) { return fq_mul_call(a, b); }
+};
+
+// acc += p (p affine; `neg` adds -p)   EFD madd-2008-s, products through policy M
+template <class M>
+__device__ __forceinline__ void xyzz_madd_t(G1XYZZ& a, const G1Affine& p_in, bool neg) {
+    if (p_in.is_inf()) return;
+    Fq py = neg ? p_in.y.neg() : p_in.y;
+    if (a.is_inf()) {
+        a.x = p_in.x; a.y = py; a.zz = Fq::one(); a.zzz = Fq::one();
+        return;
+    }
+    Fq u2 = M::mul(p_in.x, a.zz);
+    Fq s2 = M::mul(py, a.zzz);
+    Fq p = u2 - a.x;
+    Fq r = s2 - a.y;
+    if (p.is_zero()) {
+        if (r.is_zero()) {
+            G1Affine q{p_in.x, py};
+            a = xyzz_dbl_affine(q);
+        } else {
+            a = G1XYZZ::inf();
+        }
+        return;
+    }
+    Fq pp = M::mul(p, p);
+    Fq ppp = M::mul(p, pp);
+    Fq q = M::mul(a.x, pp);
+    Fq x3 = M::mul(r, r) - ppp - q.dbl();
+    a.y = M::mul(r, q - x3) - M::mul(a.y, ppp);
+    a.x = x3;
+    a.zz = M::mul(a.zz, pp);
+    a.zzz = M::mul(a.zzz, ppp);
+}
+
 // acc += p (p affine; `neg` adds -p)   EFD madd-2008-s
 __device__ __forceinline__ void xyzz_madd(G1XYZZ& a, const G1Affine& p_in, bool neg = false) {
     if (p_in.is_inf()) return;

@@ -8,8 +8,9 @@
 //                        (order inside a bucket is irrelevant: group addition commutes)
 //   4. k_accumulate      one thread per bucket, XYZZ mixed additions over its sorted run;
 //                        buckets longer than a threshold are deferred to
-//      k_accumulate_heavy (one CTA per heavy bucket, shared-memory tree) so skewed scalar
-//                        distributions (SURVEY.md §7 "hard parts") do not serialise
+//      k_accumulate_heavy / k_heavy_finish (4096-entry chunks, one CTA each, then a per-bucket
+//                        sum of the chunk partials) so narrow top windows and skewed scalar
+//                        distributions (SURVEY.md §7 "hard parts") spread over the whole GPU
 //   5. k_reduce_segments running-sum over K-bucket segments + small scalar mul by the segment base
 //      k_reduce_windows  per-window tree sum of the segment partials
 //   6. host: Horner over the <= 32 window sums (c doublings each) and the affine normalisation
@@ -128,19 +129,41 @@ __device__ __forceinline__ G1Affine load_point(const G1Affine* __restrict__ base
     return p;
 }
 
-// Variant selection (tuning hook): PM_ACC_VARIANT = <minBlocks> for the register-prefetch kernel,
-// or 10 + <minBlocks> for the shared-memory staged kernel (cp.async double buffer).
-template <int MINB>
+// ---- heavy buckets -------------------------------------------------------------------------
+// A bucket longer than `heavy_thr` is cut into chunks of kHeavyChunk sorted entries; every chunk
+// becomes a task for one CTA of k_accumulate_heavy, and k_heavy_finish adds the chunk partials of
+// each heavy bucket.  Narrow top windows (255 mod c bits) and skewed scalar distributions (repeated
+// witness values) put n / 2^k points into single buckets, so this path is hit in
+// normal operation and must spread over the whole GPU.
+constexpr uint32_t kHeavyChunk = 4096;
+struct HeavyLists {
+    uint2* tasks;        // (bucket, chunk index)
+    uint4* heavy;        // (bucket, first task, task count, 0)
+    uint32_t* counters;  // [0] = tasks, [1] = heavy buckets
+    G1XYZZ* partials;    // one per task
+};
+
+__device__ __forceinline__ void defer_heavy(const HeavyLists& hl, uint32_t t, uint32_t len) {
+    uint32_t ntask = (len + kHeavyChunk - 1) / kHeavyChunk;
+    uint32_t first = atomicAdd(&hl.counters[0], ntask);
+    for (uint32_t i = 0; i < ntask; i++) hl.tasks[first + i] = make_uint2(t, i);
+    uint32_t slot = atomicAdd(&hl.counters[1], 1u);
+    hl.heavy[slot] = make_uint4(t, first, ntask, 0u);
+}
+
+// One thread per (window, bucket): walk the bucket's sorted run with XYZZ mixed additions.
+// M selects inlined Fq products or one shared out-of-line copy (smaller loop body: the fully
+// inlined body is ~140 KB of SASS and stalls on instruction fetch).  Tuning hook:
+// PM_ACC_VARIANT = 3 -> <3, MulInline>, 24 (default) -> <4, MulCall>.
+template <int MINB, class M>
 __global__ void __launch_bounds__(128, MINB) k_accumulate(const G1Affine* __restrict__ bases, const uint32_t* __restrict__ sorted,
-                                                    const uint32_t* __restrict__ offsets, G1XYZZ* __restrict__ buckets,
-                                                    uint32_t total_buckets, uint32_t heavy_thr,
-                                                    uint32_t* __restrict__ heavy_list, uint32_t* __restrict__ heavy_count) {
+                                                          const uint32_t* __restrict__ offsets, G1XYZZ* __restrict__ buckets,
+                                                          uint32_t total_buckets, uint32_t heavy_thr, HeavyLists hl) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= total_buckets) return;
     uint32_t beg = offsets[t], end = offsets[t + 1];
     if (end - beg > heavy_thr) {
-        uint32_t slot = atomicAdd(heavy_count, 1u);
-        heavy_list[slot] = t;
+        defer_heavy(hl, t, end - beg);
         return;
     }
     G1XYZZ acc = G1XYZZ::inf();
@@ -154,7 +177,7 @@ __global__ void __launch_bounds__(128, MINB) k_accumulate(const G1Affine* __rest
                 e_next = sorted[k + 1];
                 p_next = load_point(bases, e_next & 0x7fffffffu);
             }
-            xyzz_madd(acc, p, (e >> 31) != 0);
+            xyzz_madd_t<M>(acc, p, (e >> 31) != 0);
             p = p_next;
             e = e_next;
         }
@@ -162,80 +185,21 @@ __global__ void __launch_bounds__(128, MINB) k_accumulate(const G1Affine* __rest
     buckets[t] = acc;
 }
 
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
-    uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-// Same walk, but the next point is staged into shared memory with cp.async (per-thread private
-// slots, [buffer][16-byte chunk][thread] so a warp's accesses are conflict free): no registers are
-// spent on the prefetch and the point's limbs are read from shared memory where they are consumed.
-template <int MINB>
-__global__ void __launch_bounds__(128, MINB) k_accumulate_smem(const G1Affine* __restrict__ bases, const uint32_t* __restrict__ sorted,
-                                                         const uint32_t* __restrict__ offsets, G1XYZZ* __restrict__ buckets,
-                                                         uint32_t total_buckets, uint32_t heavy_thr,
-                                                         uint32_t* __restrict__ heavy_list, uint32_t* __restrict__ heavy_count) {
-    __shared__ uint4 stage[2][6][128];
-    const uint32_t tid = threadIdx.x;
-    uint32_t t = blockIdx.x * blockDim.x + tid;
-    if (t >= total_buckets) return;
-    uint32_t beg = offsets[t], end = offsets[t + 1];
-    if (end - beg > heavy_thr) {
-        uint32_t slot = atomicAdd(heavy_count, 1u);
-        heavy_list[slot] = t;
-        return;
-    }
-    G1XYZZ acc = G1XYZZ::inf();
-    if (beg < end) {
-        uint32_t e = sorted[beg];
-        {
-            const uint4* src = reinterpret_cast<const uint4*>(bases + (e & 0x7fffffffu));
-#pragma unroll
-            for (int c = 0; c < 6; c++) cp_async16(&stage[0][c][tid], src + c);
-            cp_async_commit();
-        }
-        uint32_t buf = 0;
-        for (uint32_t k = beg; k < end; k++) {
-            uint32_t e_next = 0;
-            if (k + 1 < end) {
-                e_next = sorted[k + 1];
-                const uint4* src = reinterpret_cast<const uint4*>(bases + (e_next & 0x7fffffffu));
-#pragma unroll
-                for (int c = 0; c < 6; c++) cp_async16(&stage[buf ^ 1][c][tid], src + c);
-            }
-            cp_async_commit();
-            cp_async_wait<1>();
-            G1Affine p;
-            uint4* dst = reinterpret_cast<uint4*>(&p);
-#pragma unroll
-            for (int c = 0; c < 6; c++) dst[c] = stage[buf][c][tid];
-            xyzz_madd(acc, p, (e >> 31) != 0);
-            e = e_next;
-            buf ^= 1;
-        }
-    }
-    buckets[t] = acc;
-}
-
-// One CTA per heavy bucket: strided per-thread sums, then a shared-memory tree.
+// One CTA per task: strided per-thread sums over one chunk, then a shared-memory tree.
 __global__ void __launch_bounds__(256) k_accumulate_heavy(const G1Affine* __restrict__ bases, const uint32_t* __restrict__ sorted,
-                                                          const uint32_t* __restrict__ offsets, G1XYZZ* __restrict__ buckets,
-                                                          const uint32_t* __restrict__ heavy_list,
-                                                          const uint32_t* __restrict__ heavy_count) {
+                                                          const uint32_t* __restrict__ offsets, HeavyLists hl) {
     extern __shared__ uint4 smem_raw[];
     G1XYZZ* sh = reinterpret_cast<G1XYZZ*>(smem_raw);
-    const uint32_t nheavy = *heavy_count;
-    for (uint32_t h = blockIdx.x; h < nheavy; h += gridDim.x) {
-        uint32_t t = heavy_list[h];
-        uint32_t beg = offsets[t], end = offsets[t + 1];
+    const uint32_t ntasks = hl.counters[0];
+    for (uint32_t task = blockIdx.x; task < ntasks; task += gridDim.x) {
+        uint2 tk = hl.tasks[task];
+        uint32_t beg = offsets[tk.x] + tk.y * kHeavyChunk;
+        uint32_t end = min(offsets[tk.x + 1], beg + kHeavyChunk);
         G1XYZZ acc = G1XYZZ::inf();
         for (uint32_t k = beg + threadIdx.x; k < end; k += blockDim.x) {
             uint32_t e = sorted[k];
             G1Affine p = load_point(bases, e & 0x7fffffffu);
-            xyzz_madd(acc, p, (e >> 31) != 0);
+            xyzz_madd_t<MulCall>(acc, p, (e >> 31) != 0);
         }
         sh[threadIdx.x] = acc;
         __syncthreads();
@@ -247,7 +211,31 @@ __global__ void __launch_bounds__(256) k_accumulate_heavy(const G1Affine* __rest
             }
             __syncthreads();
         }
-        if (threadIdx.x == 0) buckets[t] = sh[0];
+        if (threadIdx.x == 0) hl.partials[task] = sh[0];
+        __syncthreads();
+    }
+}
+
+// One CTA per heavy bucket: add its chunk partials.
+__global__ void __launch_bounds__(128) k_heavy_finish(G1XYZZ* __restrict__ buckets, HeavyLists hl) {
+    __shared__ uint4 smem_raw[128 * sizeof(G1XYZZ) / sizeof(uint4)];
+    G1XYZZ* sh = reinterpret_cast<G1XYZZ*>(smem_raw);
+    const uint32_t nheavy = hl.counters[1];
+    for (uint32_t h = blockIdx.x; h < nheavy; h += gridDim.x) {
+        uint4 hb = hl.heavy[h];
+        G1XYZZ acc = G1XYZZ::inf();
+        for (uint32_t k = threadIdx.x; k < hb.z; k += blockDim.x) xyzz_add(acc, hl.partials[hb.y + k]);
+        sh[threadIdx.x] = acc;
+        __syncthreads();
+        for (uint32_t stride = blockDim.x / 2; stride > 0; stride >>= 1) {
+            if (threadIdx.x < stride) {
+                G1XYZZ a = sh[threadIdx.x];
+                xyzz_add(a, sh[threadIdx.x + stride]);
+                sh[threadIdx.x] = a;
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) buckets[hb.x] = sh[0];
         __syncthreads();
     }
 }
@@ -297,16 +285,15 @@ __global__ void __launch_bounds__(128) k_reduce_windows(const G1XYZZ* __restrict
 }  // namespace
 
 int MsmEngine::choose_window(size_t n) {
-    // balance n*ceil(256/c) bucket additions against 2^(c-1)*ceil(256/c) bucket reductions,
-    // keeping >= ~32k bucket threads in flight for the 148-SM part
-    int lg = 0;
-    while (((size_t)1 << (lg + 1)) <= n) lg++;
-    int c = lg - 4;
-    if (c < 10) c = 10;
-    if (c > 16) c = 16;
-    if (n < 1024) c = 8;
-    if (n < 64) c = 4;
-    return c;
+    // Empirical optimum on B200 (profiles/msm_window_sweep_r1.jsonl): the bucket-reduction tail grows
+    // with 2^(c-1) * ceil(256/c) while the additions shrink with ceil(256/c); c = 16 also makes the 16
+    // windows tile the 256-bit scalar exactly (no narrow top window).
+    if (n < 64) return 4;
+    if (n < 1024) return 8;
+    if (n < ((size_t)1 << 14)) return 10;
+    if (n < (size_t)92682) return 12;      // 2^16.5
+    if (n < (size_t)741455) return 14;     // 2^19.5
+    return 16;
 }
 
 MsmEngine::~MsmEngine() {
@@ -329,7 +316,8 @@ MsmEngine::Shape MsmEngine::run(const G1Affine* bases, const Fr* scalars, size_t
     const uint32_t nseg = (nb + kSegBuckets - 1) / kSegBuckets;
     const uint32_t total_segs = nseg * (uint32_t)nwin;
     size_t avg = (n + nb - 1) / nb;
-    uint32_t heavy_thr = cfg.heavy ? (uint32_t)cfg.heavy : (uint32_t)(avg * 8 > 2048 ? avg * 8 : 2048);
+    uint32_t heavy_thr = cfg.heavy ? (uint32_t)cfg.heavy : (uint32_t)(avg * 8 > 512 ? avg * 8 : 512);
+    const size_t max_tasks = n * (size_t)nwin / kHeavyChunk + total + 16;
 
     uint32_t* counts = counts_.as<uint32_t>(total + 1);
     uint32_t* offsets = offsets_.as<uint32_t>(total + 1);
@@ -337,11 +325,19 @@ MsmEngine::Shape MsmEngine::run(const G1Affine* bases, const Fr* scalars, size_t
     uint32_t* sorted = sorted_.as<uint32_t>(n * (size_t)nwin);
     G1XYZZ* buckets = buckets_.as<G1XYZZ>(total);
     G1XYZZ* segs = segs_.as<G1XYZZ>(total_segs);
-    uint32_t* heavy_list = heavy_list_.as<uint32_t>(total);
-    uint32_t* heavy_count = heavy_count_.as<uint32_t>(1);
+    HeavyLists hl;
+    {
+        // one allocation: [tasks uint2 | heavy uint4 | partials]
+        size_t bytes = max_tasks * sizeof(uint2) + (size_t)total * sizeof(uint4) + max_tasks * sizeof(G1XYZZ) + 64;
+        uint8_t* base = heavy_list_.as<uint8_t>(bytes);
+        hl.heavy = reinterpret_cast<uint4*>(base);
+        hl.partials = reinterpret_cast<G1XYZZ*>(base + (size_t)total * sizeof(uint4));
+        hl.tasks = reinterpret_cast<uint2*>(base + (size_t)total * sizeof(uint4) + max_tasks * sizeof(G1XYZZ));
+        hl.counters = heavy_count_.as<uint32_t>(2);
+    }
 
     PM_CUDA(cudaMemsetAsync(counts, 0, (total + 1) * sizeof(uint32_t), stream));
-    PM_CUDA(cudaMemsetAsync(heavy_count, 0, sizeof(uint32_t), stream));
+    PM_CUDA(cudaMemsetAsync(hl.counters, 0, 2 * sizeof(uint32_t), stream));
     const unsigned dgrid = ceil_div(n, 256);
     k_digits<false><<<dgrid, 256, 0, stream>>>(bases, scalars, n, scalar_stride, scalar_offset, c, nwin, nb, counts, nullptr);
     PM_LAUNCH_CHECK();
@@ -357,19 +353,11 @@ MsmEngine::Shape MsmEngine::run(const G1Affine* bases, const Fr* scalars, size_t
         static int variant = -1;
         if (variant < 0) {
             const char* v = getenv("PM_ACC_VARIANT");
-            variant = v ? atoi(v) : 3;
+            variant = v ? atoi(v) : 24;
         }
         const unsigned g = ceil_div(total, 128);
-#define PM_ACC_ARGS bases, sorted, offsets, buckets, total, heavy_thr, heavy_list, heavy_count
-        switch (variant) {
-            case 3: k_accumulate<3><<<g, 128, 0, stream>>>(PM_ACC_ARGS); break;
-            case 4: k_accumulate<4><<<g, 128, 0, stream>>>(PM_ACC_ARGS); break;
-            case 12: k_accumulate_smem<2><<<g, 128, 0, stream>>>(PM_ACC_ARGS); break;
-            case 13: k_accumulate_smem<3><<<g, 128, 0, stream>>>(PM_ACC_ARGS); break;
-            case 14: k_accumulate_smem<4><<<g, 128, 0, stream>>>(PM_ACC_ARGS); break;
-            default: k_accumulate<2><<<g, 128, 0, stream>>>(PM_ACC_ARGS); break;
-        }
-#undef PM_ACC_ARGS
+        if (variant == 3) k_accumulate<3, MulInline><<<g, 128, 0, stream>>>(bases, sorted, offsets, buckets, total, heavy_thr, hl);
+        else k_accumulate<4, MulCall><<<g, 128, 0, stream>>>(bases, sorted, offsets, buckets, total, heavy_thr, hl);
         PM_LAUNCH_CHECK();
     }
     if (time_accumulate) PM_CUDA(cudaEventRecord(ev_acc_end, stream));
@@ -380,14 +368,16 @@ MsmEngine::Shape MsmEngine::run(const G1Affine* bases, const Fr* scalars, size_t
             PM_CUDA(cudaFuncSetAttribute(k_accumulate_heavy, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
             attr_set = true;
         }
-        k_accumulate_heavy<<<2 * sm_count(), 256, smem, stream>>>(bases, sorted, offsets, buckets, heavy_list, heavy_count);
+        k_accumulate_heavy<<<4 * sm_count(), 256, smem, stream>>>(bases, sorted, offsets, hl);
+        PM_LAUNCH_CHECK();
+        k_heavy_finish<<<2 * sm_count(), 128, 0, stream>>>(buckets, hl);
         PM_LAUNCH_CHECK();
     }
     k_reduce_segments<<<ceil_div(total_segs, 128), 128, 0, stream>>>(buckets, nb, nseg, total_segs, segs);
     PM_LAUNCH_CHECK();
     k_reduce_windows<<<nwin, 128, 0, stream>>>(segs, nseg, winsums);
     PM_LAUNCH_CHECK();
-    launches += 7;
+    launches += 8;
     return {c, nwin};
 }
 

@@ -228,17 +228,26 @@ __global__ void k_a_at_x1(const Fr* u_at_x1, const Fr* ra, const Fr* x1_y1a, Fr*
     out[0] = u_at_x1[0] + (ra[0] + ra[1] * x1) * y1a;
 }
 
-// carries[c] = q_{(c+1)*kChunk - 1}: the quotient coefficient entering chunk c from above.
-__global__ void k_chunk_carries(const Fr* __restrict__ chunk_vals, uint64_t nchunks, const Fr* __restrict__ xp,
-                                Fr* __restrict__ carries, uint32_t* __restrict__ status) {
+// out[0] = x^kChunk, out[1] = x^(kChunk^2)
+__global__ void k_chunk_powers(const Fr* __restrict__ xp, Fr* __restrict__ out) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     Fr xc = xp[0].pow_u64((uint64_t)kChunk);
+    out[0] = xc;
+    out[1] = xc.pow_u64((uint64_t)kChunk);
+}
+
+// carries[c] = q_{(c+1)*kChunk - 1}: the quotient coefficient entering chunk c from above
+// (xcp[0] = the evaluation point raised to the chunk length).  Serial: used on <= a few hundred values.
+__global__ void k_chunk_carries(const Fr* __restrict__ chunk_vals, uint64_t nchunks, const Fr* __restrict__ xcp,
+                                Fr* __restrict__ carries, uint32_t* __restrict__ status) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    Fr xc = xcp[0];
     Fr q = Fr::zero();
     for (uint64_t c = nchunks; c-- > 0;) {
         carries[c] = q;
         q = chunk_vals[c] + xc * q;
     }
-    if (!q.is_zero()) atomicOr(status, ST_OPENING_REMAINDER);  // q == p(x1): the remainder
+    if (status != nullptr && !q.is_zero()) atomicOr(status, ST_OPENING_REMAINDER);  // q == p(x1): the remainder
 }
 
 template <class Src>
@@ -350,14 +359,40 @@ void launch_a_at_x1(const Fr* u_at_x1, const Fr* ra_ext, const Fr* x1_y1a, Fr* o
     k_a_at_x1<<<1, 32, 0, stream>>>(u_at_x1, ra_ext, x1_y1a, out);
     PM_LAUNCH_CHECK();
 }
-void launch_chunk_carries(const Fr* chunk_vals, uint64_t nchunks, const Fr* x, Fr* carries, uint32_t* status, cudaStream_t stream) {
-    k_chunk_carries<<<1, 32, 0, stream>>>(chunk_vals, nchunks, x, carries, status);
-    PM_LAUNCH_CHECK();
-}
-void launch_divide_numerator(const NumeratorSrc& src, const Fr* x, const Fr* carries, Fr* q, cudaStream_t stream) {
+// q[k-1] = p_k + x q_k for the virtual numerator (q: len-1 entries); sets ST_OPENING_REMAINDER when
+// p(x) != 0.  Two-level carry propagation: chunk values -> (chunks of chunk values) -> serial over
+// the few level-2 values -> parallel division of the chunk polynomial -> parallel division proper.
+// work: >= 2*(nchunks + 1) + 2*(nchunks/kChunk + 2) + 2 elements.
+int launch_divide_numerator(const NumeratorSrc& src, const Fr* x, Fr* q, Fr* work, uint32_t* status, cudaStream_t stream) {
     NumSrc s{src};
-    k_chunk_divide<NumSrc><<<ceil_div(src.len, kChunk), kThreads, 0, stream>>>(s, src.len, x, carries, q);
+    const uint64_t c1 = (src.len + kChunk - 1) / kChunk;
+    const uint64_t c2 = (c1 + kChunk - 1) / kChunk;
+    Fr* vals1 = work;
+    Fr* carr1 = vals1 + c1 + 1;
+    Fr* vals2 = carr1 + c1 + 1;
+    Fr* carr2 = vals2 + c2 + 1;
+    Fr* xpow = carr2 + c2 + 1;   // [x^kChunk, x^(kChunk^2)]
+    int launches = 0;
+    k_chunk_powers<<<1, 32, 0, stream>>>(x, xpow);
+    k_chunk_eval<NumSrc><<<(unsigned)c1, kThreads, 0, stream>>>(s, src.len, x, vals1);
     PM_LAUNCH_CHECK();
+    launches += 2;
+    if (c1 <= 128) {
+        k_chunk_carries<<<1, 32, 0, stream>>>(vals1, c1, xpow, carr1, status);
+        launches += 1;
+    } else {
+        PlainSrc ps{vals1, c1};
+        k_chunk_eval<PlainSrc><<<(unsigned)c2, kThreads, 0, stream>>>(ps, c1, xpow, vals2);
+        k_chunk_carries<<<1, 32, 0, stream>>>(vals2, c2, xpow + 1, carr2, status);
+        // carries of level 1 = quotient of the chunk polynomial by (Y - x^kChunk), shifted by one
+        PM_CUDA(cudaMemsetAsync(carr1 + (c1 - 1), 0, sizeof(Fr), stream));
+        k_chunk_divide<PlainSrc><<<(unsigned)c2, kThreads, 0, stream>>>(ps, c1, xpow, carr2, carr1);
+        launches += 3;
+    }
+    PM_LAUNCH_CHECK();
+    k_chunk_divide<NumSrc><<<(unsigned)c1, kThreads, 0, stream>>>(s, src.len, x, carr1, q);
+    PM_LAUNCH_CHECK();
+    return launches + 1;
 }
 void launch_materialize_numerator(const NumeratorSrc& src, Fr* out, cudaStream_t stream) {
     NumSrc s{src};

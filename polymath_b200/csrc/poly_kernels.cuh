@@ -66,11 +66,9 @@ void launch_chunk_eval_numerator(const NumeratorSrc& src, const Fr* x, Fr* chunk
 void launch_combine_chunks(const Fr* chunk_vals, uint64_t nchunks, const Fr* x, Fr* out, cudaStream_t stream);
 // a_at_x1 = u(x1) + (r0 + r1*x1) * y1_alpha ; inputs: u_at_x1 (device), ra_ext, consts2 = [x1, y1_alpha]
 void launch_a_at_x1(const Fr* u_at_x1, const Fr* ra_ext, const Fr* x1_y1a, Fr* out, cudaStream_t stream);
-// carries[c] = quotient coefficient entering chunk c from above; sets ST_OPENING_REMAINDER if p(x) != 0
-void launch_chunk_carries(const Fr* chunk_vals, uint64_t nchunks, const Fr* x, Fr* carries, uint32_t* status,
-                          cudaStream_t stream);
-// q[k-1] = p_k + x * q_k for the virtual numerator; q has len-1 entries
-void launch_divide_numerator(const NumeratorSrc& src, const Fr* x, const Fr* carries, Fr* q, cudaStream_t stream);
+// q[k-1] = p_k + x * q_k for the virtual numerator; q has len-1 entries; sets ST_OPENING_REMAINDER if
+// p(x) != 0.  `work` needs 2*(nchunks+1) + 2*(nchunks/kChunk+2) + 2 elements.  Returns the launch count.
+int launch_divide_numerator(const NumeratorSrc& src, const Fr* x, Fr* q, Fr* work, uint32_t* status, cudaStream_t stream);
 // materialise the virtual numerator (tests / debugging)
 void launch_materialize_numerator(const NumeratorSrc& src, Fr* out, cudaStream_t stream);
 

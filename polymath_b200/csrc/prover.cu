@@ -106,8 +106,7 @@ void ProverCtx::allocate_work() {
     scal_c.as<Fr>(len_c());
     q.as<Fr>(len_d());
     const uint64_t nchunks = (len_d() + kChunk - 1) / kChunk;
-    chunk_vals.as<Fr>(nchunks + 1);
-    carries.as<Fr>(nchunks + 1);
+    chunk_vals.as<Fr>(2 * (nchunks + 1) + 2 * (nchunks / kChunk + 2) + 8);
     small.as<Fr>(S_COUNT);
     status.as<uint32_t>(4);
     acc.as<G1XYZZ>(3 * kMaxMsmWindows);
@@ -243,11 +242,7 @@ void ProverCtx::phase3_partial(const uint8_t* x2, const uint8_t* c_at_x1, uint8_
     k_phase3_consts<<<1, 32, 0, s>>>(sm);
     PM_LAUNCH_CHECK();
     NumeratorSrc src = numerator_src();
-    const uint64_t nchunks = (src.len + kChunk - 1) / kChunk;
-    launch_chunk_eval_numerator(src, sm + S_X1, chunk_vals.get<Fr>(), s);
-    launch_chunk_carries(chunk_vals.get<Fr>(), nchunks, sm + S_X1, carries.get<Fr>(), st, s);
-    launch_divide_numerator(src, sm + S_X1, carries.get<Fr>(), q.get<Fr>(), s);       // prover.rs:211-225
-    rt.extra_launches += 4;
+    rt.extra_launches += 1 + launch_divide_numerator(src, sm + S_X1, q.get<Fr>(), chunk_vals.get<Fr>(), st, s);   // prover.rs:211-225
     G1XYZZ* ac = acc.get<G1XYZZ>() + 2 * kMaxMsmWindows;
     MsmEngine::Shape sd = rt.msm.run(bases_d.get<G1Affine>(), q.get<Fr>(), local_count(src.len - 1), ac, s, {}, world, rank);  // prover.rs:229
     uint8_t* hs = static_cast<uint8_t*>(host_stage);

@@ -34,9 +34,9 @@ def main():
                               "gelem_per_s": n / d.value / 1e6, "algo_gb_per_s": 64 * n / d.value / 1e6,
                               "butterfly_muls_per_s": (n / 2) * lg / (d.value * 1e-3)}), flush=True)
     acc = C.c_double()
-    for lg in [int(x) for x in a.msm.split(",") if x]:
+    for lg in [float(x) for x in a.msm.split(",") if x]:
         for w in [int(x) for x in a.windows.split(",")]:
-            n = 1 << lg
+            n = int(round(2 ** lg))
             check(lib.pm_bench_msm(n, w, a.iters, C.byref(d), C.byref(acc)))
             print(json.dumps({"kernel": "msm_g1", "log_n": lg, "window": w, "ms": d.value, "ms_accumulate": acc.value,
                               "mpts_per_s": n / d.value / 1e3}), flush=True)
