@@ -76,6 +76,10 @@ int pm_msm_g1(const uint8_t* bases, size_t base_stride, const uint8_t* scalars, 
 int pm_msm_g1_window(const uint8_t* bases, size_t base_stride, const uint8_t* scalars, size_t n, int window_bits,
                      int heavy_threshold, uint8_t out[PM_G1_BYTES]);
 
+/* Same through `levels` precomputed multiples per base (built on the fly); test hook for the fixed-base tables. */
+int pm_msm_g1_levels(const uint8_t* bases, size_t base_stride, const uint8_t* scalars, size_t n, int window_bits,
+                     int levels, uint8_t out[PM_G1_BYTES]);
+
 /* out[i] = scalars[i] * G (G = the BLS12-381 G1 generator), canonical affine.
  * Replaces `generate()` (src/generator.rs:169-177). */
 int pm_fixed_base_mul(const uint8_t* scalars, size_t n, uint8_t* out);
@@ -224,6 +228,8 @@ int pm_bench_ntt(unsigned log_n, int inverse, int iters, double* ms_avg);
 /* Average milliseconds of `iters` n-point MSMs on resident synthetic bases/scalars (after one warm-up);
  * ms_accumulate (nullable) receives the average time of the bucket-accumulation kernel alone. */
 int pm_bench_msm(size_t n, int window_bits, int iters, double* ms_avg, double* ms_accumulate);
+/* Same with `levels` precomputed multiples 2^(c*l) P per base (fixed-base tables; 0/1 = none). */
+int pm_bench_msm_levels(size_t n, int window_bits, int levels, int iters, double* ms_avg, double* ms_accumulate);
 
 /* CUDA-event stopwatch on the library's stream: start records an event, stop records another,
  * synchronises it and returns the elapsed device-timeline milliseconds. */

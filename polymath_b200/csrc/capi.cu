@@ -117,28 +117,45 @@ int pm_ntt_fr(uint8_t* data, unsigned log_n, int inverse, const uint8_t* coset_g
     });
 }
 
+static int msm_host_call(const uint8_t* bases, size_t base_stride, const uint8_t* scalars, size_t n, int window_bits,
+                         int heavy_threshold, int levels, uint8_t out[PM_G1_BYTES]);
+
 int pm_msm_g1_window(const uint8_t* bases, size_t base_stride, const uint8_t* scalars, size_t n, int window_bits,
                      int heavy_threshold, uint8_t out[PM_G1_BYTES]) {
+    return msm_host_call(bases, base_stride, scalars, n, window_bits, heavy_threshold, 1, out);
+}
+int pm_msm_g1_levels(const uint8_t* bases, size_t base_stride, const uint8_t* scalars, size_t n, int window_bits,
+                     int levels, uint8_t out[PM_G1_BYTES]) {
+    return msm_host_call(bases, base_stride, scalars, n, window_bits, 0, levels, out);
+}
+
+static int msm_host_call(const uint8_t* bases, size_t base_stride, const uint8_t* scalars, size_t n, int window_bits,
+                         int heavy_threshold, int levels, uint8_t out[PM_G1_BYTES]) {
     return guarded([&] {
+        if (levels < 1) levels = 1;
+        if (levels > 1 && window_bits <= 0) throw StatusError(PM_ERR_ARG, "levels need an explicit window");
         if (!out || (n && (!bases || !scalars)) || base_stride < PM_G1_BYTES) throw StatusError(PM_ERR_ARG, "bad msm arguments");
         Runtime& rt = runtime();
         std::vector<uint8_t> packed;
         const uint8_t* src = bases;
         if (base_stride != PM_G1_BYTES) { pack_points_host(bases, base_stride, n, packed); src = packed.data(); }
         DevBuf db, ds, dres;
-        G1Affine* pb = db.as<G1Affine>(n ? n : 1);
+        G1Affine* pb = db.as<G1Affine>((n ? n : 1) * (size_t)levels);
         Fr* ps = ds.as<Fr>(n ? n : 1);
-        G1XYZZ* wins = dres.as<G1XYZZ>(kMaxMsmWindows);
+        G1XYZZ* wins = dres.as<G1XYZZ>(kMaxMsmSums);
         PM_CUDA(cudaMemcpyAsync(pb, src, n * sizeof(G1Affine), cudaMemcpyHostToDevice, rt.stream));
         PM_CUDA(cudaMemcpyAsync(ps, scalars, n * sizeof(Fr), cudaMemcpyHostToDevice, rt.stream));
+        launch_build_levels(pb, n, levels, n, window_bits, rt.stream);
         MsmConfig cfg;
         cfg.c = window_bits;
         cfg.heavy = heavy_threshold;
+        cfg.levels = levels;
+        cfg.level_stride = n;
         MsmEngine::Shape sh = rt.msm.run(pb, ps, n, wins, rt.stream, cfg);
-        std::vector<uint8_t> hw((size_t)sh.nwin * sizeof(G1XYZZ));
+        std::vector<uint8_t> hw((size_t)sh.count() * sizeof(G1XYZZ));
         PM_CUDA(cudaMemcpyAsync(hw.data(), wins, hw.size(), cudaMemcpyDeviceToHost, rt.stream));
         PM_CUDA(cudaStreamSynchronize(rt.stream));
-        host::xyzz_to_affine_wire(host::combine_windows(hw.data(), sh.nwin, sh.c), out);
+        host::xyzz_to_affine_wire(host::combine_levels(hw.data(), sh.nwin, sh.c, sh.nlev, sh.kbits), out);
     });
 }
 
@@ -234,18 +251,27 @@ int pm_bench_ntt(unsigned log_n, int inverse, int iters, double* ms_avg) {
 }
 
 int pm_bench_msm(size_t n, int window_bits, int iters, double* ms_avg, double* ms_accumulate) {
+    return pm_bench_msm_levels(n, window_bits, 1, iters, ms_avg, ms_accumulate);
+}
+
+int pm_bench_msm_levels(size_t n, int window_bits, int levels, int iters, double* ms_avg, double* ms_accumulate) {
     return guarded([&] {
+        if (levels < 1) levels = 1;
+        if (levels > 1 && window_bits <= 0) throw StatusError(PM_ERR_ARG, "levels need an explicit window");
         if (n == 0 || iters <= 0 || !ms_avg) throw StatusError(PM_ERR_ARG, "bad bench arguments");
         Runtime& rt = runtime();
         DevBuf db, ds, dres;
-        G1Affine* pb = db.as<G1Affine>(n);
+        G1Affine* pb = db.as<G1Affine>(n * (size_t)levels);
         Fr* ps = ds.as<Fr>(n);
-        G1XYZZ* acc = dres.as<G1XYZZ>(kMaxMsmWindows);
+        G1XYZZ* acc = dres.as<G1XYZZ>(kMaxMsmSums);
         launch_fill_fr(ps, n, 0xabcdef, rt.stream);
         rt.fixed_base.run(ps, n, pb, rt.stream);       // bases = [s_i]G for pseudo-random s_i
+        launch_build_levels(pb, n, levels, n, window_bits, rt.stream);
         launch_fill_fr(ps, n, 0x5eed, rt.stream);      // uniform scalars
         MsmConfig cfg;
         cfg.c = window_bits;
+        cfg.levels = levels;
+        cfg.level_stride = n;
         rt.msm.time_accumulate = true;
         rt.msm.run(pb, ps, n, acc, rt.stream, cfg);    // warm-up
         cudaEvent_t e0, e1;

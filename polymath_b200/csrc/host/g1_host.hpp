@@ -56,6 +56,21 @@ inline XyzzH combine_windows(const uint8_t* winsums, int nwin, int c) {
     return acc;
 }
 
+// sum_g 2^(c*g) * sum_j 2^(kbits*j) * sums[g*nlev + j]   (MsmEngine::Shape)
+inline XyzzH combine_levels(const uint8_t* sums, int nwin, int c, int nlev, int kbits) {
+    XyzzH acc = XyzzH::inf();
+    for (int g = nwin - 1; g >= 0; g--) {
+        for (int k = 0; k < c; k++) xyzz_dbl(acc);
+        XyzzH grp = XyzzH::inf();
+        for (int j = nlev - 1; j >= 0; j--) {
+            for (int k = 0; k < kbits; k++) xyzz_dbl(grp);
+            xyzz_add(grp, XyzzH::from_wire(sums + ((size_t)g * nlev + j) * 192));
+        }
+        xyzz_add(acc, grp);
+    }
+    return acc;
+}
+
 // canonical affine image as 96 wire bytes ((0,0) = infinity)
 inline void xyzz_to_affine_wire(const XyzzH& a, uint8_t out[96]) {
     if (a.is_inf()) { memset(out, 0, 96); return; }

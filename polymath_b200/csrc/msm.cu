@@ -11,8 +11,8 @@
 //      k_accumulate_heavy / k_heavy_finish (4096-entry chunks, one CTA each, then a per-bucket
 //                        sum of the chunk partials) so narrow top windows and skewed scalar
 //                        distributions (SURVEY.md §7 "hard parts") spread over the whole GPU
-//   5. k_reduce_segments running-sum over K-bucket segments + small scalar mul by the segment base
-//      k_reduce_windows  per-window tree sum of the segment partials
+//   5. k_reduce_level    hierarchical running sums over 16-bucket segments (see below), k_sum_slices
+//                        tree-sums each level: a handful of partial sums per bucket set
 //   6. host: Horner over the <= 32 window sums (c doublings each) and the affine normalisation
 //      (host/g1_host.hpp) — a serial chain of ~255 doublings that costs a GPU thread milliseconds
 // Points at infinity ((0,0)) and zero scalars are skipped in step 1/3.
@@ -25,7 +25,6 @@ namespace pm {
 namespace {
 
 constexpr int kMaxWindows = kMaxMsmWindows;
-constexpr int kSegBuckets = 16;     // buckets per reduce segment
 
 __device__ __forceinline__ uint32_t window_bits(const uint32_t* s, int pos, int c) {
     int limb = pos >> 5, off = pos & 31;
@@ -38,6 +37,7 @@ __device__ __forceinline__ uint32_t window_bits(const uint32_t* s, int pos, int 
 template <bool SCATTER>
 __global__ void __launch_bounds__(256) k_digits(const G1Affine* __restrict__ bases, const Fr* __restrict__ scalars,
                                                 size_t n, size_t sc_stride, size_t sc_offset, int c, int nwin, uint32_t nb,
+                                                int levels, uint32_t level_stride,
                                                 uint32_t* __restrict__ counters, uint32_t* __restrict__ sorted) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -63,10 +63,10 @@ __global__ void __launch_bounds__(256) k_digits(const G1Affine* __restrict__ bas
         uint32_t neg = 0;
         if (d > half) { d = (1u << c) - d; neg = 1; carry = 1; } else { carry = 0; }
         if (d == 0) continue;
-        uint32_t slot = (uint32_t)w * nb + (d - 1);
+        uint32_t slot = (uint32_t)(w / levels) * nb + (d - 1);
         if (SCATTER) {
             uint32_t pos = atomicAdd(&counters[slot], 1u);
-            sorted[pos] = (uint32_t)i | (neg << 31);
+            sorted[pos] = ((uint32_t)(w % levels) * level_stride + (uint32_t)i) | (neg << 31);
         } else {
             atomicAdd(&counters[slot], 1u);
         }
@@ -129,6 +129,36 @@ __device__ __forceinline__ G1Affine load_point(const G1Affine* __restrict__ base
     return p;
 }
 
+// ---- bucket order ---------------------------------------------------------------------------
+// Buckets are walked in order of decreasing length (counting sort on min(length, kLenBins-1)) so that the
+// 32 buckets of a warp have nearly equal lengths: removes the divergence of Poisson-distributed lengths.
+constexpr uint32_t kLenBins = 2048;
+__global__ void k_len_hist(const uint32_t* __restrict__ offsets, uint32_t total, uint32_t* __restrict__ hist) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    uint32_t len = offsets[t + 1] - offsets[t];
+    atomicAdd(&hist[kLenBins - 1 - min(len, kLenBins - 1)], 1u);   // bin 0 = longest
+}
+__global__ void __launch_bounds__(1024) k_len_scan(uint32_t* __restrict__ hist) {   // exclusive scan of kLenBins entries, in place
+    __shared__ uint32_t sh[kLenBins];
+    for (uint32_t i = threadIdx.x; i < kLenBins; i += blockDim.x) sh[i] = hist[i];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t run = 0;
+        for (uint32_t i = 0; i < kLenBins; i++) { uint32_t v = sh[i]; sh[i] = run; run += v; }
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < kLenBins; i += blockDim.x) hist[i] = sh[i];
+}
+__global__ void k_len_scatter(const uint32_t* __restrict__ offsets, uint32_t total, uint32_t* __restrict__ cursor,
+                              uint32_t* __restrict__ order) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    uint32_t len = offsets[t + 1] - offsets[t];
+    uint32_t pos = atomicAdd(&cursor[kLenBins - 1 - min(len, kLenBins - 1)], 1u);
+    order[pos] = t;
+}
+
 // ---- heavy buckets -------------------------------------------------------------------------
 // A bucket longer than `heavy_thr` is cut into chunks of kHeavyChunk sorted entries; every chunk
 // becomes a task for one CTA of k_accumulate_heavy, and k_heavy_finish adds the chunk partials of
@@ -157,10 +187,12 @@ __device__ __forceinline__ void defer_heavy(const HeavyLists& hl, uint32_t t, ui
 // PM_ACC_VARIANT = 3 -> <3, MulInline>, 24 (default) -> <4, MulCall>.
 template <int MINB, class M>
 __global__ void __launch_bounds__(128, MINB) k_accumulate(const G1Affine* __restrict__ bases, const uint32_t* __restrict__ sorted,
-                                                          const uint32_t* __restrict__ offsets, G1XYZZ* __restrict__ buckets,
+                                                          const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ order,
+                                                          G1XYZZ* __restrict__ buckets,
                                                           uint32_t total_buckets, uint32_t heavy_thr, HeavyLists hl) {
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= total_buckets) return;
+    uint32_t tix = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tix >= total_buckets) return;
+    const uint32_t t = order[tix];
     uint32_t beg = offsets[t], end = offsets[t + 1];
     if (end - beg > heavy_thr) {
         defer_heavy(hl, t, end - beg);
@@ -240,35 +272,44 @@ __global__ void __launch_bounds__(128) k_heavy_finish(G1XYZZ* __restrict__ bucke
     }
 }
 
-// Segment s of window w covers buckets [s*K, (s+1)*K); bucket b has weight b+1.
-// partial = sum_{b in seg} (b - lo + 1) * B[b] + lo * sum_{b in seg} B[b]
-__global__ void __launch_bounds__(128) k_reduce_segments(const G1XYZZ* __restrict__ buckets, uint32_t nb, uint32_t nseg,
-                                                         uint32_t total_segs, G1XYZZ* __restrict__ segs) {
+// ---- bucket reduction: sum_b (b + 1) * B_b per bucket set, hierarchically ---------------------
+// With b = hi*K + lo:  sum_b (b + off) X_b = sum_hi T_hi + K * sum_hi hi * R_hi,  where for segment hi
+// T_hi = sum_lo (lo + off) X_{hi,lo} and R_hi = sum_lo X_{hi,lo} (one running-sum pass, 2K additions).
+// The second term is the same problem on the K-times shorter array R with off = 0, so level j
+// contributes 2^(kbits*j) * sum(T_j); the plain sums of the T arrays are tree-reduced and the few
+// level sums are combined on the host (combine_levels).  No data-dependent scalar multiplications.
+constexpr int kRedBits = 4;
+constexpr uint32_t kRedK = 1u << kRedBits;
+
+// X: [ngroups][m];  T, R: [ngroups][mseg]
+template <bool FIRST>
+__global__ void __launch_bounds__(128) k_reduce_level(const G1XYZZ* __restrict__ X, uint32_t m, uint32_t mseg, uint32_t ngroups,
+                                                      G1XYZZ* __restrict__ T, G1XYZZ* __restrict__ R) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= total_segs) return;
-    uint32_t w = t / nseg, s = t % nseg;
-    uint32_t lo = s * kSegBuckets;
-    uint32_t hi = min(lo + kSegBuckets, nb);
-    const G1XYZZ* wb = buckets + (size_t)w * nb;
+    if (t >= mseg * ngroups) return;
+    uint32_t g = t / mseg, sgm = t % mseg;
+    uint32_t lo = sgm * kRedK;
+    uint32_t hi = min(lo + kRedK, m);
+    const G1XYZZ* xs = X + (size_t)g * m;
     G1XYZZ running = G1XYZZ::inf(), acc = G1XYZZ::inf();
     for (uint32_t b = hi; b-- > lo;) {
-        xyzz_add(running, wb[b]);
-        xyzz_add(acc, running);
+        xyzz_add(running, xs[b]);
+        if (FIRST || b > lo) xyzz_add(acc, running);
     }
-    if (lo != 0 && !running.is_inf()) {
-        G1XYZZ scaled = xyzz_mul_small(running, lo);
-        xyzz_add(acc, scaled);
-    }
-    segs[t] = acc;
+    T[t] = acc;
+    R[t] = running;
 }
 
-// One CTA per window: sum its nseg partials.
-__global__ void __launch_bounds__(128) k_reduce_windows(const G1XYZZ* __restrict__ segs, uint32_t nseg, G1XYZZ* __restrict__ winsums) {
+// out[g * out_per_group + s] = sum of in[g][s*slice .. (s+1)*slice)
+__global__ void __launch_bounds__(128) k_sum_slices(const G1XYZZ* __restrict__ in, uint32_t pitch, uint32_t count, uint32_t slice,
+                                                    uint32_t out_per_group, uint32_t out_stride, G1XYZZ* __restrict__ out) {
     __shared__ uint4 smem_raw[128 * sizeof(G1XYZZ) / sizeof(uint4)];
     G1XYZZ* sh = reinterpret_cast<G1XYZZ*>(smem_raw);
-    const G1XYZZ* ws = segs + (size_t)blockIdx.x * nseg;
+    const uint32_t g = blockIdx.x / out_per_group, sl = blockIdx.x % out_per_group;
+    const G1XYZZ* src = in + (size_t)g * pitch;
+    const uint32_t beg = sl * slice, end = min(beg + slice, count);
     G1XYZZ acc = G1XYZZ::inf();
-    for (uint32_t k = threadIdx.x; k < nseg; k += blockDim.x) xyzz_add(acc, ws[k]);
+    for (uint32_t k = beg + threadIdx.x; k < end; k += blockDim.x) xyzz_add(acc, src[k]);
     sh[threadIdx.x] = acc;
     __syncthreads();
     for (uint32_t stride = blockDim.x / 2; stride > 0; stride >>= 1) {
@@ -279,10 +320,38 @@ __global__ void __launch_bounds__(128) k_reduce_windows(const G1XYZZ* __restrict
         }
         __syncthreads();
     }
-    if (threadIdx.x == 0) winsums[blockIdx.x] = sh[0];
+    if (threadIdx.x == 0) out[(size_t)g * out_stride + sl] = sh[0];
+}
+
+// out[i] = 2^c * in[i] in XYZZ (levels table construction)
+__global__ void __launch_bounds__(128) k_level_up(const G1Affine* __restrict__ in, size_t count, int c, G1XYZZ* __restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    G1Affine p = in[i];
+    G1XYZZ acc = G1XYZZ::from_affine(p);
+    for (int k = 0; k < c; k++) xyzz_dbl(acc);
+    out[i] = acc;
 }
 
 }  // namespace
+
+void launch_batch_to_affine(const G1XYZZ* in, size_t n, G1Affine* out, cudaStream_t stream);   // fixed_base.cu
+
+void launch_build_levels(G1Affine* bases, size_t count, int levels, size_t stride, int c, cudaStream_t stream) {
+    if (levels <= 1 || count == 0) return;
+    const size_t chunk = (size_t)1 << 22;
+    DevBuf scratch;
+    G1XYZZ* tmp = scratch.as<G1XYZZ>(count < chunk ? count : chunk);
+    for (int l = 1; l < levels; l++) {
+        for (size_t lo = 0; lo < count; lo += chunk) {
+            size_t cnt = (count - lo) < chunk ? (count - lo) : chunk;
+            k_level_up<<<ceil_div(cnt, 128), 128, 0, stream>>>(bases + (size_t)(l - 1) * stride + lo, cnt, c, tmp);
+            PM_LAUNCH_CHECK();
+            launch_batch_to_affine(tmp, cnt, bases + (size_t)l * stride + lo, stream);
+        }
+    }
+    PM_CUDA(cudaStreamSynchronize(stream));   // scratch dies here
+}
 
 int MsmEngine::choose_window(size_t n) {
     // Empirical optimum on B200 (profiles/msm_window_sweep_r1.jsonl): the bucket-reduction tail grows
@@ -305,18 +374,32 @@ MsmEngine::Shape MsmEngine::run(const G1Affine* bases, const Fr* scalars, size_t
                                 MsmConfig cfg, size_t scalar_stride, size_t scalar_offset) {
     if (n == 0) {
         PM_CUDA(cudaMemsetAsync(winsums, 0, sizeof(G1XYZZ), stream));
-        return {1, 1};
+        return {1, 1, 1, 1};
     }
     if (n >= ((size_t)1 << 31)) throw CudaError("msm: n must be < 2^31");
     const int c = cfg.c ? cfg.c : choose_window(n);
     const int nwin = (256 + c - 1) / c;
     if (nwin > kMaxWindows) throw CudaError("msm: too many windows");
+    const int levels = cfg.levels > 1 ? cfg.levels : 1;
+    const int ngroups = (nwin + levels - 1) / levels;          // bucket sets
+    if (levels > 1 && ((size_t)levels * cfg.level_stride >= ((size_t)1 << 31) || cfg.level_stride < n))
+        throw CudaError("msm: bad precomputed-level layout");
     const uint32_t nb = 1u << (c - 1);
-    const uint32_t total = (uint32_t)nwin * nb;
-    const uint32_t nseg = (nb + kSegBuckets - 1) / kSegBuckets;
-    const uint32_t total_segs = nseg * (uint32_t)nwin;
-    size_t avg = (n + nb - 1) / nb;
-    uint32_t heavy_thr = cfg.heavy ? (uint32_t)cfg.heavy : (uint32_t)(avg * 8 > 512 ? avg * 8 : 512);
+    const uint32_t total = (uint32_t)ngroups * nb;
+    // hierarchical reduction geometry: level sizes nb, nb/K, ... down to one segment
+    uint32_t lev_m[16];
+    int nlev = 0;
+    for (uint32_t m = nb;; m = (m + kRedK - 1) / kRedK) {
+        lev_m[nlev++] = m;
+        if (m <= kRedK) break;
+    }
+    if (ngroups * nlev > kMaxMsmSums) throw CudaError("msm: too many partial sums");
+    size_t seg_total = 0;   // T and R arrays of all levels
+    for (int j = 0; j < nlev; j++) seg_total += (size_t)((lev_m[j] + kRedK - 1) / kRedK) * ngroups;
+    // A bucket is split only when walking it serially would approach the whole kernel's duration:
+    // buckets run longest-first, so a run up to 1/8192 of all entries still hides behind the rest.
+    size_t share = n * (size_t)nwin / 8192;
+    uint32_t heavy_thr = cfg.heavy ? (uint32_t)cfg.heavy : (uint32_t)(share > 512 ? share : 512);
     const size_t max_tasks = n * (size_t)nwin / kHeavyChunk + total + 16;
 
     uint32_t* counts = counts_.as<uint32_t>(total + 1);
@@ -324,7 +407,9 @@ MsmEngine::Shape MsmEngine::run(const G1Affine* bases, const Fr* scalars, size_t
     uint32_t* cursors = cursors_.as<uint32_t>(total + 1);
     uint32_t* sorted = sorted_.as<uint32_t>(n * (size_t)nwin);
     G1XYZZ* buckets = buckets_.as<G1XYZZ>(total);
-    G1XYZZ* segs = segs_.as<G1XYZZ>(total_segs);
+    G1XYZZ* segs = segs_.as<G1XYZZ>(2 * seg_total + (size_t)ngroups * 64 + 64);
+    uint32_t* order = order_.as<uint32_t>((size_t)total + kLenBins);
+    uint32_t* len_hist = order + total;
     HeavyLists hl;
     {
         // one allocation: [tasks uint2 | heavy uint4 | partials]
@@ -339,11 +424,16 @@ MsmEngine::Shape MsmEngine::run(const G1Affine* bases, const Fr* scalars, size_t
     PM_CUDA(cudaMemsetAsync(counts, 0, (total + 1) * sizeof(uint32_t), stream));
     PM_CUDA(cudaMemsetAsync(hl.counters, 0, 2 * sizeof(uint32_t), stream));
     const unsigned dgrid = ceil_div(n, 256);
-    k_digits<false><<<dgrid, 256, 0, stream>>>(bases, scalars, n, scalar_stride, scalar_offset, c, nwin, nb, counts, nullptr);
+    k_digits<false><<<dgrid, 256, 0, stream>>>(bases, scalars, n, scalar_stride, scalar_offset, c, nwin, nb, levels, (uint32_t)cfg.level_stride, counts, nullptr);
     PM_LAUNCH_CHECK();
     k_scan<<<1, 1024, 0, stream>>>(counts, total, offsets, cursors);
     PM_LAUNCH_CHECK();
-    k_digits<true><<<dgrid, 256, 0, stream>>>(bases, scalars, n, scalar_stride, scalar_offset, c, nwin, nb, cursors, sorted);
+    k_digits<true><<<dgrid, 256, 0, stream>>>(bases, scalars, n, scalar_stride, scalar_offset, c, nwin, nb, levels, (uint32_t)cfg.level_stride, cursors, sorted);
+    PM_LAUNCH_CHECK();
+    PM_CUDA(cudaMemsetAsync(len_hist, 0, kLenBins * sizeof(uint32_t), stream));
+    k_len_hist<<<ceil_div(total, 256), 256, 0, stream>>>(offsets, total, len_hist);
+    k_len_scan<<<1, 1024, 0, stream>>>(len_hist);
+    k_len_scatter<<<ceil_div(total, 256), 256, 0, stream>>>(offsets, total, len_hist, order);
     PM_LAUNCH_CHECK();
     if (time_accumulate) {
         if (!ev_acc_begin) { PM_CUDA(cudaEventCreate(&ev_acc_begin)); PM_CUDA(cudaEventCreate(&ev_acc_end)); }
@@ -356,8 +446,8 @@ MsmEngine::Shape MsmEngine::run(const G1Affine* bases, const Fr* scalars, size_t
             variant = v ? atoi(v) : 24;
         }
         const unsigned g = ceil_div(total, 128);
-        if (variant == 3) k_accumulate<3, MulInline><<<g, 128, 0, stream>>>(bases, sorted, offsets, buckets, total, heavy_thr, hl);
-        else k_accumulate<4, MulCall><<<g, 128, 0, stream>>>(bases, sorted, offsets, buckets, total, heavy_thr, hl);
+        if (variant == 3) k_accumulate<3, MulInline><<<g, 128, 0, stream>>>(bases, sorted, offsets, order, buckets, total, heavy_thr, hl);
+        else k_accumulate<4, MulCall><<<g, 128, 0, stream>>>(bases, sorted, offsets, order, buckets, total, heavy_thr, hl);
         PM_LAUNCH_CHECK();
     }
     if (time_accumulate) PM_CUDA(cudaEventRecord(ev_acc_end, stream));
@@ -373,12 +463,36 @@ MsmEngine::Shape MsmEngine::run(const G1Affine* bases, const Fr* scalars, size_t
         k_heavy_finish<<<2 * sm_count(), 128, 0, stream>>>(buckets, hl);
         PM_LAUNCH_CHECK();
     }
-    k_reduce_segments<<<ceil_div(total_segs, 128), 128, 0, stream>>>(buckets, nb, nseg, total_segs, segs);
-    PM_LAUNCH_CHECK();
-    k_reduce_windows<<<nwin, 128, 0, stream>>>(segs, nseg, winsums);
-    PM_LAUNCH_CHECK();
-    launches += 8;
-    return {c, nwin};
+    {
+        const G1XYZZ* X = buckets;
+        G1XYZZ* cursor = segs;
+        G1XYZZ* scratch = segs + 2 * seg_total;     // [ngroups][64] slice partials
+        for (int j = 0; j < nlev; j++) {
+            const uint32_t m = lev_m[j], mseg = (m + kRedK - 1) / kRedK;
+            G1XYZZ* T = cursor;
+            G1XYZZ* R = cursor + (size_t)mseg * ngroups;
+            cursor = R + (size_t)mseg * ngroups;
+            const unsigned grid = ceil_div((size_t)mseg * ngroups, 128);
+            if (j == 0) k_reduce_level<true><<<grid, 128, 0, stream>>>(X, m, mseg, ngroups, T, R);
+            else k_reduce_level<false><<<grid, 128, 0, stream>>>(X, m, mseg, ngroups, T, R);
+            PM_LAUNCH_CHECK();
+            launches++;
+            // level sum: winsums[g*nlev + j] = sum_seg T[g][seg]
+            if (mseg > 4096) {
+                const uint32_t slice = (mseg + 63) / 64, nsl = (mseg + slice - 1) / slice;
+                k_sum_slices<<<ngroups * nsl, 128, 0, stream>>>(T, mseg, mseg, slice, nsl, 64, scratch);
+                k_sum_slices<<<ngroups, 128, 0, stream>>>(scratch, 64, nsl, nsl, 1, nlev, winsums + j);
+                launches += 2;
+            } else {
+                k_sum_slices<<<ngroups, 128, 0, stream>>>(T, mseg, mseg, mseg, 1, nlev, winsums + j);
+                launches++;
+            }
+            PM_LAUNCH_CHECK();
+            X = R;
+        }
+    }
+    launches += 9;
+    return {c * levels, ngroups, nlev, kRedBits};
 }
 
 }  // namespace pm

@@ -8,18 +8,25 @@ namespace pm {
 struct MsmConfig {
     int c = 0;          // window bits (0 = choose from n)
     int heavy = 0;      // heavy-bucket threshold (0 = auto)
+    // Precomputed levels (fixed bases): the base array is [levels][level_stride] with
+    // level l holding 2^(c*l) * P_i.  Window w = g*levels + l then uses level l and the bucket set of
+    // group g, so `levels` windows share one bucket set and the final Horner only spans the groups.
+    int levels = 1;
+    size_t level_stride = 0;
 };
 
 // Reusable workspace + launch sequence.  One engine per context / stream.
 class MsmEngine {
 public:
     // Enqueues sum_{i<n} scalars[i*scalar_stride + scalar_offset] * bases[i] up to the per-window sums:
-    // on completion winsums_out[w] (device, >= kMaxMsmWindows entries) holds W_w and the result is
-    // sum_w 2^(c*w) * W_w, finished on the host (host/g1_host.hpp: combine_windows).
+    // on completion winsums_out (device, >= kMaxMsmSums entries) holds the partial sums described by Shape.
     //  bases   : device, 96-byte affine points, Montgomery limbs, (0,0) = infinity
     //  scalars : device, Fr in Montgomery form (arkworks in-memory form)
     // All work is enqueued on `stream`; nothing is synchronised.
-    struct Shape { int c; int nwin; };
+    // Result layout: winsums_out[g * nlev + j] = S_{g,j};  result = sum_g 2^(c*g) * sum_j 2^(kbits*j) * S_{g,j}
+    // (g < nwin bucket sets, j < nlev levels of the hierarchical bucket reduction; c already includes the
+    // precomputed-levels factor).  Finished on the host: host/g1_host.hpp combine_levels().
+    struct Shape { int c; int nwin; int nlev; int kbits; int count() const { return nwin * nlev; } };
     Shape run(const G1Affine* bases, const Fr* scalars, size_t n, G1XYZZ* winsums_out, cudaStream_t stream,
               MsmConfig cfg = {}, size_t scalar_stride = 1, size_t scalar_offset = 0);
     static int choose_window(size_t n);
@@ -30,9 +37,13 @@ public:
     ~MsmEngine();
 
 private:
-    DevBuf counts_, offsets_, cursors_, sorted_, buckets_, segs_, heavy_list_, heavy_count_;
+    DevBuf counts_, offsets_, cursors_, sorted_, buckets_, segs_, heavy_list_, heavy_count_, order_;
 };
 
 constexpr int kMaxMsmWindows = 64;
+constexpr int kMaxMsmSums = 512;   // capacity (XYZZ records) of a winsums_out buffer: bucket sets x reduction levels
+
+// Fill levels 1..levels-1 of a [levels][stride] base array from level 0: level l = 2^c * level (l-1).
+void launch_build_levels(G1Affine* bases, size_t count, int levels, size_t stride, int c, cudaStream_t stream);
 
 }  // namespace pm

@@ -10,6 +10,7 @@
 #include "prover.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "host/g1_host.hpp"
 #include "msm.cuh"
@@ -27,7 +28,7 @@ __global__ void k_phase3_consts(Fr* small) {
     small[S_EVAL] = small[S_A_AT_X1] + small[S_X2] * small[S_C_AT_X1];
 }
 
-constexpr size_t kStageWin = (size_t)kMaxMsmWindows * sizeof(G1XYZZ);   // one MSM's window sums
+constexpr size_t kStageWin = (size_t)kMaxMsmSums * sizeof(G1XYZZ);   // one MSM's partial sums
 constexpr size_t kStageBytes = 3 * kStageWin + 256;
 constexpr size_t kStageStatus = 3 * kStageWin;
 
@@ -94,6 +95,43 @@ void ProverCtx::upload_matrix(DevMatrix& dst, const uint64_t* row_ptr, const uin
     PM_CUDA(cudaStreamSynchronize(rt.stream));  // host vectors die here
 }
 
+static ProverCtx::MsmPlan plan_for(uint64_t count) {
+    ProverCtx::MsmPlan p;
+    p.stride = count ? count : 1;
+    const char* env = getenv("PM_MSM_PRECOMP");
+    const bool enabled = !(env && atoi(env) == 0);
+    const char* envmin = getenv("PM_MSM_PRECOMP_MIN");             // test hook: minimum size that gets tables
+    const uint64_t min_count = envmin ? (uint64_t)atoll(envmin) : ((uint64_t)1 << 20);
+    if (!enabled || count < min_count) return p;                   // small MSMs: plain windows (c chosen per call)
+    p.c = count >= 6000000 ? 22 : 20;
+    if (env && atoi(env) >= 8) p.c = atoi(env);                // tuning hook: PM_MSM_PRECOMP=<window bits>
+    const int nwin = (256 + p.c - 1) / p.c;
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) free_b = 0;
+    // keep the tables of one array under a third of what is free; fall back to fewer shared levels
+    for (int div = 1; div <= nwin; div++) {
+        int lv = (nwin + div - 1) / div;
+        if ((double)lv * (double)p.stride * sizeof(G1Affine) <= 0.33 * (double)free_b &&
+            (uint64_t)lv * p.stride < ((uint64_t)1 << 31)) {
+            p.levels = lv;
+            break;
+        }
+    }
+    if (p.levels <= 1) { p.levels = 1; p.c = 0; }
+    return p;
+}
+
+void ProverCtx::plan_tables() {
+    plan_c = plan_for(local_count(len_c()));
+    plan_d = plan_for(local_count(len_d()));
+}
+
+void ProverCtx::build_tables() {
+    Runtime& rt = runtime();
+    launch_build_levels(bases_c.get<G1Affine>(), local_count(len_c()), plan_c.levels, plan_c.stride, plan_c.c, rt.stream);
+    launch_build_levels(bases_d.get<G1Affine>(), local_count(len_d()), plan_d.levels, plan_d.stride, plan_d.c, rt.stream);
+}
+
 void ProverCtx::allocate_work() {
     log_n = log2_exact(n);
     if (sigma != n + 3) throw StatusError(PM_ERR_ARG, "sigma != n + 3 (generator.rs:70)");
@@ -109,7 +147,7 @@ void ProverCtx::allocate_work() {
     chunk_vals.as<Fr>(2 * (nchunks + 1) + 2 * (nchunks / kChunk + 2) + 8);
     small.as<Fr>(S_COUNT);
     status.as<uint32_t>(4);
-    acc.as<G1XYZZ>(3 * kMaxMsmWindows);
+    acc.as<G1XYZZ>(3 * kMaxMsmSums);
     PM_CUDA(cudaMallocHost(&host_stage, kStageBytes));
     PM_CUDA(cudaEventCreate(&ev0));
     PM_CUDA(cudaEventCreate(&ev1));
@@ -163,10 +201,10 @@ void ProverCtx::phase1_partial(const uint8_t* ra, uint8_t* partials_out) {
     const G1Affine* bc = bases_c.get<G1Affine>();
     // compute_a_g1 (prover.rs:330-338) and c_g1 (prover.rs:116-123) over this rank's share of the bases
     MsmEngine::Shape sa = rt.msm.run(bc, scal_a.get<Fr>(), local_count(n + 4), ac, s, {}, world, rank);
-    MsmEngine::Shape sc = rt.msm.run(bc, scal_c.get<Fr>(), local_count(len_c()), ac + kMaxMsmWindows, s, {}, world, rank);
+    MsmEngine::Shape sc = rt.msm.run(bc, scal_c.get<Fr>(), local_count(len_c()), ac + kMaxMsmSums, s, cfg_c(), world, rank);
     uint8_t* hs = static_cast<uint8_t*>(host_stage);
-    PM_CUDA(cudaMemcpyAsync(hs, ac, sa.nwin * sizeof(G1XYZZ), cudaMemcpyDeviceToHost, s));
-    PM_CUDA(cudaMemcpyAsync(hs + kStageWin, ac + kMaxMsmWindows, sc.nwin * sizeof(G1XYZZ), cudaMemcpyDeviceToHost, s));
+    PM_CUDA(cudaMemcpyAsync(hs, ac, sa.count() * sizeof(G1XYZZ), cudaMemcpyDeviceToHost, s));
+    PM_CUDA(cudaMemcpyAsync(hs + kStageWin, ac + kMaxMsmSums, sc.count() * sizeof(G1XYZZ), cudaMemcpyDeviceToHost, s));
     PM_CUDA(cudaMemcpyAsync(hs + kStageStatus, st, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     PM_CUDA(cudaEventRecord(ev1, s));
     PM_CUDA(cudaStreamSynchronize(s));
@@ -176,8 +214,8 @@ void ProverCtx::phase1_partial(const uint8_t* ra, uint8_t* partials_out) {
     uint32_t stv;
     memcpy(&stv, hs + kStageStatus, 4);
     check_status(stv);
-    host::combine_windows(hs, sa.nwin, sa.c).to_wire(partials_out);
-    host::combine_windows(hs + kStageWin, sc.nwin, sc.c).to_wire(partials_out + sizeof(G1XYZZ));
+    host::combine_levels(hs, sa.nwin, sa.c, sa.nlev, sa.kbits).to_wire(partials_out);
+    host::combine_levels(hs + kStageWin, sc.nwin, sc.c, sc.nlev, sc.kbits).to_wire(partials_out + sizeof(G1XYZZ));
     phase = 10;   // partial done, waiting for finish
 }
 
@@ -243,10 +281,10 @@ void ProverCtx::phase3_partial(const uint8_t* x2, const uint8_t* c_at_x1, uint8_
     PM_LAUNCH_CHECK();
     NumeratorSrc src = numerator_src();
     rt.extra_launches += 1 + launch_divide_numerator(src, sm + S_X1, q.get<Fr>(), chunk_vals.get<Fr>(), st, s);   // prover.rs:211-225
-    G1XYZZ* ac = acc.get<G1XYZZ>() + 2 * kMaxMsmWindows;
-    MsmEngine::Shape sd = rt.msm.run(bases_d.get<G1Affine>(), q.get<Fr>(), local_count(src.len - 1), ac, s, {}, world, rank);  // prover.rs:229
+    G1XYZZ* ac = acc.get<G1XYZZ>() + 2 * kMaxMsmSums;
+    MsmEngine::Shape sd = rt.msm.run(bases_d.get<G1Affine>(), q.get<Fr>(), local_count(src.len - 1), ac, s, cfg_d(), world, rank);  // prover.rs:229
     uint8_t* hs = static_cast<uint8_t*>(host_stage);
-    PM_CUDA(cudaMemcpyAsync(hs, ac, sd.nwin * sizeof(G1XYZZ), cudaMemcpyDeviceToHost, s));
+    PM_CUDA(cudaMemcpyAsync(hs, ac, sd.count() * sizeof(G1XYZZ), cudaMemcpyDeviceToHost, s));
     PM_CUDA(cudaMemcpyAsync(hs + kStageStatus, st, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     PM_CUDA(cudaEventRecord(ev1, s));
     PM_CUDA(cudaStreamSynchronize(s));
@@ -256,7 +294,7 @@ void ProverCtx::phase3_partial(const uint8_t* x2, const uint8_t* c_at_x1, uint8_
     uint32_t stv;
     memcpy(&stv, hs + kStageStatus, 4);
     check_status(stv);
-    host::combine_windows(hs, sd.nwin, sd.c).to_wire(partial_out);
+    host::combine_levels(hs, sd.nwin, sd.c, sd.nlev, sd.kbits).to_wire(partial_out);
     phase = 30;
 }
 
@@ -352,8 +390,9 @@ int pm_ctx_create_sharded(const pm_pk_view* pk, int rank, int world, pm_ctx** ou
         c.upload_matrix(c.A, pk->r1cs.a_row_ptr, pk->r1cs.a_col, pk->r1cs.a_val, false);
         c.upload_matrix(c.B, pk->r1cs.b_row_ptr, pk->r1cs.b_col, pk->r1cs.b_val, false);
         c.upload_matrix(c.C, pk->r1cs.c_row_ptr, pk->r1cs.c_col, pk->r1cs.c_val, false);
-        G1Affine* bc = c.bases_c.as<G1Affine>(c.local_count(c.len_c()) + 1);
-        G1Affine* bd = c.bases_d.as<G1Affine>(c.local_count(c.len_d()) + 1);
+        c.plan_tables();
+        G1Affine* bc = c.bases_c.as<G1Affine>(c.plan_c.levels * c.plan_c.stride);
+        G1Affine* bd = c.bases_d.as<G1Affine>(c.plan_d.levels * c.plan_d.stride);
         const size_t st = pk->point_stride;
         const uint64_t n = c.n;
         upload_points(c, bc, 0, pk->x_powers_g1, st, pk->x_powers_g1_len, n + 1, "x_powers_g1");
@@ -362,6 +401,7 @@ int pm_ctx_create_sharded(const pm_pk_view* pk, int rank, int world, pm_ctx** ou
         upload_points(c, bc, n + 6, pk->x_powers_zh_by_y_alpha_g1, st, pk->x_powers_zh_by_y_alpha_g1_len, n - 1, "x_powers_zh_by_y_alpha_g1");
         upload_points(c, bc, n + 6 + (n - 1), pk->uj_wj_lcs_by_y_alpha_g1, st, pk->uj_wj_lcs_by_y_alpha_g1_len, c.cols - c.m0, "uj_wj_lcs_by_y_alpha_g1");
         upload_points(c, bd, 0, pk->x_powers_y_gamma_z_g1, st, pk->x_powers_y_gamma_z_g1_len, c.len_d(), "x_powers_y_gamma_z_g1");
+        c.build_tables();
         *out = h.release();
     });
 }
@@ -404,9 +444,11 @@ int pm_setup_sharded(const pm_r1cs_view* r1cs, const uint8_t x[PM_FR_BYTES], con
         c.upload_matrix(c.A, r1cs->a_row_ptr, r1cs->a_col, r1cs->a_val, true);
         c.upload_matrix(c.B, r1cs->b_row_ptr, r1cs->b_col, r1cs->b_val, true);
         c.upload_matrix(c.C, r1cs->c_row_ptr, r1cs->c_col, r1cs->c_val, true);
-        c.bases_c.as<G1Affine>(c.local_count(c.len_c()) + 1);
-        c.bases_d.as<G1Affine>(c.local_count(c.len_d()) + 1);
+        c.plan_tables();
+        c.bases_c.as<G1Affine>(c.plan_c.levels * c.plan_c.stride);
+        c.bases_d.as<G1Affine>(c.plan_d.levels * c.plan_d.stride);
         run_setup(c, x, z, x_g2, z_g2);
+        c.build_tables();
         *out = h.release();
     });
 }

@@ -3,6 +3,7 @@
 #include <vector>
 #include "common.cuh"
 #include "ec.cuh"
+#include "msm.cuh"
 #include "poly_kernels.cuh"
 #include "runtime.cuh"
 
@@ -24,6 +25,14 @@ struct ProverCtx {
     // arrays; the polynomial work is replicated.  world == 1: the whole key.
     int rank = 0, world = 1;
     uint64_t local_count(uint64_t total) const { return total > (uint64_t)rank ? (total - rank + world - 1) / world : 0; }
+    // Fixed-base tables for the big MSMs: each base array is [levels][stride] with level l = 2^(c*l) * P
+    // (msm.cuh MsmConfig); levels == 1 means no precomputation.  Chosen from the size and free memory.
+    struct MsmPlan { int c = 0; int levels = 1; size_t stride = 1; };
+    MsmPlan plan_c, plan_d;
+    void plan_tables();    // before the base arrays are allocated
+    void build_tables();   // after level 0 of both arrays is filled
+    MsmConfig cfg_c() const { MsmConfig m; m.c = plan_c.c; m.levels = plan_c.levels; m.level_stride = plan_c.stride; return m; }
+    MsmConfig cfg_d() const { MsmConfig m; m.c = plan_d.c; m.levels = plan_d.levels; m.level_stride = plan_d.stride; return m; }
     // key
     DevMatrix A, B, C;
     DevBuf bases_c;   // [x_powers (n+1) | x_powers_y_alpha (3) | x_powers_y_gamma (2) | zh (n-1) | lcs (cols-m0)]

@@ -46,9 +46,13 @@ def ntt_fr(values, inverse=False, coset_gen=None):
     return codec.frs_from_wire(buf.raw)
 
 
-def msm_g1(bases, scalars, window_bits=0, heavy_threshold=0, stride=96):
+def msm_g1(bases, scalars, window_bits=0, heavy_threshold=0, stride=96, levels=1):
     lib = require_device()
     n = min(len(bases), len(scalars))
+    if levels > 1:
+        out = C.create_string_buffer(96)
+        check(lib.pm_msm_g1_levels(codec.g1s_to_wire(bases[:n]), 96, codec.frs_to_wire(scalars[:n]), n, window_bits, levels, out))
+        return codec.g1_from_wire(out.raw)
     if stride == 96:
         wb = codec.g1s_to_wire(bases[:n])
     else:

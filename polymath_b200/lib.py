@@ -40,6 +40,8 @@ def load():
     lib.pm_msm_g1.restype = C.c_int
     lib.pm_msm_g1_window.argtypes = [u8p, sz, u8p, sz, C.c_int, C.c_int, u8p]
     lib.pm_msm_g1_window.restype = C.c_int
+    lib.pm_msm_g1_levels.argtypes = [u8p, sz, u8p, sz, C.c_int, C.c_int, u8p]
+    lib.pm_msm_g1_levels.restype = C.c_int
     lib.pm_fixed_base_mul.argtypes = [u8p, sz, u8p]
     lib.pm_fixed_base_mul.restype = C.c_int
     dp = C.POINTER(C.c_double)
@@ -47,6 +49,8 @@ def load():
     lib.pm_bench_field_mul.argtypes = [C.c_int, dp]
     lib.pm_bench_ntt.argtypes = [C.c_uint, C.c_int, C.c_int, dp]
     lib.pm_bench_msm.argtypes = [sz, C.c_int, C.c_int, dp, dp]
+    lib.pm_bench_msm_levels.argtypes = [sz, C.c_int, C.c_int, C.c_int, dp, dp]
+    lib.pm_bench_msm_levels.restype = C.c_int
     for name in ("pm_bench_imad_peak", "pm_bench_field_mul", "pm_bench_ntt", "pm_bench_msm"):
         getattr(lib, name).restype = C.c_int
     _lib = lib

@@ -100,6 +100,20 @@ def test_msm_matches_oracle(pmlib, n, c):
         assert want == poly.msm_naive(scalars, bases)
 
 
+@pytest.mark.parametrize("c,levels", [(10, 2), (10, 5), (10, 26), (13, 20), (16, 16), (7, 3)])
+def test_msm_precomputed_levels(pmlib, c, levels):
+    """Fixed-base tables: window w = g*levels + l reads 2^(c*l) P and shares group g's buckets."""
+    from polymath_b200 import kernels
+    rnd = random.Random(c * 100 + levels)
+    n = 700
+    bases = _bases(n, rnd)
+    bases[5] = None
+    scalars = [rnd.randrange(R_MOD) for _ in range(n)]
+    scalars[7] = 0
+    scalars[8] = R_MOD - 1
+    assert kernels.msm_g1(bases, scalars, window_bits=c, levels=levels) == poly.msm_pippenger(scalars, bases)
+
+
 def test_msm_edge_cases(pmlib):
     """Infinity bases, zero scalars, repeated points, +/- pairs, skewed scalars, heavy buckets, 104-byte stride."""
     from polymath_b200 import kernels

@@ -153,3 +153,21 @@ def test_setup_g2_and_trapdoor_api(pmlib):
     assert xg2 == curve.g2_mul(curve.G2_GEN, x)
     assert zg2 == curve.g2_mul(curve.G2_GEN, z)
     pk.close()
+
+
+@pytest.mark.parametrize("c", [8, 13])
+def test_fixed_base_tables_path(pmlib, c, monkeypatch):
+    """The precomputed-level MSM configuration the large circuits use (forced on a small one)."""
+    monkeypatch.setenv("PM_MSM_PRECOMP_MIN", "1")
+    monkeypatch.setenv("PM_MSM_PRECOMP", str(c))
+    consts = []
+
+    def mk_setup(rng):
+        consts[:] = [o_fr_rand(rng) for _ in range(20)]
+        return orc.MiMCDemo(None, None, consts), 20
+
+    def mk_prove(rng):
+        xl, xr = o_fr_rand(rng), o_fr_rand(rng)
+        return orc.MiMCDemo(xl, xr, consts), 2, [orc.mimc_hash(xl, xr, consts)]
+
+    _run_flow(mk_setup, mk_prove, seed=31 + c, proofs=2)

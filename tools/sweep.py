@@ -16,6 +16,7 @@ def main():
     ap.add_argument("--msm", default="16,18,20,22")
     ap.add_argument("--windows", default="0")
     ap.add_argument("--iters", type=int, default=3)
+    ap.add_argument("--levels", default="1", help="comma list; 0 = as many levels as windows")
     a = ap.parse_args()
     lib = require_device()
     d = C.c_double()
@@ -37,9 +38,14 @@ def main():
     for lg in [float(x) for x in a.msm.split(",") if x]:
         for w in [int(x) for x in a.windows.split(",")]:
             n = int(round(2 ** lg))
-            check(lib.pm_bench_msm(n, w, a.iters, C.byref(d), C.byref(acc)))
-            print(json.dumps({"kernel": "msm_g1", "log_n": lg, "window": w, "ms": d.value, "ms_accumulate": acc.value,
-                              "mpts_per_s": n / d.value / 1e3}), flush=True)
+            for lv in [int(x) for x in a.levels.split(",")]:
+                if lv == 0:
+                    lv = (256 + w - 1) // w
+                if lv > 1 and w == 0:
+                    continue
+                check(lib.pm_bench_msm_levels(n, w, lv, a.iters, C.byref(d), C.byref(acc)))
+                print(json.dumps({"kernel": "msm_g1", "log_n": lg, "window": w, "levels": lv, "ms": d.value,
+                                  "ms_accumulate": acc.value, "mpts_per_s": n / d.value / 1e3}), flush=True)
 
 
 if __name__ == "__main__":
