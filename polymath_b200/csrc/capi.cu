@@ -155,7 +155,7 @@ static int msm_host_call(const uint8_t* bases, size_t base_stride, const uint8_t
         std::vector<uint8_t> hw((size_t)sh.count() * sizeof(G1XYZZ));
         PM_CUDA(cudaMemcpyAsync(hw.data(), wins, hw.size(), cudaMemcpyDeviceToHost, rt.stream));
         PM_CUDA(cudaStreamSynchronize(rt.stream));
-        host::xyzz_to_affine_wire(host::combine_levels(hw.data(), sh.nwin, sh.c, sh.nlev, sh.kbits), out);
+        host::xyzz_to_affine_wire(host::combine_shifted(hw.data(), sh.nwin, sh.c, sh.nsum, sh.shift), out);
     });
 }
 

@@ -56,15 +56,18 @@ inline XyzzH combine_windows(const uint8_t* winsums, int nwin, int c) {
     return acc;
 }
 
-// sum_g 2^(c*g) * sum_j 2^(kbits*j) * sums[g*nlev + j]   (MsmEngine::Shape)
-inline XyzzH combine_levels(const uint8_t* sums, int nwin, int c, int nlev, int kbits) {
+// sum_g 2^(c*g) * sum_s 2^(shift[s]) * sums[g*nsum + s]   (MsmEngine::Shape)
+inline XyzzH combine_shifted(const uint8_t* sums, int nwin, int c, int nsum, const uint8_t* shift) {
+    int max_shift = 0;
+    for (int s = 0; s < nsum; s++) if (shift[s] > max_shift) max_shift = shift[s];
     XyzzH acc = XyzzH::inf();
     for (int g = nwin - 1; g >= 0; g--) {
         for (int k = 0; k < c; k++) xyzz_dbl(acc);
         XyzzH grp = XyzzH::inf();
-        for (int j = nlev - 1; j >= 0; j--) {
-            for (int k = 0; k < kbits; k++) xyzz_dbl(grp);
-            xyzz_add(grp, XyzzH::from_wire(sums + ((size_t)g * nlev + j) * 192));
+        for (int sh = max_shift; sh >= 0; sh--) {
+            xyzz_dbl(grp);
+            for (int s = 0; s < nsum; s++)
+                if (shift[s] == sh) xyzz_add(grp, XyzzH::from_wire(sums + ((size_t)g * nsum + s) * 192));
         }
         xyzz_add(acc, grp);
     }

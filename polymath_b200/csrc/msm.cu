@@ -73,53 +73,6 @@ __global__ void __launch_bounds__(256) k_digits(const G1Affine* __restrict__ bas
     }
 }
 
-// Single-CTA exclusive scan of `total` counters; writes offsets[0..total] and a copy into cursors[0..total).
-__global__ void __launch_bounds__(1024) k_scan(const uint32_t* __restrict__ counts, uint32_t total,
-                                               uint32_t* __restrict__ offsets, uint32_t* __restrict__ cursors) {
-    __shared__ uint32_t warp_sums[32];
-    __shared__ uint32_t carry_s;
-    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (tid == 0) carry_s = 0;
-    __syncthreads();
-    // process in tiles of 1024*4 for coalesced access
-    for (uint32_t base = 0; base < total; base += 4096) {
-        uint32_t idx = base + tid * 4;
-        uint32_t v[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) v[k] = (idx + k < total) ? counts[idx + k] : 0;
-        uint32_t local = v[0] + v[1] + v[2] + v[3];
-        uint32_t incl = local;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += t;
-        }
-        if (lane == 31) warp_sums[wid] = incl;
-        __syncthreads();
-        if (wid == 0) {
-            uint32_t ws = warp_sums[lane];
-            uint32_t wi = ws;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                uint32_t t = __shfl_up_sync(0xffffffffu, wi, d);
-                if (lane >= d) wi += t;
-            }
-            warp_sums[lane] = wi - ws;  // exclusive
-        }
-        __syncthreads();
-        uint32_t excl = carry_s + warp_sums[wid] + incl - local;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            if (idx + k < total) { offsets[idx + k] = excl; cursors[idx + k] = excl; }
-            excl += v[k];
-        }
-        __syncthreads();
-        if (tid == 1023) carry_s = excl;
-        __syncthreads();
-    }
-    if (tid == 0) offsets[total] = carry_s;
-}
-
 __device__ __forceinline__ G1Affine load_point(const G1Affine* __restrict__ bases, uint32_t idx) {
     G1Affine p;
     const uint4* src = reinterpret_cast<const uint4*>(bases + idx);
@@ -323,6 +276,119 @@ __global__ void __launch_bounds__(128) k_sum_slices(const G1XYZZ* __restrict__ i
     if (threadIdx.x == 0) out[(size_t)g * out_stride + sl] = sh[0];
 }
 
+// Top of the reduction (arrays of <= kTopMax elements): sum_i (i + off) X_i = [off] * sum_i X_i +
+// sum_bit 2^bit * sum_{i : bit set} X_i.  One CTA per (bucket set, masked sum); the masked sums go to the host.
+constexpr uint32_t kTopMax = 8192;
+__global__ void __launch_bounds__(256) k_reduce_top(const G1XYZZ* __restrict__ X, uint32_t m, uint32_t nsums, int with_ones,
+                                                    uint32_t out_stride, G1XYZZ* __restrict__ out) {
+    __shared__ uint4 smem_raw[256 * sizeof(G1XYZZ) / sizeof(uint4)];
+    G1XYZZ* sh = reinterpret_cast<G1XYZZ*>(smem_raw);
+    const uint32_t g = blockIdx.x / nsums, s = blockIdx.x % nsums;
+    const G1XYZZ* xs = X + (size_t)g * m;
+    const bool all = with_ones && s == 0;
+    const uint32_t bit = s - (with_ones ? 1u : 0u);
+    G1XYZZ acc = G1XYZZ::inf();
+    for (uint32_t i = threadIdx.x; i < m; i += blockDim.x)
+        if (all || ((i >> bit) & 1u)) xyzz_add(acc, xs[i]);
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (uint32_t stride = blockDim.x / 2; stride > 0; stride >>= 1) {
+        if (threadIdx.x < stride) {
+            G1XYZZ a = sh[threadIdx.x];
+            xyzz_add(a, sh[threadIdx.x + stride]);
+            sh[threadIdx.x] = a;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[(size_t)g * out_stride + s] = sh[0];
+}
+
+// ---- parallel exclusive scan of the histogram (three small kernels) ---------------------------
+constexpr uint32_t kScanTile = 4096;   // elements per CTA (1024 threads x 4)
+__global__ void __launch_bounds__(1024) k_scan_tiles(const uint32_t* __restrict__ counts, uint32_t total,
+                                                     uint32_t* __restrict__ offsets, uint32_t* __restrict__ tile_sums) {
+    __shared__ uint32_t warp_sums[32];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t idx = blockIdx.x * kScanTile + tid * 4;
+    uint32_t v[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) v[k] = (idx + k < total) ? counts[idx + k] : 0;
+    uint32_t local = v[0] + v[1] + v[2] + v[3];
+    uint32_t incl = local;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    if (lane == 31) warp_sums[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t ws = warp_sums[lane], wi = ws;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, wi, d);
+            if (lane >= d) wi += t;
+        }
+        warp_sums[lane] = wi - ws;
+        if (lane == 31) tile_sums[blockIdx.x] = wi;
+    }
+    __syncthreads();
+    uint32_t excl = warp_sums[wid] + incl - local;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if (idx + k < total) offsets[idx + k] = excl;
+        excl += v[k];
+    }
+}
+// exclusive scan of the tile sums by one CTA (ntiles <= a few thousand); tile_sums[ntiles] = grand total
+__global__ void __launch_bounds__(1024) k_scan_tile_sums(uint32_t* __restrict__ tile_sums, uint32_t ntiles) {
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t carry_s;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) carry_s = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < ntiles; base += 1024) {
+        uint32_t i = base + tid;
+        uint32_t v = i < ntiles ? tile_sums[i] : 0, incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        if (lane == 31) warp_sums[wid] = incl;
+        __syncthreads();
+        if (wid == 0) {
+            uint32_t ws = warp_sums[lane], wi = ws;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                uint32_t t = __shfl_up_sync(0xffffffffu, wi, d);
+                if (lane >= d) wi += t;
+            }
+            warp_sums[lane] = wi - ws;
+        }
+        __syncthreads();
+        uint32_t excl = carry_s + warp_sums[wid] + incl - v;
+        if (i < ntiles) tile_sums[i] = excl;
+        __syncthreads();
+        if (tid == 1023) carry_s = excl + v;
+        __syncthreads();
+    }
+    if (tid == 0) tile_sums[ntiles] = carry_s;
+}
+__global__ void __launch_bounds__(1024) k_scan_apply(uint32_t total, const uint32_t* __restrict__ tile_sums, uint32_t ntiles,
+                                                     uint32_t* __restrict__ offsets, uint32_t* __restrict__ cursors) {
+    const uint32_t idx = blockIdx.x * kScanTile + threadIdx.x * 4;
+    const uint32_t base = tile_sums[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+        if (idx + k < total) {
+            uint32_t o = offsets[idx + k] + base;
+            offsets[idx + k] = o;
+            cursors[idx + k] = o;
+        }
+    if (blockIdx.x == 0 && threadIdx.x == 0) offsets[total] = tile_sums[ntiles];
+}
+
 // out[i] = 2^c * in[i] in XYZZ (levels table construction)
 __global__ void __launch_bounds__(128) k_level_up(const G1Affine* __restrict__ in, size_t count, int c, G1XYZZ* __restrict__ out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -374,7 +440,7 @@ MsmEngine::Shape MsmEngine::run(const G1Affine* bases, const Fr* scalars, size_t
                                 MsmConfig cfg, size_t scalar_stride, size_t scalar_offset) {
     if (n == 0) {
         PM_CUDA(cudaMemsetAsync(winsums, 0, sizeof(G1XYZZ), stream));
-        return {1, 1, 1, 1};
+        return Shape();
     }
     if (n >= ((size_t)1 << 31)) throw CudaError("msm: n must be < 2^31");
     const int c = cfg.c ? cfg.c : choose_window(n);
@@ -386,16 +452,29 @@ MsmEngine::Shape MsmEngine::run(const G1Affine* bases, const Fr* scalars, size_t
         throw CudaError("msm: bad precomputed-level layout");
     const uint32_t nb = 1u << (c - 1);
     const uint32_t total = (uint32_t)ngroups * nb;
-    // hierarchical reduction geometry: level sizes nb, nb/K, ... down to one segment
+    // hierarchical reduction geometry: 16-ary levels while the array is longer than kTopMax, then bit sums
     uint32_t lev_m[16];
     int nlev = 0;
-    for (uint32_t m = nb;; m = (m + kRedK - 1) / kRedK) {
-        lev_m[nlev++] = m;
-        if (m <= kRedK) break;
+    uint32_t m_top = nb;
+    while (m_top > kTopMax) {
+        lev_m[nlev++] = m_top;
+        m_top = (m_top + kRedK - 1) / kRedK;
     }
-    if (ngroups * nlev > kMaxMsmSums) throw CudaError("msm: too many partial sums");
+    int top_bits = 0;
+    while ((1u << top_bits) < m_top) top_bits++;
+    const int with_ones = nlev == 0 ? 1 : 0;       // weights start at 1 only when no level ran (off = 1)
+    const int ntop = top_bits + with_ones;
+    Shape shape;
+    shape.c = c * levels;
+    shape.nwin = ngroups;
+    shape.nsum = nlev + ntop;
+    if (shape.nsum > 32 || shape.count() > kMaxMsmSums) throw CudaError("msm: too many partial sums");
+    for (int j = 0; j < nlev; j++) shape.shift[j] = (uint8_t)(kRedBits * j);
+    for (int s2 = 0; s2 < ntop; s2++)
+        shape.shift[nlev + s2] = (uint8_t)(kRedBits * nlev + (with_ones ? (s2 == 0 ? 0 : s2 - 1) : s2));
     size_t seg_total = 0;   // T and R arrays of all levels
     for (int j = 0; j < nlev; j++) seg_total += (size_t)((lev_m[j] + kRedK - 1) / kRedK) * ngroups;
+    const uint32_t ntiles = (total + kScanTile - 1) / kScanTile;
     // A bucket is split only when walking it serially would approach the whole kernel's duration:
     // buckets run longest-first, so a run up to 1/8192 of all entries still hides behind the rest.
     size_t share = n * (size_t)nwin / 8192;
@@ -404,7 +483,8 @@ MsmEngine::Shape MsmEngine::run(const G1Affine* bases, const Fr* scalars, size_t
 
     uint32_t* counts = counts_.as<uint32_t>(total + 1);
     uint32_t* offsets = offsets_.as<uint32_t>(total + 1);
-    uint32_t* cursors = cursors_.as<uint32_t>(total + 1);
+    uint32_t* cursors = cursors_.as<uint32_t>((size_t)total + 1 + ntiles + 1);
+    uint32_t* tile_sums = cursors + total + 1;
     uint32_t* sorted = sorted_.as<uint32_t>(n * (size_t)nwin);
     G1XYZZ* buckets = buckets_.as<G1XYZZ>(total);
     G1XYZZ* segs = segs_.as<G1XYZZ>(2 * seg_total + (size_t)ngroups * 64 + 64);
@@ -426,7 +506,9 @@ MsmEngine::Shape MsmEngine::run(const G1Affine* bases, const Fr* scalars, size_t
     const unsigned dgrid = ceil_div(n, 256);
     k_digits<false><<<dgrid, 256, 0, stream>>>(bases, scalars, n, scalar_stride, scalar_offset, c, nwin, nb, levels, (uint32_t)cfg.level_stride, counts, nullptr);
     PM_LAUNCH_CHECK();
-    k_scan<<<1, 1024, 0, stream>>>(counts, total, offsets, cursors);
+    k_scan_tiles<<<ntiles, 1024, 0, stream>>>(counts, total, offsets, tile_sums);
+    k_scan_tile_sums<<<1, 1024, 0, stream>>>(tile_sums, ntiles);
+    k_scan_apply<<<ntiles, 1024, 0, stream>>>(total, tile_sums, ntiles, offsets, cursors);
     PM_LAUNCH_CHECK();
     k_digits<true><<<dgrid, 256, 0, stream>>>(bases, scalars, n, scalar_stride, scalar_offset, c, nwin, nb, levels, (uint32_t)cfg.level_stride, cursors, sorted);
     PM_LAUNCH_CHECK();
@@ -467,6 +549,8 @@ MsmEngine::Shape MsmEngine::run(const G1Affine* bases, const Fr* scalars, size_t
         const G1XYZZ* X = buckets;
         G1XYZZ* cursor = segs;
         G1XYZZ* scratch = segs + 2 * seg_total;     // [ngroups][64] slice partials
+        const int nsum = shape.nsum;
+        uint32_t m_last = nb;
         for (int j = 0; j < nlev; j++) {
             const uint32_t m = lev_m[j], mseg = (m + kRedK - 1) / kRedK;
             G1XYZZ* T = cursor;
@@ -477,22 +561,26 @@ MsmEngine::Shape MsmEngine::run(const G1Affine* bases, const Fr* scalars, size_t
             else k_reduce_level<false><<<grid, 128, 0, stream>>>(X, m, mseg, ngroups, T, R);
             PM_LAUNCH_CHECK();
             launches++;
-            // level sum: winsums[g*nlev + j] = sum_seg T[g][seg]
+            // level sum: winsums[g*nsum + j] = sum_seg T[g][seg]
             if (mseg > 4096) {
                 const uint32_t slice = (mseg + 63) / 64, nsl = (mseg + slice - 1) / slice;
                 k_sum_slices<<<ngroups * nsl, 128, 0, stream>>>(T, mseg, mseg, slice, nsl, 64, scratch);
-                k_sum_slices<<<ngroups, 128, 0, stream>>>(scratch, 64, nsl, nsl, 1, nlev, winsums + j);
+                k_sum_slices<<<ngroups, 128, 0, stream>>>(scratch, 64, nsl, nsl, 1, nsum, winsums + j);
                 launches += 2;
             } else {
-                k_sum_slices<<<ngroups, 128, 0, stream>>>(T, mseg, mseg, mseg, 1, nlev, winsums + j);
+                k_sum_slices<<<ngroups, 128, 0, stream>>>(T, mseg, mseg, mseg, 1, nsum, winsums + j);
                 launches++;
             }
             PM_LAUNCH_CHECK();
             X = R;
+            m_last = mseg;
         }
+        k_reduce_top<<<ngroups * ntop, 256, 0, stream>>>(X, m_last, (uint32_t)ntop, with_ones, (uint32_t)nsum, winsums + nlev);
+        PM_LAUNCH_CHECK();
+        launches++;
     }
     launches += 9;
-    return {c * levels, ngroups, nlev, kRedBits};
+    return shape;
 }
 
 }  // namespace pm

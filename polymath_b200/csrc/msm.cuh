@@ -23,10 +23,14 @@ public:
     //  bases   : device, 96-byte affine points, Montgomery limbs, (0,0) = infinity
     //  scalars : device, Fr in Montgomery form (arkworks in-memory form)
     // All work is enqueued on `stream`; nothing is synchronised.
-    // Result layout: winsums_out[g * nlev + j] = S_{g,j};  result = sum_g 2^(c*g) * sum_j 2^(kbits*j) * S_{g,j}
-    // (g < nwin bucket sets, j < nlev levels of the hierarchical bucket reduction; c already includes the
-    // precomputed-levels factor).  Finished on the host: host/g1_host.hpp combine_levels().
-    struct Shape { int c; int nwin; int nlev; int kbits; int count() const { return nwin * nlev; } };
+    // Result layout: winsums_out[g * nsum + s] = S_{g,s};  result = sum_g 2^(c*g) * sum_s 2^(shift[s]) * S_{g,s}
+    // (g < nwin bucket sets; s < nsum partial sums of the hierarchical bucket reduction; c already includes
+    // the precomputed-levels factor).  Finished on the host: host/g1_host.hpp combine_shifted().
+    struct Shape {
+        int c = 1, nwin = 1, nsum = 1;
+        uint8_t shift[32] = {0};
+        int count() const { return nwin * nsum; }
+    };
     Shape run(const G1Affine* bases, const Fr* scalars, size_t n, G1XYZZ* winsums_out, cudaStream_t stream,
               MsmConfig cfg = {}, size_t scalar_stride = 1, size_t scalar_offset = 0);
     static int choose_window(size_t n);

@@ -214,8 +214,8 @@ void ProverCtx::phase1_partial(const uint8_t* ra, uint8_t* partials_out) {
     uint32_t stv;
     memcpy(&stv, hs + kStageStatus, 4);
     check_status(stv);
-    host::combine_levels(hs, sa.nwin, sa.c, sa.nlev, sa.kbits).to_wire(partials_out);
-    host::combine_levels(hs + kStageWin, sc.nwin, sc.c, sc.nlev, sc.kbits).to_wire(partials_out + sizeof(G1XYZZ));
+    host::combine_shifted(hs, sa.nwin, sa.c, sa.nsum, sa.shift).to_wire(partials_out);
+    host::combine_shifted(hs + kStageWin, sc.nwin, sc.c, sc.nsum, sc.shift).to_wire(partials_out + sizeof(G1XYZZ));
     phase = 10;   // partial done, waiting for finish
 }
 
@@ -294,7 +294,7 @@ void ProverCtx::phase3_partial(const uint8_t* x2, const uint8_t* c_at_x1, uint8_
     uint32_t stv;
     memcpy(&stv, hs + kStageStatus, 4);
     check_status(stv);
-    host::combine_levels(hs, sd.nwin, sd.c, sd.nlev, sd.kbits).to_wire(partial_out);
+    host::combine_shifted(hs, sd.nwin, sd.c, sd.nsum, sd.shift).to_wire(partial_out);
     phase = 30;
 }
 
