@@ -17,7 +17,9 @@
  *    point at infinity is (0,0) for stride 96, or flagged by a non-zero byte at offset
  *    96 for stride >= 104 (arkworks `Affine { x, y, infinity }`).  Points are written
  *    packed (96 B, infinity = (0,0)) and are the canonical affine image;
- *  - one context may be used by one thread at a time; distinct contexts are independent;
+ *  - calls are thread-safe: the contexts of a process share one CUDA stream and one set of kernel
+ *    workspaces, so the library serialises its entry points internally (one proof at a time per GPU —
+ *    a single proof already fills the device); a context's phases must still be called in order;
  *  - all work runs on the CUDA device current to the calling thread (one process per GPU).
  */
 #ifndef POLYMATH_B200_H

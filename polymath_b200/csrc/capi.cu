@@ -22,6 +22,11 @@ Runtime& runtime() {
     return rt;
 }
 
+std::recursive_mutex& api_mutex() {
+    static std::recursive_mutex m;
+    return m;
+}
+
 Runtime::Runtime() {
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);

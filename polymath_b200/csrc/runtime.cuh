@@ -2,6 +2,7 @@
 // each engine (grow-only workspaces).  One process drives one GPU (the CUDA device current
 // at first use).
 #pragma once
+#include <mutex>
 #include <string>
 #include <vector>
 #include "common.cuh"
@@ -27,9 +28,13 @@ struct Runtime {
 };
 
 Runtime& runtime();
+// All contexts of a process share one stream and one set of engine workspaces, so device work of
+// different contexts is serialised: every C-ABI entry point holds this lock for its duration.
+std::recursive_mutex& api_mutex();
 
 template <class F>
 int guarded(F&& f) {
+    std::lock_guard<std::recursive_mutex> lock(api_mutex());
     try {
         f();
         return PM_OK;
