@@ -37,7 +37,7 @@ def ark_window(n):
     return ((n - 1).bit_length()) * 69 // 100 + 2
 
 
-def cpu_baseline(log_n, msm_log=16, ntt_log=18):
+def cpu_baseline(log_n, msm_log=21, ntt_log=22):
     """Time the C++/OpenMP port on a bounded sample and scale to one prove at n = 2^log_n.
 
     prove(n) = MSMs over ~14n + 29 points + 3 iNTT(n) + NTT(2n) + iNTT(2n).
@@ -48,14 +48,15 @@ def cpu_baseline(log_n, msm_log=16, ntt_log=18):
     m = 1 << msm_log
     rnd = random.Random(7)
     bases = cpp.make_bases_wire(m)
-    scalars = b"".join(rnd.getrandbits(254).to_bytes(32, "little") for _ in range(m))
+    scalars = bytearray(os.urandom(32 * m))
+    scalars[31::32] = bytes(b & 0x3F for b in scalars[31::32])     # < 2^254 < r: valid Montgomery limbs
+    scalars = bytes(scalars)
     cpp.msm_wire(bases[:96 * 1024], scalars[:32 * 1024], 1024)   # warm up threads
     t0 = time.perf_counter()
     cpp.msm_wire(bases, scalars, m)
     t_msm = time.perf_counter() - t0
     buf = bytearray(os.urandom(32 << ntt_log))
-    for i in range(31, len(buf), 32):
-        buf[i] &= 0x3F
+    buf[31::32] = bytes(b & 0x3F for b in buf[31::32])
     t0 = time.perf_counter()
     cpp.ntt_wire(buf, ntt_log, False)
     t_ntt = time.perf_counter() - t0
@@ -283,7 +284,10 @@ def run_ours(args):
         "kernel": "k_accumulate (bucket accumulation of the [d]_1 MSM)", "bound": "imad",
         "achieved": achieved, "peak": imad_peak / 1e12, "unit": "TIMAD/s",
         "frac": (achieved / (imad_peak / 1e12)) if achieved else None,
-        "traffic": None, "kernel_ms": acc, "kernel_share_of_step": acc / value if value else None,
+        # dram__bytes_read.sum + dram__bytes_write.sum of this launch, ncu --set full (profiles/r1_c_summary.md);
+        # valid for the 1-GPU 2^20 workload the capture was taken on, null otherwise
+        "traffic": 26.67e9 if (world == 1 and log_n == 20) else None,
+        "kernel_ms": acc, "kernel_share_of_step": acc / value if value else None,
         "peak_source": "measured live: dependency-free IMAD.WIDE.U32 issue rate (pm_bench_imad_peak); "
                        "north_star names the INT32 IMAD pipe as the roofline for MSM / field multiplication",
         "algorithmic": "%d points x %d windows (arkworks window rule c=%d) x 10 Fq-modmul x 300 IMAD" % (d_points, w_ark, c_ark),
@@ -298,7 +302,9 @@ def run_ours(args):
     ntt_ms = d.value
     ntt_gbs = 64.0 * (2 * n) / (ntt_ms * 1e-3) / 1e9
     roofline_hbm = {"kernel": "Fr NTT 2^%d (column + row pass)" % (log_n + 1), "bound": "hbm", "achieved": ntt_gbs,
-                    "peak": hbm_peak, "unit": "GB/s", "frac": ntt_gbs / hbm_peak, "traffic": None,
+                    "peak": hbm_peak, "unit": "GB/s", "frac": ntt_gbs / hbm_peak,
+                    "traffic": 171.6e6 if log_n == 20 else None,
+                    "note": "a 255-bit-field NTT is multiplier-bound: fmaheavy pipe 65-68 % active at 4 % of HBM peak (profiles/r1_c_summary.md)",
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
                     "gelem_per_s": (2 * n) / (ntt_ms * 1e-3) / 1e9}
     acc_d = C.c_double()
