@@ -34,10 +34,13 @@ Runtime::Runtime() {
         throw CudaError(std::string("no CUDA device available (the product path has no CPU fallback): ") +
                         cudaGetErrorString(e));
     PM_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    PM_CUDA(cudaStreamCreateWithFlags(&stream2, cudaStreamNonBlocking));
+    PM_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    PM_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
 }
 
 uint64_t Runtime::total_launches() const {
-    return extra_launches + ntt.launches + msm.launches + fixed_base.launches;
+    return extra_launches + ntt.launches + msm.launches + msm2.launches + fixed_base.launches;
 }
 
 // Pack caller-strided affine points into the device layout (96 B, (0,0) = infinity).

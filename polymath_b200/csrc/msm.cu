@@ -58,17 +58,32 @@ __global__ void __launch_bounds__(256) k_digits(const G1Affine* __restrict__ bas
     for (int k = 0; k < 8; k++) limbs[k] = s.v[k];
     const uint32_t half = 1u << (c - 1);
     uint32_t carry = 0;
-    for (int w = 0; w < nwin; w++) {
-        uint32_t d = window_bits(limbs, w * c, c) + carry;
-        uint32_t neg = 0;
-        if (d > half) { d = (1u << c) - d; neg = 1; carry = 1; } else { carry = 0; }
-        if (d == 0) continue;
-        uint32_t slot = (uint32_t)(w / levels) * nb + (d - 1);
+    // windows in batches of four: the four atomics of a batch are in flight together
+    for (int w0 = 0; w0 < nwin; w0 += 4) {
+        uint32_t slot[4], val[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int w = w0 + k;
+            slot[k] = 0xffffffffu;
+            if (w < nwin) {
+                uint32_t d = window_bits(limbs, w * c, c) + carry;
+                uint32_t neg = 0;
+                if (d > half) { d = (1u << c) - d; neg = 1; carry = 1; } else { carry = 0; }
+                if (d != 0) {
+                    slot[k] = (uint32_t)(w / levels) * nb + (d - 1);
+                    val[k] = ((uint32_t)(w % levels) * level_stride + (uint32_t)i) | (neg << 31);
+                }
+            }
+        }
         if (SCATTER) {
-            uint32_t pos = atomicAdd(&counters[slot], 1u);
-            sorted[pos] = ((uint32_t)(w % levels) * level_stride + (uint32_t)i) | (neg << 31);
+            uint32_t pos[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) if (slot[k] != 0xffffffffu) pos[k] = atomicAdd(&counters[slot[k]], 1u);
+#pragma unroll
+            for (int k = 0; k < 4; k++) if (slot[k] != 0xffffffffu) sorted[pos[k]] = val[k];
         } else {
-            atomicAdd(&counters[slot], 1u);
+#pragma unroll
+            for (int k = 0; k < 4; k++) if (slot[k] != 0xffffffffu) atomicAdd(&counters[slot[k]], 1u);
         }
     }
 }
@@ -487,7 +502,7 @@ MsmEngine::Shape MsmEngine::run(const G1Affine* bases, const Fr* scalars, size_t
     uint32_t* tile_sums = cursors + total + 1;
     uint32_t* sorted = sorted_.as<uint32_t>(n * (size_t)nwin);
     G1XYZZ* buckets = buckets_.as<G1XYZZ>(total);
-    G1XYZZ* segs = segs_.as<G1XYZZ>(2 * seg_total + (size_t)ngroups * 64 + 64);
+    G1XYZZ* segs = segs_.as<G1XYZZ>(2 * seg_total + (size_t)ngroups * 256 + 64);
     uint32_t* order = order_.as<uint32_t>((size_t)total + kLenBins);
     uint32_t* len_hist = order + total;
     HeavyLists hl;
@@ -562,10 +577,14 @@ MsmEngine::Shape MsmEngine::run(const G1Affine* bases, const Fr* scalars, size_t
             PM_LAUNCH_CHECK();
             launches++;
             // level sum: winsums[g*nsum + j] = sum_seg T[g][seg]
-            if (mseg > 4096) {
-                const uint32_t slice = (mseg + 63) / 64, nsl = (mseg + slice - 1) / slice;
-                k_sum_slices<<<ngroups * nsl, 128, 0, stream>>>(T, mseg, mseg, slice, nsl, 64, scratch);
-                k_sum_slices<<<ngroups, 128, 0, stream>>>(scratch, 64, nsl, nsl, 1, nsum, winsums + j);
+            if (mseg > 512) {
+                // two stages: slices of <= 512 elements per 128-thread CTA (4 serial + 7 tree additions), then
+                // the <= 256 slice sums by one CTA per bucket set
+                uint32_t slice = (mseg + 255) / 256;
+                if (slice < 256) slice = 256;
+                const uint32_t nsl = (mseg + slice - 1) / slice;
+                k_sum_slices<<<ngroups * nsl, 128, 0, stream>>>(T, mseg, mseg, slice, nsl, 256, scratch);
+                k_sum_slices<<<ngroups, 128, 0, stream>>>(scratch, 256, nsl, nsl, 1, nsum, winsums + j);
                 launches += 2;
             } else {
                 k_sum_slices<<<ngroups, 128, 0, stream>>>(T, mseg, mseg, mseg, 1, nsum, winsums + j);

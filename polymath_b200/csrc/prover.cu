@@ -199,12 +199,18 @@ void ProverCtx::phase1_partial(const uint8_t* ra, uint8_t* partials_out) {
     rt.extra_launches += 9;
     G1XYZZ* ac = acc.get<G1XYZZ>();
     const G1Affine* bc = bases_c.get<G1Affine>();
-    // compute_a_g1 (prover.rs:330-338) and c_g1 (prover.rs:116-123) over this rank's share of the bases
-    MsmEngine::Shape sa = rt.msm.run(bc, scal_a.get<Fr>(), local_count(n + 4), ac, s, {}, world, rank);
-    MsmEngine::Shape sc = rt.msm.run(bc, scal_c.get<Fr>(), local_count(len_c()), ac + kMaxMsmSums, s, cfg_c(), world, rank);
+    // compute_a_g1 (prover.rs:330-338) and c_g1 (prover.rs:116-123) over this rank's share of the bases.
+    // The two MSMs are independent: the a-side runs on the side stream with its own workspace so that its
+    // sort / reduction tail hides behind the c-side bucket accumulation.
     uint8_t* hs = static_cast<uint8_t*>(host_stage);
-    PM_CUDA(cudaMemcpyAsync(hs, ac, sa.count() * sizeof(G1XYZZ), cudaMemcpyDeviceToHost, s));
+    PM_CUDA(cudaEventRecord(rt.ev_fork, s));
+    PM_CUDA(cudaStreamWaitEvent(rt.stream2, rt.ev_fork, 0));
+    MsmEngine::Shape sa = rt.msm2.run(bc, scal_a.get<Fr>(), local_count(n + 4), ac, rt.stream2, {}, world, rank);
+    PM_CUDA(cudaMemcpyAsync(hs, ac, sa.count() * sizeof(G1XYZZ), cudaMemcpyDeviceToHost, rt.stream2));
+    PM_CUDA(cudaEventRecord(rt.ev_join, rt.stream2));
+    MsmEngine::Shape sc = rt.msm.run(bc, scal_c.get<Fr>(), local_count(len_c()), ac + kMaxMsmSums, s, cfg_c(), world, rank);
     PM_CUDA(cudaMemcpyAsync(hs + kStageWin, ac + kMaxMsmSums, sc.count() * sizeof(G1XYZZ), cudaMemcpyDeviceToHost, s));
+    PM_CUDA(cudaStreamWaitEvent(s, rt.ev_join, 0));
     PM_CUDA(cudaMemcpyAsync(hs + kStageStatus, st, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     PM_CUDA(cudaEventRecord(ev1, s));
     PM_CUDA(cudaStreamSynchronize(s));

@@ -20,8 +20,11 @@ struct StatusError : std::runtime_error {
 struct Runtime {
     Runtime();
     cudaStream_t stream = nullptr;
+    // side stream + second MSM workspace: independent MSMs of one phase overlap their latency-bound tails
+    cudaStream_t stream2 = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     NttEngine ntt;
-    MsmEngine msm;
+    MsmEngine msm, msm2;
     FixedBaseEngine fixed_base;
     uint64_t extra_launches = 0;
     uint64_t total_launches() const;
