@@ -82,6 +82,11 @@ int pm_msm_g1_window(const uint8_t* bases, size_t base_stride, const uint8_t* sc
 int pm_msm_g1_levels(const uint8_t* bases, size_t base_stride, const uint8_t* scalars, size_t n, int window_bits,
                      int levels, uint8_t out[PM_G1_BYTES]);
 
+/* Process-wide tuning of the bucket accumulation of every later MSM (standalone and inside the prover):
+ * rounds = number of batched-affine pair rounds before the XYZZ walk (-1 = automatic, 0 = none),
+ * group = buckets per thread in a round (0 = automatic).  Results never depend on it; test and sweep hook. */
+int pm_msm_set_tuning(int rounds, int group);
+
 /* out[i] = scalars[i] * G (G = the BLS12-381 G1 generator), canonical affine.
  * Replaces `generate()` (src/generator.rs:169-177). */
 int pm_fixed_base_mul(const uint8_t* scalars, size_t n, uint8_t* out);

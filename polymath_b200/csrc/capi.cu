@@ -167,6 +167,10 @@ static int msm_host_call(const uint8_t* bases, size_t base_stride, const uint8_t
     });
 }
 
+int pm_msm_set_tuning(int rounds, int group) {
+    return guarded([&] { MsmEngine::set_tuning(rounds, group); });
+}
+
 int pm_msm_g1(const uint8_t* bases, size_t base_stride, const uint8_t* scalars, size_t n, uint8_t out[PM_G1_BYTES]) {
     return pm_msm_g1_window(bases, base_stride, scalars, n, 0, 0, out);
 }

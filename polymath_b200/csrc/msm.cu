@@ -6,7 +6,12 @@
 //   2. k_scan            exclusive prefix of the histogram -> bucket offsets
 //   3. k_digits<SCATTER> counting-sort scatter of (point index | sign) by (window, bucket)
 //                        (order inside a bucket is irrelevant: group addition commutes)
-//   4. k_accumulate      one thread per bucket, XYZZ mixed additions over its sorted run;
+//   4a. pair rounds      (large MSMs) batched-AFFINE tree reduction of every bucket's run: round r adds the
+//                        entries of a run pairwise (2i, 2i+1) -> half as many affine points, with ONE shared
+//                        inversion per round (Montgomery's trick: k_pairs_forward prefix products,
+//                        k_batch_invert, k_pairs_backward) = 6 Fq products per addition instead of the 10 of
+//                        an XYZZ mixed addition
+//   4. k_accumulate      one thread per bucket, XYZZ mixed additions over its (remaining) run;
 //                        buckets longer than a threshold are deferred to
 //      k_accumulate_heavy / k_heavy_finish (4096-entry chunks, one CTA each, then a per-bucket
 //                        sum of the chunk partials) so narrow top windows and skewed scalar
@@ -25,6 +30,8 @@ namespace pm {
 namespace {
 
 constexpr int kMaxWindows = kMaxMsmWindows;
+constexpr int kMaxRounds = 10;
+constexpr size_t kMaxRoundsWorkspace = (size_t)28 << 30;   // bytes; larger MSMs use the XYZZ walk only
 
 __device__ __forceinline__ uint32_t window_bits(const uint32_t* s, int pos, int c) {
     int limb = pos >> 5, off = pos & 31;
@@ -88,7 +95,7 @@ __global__ void __launch_bounds__(256) k_digits(const G1Affine* __restrict__ bas
     }
 }
 
-__device__ __forceinline__ G1Affine load_point(const G1Affine* __restrict__ bases, uint32_t idx) {
+__device__ __forceinline__ G1Affine load_point(const G1Affine* __restrict__ bases, uint64_t idx) {
     G1Affine p;
     const uint4* src = reinterpret_cast<const uint4*>(bases + idx);
     uint4* dst = reinterpret_cast<uint4*>(&p);
@@ -149,6 +156,236 @@ __device__ __forceinline__ void defer_heavy(const HeavyLists& hl, uint32_t t, ui
     hl.heavy[slot] = make_uint4(t, first, ntask, 0u);
 }
 
+// ---- batched-affine pair rounds ----------------------------------------------------------------
+// With R rounds planned, every bucket's run in the sorted list starts at a multiple of A = 2^R and is padded
+// with sentinel entries (infinity) to a multiple of A (k_scan_tiles pads the counts, k_pad_runs writes the
+// sentinels).  Round r then is one flat, bucket-oblivious pass  X_{r+1}[p] = X_r[2p] + X_r[2p+1]  over all
+// S_r / 2 slot pairs (S_0 = offsets[total], S_{r+1} = S_r / 2): pairs never straddle a bucket, after R rounds
+// bucket t owns X_R[offsets[t] >> R .. offsets[t+1] >> R), and heavy buckets need no special care.
+// X_0 is the sorted (index | sign) list into the base table; X_{r>=1} are scratch arrays stored as six planes
+// of 16-byte chunks (plane k, element e -> planes[k * cap + e]) so that the loads of a warp coalesce.
+// All additions of a round are independent, so their denominators are inverted together (Montgomery's trick,
+// two levels):
+//   k_pairs_forward   thread = kPairsPerThread slot pairs (strided by the CTA); stores the exclusive prefix
+//                     product of its denominators x2 - x1 (planes, like the points), thread total -> T
+//   k_batch_invert    T -> T^-1 element-wise (same trick over T, one Fermat inverse per thread)
+//   k_pairs_backward  walks the same pairs backwards: 1/d_i = prefix_i * (running inverse), then
+//                     lambda = (y2 - y1)/d, x3 = lambda^2 - x1 - x2, y3 = lambda (x1 - x3) - y1
+// Per slot pair: 1 + 5 Fq products (+ 3/kPairsPerThread for the second level), against 10 for an XYZZ
+// mixed addition.  Exceptional pairs (an operand at infinity — all padding —, P + P, P + (-P)) are classified
+// identically in both passes (pair_kind) and contribute no denominator, or 2y for a doubling.
+constexpr int kPairsPerThread = 16;
+constexpr uint32_t kPairTile = 128 * kPairsPerThread;   // slot pairs per CTA
+constexpr uint32_t kPadEntry = 0xffffffffu;             // sorted-list sentinel: the point at infinity
+
+struct FqPlanes {      // n field elements as three planes of 16-byte chunks
+    uint4* base;
+    size_t cap;
+    __device__ __forceinline__ Fq load(size_t e) const {
+        Fq r;
+        uint4* d4 = reinterpret_cast<uint4*>(&r);
+#pragma unroll
+        for (int k = 0; k < 3; k++) d4[k] = base[(size_t)k * cap + e];
+        return r;
+    }
+    __device__ __forceinline__ void store(size_t e, const Fq& v) const {
+        const uint4* s4 = reinterpret_cast<const uint4*>(&v);
+#pragma unroll
+        for (int k = 0; k < 3; k++) base[(size_t)k * cap + e] = s4[k];
+    }
+};
+struct PointPlanes {   // n affine points as six planes (x: planes 0-2, y: planes 3-5)
+    uint4* base;
+    size_t cap;
+    __device__ __forceinline__ Fq load_x(size_t e) const { return FqPlanes{base, cap}.load(e); }
+    __device__ __forceinline__ Fq load_y(size_t e) const { return FqPlanes{base + 3 * cap, cap}.load(e); }
+    __device__ __forceinline__ G1Affine load(size_t e) const { return {load_x(e), load_y(e)}; }
+    __device__ __forceinline__ void store(size_t e, const G1Affine& v) const {
+        FqPlanes{base, cap}.store(e, v.x);
+        FqPlanes{base + 3 * cap, cap}.store(e, v.y);
+    }
+};
+
+__device__ __forceinline__ Fq load_fq(const Fq* src) {
+    Fq r;
+    const uint4* s4 = reinterpret_cast<const uint4*>(src);
+    uint4* d4 = reinterpret_cast<uint4*>(&r);
+#pragma unroll
+    for (int k = 0; k < 3; k++) d4[k] = __ldg(s4 + k);
+    return r;
+}
+__device__ __forceinline__ void store_fq(Fq* dst, const Fq& v) {
+    const uint4* s4 = reinterpret_cast<const uint4*>(&v);
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+    for (int k = 0; k < 3; k++) d4[k] = s4[k];
+}
+
+enum PairKind : int { kPairAdd = 0, kPairDouble = 1, kPairFirst = 2, kPairSecond = 3, kPairInfinity = 4 };
+__device__ __forceinline__ int pair_kind(const G1Affine& a, const G1Affine& b) {
+    if (a.is_inf()) return kPairSecond;     // also both infinite: the result is b = infinity
+    if (b.is_inf()) return kPairFirst;
+    if (a.x == b.x) return (a.y == b.y && !a.y.is_zero()) ? kPairDouble : kPairInfinity;
+    return kPairAdd;
+}
+
+// sentinel entries stay at the end of every padded run
+__global__ void k_pad_runs(const uint32_t* __restrict__ counts, const uint32_t* __restrict__ offsets, uint32_t total,
+                           uint32_t* __restrict__ sorted) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const uint32_t end = offsets[t + 1];
+    for (uint32_t k = offsets[t] + counts[t]; k < end; k++) sorted[k] = kPadEntry;
+}
+
+// operands of slot pair p in round storage: FIRST reads two (index | sign) entries and gathers from the table
+template <bool FIRST>
+struct PairSource {
+    const G1Affine* table;
+    const uint32_t* sorted;
+    PointPlanes in;
+    // x coordinates only; returns false when an operand is padding (FIRST only)
+    __device__ __forceinline__ bool load_x(size_t p, uint2& e, Fq& x1, Fq& x2) const {
+        if (FIRST) {
+            e = *reinterpret_cast<const uint2*>(sorted + 2 * p);
+            if (e.x == kPadEntry || e.y == kPadEntry) return false;
+            x1 = load_fq(&table[e.x & 0x7fffffffu].x);
+            x2 = load_fq(&table[e.y & 0x7fffffffu].x);
+        } else {
+            x1 = in.load_x(2 * p);
+            x2 = in.load_x(2 * p + 1);
+        }
+        return true;
+    }
+    __device__ __forceinline__ void load_y(size_t p, const uint2& e, Fq& y1, Fq& y2) const {
+        if (FIRST) {
+            y1 = load_fq(&table[e.x & 0x7fffffffu].y);
+            y2 = load_fq(&table[e.y & 0x7fffffffu].y);
+            if (e.x >> 31) y1 = y1.neg();
+            if (e.y >> 31) y2 = y2.neg();
+        } else {
+            y1 = in.load_y(2 * p);
+            y2 = in.load_y(2 * p + 1);
+        }
+    }
+    __device__ __forceinline__ void load_pair(size_t p, G1Affine& a, G1Affine& b) const {
+        if (FIRST) {
+            uint2 e = *reinterpret_cast<const uint2*>(sorted + 2 * p);
+            a = G1Affine::inf();
+            b = G1Affine::inf();
+            if (e.x != kPadEntry) {
+                a = load_point(table, e.x & 0x7fffffffu);
+                if (e.x >> 31) a.y = a.y.neg();
+            }
+            if (e.y != kPadEntry) {
+                b = load_point(table, e.y & 0x7fffffffu);
+                if (e.y >> 31) b.y = b.y.neg();
+            }
+        } else {
+            a = in.load(2 * p);
+            b = in.load(2 * p + 1);
+        }
+    }
+};
+
+// slot pairs of round r: (S_0 >> r) / 2 with S_0 = *slots0
+__device__ __forceinline__ size_t round_pairs(const uint32_t* __restrict__ slots0, int r) { return (size_t)(*slots0 >> r) >> 1; }
+
+template <bool FIRST>
+__global__ void __launch_bounds__(128) k_pairs_forward(PairSource<FIRST> src, const uint32_t* __restrict__ slots0, int r,
+                                                       FqPlanes prefix, Fq* __restrict__ T) {
+    const size_t npairs = round_pairs(slots0, r);
+    const size_t base = (size_t)blockIdx.x * kPairTile;
+    if (base >= npairs) return;
+    Fq acc = Fq::one();
+    for (int i = 0; i < kPairsPerThread; i++) {
+        const size_t p = base + (size_t)i * 128 + threadIdx.x;
+        if (p >= npairs) break;
+        uint2 e = make_uint2(0u, 0u);
+        Fq x1, x2, d;
+        bool has = src.load_x(p, e, x1, x2);
+        if (has) {
+            d = x2 - x1;
+            if (d.is_zero() || x1.is_zero() || x2.is_zero()) {
+                // rare: decide with the full points, exactly as the backward pass will
+                G1Affine a, b;
+                a.x = x1;
+                b.x = x2;
+                src.load_y(p, e, a.y, b.y);
+                const int kind = pair_kind(a, b);
+                if (kind == kPairDouble) d = a.y.dbl();
+                else if (kind != kPairAdd) has = false;
+            }
+        }
+        prefix.store(p, acc);
+        if (has) acc = fq_mul_call(acc, d);
+    }
+    store_fq(T + (size_t)blockIdx.x * 128 + threadIdx.x, acc);
+}
+
+// T[i] <- T[i]^-1 for the thread totals of k_pairs_forward in round r (all non-zero): thread j owns j, j + nthr, ...
+__global__ void __launch_bounds__(128) k_batch_invert(Fq* __restrict__ T, const uint32_t* __restrict__ slots0, int r, uint32_t nthr,
+                                                      Fq* __restrict__ pre) {
+    const size_t npairs = round_pairs(slots0, r);
+    const size_t n = (npairs + kPairTile - 1) / kPairTile * 128;
+    const size_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nthr || j >= n) return;
+    Fq acc = Fq::one();
+    uint32_t cnt = 0;
+    for (size_t idx = j; idx < n; idx += nthr, cnt++) {
+        store_fq(pre + idx, acc);
+        acc = fq_mul_call(acc, load_fq(T + idx));
+    }
+    Fq inv = acc.inv();
+    for (uint32_t k = cnt; k-- > 0;) {
+        const size_t idx = j + (size_t)k * nthr;
+        Fq t = load_fq(T + idx);
+        store_fq(T + idx, fq_mul_call(inv, load_fq(pre + idx)));
+        inv = fq_mul_call(inv, t);
+    }
+}
+
+template <bool FIRST>
+__global__ void __launch_bounds__(128, 4) k_pairs_backward(PairSource<FIRST> src, const uint32_t* __restrict__ slots0, int r,
+                                                           FqPlanes prefix, const Fq* __restrict__ Tinv, PointPlanes next) {
+    const size_t npairs = round_pairs(slots0, r);
+    const size_t base = (size_t)blockIdx.x * kPairTile;
+    if (base >= npairs) return;
+    // threads of a partial last tile that own no pair hold T = 1
+    Fq inv = load_fq(Tinv + (size_t)blockIdx.x * 128 + threadIdx.x);
+    for (int i = kPairsPerThread; i-- > 0;) {
+        const size_t p = base + (size_t)i * 128 + threadIdx.x;
+        if (p >= npairs) continue;
+        G1Affine a, b;
+        src.load_pair(p, a, b);
+        G1Affine res;
+        Fq d = b.x - a.x, num;
+        int kind = kPairAdd;
+        if (d.is_zero() || a.x.is_zero() || b.x.is_zero()) kind = pair_kind(a, b);
+        if (kind == kPairAdd) {
+            num = b.y - a.y;
+        } else if (kind == kPairDouble) {
+            d = a.y.dbl();
+            Fq xx = fq_mul_call(a.x, a.x);
+            num = xx.dbl() + xx;
+        }
+        if (kind <= kPairDouble) {
+            Fq inv_d = fq_mul_call(inv, prefix.load(p));
+            inv = fq_mul_call(inv, d);
+            Fq lam = fq_mul_call(num, inv_d);
+            res.x = fq_mul_call(lam, lam) - a.x - b.x;
+            res.y = fq_mul_call(lam, a.x - res.x) - a.y;
+        } else if (kind == kPairFirst) {
+            res = a;
+        } else if (kind == kPairSecond) {
+            res = b;
+        } else {
+            res = G1Affine::inf();
+        }
+        next.store(p, res);
+    }
+}
+
 // One thread per (window, bucket): walk the bucket's sorted run with XYZZ mixed additions.
 // M selects inlined Fq products or one shared out-of-line copy (smaller loop body: the fully
 // inlined body is ~140 KB of SASS and stalls on instruction fetch).  Tuning hook:
@@ -185,21 +422,47 @@ __global__ void __launch_bounds__(128, MINB) k_accumulate(const G1Affine* __rest
     buckets[t] = acc;
 }
 
+// After R pair rounds: bucket t owns X_R[offsets[t] >> R .. offsets[t+1] >> R); one thread per bucket finishes the
+// few remaining points in XYZZ.  Runs still longer than heavy_thr (hot buckets) go to the chunked path.
+__global__ void __launch_bounds__(128, 4) k_accumulate_rounds(PointPlanes pts, const uint32_t* __restrict__ offsets, int R,
+                                                              G1XYZZ* __restrict__ buckets, uint32_t total_buckets,
+                                                              uint32_t heavy_thr, HeavyLists hl) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total_buckets) return;
+    const uint32_t beg = offsets[t] >> R, end = offsets[t + 1] >> R;
+    if (end - beg > heavy_thr) {
+        defer_heavy(hl, t, end - beg);
+        return;
+    }
+    G1XYZZ acc = G1XYZZ::inf();
+    for (uint32_t k = beg; k < end; k++) xyzz_madd_t<MulCall>(acc, pts.load(k), false);
+    buckets[t] = acc;
+}
+
 // One CTA per task: strided per-thread sums over one chunk, then a shared-memory tree.
+// ROUNDS: the chunk is a range of X_R (after R pair rounds) instead of the sorted list.
+template <bool ROUNDS>
 __global__ void __launch_bounds__(256) k_accumulate_heavy(const G1Affine* __restrict__ bases, const uint32_t* __restrict__ sorted,
+                                                          PointPlanes pts, int R,
                                                           const uint32_t* __restrict__ offsets, HeavyLists hl) {
     extern __shared__ uint4 smem_raw[];
     G1XYZZ* sh = reinterpret_cast<G1XYZZ*>(smem_raw);
     const uint32_t ntasks = hl.counters[0];
     for (uint32_t task = blockIdx.x; task < ntasks; task += gridDim.x) {
         uint2 tk = hl.tasks[task];
-        uint32_t beg = offsets[tk.x] + tk.y * kHeavyChunk;
-        uint32_t end = min(offsets[tk.x + 1], beg + kHeavyChunk);
+        const uint32_t run_beg = ROUNDS ? offsets[tk.x] >> R : offsets[tk.x];
+        const uint32_t run_end = ROUNDS ? offsets[tk.x + 1] >> R : offsets[tk.x + 1];
+        uint32_t beg = run_beg + tk.y * kHeavyChunk;
+        uint32_t end = min(run_end, beg + kHeavyChunk);
         G1XYZZ acc = G1XYZZ::inf();
         for (uint32_t k = beg + threadIdx.x; k < end; k += blockDim.x) {
-            uint32_t e = sorted[k];
-            G1Affine p = load_point(bases, e & 0x7fffffffu);
-            xyzz_madd_t<MulCall>(acc, p, (e >> 31) != 0);
+            if (ROUNDS) {
+                xyzz_madd_t<MulCall>(acc, pts.load(k), false);
+            } else {
+                uint32_t e = sorted[k];
+                G1Affine p = load_point(bases, e & 0x7fffffffu);
+                xyzz_madd_t<MulCall>(acc, p, (e >> 31) != 0);
+            }
         }
         sh[threadIdx.x] = acc;
         __syncthreads();
@@ -320,14 +583,15 @@ __global__ void __launch_bounds__(256) k_reduce_top(const G1XYZZ* __restrict__ X
 
 // ---- parallel exclusive scan of the histogram (three small kernels) ---------------------------
 constexpr uint32_t kScanTile = 4096;   // elements per CTA (1024 threads x 4)
-__global__ void __launch_bounds__(1024) k_scan_tiles(const uint32_t* __restrict__ counts, uint32_t total,
+// pad_mask = A - 1: every count is rounded up to a multiple of A (pair rounds), 0 = plain scan
+__global__ void __launch_bounds__(1024) k_scan_tiles(const uint32_t* __restrict__ counts, uint32_t total, uint32_t pad_mask,
                                                      uint32_t* __restrict__ offsets, uint32_t* __restrict__ tile_sums) {
     __shared__ uint32_t warp_sums[32];
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint32_t idx = blockIdx.x * kScanTile + tid * 4;
     uint32_t v[4];
 #pragma unroll
-    for (int k = 0; k < 4; k++) v[k] = (idx + k < total) ? counts[idx + k] : 0;
+    for (int k = 0; k < 4; k++) v[k] = (idx + k < total) ? ((counts[idx + k] + pad_mask) & ~pad_mask) : 0;
     uint32_t local = v[0] + v[1] + v[2] + v[3];
     uint32_t incl = local;
 #pragma unroll
@@ -434,6 +698,12 @@ void launch_build_levels(G1Affine* bases, size_t count, int levels, size_t strid
     PM_CUDA(cudaStreamSynchronize(stream));   // scratch dies here
 }
 
+static int g_tuning_rounds = -1, g_tuning_group = 0;
+void MsmEngine::set_tuning(int rounds, int group) {
+    g_tuning_rounds = rounds;
+    g_tuning_group = group;
+}
+
 int MsmEngine::choose_window(size_t n) {
     // Empirical optimum on B200 (profiles/msm_window_sweep_r1.jsonl): the bucket-reduction tail grows
     // with 2^(c-1) * ceil(256/c) while the additions shrink with ceil(256/c); c = 16 also makes the 16
@@ -495,12 +765,49 @@ MsmEngine::Shape MsmEngine::run(const G1Affine* bases, const Fr* scalars, size_t
     size_t share = n * (size_t)nwin / 8192;
     uint32_t heavy_thr = cfg.heavy ? (uint32_t)cfg.heavy : (uint32_t)(share > 512 ? share : 512);
     const size_t max_tasks = n * (size_t)nwin / kHeavyChunk + total + 16;
+    const size_t entries = n * (size_t)nwin;   // upper bound of the sorted list
+
+    // ---- batched-affine pair rounds (see k_pairs_forward): choose R from the mean run length ----
+    const int forced_rounds = cfg.rounds >= 0 ? cfg.rounds : g_tuning_rounds;
+    int rounds = 0;
+    {
+        const double lambda = (double)entries / (double)total;
+        if (forced_rounds >= 0) {
+            rounds = forced_rounds;
+        } else if (entries >= ((size_t)1 << 20)) {
+            // Fq products per bucket: 6 per slot pair of the padded run, 10 per XYZZ addition of what is left,
+            // plus a fixed cost per round (inversion pass, launches) of about 16 M products per MSM
+            double best = 1e300;
+            for (int r = 0; r <= 6; r++) {
+                const double a = (double)(1u << r), lp = lambda + (a - 1) / 2, rest = lp / a;
+                double cost = 6.0 * lp * (1.0 - 1.0 / a) + 10.0 * (rest > 1 ? rest - 1 : 0) + r * 16e6 / (double)total;
+                if (cost < best) { best = cost; rounds = r; }
+            }
+            static int bias = -100;
+            if (bias == -100) {
+                const char* v = getenv("PM_MSM_ROUNDS_BIAS");
+                bias = v ? atoi(v) : 0;
+            }
+            rounds += bias;
+            if (rounds < 0) rounds = 0;
+        }
+        if (rounds > kMaxRounds) rounds = kMaxRounds;
+        // padded list / workspace must stay addressable and affordable, else use the XYZZ walk only
+        while (rounds > 0) {
+            const size_t slots = entries + (size_t)total * ((1u << rounds) - 1);
+            const size_t need = slots / 2 * (sizeof(G1Affine) + sizeof(Fq)) + slots / 4 * sizeof(G1Affine) + slots * 4;
+            if (slots < ((size_t)1 << 32) - 4096 && (forced_rounds >= 0 || need <= kMaxRoundsWorkspace)) break;
+            rounds--;
+        }
+    }
+    const uint32_t pad_mask = (1u << rounds) - 1u;
+    const size_t slots_max = (entries + (size_t)total * pad_mask + 1) & ~(size_t)1;   // upper bound of S_0
 
     uint32_t* counts = counts_.as<uint32_t>(total + 1);
     uint32_t* offsets = offsets_.as<uint32_t>(total + 1);
     uint32_t* cursors = cursors_.as<uint32_t>((size_t)total + 1 + ntiles + 1);
     uint32_t* tile_sums = cursors + total + 1;
-    uint32_t* sorted = sorted_.as<uint32_t>(n * (size_t)nwin);
+    uint32_t* sorted = sorted_.as<uint32_t>(slots_max + 2);
     G1XYZZ* buckets = buckets_.as<G1XYZZ>(total);
     G1XYZZ* segs = segs_.as<G1XYZZ>(2 * seg_total + (size_t)ngroups * 256 + 64);
     uint32_t* order = order_.as<uint32_t>((size_t)total + kLenBins);
@@ -521,21 +828,62 @@ MsmEngine::Shape MsmEngine::run(const G1Affine* bases, const Fr* scalars, size_t
     const unsigned dgrid = ceil_div(n, 256);
     k_digits<false><<<dgrid, 256, 0, stream>>>(bases, scalars, n, scalar_stride, scalar_offset, c, nwin, nb, levels, (uint32_t)cfg.level_stride, counts, nullptr);
     PM_LAUNCH_CHECK();
-    k_scan_tiles<<<ntiles, 1024, 0, stream>>>(counts, total, offsets, tile_sums);
+    k_scan_tiles<<<ntiles, 1024, 0, stream>>>(counts, total, pad_mask, offsets, tile_sums);
     k_scan_tile_sums<<<1, 1024, 0, stream>>>(tile_sums, ntiles);
     k_scan_apply<<<ntiles, 1024, 0, stream>>>(total, tile_sums, ntiles, offsets, cursors);
     PM_LAUNCH_CHECK();
     k_digits<true><<<dgrid, 256, 0, stream>>>(bases, scalars, n, scalar_stride, scalar_offset, c, nwin, nb, levels, (uint32_t)cfg.level_stride, cursors, sorted);
     PM_LAUNCH_CHECK();
-    PM_CUDA(cudaMemsetAsync(len_hist, 0, kLenBins * sizeof(uint32_t), stream));
-    k_len_hist<<<ceil_div(total, 256), 256, 0, stream>>>(offsets, total, len_hist);
-    k_len_scan<<<1, 1024, 0, stream>>>(len_hist);
-    k_len_scatter<<<ceil_div(total, 256), 256, 0, stream>>>(offsets, total, len_hist, order);
-    PM_LAUNCH_CHECK();
+    if (rounds > 0) {
+        k_pad_runs<<<ceil_div(total, 256), 256, 0, stream>>>(counts, offsets, total, sorted);
+        PM_LAUNCH_CHECK();
+    } else {
+        PM_CUDA(cudaMemsetAsync(len_hist, 0, kLenBins * sizeof(uint32_t), stream));
+        k_len_hist<<<ceil_div(total, 256), 256, 0, stream>>>(offsets, total, len_hist);
+        k_len_scan<<<1, 1024, 0, stream>>>(len_hist);
+        k_len_scatter<<<ceil_div(total, 256), 256, 0, stream>>>(offsets, total, len_hist, order);
+        PM_LAUNCH_CHECK();
+    }
     if (time_accumulate) {
         if (!ev_acc_begin) { PM_CUDA(cudaEventCreate(&ev_acc_begin)); PM_CUDA(cudaEventCreate(&ev_acc_end)); }
         PM_CUDA(cudaEventRecord(ev_acc_begin, stream));
     }
+    PointPlanes run_pts{nullptr, 0};
+    if (rounds > 0) {
+        const size_t cap_a = slots_max / 2 + 2, cap_b = slots_max / 4 + 2;
+        PointPlanes ping{pairs_a_.as<uint4>(6 * cap_a), cap_a};
+        PointPlanes pong{rounds > 1 ? pairs_b_.as<uint4>(6 * cap_b) : nullptr, cap_b};
+        FqPlanes prefix{prefix_.as<uint4>(3 * cap_a), cap_a};
+        const size_t t_max = (slots_max / 2 + kPairTile - 1) / kPairTile * 128 + 128;
+        Fq* tvals = tvals_.as<Fq>(t_max);
+        Fq* tpre = tpre_.as<Fq>(t_max);
+        const uint32_t* slots0 = offsets + total;
+        for (int r = 0; r < rounds; r++) {
+            const size_t pairs_max = (slots_max >> r) >> 1;
+            const unsigned g = ceil_div(pairs_max, kPairTile);
+            if (g == 0) break;
+            PointPlanes dst = (r & 1) ? pong : ping;
+            // Fermat inverses are a serial chain of ~570 products: spread T over about one warp per scheduler
+            const size_t tcount = (size_t)g * 128;
+            const uint32_t inv_threads = (uint32_t)(tcount < (size_t)sm_count() * 128 ? tcount : (size_t)sm_count() * 128);
+            if (r == 0) {
+                PairSource<true> src{bases, sorted, run_pts};
+                k_pairs_forward<true><<<g, 128, 0, stream>>>(src, slots0, r, prefix, tvals);
+                k_batch_invert<<<ceil_div(inv_threads, 128), 128, 0, stream>>>(tvals, slots0, r, inv_threads, tpre);
+                k_pairs_backward<true><<<g, 128, 0, stream>>>(src, slots0, r, prefix, tvals, dst);
+            } else {
+                PairSource<false> src{bases, sorted, run_pts};
+                k_pairs_forward<false><<<g, 128, 0, stream>>>(src, slots0, r, prefix, tvals);
+                k_batch_invert<<<ceil_div(inv_threads, 128), 128, 0, stream>>>(tvals, slots0, r, inv_threads, tpre);
+                k_pairs_backward<false><<<g, 128, 0, stream>>>(src, slots0, r, prefix, tvals, dst);
+            }
+            PM_LAUNCH_CHECK();
+            run_pts = dst;
+            launches += 3;
+        }
+    }
+    // runs are cut into chunked tasks only when walking them serially would approach the kernel's duration
+    const uint32_t walk_heavy_thr = rounds > 0 && !cfg.heavy ? (heavy_thr >> rounds > 64 ? heavy_thr >> rounds : 64) : heavy_thr;
     {
         static int variant = -1;
         if (variant < 0) {
@@ -543,7 +891,8 @@ MsmEngine::Shape MsmEngine::run(const G1Affine* bases, const Fr* scalars, size_t
             variant = v ? atoi(v) : 24;
         }
         const unsigned g = ceil_div(total, 128);
-        if (variant == 3) k_accumulate<3, MulInline><<<g, 128, 0, stream>>>(bases, sorted, offsets, order, buckets, total, heavy_thr, hl);
+        if (rounds > 0) k_accumulate_rounds<<<g, 128, 0, stream>>>(run_pts, offsets, rounds, buckets, total, walk_heavy_thr, hl);
+        else if (variant == 3) k_accumulate<3, MulInline><<<g, 128, 0, stream>>>(bases, sorted, offsets, order, buckets, total, heavy_thr, hl);
         else k_accumulate<4, MulCall><<<g, 128, 0, stream>>>(bases, sorted, offsets, order, buckets, total, heavy_thr, hl);
         PM_LAUNCH_CHECK();
     }
@@ -552,10 +901,12 @@ MsmEngine::Shape MsmEngine::run(const G1Affine* bases, const Fr* scalars, size_t
         static bool attr_set = false;
         const int smem = 256 * (int)sizeof(G1XYZZ);
         if (!attr_set) {
-            PM_CUDA(cudaFuncSetAttribute(k_accumulate_heavy, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            PM_CUDA(cudaFuncSetAttribute(k_accumulate_heavy<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            PM_CUDA(cudaFuncSetAttribute(k_accumulate_heavy<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
             attr_set = true;
         }
-        k_accumulate_heavy<<<4 * sm_count(), 256, smem, stream>>>(bases, sorted, offsets, hl);
+        if (rounds > 0) k_accumulate_heavy<true><<<4 * sm_count(), 256, smem, stream>>>(bases, sorted, run_pts, rounds, offsets, hl);
+        else k_accumulate_heavy<false><<<4 * sm_count(), 256, smem, stream>>>(bases, sorted, run_pts, 0, offsets, hl);
         PM_LAUNCH_CHECK();
         k_heavy_finish<<<2 * sm_count(), 128, 0, stream>>>(buckets, hl);
         PM_LAUNCH_CHECK();

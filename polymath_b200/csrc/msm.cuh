@@ -13,6 +13,10 @@ struct MsmConfig {
     // group g, so `levels` windows share one bucket set and the final Horner only spans the groups.
     int levels = 1;
     size_t level_stride = 0;
+    // Batched-affine pair rounds before the XYZZ walk (msm.cu: k_pairs_*): -1 = choose from the mean run
+    // length, 0 = none, k = exactly k rounds; group = buckets per thread in a round (0 = auto).
+    int rounds = -1;
+    int group = 0;
 };
 
 // Reusable workspace + launch sequence.  One engine per context / stream.
@@ -34,6 +38,8 @@ public:
     Shape run(const G1Affine* bases, const Fr* scalars, size_t n, G1XYZZ* winsums_out, cudaStream_t stream,
               MsmConfig cfg = {}, size_t scalar_stride = 1, size_t scalar_offset = 0);
     static int choose_window(size_t n);
+    // process-wide default for MsmConfig::rounds / group when a call leaves them automatic (tests, tuning sweeps)
+    static void set_tuning(int rounds, int group);
     size_t launches = 0;   // kernels launched so far (bench accounting)
     // timing hook for bench.py's roofline: CUDA events around the bucket-accumulation kernel of the last run
     cudaEvent_t ev_acc_begin = nullptr, ev_acc_end = nullptr;
@@ -42,6 +48,7 @@ public:
 
 private:
     DevBuf counts_, offsets_, cursors_, sorted_, buckets_, segs_, heavy_list_, heavy_count_, order_;
+    DevBuf pairs_a_, pairs_b_, prefix_, tvals_, tpre_;   // pair rounds
 };
 
 constexpr int kMaxMsmWindows = 64;

@@ -42,6 +42,8 @@ def load():
     lib.pm_msm_g1_window.restype = C.c_int
     lib.pm_msm_g1_levels.argtypes = [u8p, sz, u8p, sz, C.c_int, C.c_int, u8p]
     lib.pm_msm_g1_levels.restype = C.c_int
+    lib.pm_msm_set_tuning.argtypes = [C.c_int, C.c_int]
+    lib.pm_msm_set_tuning.restype = C.c_int
     lib.pm_fixed_base_mul.argtypes = [u8p, sz, u8p]
     lib.pm_fixed_base_mul.restype = C.c_int
     dp = C.POINTER(C.c_double)

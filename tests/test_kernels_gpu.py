@@ -144,6 +144,57 @@ def test_msm_edge_cases(pmlib):
     assert kernels.msm_g1(bases, scalars[:100]) == poly.msm_pippenger(scalars[:100], bases[:100])
 
 
+@pytest.fixture
+def msm_tuning(pmlib):
+    from polymath_b200 import kernels
+    yield kernels.msm_set_tuning
+    kernels.msm_set_tuning(-1, 0)
+
+
+@pytest.mark.parametrize("n,c,rounds,group", [(1500, 6, 1, 0), (1500, 6, 2, 1), (1500, 6, 3, 3), (1500, 6, 6, 16),
+                                               (1500, 6, 9, 0), (4096, 4, 5, 2), (300, 8, 2, 5), (33, 4, 4, 1),
+                                               (2, 4, 1, 1), (1, 0, 3, 0)])
+def test_msm_pair_rounds(msm_tuning, n, c, rounds, group):
+    """Batched-affine pair rounds (k_pairs_forward / k_batch_invert / k_pairs_backward) before the XYZZ walk."""
+    from polymath_b200 import kernels
+    rnd = random.Random(4000 + n + c)
+    bases = _bases(n, rnd)
+    scalars = [rnd.randrange(R_MOD) for _ in range(n)]
+    want = poly.msm_pippenger(scalars, bases)
+    msm_tuning(rounds, group)
+    assert kernels.msm_g1(bases, scalars, window_bits=c) == want
+    if c:
+        assert kernels.msm_g1(bases, scalars, window_bits=c, levels=3) == want
+
+
+@pytest.mark.parametrize("rounds,group", [(1, 1), (2, 0), (3, 2), (5, 7), (8, 1)])
+def test_msm_pair_rounds_exceptional_pairs(msm_tuning, rounds, group):
+    """P + P, P + (-P), infinity operands and results inside the pair rounds; heavy buckets skipped by them."""
+    from polymath_b200 import kernels
+    rnd = random.Random(78)
+    distinct = _bases(6, rnd)
+    n = 900
+    # few distinct points, few distinct scalars: every bucket run is full of equal and opposite points
+    bases = [distinct[rnd.randrange(6)] for _ in range(n)]
+    for i in range(0, n, 5):
+        bases[i] = curve.g1_neg(bases[i - 1])
+    for i in range(0, n, 11):
+        bases[i] = None
+    pool = [rnd.randrange(R_MOD) for _ in range(4)] + [1, 2, R_MOD - 1, 3]
+    scalars = [pool[rnd.randrange(len(pool))] for _ in range(n)]
+    for i in range(0, n, 17):
+        scalars[i] = 0
+    want = poly.msm_pippenger(scalars, bases)
+    msm_tuning(rounds, group)
+    assert kernels.msm_g1(bases, scalars, window_bits=5) == want
+    assert kernels.msm_g1(bases, scalars, window_bits=8, heavy_threshold=16) == want
+    assert kernels.msm_g1(bases, scalars, window_bits=7, levels=4) == want
+    # the run of one bucket is P, P, P, ... (pure doubling tree) and P, -P, P, -P (all cancel)
+    assert kernels.msm_g1([distinct[0]] * 64, [5] * 64, window_bits=4) == curve.g1_mul(distinct[0], 320)
+    assert kernels.msm_g1([distinct[0], curve.g1_neg(distinct[0])] * 32, [5] * 64, window_bits=4) is None
+    assert kernels.msm_g1([distinct[0], curve.g1_neg(distinct[0])] * 32 + [distinct[1]], [5] * 65, window_bits=4) == curve.g1_mul(distinct[1], 5)
+
+
 def test_msm_linearity_large(pmlib):
     """2^18 points: MSM(k*s) == k*MSM(s) and MSM(s) + MSM(t) == MSM(s+t), bases generated on the device."""
     from polymath_b200 import kernels
@@ -156,3 +207,8 @@ def test_msm_linearity_large(pmlib):
     # sum_i s_i * (b_i * G) = (sum_i s_i * b_i) * G
     dot = sum(x * y for x, y in zip(s, base_scalars)) % R_MOD
     assert kernels.msm_g1(bases, s) == curve.g1_mul(curve.G1_GEN, dot)
+    kernels.msm_set_tuning(0, 0)                      # XYZZ walk only
+    try:
+        assert kernels.msm_g1(bases, s) == curve.g1_mul(curve.G1_GEN, dot)
+    finally:
+        kernels.msm_set_tuning(-1, 0)

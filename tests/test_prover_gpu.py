@@ -171,3 +171,24 @@ def test_fixed_base_tables_path(pmlib, c, monkeypatch):
         return orc.MiMCDemo(xl, xr, consts), 2, [orc.mimc_hash(xl, xr, consts)]
 
     _run_flow(mk_setup, mk_prove, seed=31 + c, proofs=2)
+
+
+@pytest.mark.parametrize("rounds,group", [(2, 0), (4, 3)])
+def test_prover_with_pair_rounds(pmlib, rounds, group):
+    """The batched-affine accumulation the large circuits use (forced on a small one): proofs stay byte-identical."""
+    from polymath_b200 import kernels
+    consts = []
+
+    def mk_setup(rng):
+        consts[:] = [o_fr_rand(rng) for _ in range(40)]
+        return orc.MiMCDemo(None, None, consts), 40
+
+    def mk_prove(rng):
+        xl, xr = o_fr_rand(rng), o_fr_rand(rng)
+        return orc.MiMCDemo(xl, xr, consts), 2, [orc.mimc_hash(xl, xr, consts)]
+
+    kernels.msm_set_tuning(rounds, group)
+    try:
+        _run_flow(mk_setup, mk_prove, seed=77 + rounds, proofs=1)
+    finally:
+        kernels.msm_set_tuning(-1, 0)

@@ -17,13 +17,18 @@ def main():
     ap.add_argument("--windows", default="0")
     ap.add_argument("--iters", type=int, default=3)
     ap.add_argument("--levels", default="1", help="comma list; 0 = as many levels as windows")
+    ap.add_argument("--rounds", default="-1", help="comma list of pair-round settings (-1 = automatic, 0 = XYZZ walk only)")
+    ap.add_argument("--group", type=int, default=0)
+    ap.add_argument("--skip-basics", action="store_true")
     a = ap.parse_args()
     lib = require_device()
     d = C.c_double()
-    check(lib.pm_bench_imad_peak(C.byref(d)))
-    imad = d.value
-    print(json.dumps({"kernel": "imad_wide_peak", "mads_per_s": imad}), flush=True)
-    for f, name, cost in ((0, "fr_mul", 136), (1, "fq_mul", 300)):
+    imad = 1.0
+    if not a.skip_basics:
+        check(lib.pm_bench_imad_peak(C.byref(d)))
+        imad = d.value
+        print(json.dumps({"kernel": "imad_wide_peak", "mads_per_s": imad}), flush=True)
+    for f, name, cost in (() if a.skip_basics else ((0, "fr_mul", 136), (1, "fq_mul", 300))):
         check(lib.pm_bench_field_mul(f, C.byref(d)))
         print(json.dumps({"kernel": name, "muls_per_s": d.value, "imad_equiv_per_s": d.value * cost,
                           "frac_of_imad_peak": d.value * cost / imad}), flush=True)
@@ -43,9 +48,12 @@ def main():
                     lv = (256 + w - 1) // w
                 if lv > 1 and w == 0:
                     continue
-                check(lib.pm_bench_msm_levels(n, w, lv, a.iters, C.byref(d), C.byref(acc)))
-                print(json.dumps({"kernel": "msm_g1", "log_n": lg, "window": w, "levels": lv, "ms": d.value,
-                                  "ms_accumulate": acc.value, "mpts_per_s": n / d.value / 1e3}), flush=True)
+                for rd in [int(x) for x in a.rounds.split(",")]:
+                    check(lib.pm_msm_set_tuning(rd, a.group))
+                    check(lib.pm_bench_msm_levels(n, w, lv, a.iters, C.byref(d), C.byref(acc)))
+                    print(json.dumps({"kernel": "msm_g1", "log_n": lg, "window": w, "levels": lv, "rounds": rd, "ms": d.value,
+                                      "ms_accumulate": acc.value, "mpts_per_s": n / d.value / 1e3}), flush=True)
+                check(lib.pm_msm_set_tuning(-1, 0))
 
 
 if __name__ == "__main__":
