@@ -62,6 +62,9 @@ int pm_fr_mul_batch(const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n);
 /* out[i] = a[i] * b[i] in Fq (base-field product used inside all G1 arithmetic). */
 int pm_fq_mul_batch(const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n);
 /* out[i] = a[i] + b[i]  /  a[i] - b[i] in Fr. */
+/* out[i] = a[i]^-1 (0 -> 0): ark-ff `Field::inverse` (src/common.rs:41,46; every projective -> affine conversion). */
+int pm_fr_inv_batch(const uint8_t* a, uint8_t* out, size_t n);
+int pm_fq_inv_batch(const uint8_t* a, uint8_t* out, size_t n);
 int pm_fr_add_batch(const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n);
 int pm_fr_sub_batch(const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n);
 

@@ -1,6 +1,7 @@
 // C ABI of libpolymath_b200.so — standalone kernel entry points (include/polymath_b200.h).
 // Host buffers in, host buffers out; every call stages through device memory owned here.
 #include <mutex>
+#include <cstdlib>
 #include <vector>
 
 #include "../../include/polymath_b200.h"
@@ -98,6 +99,8 @@ int pm_fr_mul_batch(const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n) 
 int pm_fr_add_batch(const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n) { return field_batch<Fr>(FieldOp::Add, a, b, out, n, false); }
 int pm_fr_sub_batch(const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n) { return field_batch<Fr>(FieldOp::Sub, a, b, out, n, false); }
 int pm_fq_mul_batch(const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n) { return field_batch<Fq>(FieldOp::Mul, a, b, out, n, true); }
+int pm_fr_inv_batch(const uint8_t* a, uint8_t* out, size_t n) { return field_batch<Fr>(FieldOp::Inv, a, a, out, n, false); }
+int pm_fq_inv_batch(const uint8_t* a, uint8_t* out, size_t n) { return field_batch<Fq>(FieldOp::Inv, a, a, out, n, true); }
 
 int pm_ntt_fr(uint8_t* data, unsigned log_n, int inverse, const uint8_t* coset_gen) {
     return guarded([&] {

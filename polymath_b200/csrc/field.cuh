@@ -245,14 +245,93 @@ struct alignas(16) Fp {
         uint32_t w[2] = {(uint32_t)e, (uint32_t)(e >> 32)};
         return pow(w, 2);
     }
-    // Fermat inverse a^(p-2); inverse of zero is zero
-    __device__ Fp inv() const {
+    // Fermat inverse a^(p-2); inverse of zero is zero.  ~1.5 * bits dependent products: kept as the
+    // cross-check of inv() (field_kernels.cu: k_inv_selftest).
+    __device__ Fp inv_fermat() const {
         uint32_t e[N];
         e[0] = ptx::sub_cc(P::mod()[0], 2u);
 #pragma unroll
         for (int i = 1; i < N - 1; i++) e[i] = ptx::subc_cc(P::mod()[i], 0u);
         e[N - 1] = ptx::subc(P::mod()[N - 1], 0u);
         return pow(e, N);
+    }
+
+    // x / 2^k mod p for 1 <= k <= 31: add the multiple of p that clears the low k bits, then shift
+    __device__ __forceinline__ static void div_pow2(uint32_t* x, int k) {
+        const uint32_t m = (x[0] * P::INV) & ((1u << k) - 1u);
+        uint32_t t[N + 1];
+        uint64_t carry = 0;
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            uint64_t sum = (uint64_t)m * P::mod()[i] + x[i] + carry;
+            t[i] = (uint32_t)sum;
+            carry = sum >> 32;
+        }
+        t[N] = (uint32_t)carry;
+#pragma unroll
+        for (int i = 0; i < N; i++) x[i] = __funnelshift_r(t[i], t[i + 1], k);
+    }
+    // Inverse by the binary extended Euclidean algorithm (subtract, then strip all trailing zero bits at
+    // once); inverse of zero is zero.  Invariants: x1 * a = u * R^2, x2 * a = v * R^2 (mod p) on the integer
+    // behind the Montgomery form, so the result is again in Montgomery form.  About 0.7 * 2 * bits rounds of
+    // ~100 ALU/IMAD instructions instead of ~1.5 * bits full products.
+    __device__ __noinline__ Fp inv() const {
+        if (is_zero()) return zero();
+        uint32_t u[N], v[N], x1[N], x2[N];
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            u[i] = this->v[i];
+            v[i] = P::mod()[i];
+            x1[i] = P::r2()[i];
+            x2[i] = 0;
+        }
+        for (;;) {
+            // strip the trailing zeros of u (u != 0), dividing x1 alongside
+            while ((u[0] & 1u) == 0) {
+                int k = u[0] ? __ffs((int)u[0]) - 1 : 31;
+                if (k > 31) k = 31;
+#pragma unroll
+                for (int i = 0; i < N; i++) u[i] = __funnelshift_r(u[i], i + 1 < N ? u[i + 1] : 0u, k);
+                div_pow2(x1, k);
+            }
+            // d = u - v
+            uint32_t d[N];
+            d[0] = ptx::sub_cc(u[0], v[0]);
+#pragma unroll
+            for (int i = 1; i < N; i++) d[i] = ptx::subc_cc(u[i], v[i]);
+            const uint32_t borrow = ptx::subc(0, 0);
+            uint32_t nz = 0;
+#pragma unroll
+            for (int i = 0; i < N; i++) nz |= d[i];
+            if (nz == 0) break;                     // u == v == gcd = 1
+            if (borrow) {
+                // u < v: swap the pairs, d = v - u
+#pragma unroll
+                for (int i = 0; i < N; i++) {
+                    uint32_t t = u[i]; u[i] = v[i]; v[i] = t;
+                    t = x1[i]; x1[i] = x2[i]; x2[i] = t;
+                }
+                d[0] = ptx::sub_cc(u[0], v[0]);
+#pragma unroll
+                for (int i = 1; i < N - 1; i++) d[i] = ptx::subc_cc(u[i], v[i]);
+                d[N - 1] = ptx::subc(u[N - 1], v[N - 1]);
+            }
+            // u <- u - v (even, non-zero), x1 <- x1 - x2 mod p
+#pragma unroll
+            for (int i = 0; i < N; i++) u[i] = d[i];
+            x1[0] = ptx::sub_cc(x1[0], x2[0]);
+#pragma unroll
+            for (int i = 1; i < N; i++) x1[i] = ptx::subc_cc(x1[i], x2[i]);
+            const uint32_t b2 = ptx::subc(0, 0);
+            x1[0] = ptx::add_cc(x1[0], P::mod()[0] & b2);
+#pragma unroll
+            for (int i = 1; i < N - 1; i++) x1[i] = ptx::addc_cc(x1[i], P::mod()[i] & b2);
+            x1[N - 1] = ptx::addc(x1[N - 1], P::mod()[N - 1] & b2);
+        }
+        Fp r;
+#pragma unroll
+        for (int i = 0; i < N; i++) r.v[i] = x1[i];
+        return r;
     }
 };
 

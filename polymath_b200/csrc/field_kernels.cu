@@ -14,7 +14,7 @@ __global__ void __launch_bounds__(256) k_batch(const F* __restrict__ a, const F*
     size_t stride = (size_t)gridDim.x * blockDim.x;
     for (; i < n; i += stride) {
         F x = a[i], y = b[i];
-        out[i] = OP == 0 ? x * y : (OP == 1 ? x + y : x - y);
+        out[i] = OP == 0 ? x * y : (OP == 1 ? x + y : (OP == 2 ? x - y : x.inv()));
     }
 }
 
@@ -28,6 +28,7 @@ void launch(FieldOp op, const F* a, const F* b, F* out, size_t n, cudaStream_t s
         case FieldOp::Mul: k_batch<F, 0><<<grid, 256, 0, stream>>>(a, b, out, n); break;
         case FieldOp::Add: k_batch<F, 1><<<grid, 256, 0, stream>>>(a, b, out, n); break;
         case FieldOp::Sub: k_batch<F, 2><<<grid, 256, 0, stream>>>(a, b, out, n); break;
+        case FieldOp::Inv: k_batch<F, 3><<<grid, 256, 0, stream>>>(a, b, out, n); break;
     }
     PM_LAUNCH_CHECK();
 }

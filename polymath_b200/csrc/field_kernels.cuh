@@ -5,7 +5,7 @@
 
 namespace pm {
 
-enum class FieldOp { Mul, Add, Sub };
+enum class FieldOp { Mul, Add, Sub, Inv };   // Inv: out = a^-1 (b ignored)
 void launch_fr_batch(FieldOp op, const Fr* a, const Fr* b, Fr* out, size_t n, cudaStream_t stream);
 void launch_fq_batch(FieldOp op, const Fq* a, const Fq* b, Fq* out, size_t n, cudaStream_t stream);
 

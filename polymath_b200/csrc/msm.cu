@@ -108,11 +108,16 @@ __device__ __forceinline__ G1Affine load_point(const G1Affine* __restrict__ base
 // Buckets are walked in order of decreasing length (counting sort on min(length, kLenBins-1)) so that the
 // 32 buckets of a warp have nearly equal lengths: removes the divergence of Poisson-distributed lengths.
 constexpr uint32_t kLenBins = 2048;
-__global__ void k_len_hist(const uint32_t* __restrict__ offsets, uint32_t total, uint32_t* __restrict__ hist) {
+// (warp-aggregated atomics: after the pair rounds nearly all runs share a few lengths)
+__global__ void k_len_hist(const uint32_t* __restrict__ offsets, uint32_t total, int shift, uint32_t* __restrict__ hist) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= total) return;
-    uint32_t len = offsets[t + 1] - offsets[t];
-    atomicAdd(&hist[kLenBins - 1 - min(len, kLenBins - 1)], 1u);   // bin 0 = longest
+    const bool active = t < total;
+    const unsigned mask = __ballot_sync(0xffffffffu, active);
+    if (!active) return;
+    uint32_t len = (offsets[t + 1] - offsets[t]) >> shift;
+    const uint32_t bin = kLenBins - 1 - min(len, kLenBins - 1);   // bin 0 = longest
+    const unsigned peers = __match_any_sync(mask, bin);
+    if ((threadIdx.x & 31u) == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&hist[bin], (uint32_t)__popc(peers));
 }
 __global__ void __launch_bounds__(1024) k_len_scan(uint32_t* __restrict__ hist) {   // exclusive scan of kLenBins entries, in place
     __shared__ uint32_t sh[kLenBins];
@@ -125,13 +130,21 @@ __global__ void __launch_bounds__(1024) k_len_scan(uint32_t* __restrict__ hist) 
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < kLenBins; i += blockDim.x) hist[i] = sh[i];
 }
-__global__ void k_len_scatter(const uint32_t* __restrict__ offsets, uint32_t total, uint32_t* __restrict__ cursor,
+__global__ void k_len_scatter(const uint32_t* __restrict__ offsets, uint32_t total, int shift, uint32_t* __restrict__ cursor,
                               uint32_t* __restrict__ order) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= total) return;
-    uint32_t len = offsets[t + 1] - offsets[t];
-    uint32_t pos = atomicAdd(&cursor[kLenBins - 1 - min(len, kLenBins - 1)], 1u);
-    order[pos] = t;
+    const bool active = t < total;
+    const unsigned mask = __ballot_sync(0xffffffffu, active);
+    if (!active) return;
+    uint32_t len = (offsets[t + 1] - offsets[t]) >> shift;
+    const uint32_t bin = kLenBins - 1 - min(len, kLenBins - 1);
+    const unsigned peers = __match_any_sync(mask, bin);
+    const int leader = __ffs(peers) - 1;
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t base = 0;
+    if (lane == (uint32_t)leader) base = atomicAdd(&cursor[bin], (uint32_t)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    order[base + __popc(peers & ((1u << lane) - 1u))] = t;
 }
 
 // ---- heavy buckets -------------------------------------------------------------------------
@@ -174,7 +187,7 @@ __device__ __forceinline__ void defer_heavy(const HeavyLists& hl, uint32_t t, ui
 // Per slot pair: 1 + 5 Fq products (+ 3/kPairsPerThread for the second level), against 10 for an XYZZ
 // mixed addition.  Exceptional pairs (an operand at infinity — all padding —, P + P, P + (-P)) are classified
 // identically in both passes (pair_kind) and contribute no denominator, or 2y for a doubling.
-constexpr int kPairsPerThread = 16;
+constexpr int kPairsPerThread = 32;
 constexpr uint32_t kPairTile = 128 * kPairsPerThread;   // slot pairs per CTA
 constexpr uint32_t kPadEntry = 0xffffffffu;             // sorted-list sentinel: the point at infinity
 
@@ -323,24 +336,47 @@ __global__ void __launch_bounds__(128) k_pairs_forward(PairSource<FIRST> src, co
     store_fq(T + (size_t)blockIdx.x * 128 + threadIdx.x, acc);
 }
 
-// T[i] <- T[i]^-1 for the thread totals of k_pairs_forward in round r (all non-zero): thread j owns j, j + nthr, ...
-__global__ void __launch_bounds__(128) k_batch_invert(Fq* __restrict__ T, const uint32_t* __restrict__ slots0, int r, uint32_t nthr,
-                                                      Fq* __restrict__ pre) {
-    const size_t npairs = round_pairs(slots0, r);
-    const size_t n = (npairs + kPairTile - 1) / kPairTile * 128;
-    const size_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= nthr || j >= n) return;
+// ---- inversion of the thread totals T of round r (all non-zero), Montgomery's trick over a small tree ----
+// Level sizes: n_0 = thread totals of k_pairs_forward, n_{l+1} = ceil(n_l / kInvFan).  k_invert_up multiplies
+// kInvFan strided elements of level l into one element of level l+1 (exclusive prefixes kept), k_invert_top
+// takes the Fermat inverse of the few top elements, k_invert_down walks back.  3 products per element and
+// level; the serial Fermat chains (~570 products) run in a few thousand threads only.
+constexpr uint32_t kInvFan = 32;
+constexpr int kInvLevels = 2;
+__device__ __forceinline__ size_t invert_level_size(const uint32_t* __restrict__ slots0, int r, int level) {
+    size_t n = (round_pairs(slots0, r) + kPairTile - 1) / kPairTile * 128;
+    for (int l = 0; l < level; l++) n = (n + kInvFan - 1) / kInvFan;
+    return n;
+}
+__global__ void __launch_bounds__(128) k_invert_up(const Fq* __restrict__ lo, Fq* __restrict__ pre, Fq* __restrict__ hi,
+                                                   const uint32_t* __restrict__ slots0, int r, int level) {
+    const size_t n = invert_level_size(slots0, r, level), m = (n + kInvFan - 1) / kInvFan;
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
     Fq acc = Fq::one();
-    uint32_t cnt = 0;
-    for (size_t idx = j; idx < n; idx += nthr, cnt++) {
+    for (size_t idx = j; idx < n; idx += m) {
         store_fq(pre + idx, acc);
-        acc = fq_mul_call(acc, load_fq(T + idx));
+        acc = fq_mul_call(acc, load_fq(lo + idx));
     }
-    Fq inv = acc.inv();
-    for (uint32_t k = cnt; k-- > 0;) {
-        const size_t idx = j + (size_t)k * nthr;
-        Fq t = load_fq(T + idx);
-        store_fq(T + idx, fq_mul_call(inv, load_fq(pre + idx)));
+    store_fq(hi + j, acc);
+}
+__global__ void __launch_bounds__(128) k_invert_top(Fq* __restrict__ top, const uint32_t* __restrict__ slots0, int r, int level) {
+    const size_t n = invert_level_size(slots0, r, level);
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    store_fq(top + j, load_fq(top + j).inv());
+}
+__global__ void __launch_bounds__(128) k_invert_down(Fq* __restrict__ lo, const Fq* __restrict__ pre, const Fq* __restrict__ hi,
+                                                     const uint32_t* __restrict__ slots0, int r, int level) {
+    const size_t n = invert_level_size(slots0, r, level), m = (n + kInvFan - 1) / kInvFan;
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    Fq inv = load_fq(hi + j);
+    const size_t cnt = (n - j + m - 1) / m;
+    for (size_t k = cnt; k-- > 0;) {
+        const size_t idx = j + k * m;
+        Fq t = load_fq(lo + idx);
+        store_fq(lo + idx, fq_mul_call(inv, load_fq(pre + idx)));
         inv = fq_mul_call(inv, t);
     }
 }
@@ -424,11 +460,13 @@ __global__ void __launch_bounds__(128, MINB) k_accumulate(const G1Affine* __rest
 
 // After R pair rounds: bucket t owns X_R[offsets[t] >> R .. offsets[t+1] >> R); one thread per bucket finishes the
 // few remaining points in XYZZ.  Runs still longer than heavy_thr (hot buckets) go to the chunked path.
-__global__ void __launch_bounds__(128, 4) k_accumulate_rounds(PointPlanes pts, const uint32_t* __restrict__ offsets, int R,
+__global__ void __launch_bounds__(128, 4) k_accumulate_rounds(PointPlanes pts, const uint32_t* __restrict__ offsets,
+                                                              const uint32_t* __restrict__ order, int R,
                                                               G1XYZZ* __restrict__ buckets, uint32_t total_buckets,
                                                               uint32_t heavy_thr, HeavyLists hl) {
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= total_buckets) return;
+    uint32_t tix = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tix >= total_buckets) return;
+    const uint32_t t = order[tix];
     const uint32_t beg = offsets[t] >> R, end = offsets[t + 1] >> R;
     if (end - beg > heavy_thr) {
         defer_heavy(hl, t, end - beg);
@@ -837,13 +875,13 @@ MsmEngine::Shape MsmEngine::run(const G1Affine* bases, const Fr* scalars, size_t
     if (rounds > 0) {
         k_pad_runs<<<ceil_div(total, 256), 256, 0, stream>>>(counts, offsets, total, sorted);
         PM_LAUNCH_CHECK();
-    } else {
-        PM_CUDA(cudaMemsetAsync(len_hist, 0, kLenBins * sizeof(uint32_t), stream));
-        k_len_hist<<<ceil_div(total, 256), 256, 0, stream>>>(offsets, total, len_hist);
-        k_len_scan<<<1, 1024, 0, stream>>>(len_hist);
-        k_len_scatter<<<ceil_div(total, 256), 256, 0, stream>>>(offsets, total, len_hist, order);
-        PM_LAUNCH_CHECK();
     }
+    // walk order: by the run length the XYZZ walk will see (after the pair rounds)
+    PM_CUDA(cudaMemsetAsync(len_hist, 0, kLenBins * sizeof(uint32_t), stream));
+    k_len_hist<<<ceil_div(total, 256), 256, 0, stream>>>(offsets, total, rounds, len_hist);
+    k_len_scan<<<1, 1024, 0, stream>>>(len_hist);
+    k_len_scatter<<<ceil_div(total, 256), 256, 0, stream>>>(offsets, total, rounds, len_hist, order);
+    PM_LAUNCH_CHECK();
     if (time_accumulate) {
         if (!ev_acc_begin) { PM_CUDA(cudaEventCreate(&ev_acc_begin)); PM_CUDA(cudaEventCreate(&ev_acc_end)); }
         PM_CUDA(cudaEventRecord(ev_acc_begin, stream));
@@ -854,32 +892,48 @@ MsmEngine::Shape MsmEngine::run(const G1Affine* bases, const Fr* scalars, size_t
         PointPlanes ping{pairs_a_.as<uint4>(6 * cap_a), cap_a};
         PointPlanes pong{rounds > 1 ? pairs_b_.as<uint4>(6 * cap_b) : nullptr, cap_b};
         FqPlanes prefix{prefix_.as<uint4>(3 * cap_a), cap_a};
-        const size_t t_max = (slots_max / 2 + kPairTile - 1) / kPairTile * 128 + 128;
-        Fq* tvals = tvals_.as<Fq>(t_max);
-        Fq* tpre = tpre_.as<Fq>(t_max);
+        // thread totals and the levels of the inversion tree above them: [T_0 | T_1 | T_2], prefixes [pre_0 | pre_1]
+        size_t lvl[kInvLevels + 1];
+        lvl[0] = (slots_max / 2 + kPairTile - 1) / kPairTile * 128 + 128;
+        for (int l = 0; l < kInvLevels; l++) lvl[l + 1] = (lvl[l] + kInvFan - 1) / kInvFan + 1;
+        Fq* tlev[kInvLevels + 1];
+        Fq* plev[kInvLevels];
+        tlev[0] = tvals_.as<Fq>(lvl[0] + lvl[1] + lvl[2]);
+        plev[0] = tpre_.as<Fq>(lvl[0] + lvl[1]);
+        for (int l = 0; l < kInvLevels; l++) tlev[l + 1] = tlev[l] + lvl[l];
+        plev[1] = plev[0] + lvl[0];
+        Fq* tvals = tlev[0];
         const uint32_t* slots0 = offsets + total;
         for (int r = 0; r < rounds; r++) {
             const size_t pairs_max = (slots_max >> r) >> 1;
             const unsigned g = ceil_div(pairs_max, kPairTile);
             if (g == 0) break;
             PointPlanes dst = (r & 1) ? pong : ping;
-            // Fermat inverses are a serial chain of ~570 products: spread T over about one warp per scheduler
-            const size_t tcount = (size_t)g * 128;
-            const uint32_t inv_threads = (uint32_t)(tcount < (size_t)sm_count() * 128 ? tcount : (size_t)sm_count() * 128);
+            // level sizes for the grids (upper bounds; the kernels derive the exact ones from slots0)
+            size_t nl[kInvLevels + 1];
+            nl[0] = (size_t)g * 128;
+            for (int l = 0; l < kInvLevels; l++) nl[l + 1] = (nl[l] + kInvFan - 1) / kInvFan;
+            auto invert = [&]() {
+                for (int l = 0; l < kInvLevels; l++)
+                    k_invert_up<<<ceil_div(nl[l + 1], 128), 128, 0, stream>>>(tlev[l], plev[l], tlev[l + 1], slots0, r, l);
+                k_invert_top<<<ceil_div(nl[kInvLevels], 128), 128, 0, stream>>>(tlev[kInvLevels], slots0, r, kInvLevels);
+                for (int l = kInvLevels; l-- > 0;)
+                    k_invert_down<<<ceil_div(nl[l + 1], 128), 128, 0, stream>>>(tlev[l], plev[l], tlev[l + 1], slots0, r, l);
+            };
             if (r == 0) {
                 PairSource<true> src{bases, sorted, run_pts};
                 k_pairs_forward<true><<<g, 128, 0, stream>>>(src, slots0, r, prefix, tvals);
-                k_batch_invert<<<ceil_div(inv_threads, 128), 128, 0, stream>>>(tvals, slots0, r, inv_threads, tpre);
+                invert();
                 k_pairs_backward<true><<<g, 128, 0, stream>>>(src, slots0, r, prefix, tvals, dst);
             } else {
                 PairSource<false> src{bases, sorted, run_pts};
                 k_pairs_forward<false><<<g, 128, 0, stream>>>(src, slots0, r, prefix, tvals);
-                k_batch_invert<<<ceil_div(inv_threads, 128), 128, 0, stream>>>(tvals, slots0, r, inv_threads, tpre);
+                invert();
                 k_pairs_backward<false><<<g, 128, 0, stream>>>(src, slots0, r, prefix, tvals, dst);
             }
             PM_LAUNCH_CHECK();
             run_pts = dst;
-            launches += 3;
+            launches += 3 + 2 * kInvLevels;
         }
     }
     // runs are cut into chunked tasks only when walking them serially would approach the kernel's duration
@@ -891,7 +945,7 @@ MsmEngine::Shape MsmEngine::run(const G1Affine* bases, const Fr* scalars, size_t
             variant = v ? atoi(v) : 24;
         }
         const unsigned g = ceil_div(total, 128);
-        if (rounds > 0) k_accumulate_rounds<<<g, 128, 0, stream>>>(run_pts, offsets, rounds, buckets, total, walk_heavy_thr, hl);
+        if (rounds > 0) k_accumulate_rounds<<<g, 128, 0, stream>>>(run_pts, offsets, order, rounds, buckets, total, walk_heavy_thr, hl);
         else if (variant == 3) k_accumulate<3, MulInline><<<g, 128, 0, stream>>>(bases, sorted, offsets, order, buckets, total, heavy_thr, hl);
         else k_accumulate<4, MulCall><<<g, 128, 0, stream>>>(bases, sorted, offsets, order, buckets, total, heavy_thr, hl);
         PM_LAUNCH_CHECK();

@@ -35,6 +35,20 @@ def fq_mul_batch(a, b):
     return [codec.fq_from_wire(out.raw[i:i + 48]) for i in range(0, len(a) * 48, 48)]
 
 
+def fr_inv_batch(a):
+    lib = require_device()
+    out = C.create_string_buffer(len(a) * 32)
+    check(lib.pm_fr_inv_batch(codec.frs_to_wire(a), out, len(a)))
+    return codec.frs_from_wire(out.raw)
+
+
+def fq_inv_batch(a):
+    lib = require_device()
+    out = C.create_string_buffer(len(a) * 48)
+    check(lib.pm_fq_inv_batch(b"".join(codec.fq_to_wire(v) for v in a), out, len(a)))
+    return [codec.fq_from_wire(out.raw[i:i + 48]) for i in range(0, len(a) * 48, 48)]
+
+
 def ntt_fr(values, inverse=False, coset_gen=None):
     lib = require_device()
     n = len(values)

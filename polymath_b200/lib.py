@@ -34,6 +34,10 @@ def load():
         f = getattr(lib, name)
         f.argtypes = [u8p, u8p, u8p, sz]
         f.restype = C.c_int
+    for name in ("pm_fr_inv_batch", "pm_fq_inv_batch"):
+        f = getattr(lib, name)
+        f.argtypes = [u8p, u8p, sz]
+        f.restype = C.c_int
     lib.pm_ntt_fr.argtypes = [u8p, C.c_uint, C.c_int, u8p]
     lib.pm_ntt_fr.restype = C.c_int
     lib.pm_msm_g1.argtypes = [u8p, sz, u8p, sz, u8p]

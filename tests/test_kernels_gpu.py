@@ -30,6 +30,16 @@ def test_fq_mul(pmlib):
     assert kernels.fq_mul_batch(a, b) == [x * y % Q_MOD for x, y in zip(a, b)]
 
 
+def test_field_inverse(pmlib):
+    """Binary extended-Euclid inverse (field.cuh: Fp::inv) against Fermat's little theorem; 0 -> 0."""
+    from polymath_b200 import kernels
+    rnd = random.Random(3)
+    a = EDGE_FR + [1 << k for k in range(1, 255, 7)] + [rnd.randrange(R_MOD) for _ in range(3000)]
+    assert kernels.fr_inv_batch(a) == [pow(x, R_MOD - 2, R_MOD) for x in a]
+    b = EDGE_FQ + [1 << k for k in range(1, 381, 7)] + [Q_MOD - (1 << k) for k in range(0, 380, 11)] + [rnd.randrange(Q_MOD) for _ in range(3000)]
+    assert kernels.fq_inv_batch(b) == [pow(x, Q_MOD - 2, Q_MOD) for x in b]
+
+
 @pytest.mark.parametrize("log_n", list(range(0, 15)))
 def test_ntt_matches_oracle(pmlib, log_n):
     from polymath_b200 import kernels
