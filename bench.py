@@ -26,6 +26,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC_FMT = "prove_ms_2p{log_n}_sap_constraints"
+TRAFFIC_BWD = None     # bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/)
 
 
 # --------------------------------------------------------------------------------------------
@@ -229,12 +230,14 @@ def run_ours(args):
     sampler.start()
     check(lib.pm_timer_start())
     wall0 = time.perf_counter()
-    acc_ms = []
+    acc_ms, bwd_ms, msm_geom = [], [], (0, 0)
     for _ in range(args.steps):
         last_proof = prove_resident()
-        km = (C.c_double * 2)()
-        check(lib.pm_bench_last_kernel_ms(km))
+        km = (C.c_double * 4)()
+        check(lib.pm_bench_last_msm(km))        # the [d]_1 MSM is the last one of a prove
         acc_ms.append(km[0])
+        bwd_ms.append(km[1])
+        msm_geom = (int(km[2]), int(km[3]))
     ms = C.c_double()
     check(lib.pm_timer_stop(C.byref(ms)))
     barrier()
@@ -270,28 +273,57 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
-    # roofline of the dominant kernel: bucket accumulation of the [d]_1 MSM (10n + 22 points) -----
+    # roofline of the dominant kernel ---------------------------------------------------------------
+    # The [d]_1 MSM (10n + 22 points) is 2/3 of a prove; its bucket accumulation runs as R batched-affine
+    # pair rounds + a short XYZZ walk.  The heaviest single launch is the first round's k_pairs_backward:
+    # half of all bucket additions of the MSM (entries / 2 affine additions).  Algorithmic convention of
+    # one bucket addition = one XYZZ mixed addition = 10 Fq-modmul x 300 IMAD; the kernel
+    # executes 5 products per addition (plus 1 in k_pairs_forward), reported as `executed_frac`.
     d = C.c_double()
     check(lib.pm_bench_imad_peak(C.byref(d)))
     imad_peak = d.value
     d_points = (10 * n + 22) // world
     c_ark = ark_window(10 * n + 22)
     w_ark = (255 + c_ark - 1) // c_ark
-    algo_imad = d_points * w_ark * 10 * 300          # N*W madds x 10 Fq-modmul x 300 IMAD
-    acc = sorted(acc_ms)[len(acc_ms) // 2] if acc_ms else 0.0
-    achieved = algo_imad / (acc * 1e-3) / 1e12 if acc > 0 else None
-    roofline = {
-        "kernel": "k_accumulate (bucket accumulation of the [d]_1 MSM)", "bound": "imad",
-        "achieved": achieved, "peak": imad_peak / 1e12, "unit": "TIMAD/s",
-        "frac": (achieved / (imad_peak / 1e12)) if achieved else None,
-        # dram__bytes_read.sum + dram__bytes_write.sum of this launch, ncu --set full (profiles/r1_c_summary.md);
-        # valid for the 1-GPU 2^20 workload the capture was taken on, null otherwise
-        "traffic": 26.67e9 if (world == 1 and log_n == 20) else None,
-        "kernel_ms": acc, "kernel_share_of_step": acc / value if value else None,
-        "peak_source": "measured live: dependency-free IMAD.WIDE.U32 issue rate (pm_bench_imad_peak); "
-                       "north_star names the INT32 IMAD pipe as the roofline for MSM / field multiplication",
+    med = lambda v: sorted(v)[len(v) // 2] if v else 0.0
+    acc, bwd = med(acc_ms), med(bwd_ms)
+    rounds, entries = msm_geom
+    stage_imad = d_points * w_ark * 10 * 300          # whole stage: N*W madds x 10 Fq-modmul x 300 IMAD
+    stage = {
+        "kernels": "k_pairs_forward / k_invert_* / k_pairs_backward x %d rounds + k_accumulate_rounds" % rounds if rounds
+                   else "k_accumulate (XYZZ walk)",
+        "ms": acc, "share_of_step": acc / value if value else None,
+        "achieved": stage_imad / (acc * 1e-3) / 1e12 if acc > 0 else None, "unit": "TIMAD/s",
+        "frac": stage_imad / (acc * 1e-3) / imad_peak if acc > 0 else None,
         "algorithmic": "%d points x %d windows (arkworks window rule c=%d) x 10 Fq-modmul x 300 IMAD" % (d_points, w_ark, c_ark),
     }
+    if rounds and bwd > 0:
+        adds = entries // 2
+        algo_imad = adds * 10 * 300
+        roofline = {
+            "kernel": "k_pairs_backward<first round> (batched-affine bucket additions of the [d]_1 MSM)", "bound": "imad",
+            "achieved": algo_imad / (bwd * 1e-3) / 1e12, "peak": imad_peak / 1e12, "unit": "TIMAD/s",
+            "frac": algo_imad / (bwd * 1e-3) / imad_peak,
+            "executed_frac": adds * 5 * 300 / (bwd * 1e-3) / imad_peak,
+            # dram__bytes_read.sum + dram__bytes_write.sum of this launch, ncu --set full (profiles/r1_d_summary.md);
+            # valid for the 1-GPU 2^20 workload the capture was taken on, null otherwise
+            "traffic": TRAFFIC_BWD if (world == 1 and log_n == 20) else None,
+            "algorithmic_bytes": adds * (2 * 96 + 48 + 96),
+            "kernel_ms": bwd, "kernel_share_of_step": bwd / value if value else None,
+            "peak_source": "measured live: dependency-free IMAD.WIDE.U32 issue rate (pm_bench_imad_peak); "
+                           "north_star names the INT32 IMAD pipe as the roofline for MSM / field multiplication",
+            "algorithmic": "%d bucket additions (sorted entries / 2) x 10 Fq-modmul x 300 IMAD (SURVEY.md 8d: one XYZZ mixed "
+                           "addition each); the kernel executes 5 products per addition" % adds,
+            "stage": stage,
+        }
+    else:
+        roofline = {
+            "kernel": "k_accumulate (bucket accumulation of the [d]_1 MSM)", "bound": "imad",
+            "achieved": stage["achieved"], "peak": imad_peak / 1e12, "unit": "TIMAD/s", "frac": stage["frac"],
+            "traffic": None, "kernel_ms": acc, "kernel_share_of_step": stage["share_of_step"],
+            "peak_source": "measured live: dependency-free IMAD.WIDE.U32 issue rate (pm_bench_imad_peak)",
+            "algorithmic": stage["algorithmic"],
+        }
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))

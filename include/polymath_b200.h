@@ -86,9 +86,9 @@ int pm_msm_g1_levels(const uint8_t* bases, size_t base_stride, const uint8_t* sc
                      int levels, uint8_t out[PM_G1_BYTES]);
 
 /* Process-wide tuning of the bucket accumulation of every later MSM (standalone and inside the prover):
- * rounds = number of batched-affine pair rounds before the XYZZ walk (-1 = automatic, 0 = none),
- * group = buckets per thread in a round (0 = automatic).  Results never depend on it; test and sweep hook. */
-int pm_msm_set_tuning(int rounds, int group);
+ * rounds = number of batched-affine pair rounds before the XYZZ walk (-1 = automatic, 0 = none).
+ * Results never depend on it; test and sweep hook. */
+int pm_msm_set_tuning(int rounds);
 
 /* out[i] = scalars[i] * G (G = the BLS12-381 G1 generator), canonical affine.
  * Replaces `generate()` (src/generator.rs:169-177). */
@@ -249,6 +249,10 @@ int pm_timer_stop(double* ms);
  * ms[0] = bucket-accumulation kernel of the last MSM, ms[1] = passes of the last NTT. */
 int pm_bench_set_kernel_timing(int enable);
 int pm_bench_last_kernel_ms(double ms[2]);
+/* Last MSM of the main engine (kernel timing enabled): out[0] = ms of the whole bucket-accumulation stage,
+ * out[1] = ms of its heaviest kernel (first-round k_pairs_backward; 0 when no pair rounds ran),
+ * out[2] = pair rounds used, out[3] = sorted-list entries (points x windows, upper bound). */
+int pm_bench_last_msm(double out[4]);
 
 #ifdef __cplusplus
 }

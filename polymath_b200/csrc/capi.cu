@@ -170,8 +170,8 @@ static int msm_host_call(const uint8_t* bases, size_t base_stride, const uint8_t
     });
 }
 
-int pm_msm_set_tuning(int rounds, int group) {
-    return guarded([&] { MsmEngine::set_tuning(rounds, group); });
+int pm_msm_set_tuning(int rounds) {
+    return guarded([&] { MsmEngine::set_tuning(rounds); });
 }
 
 int pm_msm_g1(const uint8_t* bases, size_t base_stride, const uint8_t* scalars, size_t n, uint8_t out[PM_G1_BYTES]) {
@@ -228,6 +228,21 @@ int pm_bench_last_kernel_ms(double ms[2]) {
         float f = 0;
         if (rt.msm.ev_acc_begin && cudaEventElapsedTime(&f, rt.msm.ev_acc_begin, rt.msm.ev_acc_end) == cudaSuccess) ms[0] = f;
         if (rt.ntt.ev_begin && cudaEventElapsedTime(&f, rt.ntt.ev_begin, rt.ntt.ev_end) == cudaSuccess) ms[1] = f;
+        cudaGetLastError();
+    });
+}
+
+int pm_bench_last_msm(double out[4]) {
+    return guarded([&] {
+        Runtime& rt = runtime();
+        out[0] = out[1] = out[2] = out[3] = 0;
+        PM_CUDA(cudaStreamSynchronize(rt.stream));
+        float f = 0;
+        if (rt.msm.ev_acc_begin && cudaEventElapsedTime(&f, rt.msm.ev_acc_begin, rt.msm.ev_acc_end) == cudaSuccess) out[0] = f;
+        if (rt.msm.last_rounds > 0 && rt.msm.ev_bwd_begin &&
+            cudaEventElapsedTime(&f, rt.msm.ev_bwd_begin, rt.msm.ev_bwd_end) == cudaSuccess) out[1] = f;
+        out[2] = rt.msm.last_rounds;
+        out[3] = (double)rt.msm.last_entries;
         cudaGetLastError();
     });
 }

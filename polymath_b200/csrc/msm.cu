@@ -736,11 +736,8 @@ void launch_build_levels(G1Affine* bases, size_t count, int levels, size_t strid
     PM_CUDA(cudaStreamSynchronize(stream));   // scratch dies here
 }
 
-static int g_tuning_rounds = -1, g_tuning_group = 0;
-void MsmEngine::set_tuning(int rounds, int group) {
-    g_tuning_rounds = rounds;
-    g_tuning_group = group;
-}
+static int g_tuning_rounds = -1;
+void MsmEngine::set_tuning(int rounds) { g_tuning_rounds = rounds; }
 
 int MsmEngine::choose_window(size_t n) {
     // Empirical optimum on B200 (profiles/msm_window_sweep_r1.jsonl): the bucket-reduction tail grows
@@ -757,6 +754,8 @@ int MsmEngine::choose_window(size_t n) {
 MsmEngine::~MsmEngine() {
     if (ev_acc_begin) cudaEventDestroy(ev_acc_begin);
     if (ev_acc_end) cudaEventDestroy(ev_acc_end);
+    if (ev_bwd_begin) cudaEventDestroy(ev_bwd_begin);
+    if (ev_bwd_end) cudaEventDestroy(ev_bwd_end);
 }
 
 MsmEngine::Shape MsmEngine::run(const G1Affine* bases, const Fr* scalars, size_t n, G1XYZZ* winsums, cudaStream_t stream,
@@ -813,14 +812,18 @@ MsmEngine::Shape MsmEngine::run(const G1Affine* bases, const Fr* scalars, size_t
         if (forced_rounds >= 0) {
             rounds = forced_rounds;
         } else if (entries >= ((size_t)1 << 20)) {
-            // Fq products per bucket: 6 per slot pair of the padded run, 10 per XYZZ addition of what is left,
-            // plus a fixed cost per round (inversion pass, launches) of about 16 M products per MSM
+            // Cost per bucket in ns, constants measured on B200 (profiles/r1_d_summary.md): a slot pair of the padded
+            // run costs 0.205 (backward) + 0.083 / 0.044 (forward: first round gathers, later rounds stream), an XYZZ
+            // addition of what is left 0.38, and every round a fixed ~0.55 ms (inversion tree, launches)
             double best = 1e300;
             for (int r = 0; r <= 6; r++) {
                 const double a = (double)(1u << r), lp = lambda + (a - 1) / 2, rest = lp / a;
-                double cost = 6.0 * lp * (1.0 - 1.0 / a) + 10.0 * (rest > 1 ? rest - 1 : 0) + r * 16e6 / (double)total;
+                double cost = (r ? 0.365 * 0 : 0) + 0.38 * (rest > 1 ? rest - 1 : 0) + r * 0.55e6 / (double)total;
+                for (int k = 0; k < r; k++) cost += lp / (double)(2u << k) * (0.205 + (k ? 0.044 : 0.083));
+                if (r == 0) cost = 0.365 * (lambda > 1 ? lambda - 1 : 0);
                 if (cost < best) { best = cost; rounds = r; }
             }
+            rounds += cfg.rounds_bias;
             static int bias = -100;
             if (bias == -100) {
                 const char* v = getenv("PM_MSM_ROUNDS_BIAS");
@@ -883,9 +886,14 @@ MsmEngine::Shape MsmEngine::run(const G1Affine* bases, const Fr* scalars, size_t
     k_len_scatter<<<ceil_div(total, 256), 256, 0, stream>>>(offsets, total, rounds, len_hist, order);
     PM_LAUNCH_CHECK();
     if (time_accumulate) {
-        if (!ev_acc_begin) { PM_CUDA(cudaEventCreate(&ev_acc_begin)); PM_CUDA(cudaEventCreate(&ev_acc_end)); }
+        if (!ev_acc_begin) {
+            PM_CUDA(cudaEventCreate(&ev_acc_begin)); PM_CUDA(cudaEventCreate(&ev_acc_end));
+            PM_CUDA(cudaEventCreate(&ev_bwd_begin)); PM_CUDA(cudaEventCreate(&ev_bwd_end));
+        }
         PM_CUDA(cudaEventRecord(ev_acc_begin, stream));
     }
+    last_rounds = rounds;
+    last_entries = entries;
     PointPlanes run_pts{nullptr, 0};
     if (rounds > 0) {
         const size_t cap_a = slots_max / 2 + 2, cap_b = slots_max / 4 + 2;
@@ -924,7 +932,9 @@ MsmEngine::Shape MsmEngine::run(const G1Affine* bases, const Fr* scalars, size_t
                 PairSource<true> src{bases, sorted, run_pts};
                 k_pairs_forward<true><<<g, 128, 0, stream>>>(src, slots0, r, prefix, tvals);
                 invert();
+                if (time_accumulate) PM_CUDA(cudaEventRecord(ev_bwd_begin, stream));
                 k_pairs_backward<true><<<g, 128, 0, stream>>>(src, slots0, r, prefix, tvals, dst);
+                if (time_accumulate) PM_CUDA(cudaEventRecord(ev_bwd_end, stream));
             } else {
                 PairSource<false> src{bases, sorted, run_pts};
                 k_pairs_forward<false><<<g, 128, 0, stream>>>(src, slots0, r, prefix, tvals);

@@ -14,9 +14,10 @@ struct MsmConfig {
     int levels = 1;
     size_t level_stride = 0;
     // Batched-affine pair rounds before the XYZZ walk (msm.cu: k_pairs_*): -1 = choose from the mean run
-    // length, 0 = none, k = exactly k rounds; group = buckets per thread in a round (0 = auto).
+    // length, 0 = none, k = exactly k rounds.  rounds_bias shifts the automatic choice (an MSM that runs beside
+    // another one on a second stream hides the fixed per-round latency and can afford one more round).
     int rounds = -1;
-    int group = 0;
+    int rounds_bias = 0;
 };
 
 // Reusable workspace + launch sequence.  One engine per context / stream.
@@ -38,11 +39,16 @@ public:
     Shape run(const G1Affine* bases, const Fr* scalars, size_t n, G1XYZZ* winsums_out, cudaStream_t stream,
               MsmConfig cfg = {}, size_t scalar_stride = 1, size_t scalar_offset = 0);
     static int choose_window(size_t n);
-    // process-wide default for MsmConfig::rounds / group when a call leaves them automatic (tests, tuning sweeps)
-    static void set_tuning(int rounds, int group);
+    // process-wide default for MsmConfig::rounds when a call leaves it automatic (tests, tuning sweeps)
+    static void set_tuning(int rounds);
     size_t launches = 0;   // kernels launched so far (bench accounting)
     // timing hook for bench.py's roofline: CUDA events around the bucket-accumulation kernel of the last run
     cudaEvent_t ev_acc_begin = nullptr, ev_acc_end = nullptr;
+    // ... and around the first-round k_pairs_backward launch inside it (the heaviest single kernel), with the
+    // geometry of the last run: pair rounds used, slot pairs of the first round (upper bound), entries (n * windows)
+    cudaEvent_t ev_bwd_begin = nullptr, ev_bwd_end = nullptr;
+    int last_rounds = 0;
+    size_t last_entries = 0;
     bool time_accumulate = false;
     ~MsmEngine();
 

@@ -205,10 +205,20 @@ void ProverCtx::phase1_partial(const uint8_t* ra, uint8_t* partials_out) {
     uint8_t* hs = static_cast<uint8_t*>(host_stage);
     PM_CUDA(cudaEventRecord(rt.ev_fork, s));
     PM_CUDA(cudaStreamWaitEvent(rt.stream2, rt.ev_fork, 0));
-    MsmEngine::Shape sa = rt.msm2.run(bc, scal_a.get<Fr>(), local_count(n + 4), ac, rt.stream2, {}, world, rank);
+    // beside each other on two streams the MSMs hide their latency-bound inversion passes: one more pair round pays
+    static int p1_bias = -100;
+    if (p1_bias == -100) {
+        const char* v = getenv("PM_P1_ROUNDS_BIAS");
+        p1_bias = v ? atoi(v) : 1;
+    }
+    MsmConfig cfg_a;
+    cfg_a.rounds_bias = p1_bias;
+    MsmConfig cfg_cs = cfg_c();
+    cfg_cs.rounds_bias = p1_bias;
+    MsmEngine::Shape sa = rt.msm2.run(bc, scal_a.get<Fr>(), local_count(n + 4), ac, rt.stream2, cfg_a, world, rank);
     PM_CUDA(cudaMemcpyAsync(hs, ac, sa.count() * sizeof(G1XYZZ), cudaMemcpyDeviceToHost, rt.stream2));
     PM_CUDA(cudaEventRecord(rt.ev_join, rt.stream2));
-    MsmEngine::Shape sc = rt.msm.run(bc, scal_c.get<Fr>(), local_count(len_c()), ac + kMaxMsmSums, s, cfg_c(), world, rank);
+    MsmEngine::Shape sc = rt.msm.run(bc, scal_c.get<Fr>(), local_count(len_c()), ac + kMaxMsmSums, s, cfg_cs, world, rank);
     PM_CUDA(cudaMemcpyAsync(hs + kStageWin, ac + kMaxMsmSums, sc.count() * sizeof(G1XYZZ), cudaMemcpyDeviceToHost, s));
     PM_CUDA(cudaStreamWaitEvent(s, rt.ev_join, 0));
     PM_CUDA(cudaMemcpyAsync(hs + kStageStatus, st, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));

@@ -76,10 +76,10 @@ def msm_g1(bases, scalars, window_bits=0, heavy_threshold=0, stride=96, levels=1
     return codec.g1_from_wire(out.raw)
 
 
-def msm_set_tuning(rounds=-1, group=0):
-    """Pair-round tuning of every later MSM (-1 / 0 = automatic); results never depend on it."""
+def msm_set_tuning(rounds=-1):
+    """Pair rounds of every later MSM (-1 = automatic, 0 = XYZZ walk only); results never depend on it."""
     lib = require_device()
-    check(lib.pm_msm_set_tuning(rounds, group))
+    check(lib.pm_msm_set_tuning(rounds))
 
 
 def fixed_base_mul(scalars):

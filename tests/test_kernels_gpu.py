@@ -158,27 +158,26 @@ def test_msm_edge_cases(pmlib):
 def msm_tuning(pmlib):
     from polymath_b200 import kernels
     yield kernels.msm_set_tuning
-    kernels.msm_set_tuning(-1, 0)
+    kernels.msm_set_tuning(-1)
 
 
-@pytest.mark.parametrize("n,c,rounds,group", [(1500, 6, 1, 0), (1500, 6, 2, 1), (1500, 6, 3, 3), (1500, 6, 6, 16),
-                                               (1500, 6, 9, 0), (4096, 4, 5, 2), (300, 8, 2, 5), (33, 4, 4, 1),
-                                               (2, 4, 1, 1), (1, 0, 3, 0)])
-def test_msm_pair_rounds(msm_tuning, n, c, rounds, group):
+@pytest.mark.parametrize("n,c,rounds", [(1500, 6, 1), (1500, 6, 2), (1500, 6, 3), (1500, 6, 6), (1500, 6, 9), (4096, 4, 5),
+                                         (300, 8, 2), (33, 4, 4), (2, 4, 1), (1, 0, 3)])
+def test_msm_pair_rounds(msm_tuning, n, c, rounds):
     """Batched-affine pair rounds (k_pairs_forward / k_batch_invert / k_pairs_backward) before the XYZZ walk."""
     from polymath_b200 import kernels
     rnd = random.Random(4000 + n + c)
     bases = _bases(n, rnd)
     scalars = [rnd.randrange(R_MOD) for _ in range(n)]
     want = poly.msm_pippenger(scalars, bases)
-    msm_tuning(rounds, group)
+    msm_tuning(rounds)
     assert kernels.msm_g1(bases, scalars, window_bits=c) == want
     if c:
         assert kernels.msm_g1(bases, scalars, window_bits=c, levels=3) == want
 
 
-@pytest.mark.parametrize("rounds,group", [(1, 1), (2, 0), (3, 2), (5, 7), (8, 1)])
-def test_msm_pair_rounds_exceptional_pairs(msm_tuning, rounds, group):
+@pytest.mark.parametrize("rounds", [1, 2, 3, 5, 8])
+def test_msm_pair_rounds_exceptional_pairs(msm_tuning, rounds):
     """P + P, P + (-P), infinity operands and results inside the pair rounds; heavy buckets skipped by them."""
     from polymath_b200 import kernels
     rnd = random.Random(78)
@@ -195,7 +194,7 @@ def test_msm_pair_rounds_exceptional_pairs(msm_tuning, rounds, group):
     for i in range(0, n, 17):
         scalars[i] = 0
     want = poly.msm_pippenger(scalars, bases)
-    msm_tuning(rounds, group)
+    msm_tuning(rounds)
     assert kernels.msm_g1(bases, scalars, window_bits=5) == want
     assert kernels.msm_g1(bases, scalars, window_bits=8, heavy_threshold=16) == want
     assert kernels.msm_g1(bases, scalars, window_bits=7, levels=4) == want
@@ -217,8 +216,8 @@ def test_msm_linearity_large(pmlib):
     # sum_i s_i * (b_i * G) = (sum_i s_i * b_i) * G
     dot = sum(x * y for x, y in zip(s, base_scalars)) % R_MOD
     assert kernels.msm_g1(bases, s) == curve.g1_mul(curve.G1_GEN, dot)
-    kernels.msm_set_tuning(0, 0)                      # XYZZ walk only
+    kernels.msm_set_tuning(0)                         # XYZZ walk only
     try:
         assert kernels.msm_g1(bases, s) == curve.g1_mul(curve.G1_GEN, dot)
     finally:
-        kernels.msm_set_tuning(-1, 0)
+        kernels.msm_set_tuning(-1)

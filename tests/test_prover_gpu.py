@@ -173,8 +173,8 @@ def test_fixed_base_tables_path(pmlib, c, monkeypatch):
     _run_flow(mk_setup, mk_prove, seed=31 + c, proofs=2)
 
 
-@pytest.mark.parametrize("rounds,group", [(2, 0), (4, 3)])
-def test_prover_with_pair_rounds(pmlib, rounds, group):
+@pytest.mark.parametrize("rounds", [2, 4])
+def test_prover_with_pair_rounds(pmlib, rounds):
     """The batched-affine accumulation the large circuits use (forced on a small one): proofs stay byte-identical."""
     from polymath_b200 import kernels
     consts = []
@@ -187,8 +187,8 @@ def test_prover_with_pair_rounds(pmlib, rounds, group):
         xl, xr = o_fr_rand(rng), o_fr_rand(rng)
         return orc.MiMCDemo(xl, xr, consts), 2, [orc.mimc_hash(xl, xr, consts)]
 
-    kernels.msm_set_tuning(rounds, group)
+    kernels.msm_set_tuning(rounds)
     try:
         _run_flow(mk_setup, mk_prove, seed=77 + rounds, proofs=1)
     finally:
-        kernels.msm_set_tuning(-1, 0)
+        kernels.msm_set_tuning(-1)

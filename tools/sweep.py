@@ -18,7 +18,6 @@ def main():
     ap.add_argument("--iters", type=int, default=3)
     ap.add_argument("--levels", default="1", help="comma list; 0 = as many levels as windows")
     ap.add_argument("--rounds", default="-1", help="comma list of pair-round settings (-1 = automatic, 0 = XYZZ walk only)")
-    ap.add_argument("--group", type=int, default=0)
     ap.add_argument("--skip-basics", action="store_true")
     a = ap.parse_args()
     lib = require_device()
@@ -49,11 +48,11 @@ def main():
                 if lv > 1 and w == 0:
                     continue
                 for rd in [int(x) for x in a.rounds.split(",")]:
-                    check(lib.pm_msm_set_tuning(rd, a.group))
+                    check(lib.pm_msm_set_tuning(rd))
                     check(lib.pm_bench_msm_levels(n, w, lv, a.iters, C.byref(d), C.byref(acc)))
                     print(json.dumps({"kernel": "msm_g1", "log_n": lg, "window": w, "levels": lv, "rounds": rd, "ms": d.value,
                                       "ms_accumulate": acc.value, "mpts_per_s": n / d.value / 1e3}), flush=True)
-                check(lib.pm_msm_set_tuning(-1, 0))
+                check(lib.pm_msm_set_tuning(-1))
 
 
 if __name__ == "__main__":
