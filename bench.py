@@ -26,7 +26,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC_FMT = "prove_ms_2p{log_n}_sap_constraints"
-TRAFFIC_BWD = None     # bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/)
+TRAFFIC_BWD = 34.59e9   # dram__bytes_read.sum + dram__bytes_write.sum of that launch, ncu --set full (profiles/r1_e_summary.md)
 
 
 # --------------------------------------------------------------------------------------------
@@ -242,7 +242,6 @@ def run_ours(args):
     check(lib.pm_timer_stop(C.byref(ms)))
     barrier()
     wall_resident = (time.perf_counter() - wall0) * 1e3
-    clocks = sampler.stop()
     launches = lib.pm_kernel_launches() - launches0
     check(lib.pm_bench_set_kernel_timing(0))
     dev_ms = ms.value
@@ -261,6 +260,7 @@ def run_ours(args):
         prove_e2e()
     check(lib.pm_timer_stop(C.byref(ms)))
     barrier()
+    clocks = sampler.stop()          # sampled over both timed legs (resident + e2e)
     e2e_ms = ms.value
     if world > 1:
         t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
@@ -305,7 +305,7 @@ def run_ours(args):
             "achieved": algo_imad / (bwd * 1e-3) / 1e12, "peak": imad_peak / 1e12, "unit": "TIMAD/s",
             "frac": algo_imad / (bwd * 1e-3) / imad_peak,
             "executed_frac": adds * 5 * 300 / (bwd * 1e-3) / imad_peak,
-            # dram__bytes_read.sum + dram__bytes_write.sum of this launch, ncu --set full (profiles/r1_d_summary.md);
+            # dram__bytes_read.sum + dram__bytes_write.sum of this launch, ncu --set full (profiles/r1_e_summary.md);
             # valid for the 1-GPU 2^20 workload the capture was taken on, null otherwise
             "traffic": TRAFFIC_BWD if (world == 1 and log_n == 20) else None,
             "algorithmic_bytes": adds * (2 * 96 + 48 + 96),

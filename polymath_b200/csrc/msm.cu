@@ -812,7 +812,7 @@ MsmEngine::Shape MsmEngine::run(const G1Affine* bases, const Fr* scalars, size_t
         if (forced_rounds >= 0) {
             rounds = forced_rounds;
         } else if (entries >= ((size_t)1 << 20)) {
-            // Cost per bucket in ns, constants measured on B200 (profiles/r1_d_summary.md): a slot pair of the padded
+            // Cost per bucket in ns, constants measured on B200 (profiles/r1_e_summary.md): a slot pair of the padded
             // run costs 0.205 (backward) + 0.083 / 0.044 (forward: first round gathers, later rounds stream), an XYZZ
             // addition of what is left 0.38, and every round a fixed ~0.55 ms (inversion tree, launches)
             double best = 1e300;
