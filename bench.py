@@ -268,6 +268,32 @@ def run_ours(args):
         e2e_ms = float(t.item())
     e2e_value = e2e_ms / args.steps
 
+    # standalone kernel sweep across the ranks (BASELINE.json configs[4]): sharded Fr NTT with one NCCL all-to-all,
+    # G1 MSM split by point range (every rank a 1/world share; the 192-byte partial sums are not timed)
+    sweep_dist = {}
+    if world > 1:
+        from polymath_b200 import sharded as _sh
+        ntt_log = 24
+        sn = _sh.ShardedNtt(ntt_log, rank, world)
+        sn.data.random_(0, 256)
+        sn.data.view(-1, 32)[:, 31] &= 0x3F                 # < 2^254 < r: valid Montgomery limbs
+        sn.run()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            sn.run()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1) / 5], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sweep_dist["fr_ntt_gelem_per_s_2p%d_sharded" % ntt_log] = (1 << ntt_log) / (float(t.item()) * 1e-3) / 1e9
+        dms, dacc = C.c_double(), C.c_double()
+        check(lib.pm_bench_msm((1 << 24) // world, 0, 2, C.byref(dms), C.byref(dacc)))
+        t = torch.tensor([dms.value], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sweep_dist["g1_msm_mpts_per_s_2p24_sharded"] = (1 << 24) / (float(t.item()) * 1e-3) / 1e6
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -366,7 +392,8 @@ def run_ours(args):
         "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu,
         "phase_ms": {"phase1": phase_ms[0], "phase2": phase_ms[1], "phase3": phase_ms[2]},
         "wall_ms_per_step": wall_resident / args.steps, "setup_s": setup_s,
-        "kernel_sweep": {"g1_msm_mpts_per_s_2p22": msm_mpts, "fr_ntt_gelem_per_s_2p%d" % (log_n + 1): roofline_hbm["gelem_per_s"]},
+        "kernel_sweep": dict({"g1_msm_mpts_per_s_2p22": msm_mpts, "fr_ntt_gelem_per_s_2p%d" % (log_n + 1): roofline_hbm["gelem_per_s"]},
+                             **sweep_dist),
         "proof_hex": last_proof.hex(),
     }
     print(json.dumps(out), flush=True)

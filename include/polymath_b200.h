@@ -74,6 +74,19 @@ int pm_fr_sub_batch(const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n);
  * coset_gen (nullable, 32 B): forward evaluates on coset_gen*H; inverse interpolates from it. */
 int pm_ntt_fr(uint8_t* data, unsigned log_n, int inverse, const uint8_t* coset_gen);
 
+/* Sharded NTT of size 2^log_n over G = 2^log_g ranks (G <= 8), one process per GPU; same transform as pm_ntt_fr.
+ * Rank g holds the interleaved subsequence x[j*G + g], j < 2^log_n / G, in DEVICE memory (32-byte Montgomery Fr).
+ *   pm_ntt_dist_local   : local (N/G)-point transform in place in `data_dev`, twiddled and packed destination-major
+ *                         into `send_dev` (G equal blocks: block h goes to rank h);
+ *   <one all-to-all of the blocks: send block h -> rank h, received block g <- rank g>  (caller: NCCL / NVLink)
+ *   pm_ntt_dist_combine : G-point transform across the received blocks `recv_dev` -> `out_dev`:
+ *                         X[k] for k = rank (mod G) at local index (k - rank)/G, i.e. interleaved like the input.
+ * All pointers are device pointers of 2^log_n / G elements; work is enqueued on `cuda_stream` (a cudaStream_t;
+ * NULL = the default stream, as in the CUDA runtime) and not synchronised.  Replaces `Radix2EvaluationDomain::{fft, ifft_in_place}` (src/prover.rs:241,319,325)
+ * for domains sharded across GPUs. */
+int pm_ntt_dist_local(void* data_dev, void* send_dev, unsigned log_n, unsigned log_g, unsigned rank, int inverse, void* cuda_stream);
+int pm_ntt_dist_combine(const void* recv_dev, void* out_dev, unsigned log_n, unsigned log_g, int inverse, void* cuda_stream);
+
 /* out = sum_i scalars[i] * bases[i].  Replaces `VariableBaseMSM::msm_unchecked` behind
  * `msm()` (src/prover.rs:380-384). */
 int pm_msm_g1(const uint8_t* bases, size_t base_stride, const uint8_t* scalars, size_t n, uint8_t out[PM_G1_BYTES]);

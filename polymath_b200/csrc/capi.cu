@@ -128,6 +128,23 @@ int pm_ntt_fr(uint8_t* data, unsigned log_n, int inverse, const uint8_t* coset_g
     });
 }
 
+int pm_ntt_dist_local(void* data_dev, void* send_dev, unsigned log_n, unsigned log_g, unsigned rank, int inverse, void* cuda_stream) {
+    return guarded([&] {
+        if (!data_dev || !send_dev) throw StatusError(PM_ERR_ARG, "null device buffer");
+        Runtime& rt = runtime();
+        cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);   // NULL = the default stream, as in the CUDA runtime
+        rt.ntt.dist_local(static_cast<Fr*>(data_dev), static_cast<Fr*>(send_dev), (int)log_n, (int)log_g, rank, inverse != 0, s);
+    });
+}
+int pm_ntt_dist_combine(const void* recv_dev, void* out_dev, unsigned log_n, unsigned log_g, int inverse, void* cuda_stream) {
+    return guarded([&] {
+        if (!recv_dev || !out_dev) throw StatusError(PM_ERR_ARG, "null device buffer");
+        Runtime& rt = runtime();
+        cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+        rt.ntt.dist_combine(static_cast<const Fr*>(recv_dev), static_cast<Fr*>(out_dev), (int)log_n, (int)log_g, inverse != 0, s);
+    });
+}
+
 static int msm_host_call(const uint8_t* bases, size_t base_stride, const uint8_t* scalars, size_t n, int window_bits,
                          int heavy_threshold, int levels, uint8_t out[PM_G1_BYTES]);
 

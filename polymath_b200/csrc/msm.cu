@@ -31,7 +31,6 @@ namespace {
 
 constexpr int kMaxWindows = kMaxMsmWindows;
 constexpr int kMaxRounds = 10;
-constexpr size_t kMaxRoundsWorkspace = (size_t)28 << 30;   // bytes; larger MSMs use the XYZZ walk only
 
 __device__ __forceinline__ uint32_t window_bits(const uint32_t* s, int pos, int c) {
     int limb = pos >> 5, off = pos & 31;
@@ -833,12 +832,20 @@ MsmEngine::Shape MsmEngine::run(const G1Affine* bases, const Fr* scalars, size_t
             if (rounds < 0) rounds = 0;
         }
         if (rounds > kMaxRounds) rounds = kMaxRounds;
-        // padded list / workspace must stay addressable and affordable, else use the XYZZ walk only
+        // padded list / workspace must stay addressable and fit into the device memory that is still free (plus what
+        // this engine already holds for the purpose), else use the XYZZ walk only
         while (rounds > 0) {
             const size_t slots = entries + (size_t)total * ((1u << rounds) - 1);
-            const size_t need = slots / 2 * (sizeof(G1Affine) + sizeof(Fq)) + slots / 4 * sizeof(G1Affine) + slots * 4;
-            if (slots < ((size_t)1 << 32) - 4096 && (forced_rounds >= 0 || need <= kMaxRoundsWorkspace)) break;
-            rounds--;
+            const size_t need = (slots / 2 + 2) * (sizeof(G1Affine) + sizeof(Fq)) + (slots / 4 + 2) * sizeof(G1Affine) + slots * 4;
+            const size_t held = pairs_a_.cap + pairs_b_.cap + prefix_.cap + sorted_.cap;
+            bool fits = forced_rounds >= 0 || need <= held;
+            if (!fits) {
+                size_t free_b = 0, total_b = 0;
+                PM_CUDA(cudaMemGetInfo(&free_b, &total_b));
+                fits = need <= held + free_b / 10 * 8;
+            }
+            if (slots < ((size_t)1 << 32) - 4096 && fits) break;
+            rounds = 0;
         }
     }
     const uint32_t pad_mask = (1u << rounds) - 1u;

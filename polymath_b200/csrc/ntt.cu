@@ -245,6 +245,50 @@ __global__ void k_scale_by_powers(Fr* data, size_t n, const Fr* g) {
     data[i] = data[i] * gi;
 }
 
+// ---- sharded transform over G = 2^log_g ranks ("four-step, one all-to-all") -------------------
+// Rank g owns the interleaved subsequence x[j*G + g] (the same split the MSM shards use).  With n = n2*G + g and
+// k = k1*(N/G) + k2:   X[k] = sum_g w_G^(g*k1) * w_N^(g*k2) * Y_g[k2],   Y_g = (N/G)-point transform of rank g's data.
+// k_dist_twiddle_pack: multiplies Y_g[k2] by w_N^(g*k2) and lays it out destination-major (rank h receives the
+// k2 = h + G*b), ready for one all-to-all; k_dist_combine: the G-point transform across the received blocks.
+// Rank h ends up with X[k] for k = h (mod G) at local index (k - h)/G — interleaved again.
+__global__ void __launch_bounds__(256) k_dist_twiddle_pack(const Fr* __restrict__ y, Fr* __restrict__ send, PassArgs a, int log_g,
+                                                           uint32_t rank) {
+    const size_t n2 = (size_t)1 << (a.log_n - log_g);
+    const size_t per = n2 >> log_g;                       // elements per destination
+    const size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= n2) return;
+    const size_t h = o / per, b = o - h * per;
+    const uint64_t k2 = h + ((uint64_t)b << log_g);
+    Fr v = y[k2];
+    const uint64_t e = (uint64_t)rank * k2;               // < N
+    if (e != 0) v = v * interpass_twiddle(a, e);
+    send[o] = v;
+}
+
+template <int LOG_G>
+__global__ void __launch_bounds__(256) k_dist_combine(const Fr* __restrict__ recv, Fr* __restrict__ out, size_t per,
+                                                      const Fr* __restrict__ wg, const Fr* __restrict__ scale) {
+    constexpr int G = 1 << LOG_G;
+    const size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= per) return;
+    Fr x[G], w[G];
+#pragma unroll
+    for (int g = 0; g < G; g++) { x[g] = recv[(size_t)g * per + b]; w[g] = wg[g]; }
+    Fr sc;
+    if (scale) sc = scale[0];
+#pragma unroll
+    for (int k1 = 0; k1 < G; k1++) {
+        Fr acc = x[0];
+#pragma unroll
+        for (int g = 1; g < G; g++) {
+            const int e = (g * k1) & (G - 1);
+            acc = acc + (e == 0 ? x[g] : x[g] * w[e]);
+        }
+        if (scale) acc = acc * sc;
+        out[(size_t)k1 * per + b] = acc;
+    }
+}
+
 constexpr int kSmemBytes = 2 * kPlane * (int)sizeof(uint4) + (1 << (kCoreBits - 1)) * (int)sizeof(Fr);
 
 }  // namespace
@@ -271,6 +315,7 @@ const NttEngine::Tables& NttEngine::tables(int log_n, cudaStream_t stream) {
     }
     k_build_ninv<<<1, 32, 0, stream>>>(t->n_inv.as<Fr>(1), log_n);
     PM_LAUNCH_CHECK();
+    PM_CUDA(cudaStreamSynchronize(stream));   // built once; later runs may use another stream
     auto& ref = *t;
     tables_[log_n] = std::move(t);
     return ref;
@@ -348,6 +393,40 @@ void NttEngine::run(Fr* data, int log_n, bool inverse, cudaStream_t stream) {
     }
     PM_CUDA(cudaMemcpyAsync(data, scratch, n * sizeof(Fr), cudaMemcpyDeviceToDevice, stream));
     if (time_passes) PM_CUDA(cudaEventRecord(ev_end, stream));
+}
+
+void NttEngine::dist_local(Fr* data, Fr* send, int log_n, int log_g, uint32_t rank, bool inverse, cudaStream_t stream) {
+    if (log_g < 0 || log_g > 3 || log_n < 2 * log_g || log_n > 32) throw CudaError("sharded ntt: bad geometry");
+    if (rank >= (1u << log_g)) throw CudaError("sharded ntt: bad rank");
+    run(data, log_n - log_g, inverse, stream);
+    const Tables& t = tables(log_n, stream);
+    PassArgs a{};
+    a.log_n = log_n;
+    a.tw0 = (inverse ? t.tw_inv[0] : t.tw_fwd[0]).get<Fr>();
+    a.tw1 = (inverse ? t.tw_inv[1] : t.tw_fwd[1]).get<Fr>();
+    a.tw2 = (inverse ? t.tw_inv[2] : t.tw_fwd[2]).get<Fr>();
+    const size_t n2 = (size_t)1 << (log_n - log_g);
+    k_dist_twiddle_pack<<<ceil_div(n2, 256), 256, 0, stream>>>(data, send, a, log_g, rank);
+    PM_LAUNCH_CHECK();
+    launches++;
+}
+
+void NttEngine::dist_combine(const Fr* recv, Fr* out, int log_n, int log_g, bool inverse, cudaStream_t stream) {
+    if (log_g < 0 || log_g > 3 || log_n < 2 * log_g || log_n > 32) throw CudaError("sharded ntt: bad geometry");
+    const size_t per = (size_t)1 << (log_n - 2 * log_g);
+    if (log_g == 0) {
+        PM_CUDA(cudaMemcpyAsync(out, recv, per * sizeof(Fr), cudaMemcpyDeviceToDevice, stream));
+        return;
+    }
+    const Tables& t = tables(log_g, stream);      // tw[0][k] = w_G^k, n_inv = G^-1
+    const Fr* wg = (inverse ? t.tw_inv[0] : t.tw_fwd[0]).get<Fr>();
+    const Fr* scale = inverse ? t.n_inv.get<Fr>() : nullptr;
+    const unsigned grid = ceil_div(per, 256);
+    if (log_g == 1) k_dist_combine<1><<<grid, 256, 0, stream>>>(recv, out, per, wg, scale);
+    else if (log_g == 2) k_dist_combine<2><<<grid, 256, 0, stream>>>(recv, out, per, wg, scale);
+    else k_dist_combine<3><<<grid, 256, 0, stream>>>(recv, out, per, wg, scale);
+    PM_LAUNCH_CHECK();
+    launches++;
 }
 
 void launch_scale_by_powers(Fr* data, size_t n, const Fr* g_dev, cudaStream_t stream) {

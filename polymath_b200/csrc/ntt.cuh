@@ -13,6 +13,13 @@ public:
     //   forward: out[i] = sum_j in[j] * w^(i*j), w = Radix2EvaluationDomain::group_gen
     //   inverse: out = n^-1 * (transform with w^-1)
     void run(Fr* data, int log_n, bool inverse, cudaStream_t stream);
+    // Sharded transform of size 2^log_n over 2^log_g ranks, rank g holding the interleaved subsequence x[j*G + g]
+    // (2^(log_n - log_g) elements).  dist_local: local transform in place + twiddle, packed destination-major into
+    // `send` for ONE all-to-all (equal blocks of 2^(log_n - 2 log_g) elements); dist_combine: G-point transform across
+    // the received blocks -> X[k], k = rank (mod G), at local index (k - rank)/G.  The exchange itself belongs to
+    // the caller (NCCL all-to-all over NVLink, polymath_b200/sharded.py).
+    void dist_local(Fr* data, Fr* send, int log_n, int log_g, uint32_t rank, bool inverse, cudaStream_t stream);
+    void dist_combine(const Fr* recv, Fr* out, int log_n, int log_g, bool inverse, cudaStream_t stream);
     size_t launches = 0;
     // CUDA events around the passes of the last run (bench.py roofline)
     bool time_passes = false;

@@ -61,7 +61,74 @@ def bind(lib):
     lib.pm_prove_phase3_partial.argtypes = [vp, u8p, u8p, u8p]
     lib.pm_prove_phase3_finish.argtypes = [vp, u8p, C.c_int, u8p]
     lib.pm_host_sum_partials.argtypes = [u8p, C.c_int, C.c_size_t, u8p]
+    lib.pm_ntt_dist_local.argtypes = [vp, vp, C.c_uint, C.c_uint, C.c_uint, C.c_int, vp]
+    lib.pm_ntt_dist_combine.argtypes = [vp, vp, C.c_uint, C.c_uint, C.c_int, vp]
     lib._sharded_bound = True
+
+
+def ntt_send_order(log_n: int, world: int):
+    """k2 index (into the rank's local (N/world)-point transform) of every position of the send buffer of the
+    sharded NTT: destination-major, block h = the k2 = h (mod world) in increasing order (mirrors
+    k_dist_twiddle_pack in csrc/ntt.cu)."""
+    n2 = (1 << log_n) // world
+    per = n2 // world
+    return [h + world * b for h in range(world) for b in range(per)]
+
+
+def ntt_exchange(send, recv, world: int, group=None):
+    """The one all-to-all of the sharded NTT: equal blocks, block h of `send` goes to rank h."""
+    import torch.distributed as dist
+    if world == 1:
+        recv.copy_(send)
+    else:
+        dist.all_to_all_single(recv, send, group=group)
+
+
+class ShardedNtt:
+    """Fr NTT of size 2^log_n sharded over the ranks of a process group (four-step, ONE all-to-all).
+
+    Rank g holds the interleaved subsequence x[j*world + g] as a CUDA uint8 tensor of 32-byte Montgomery elements
+    (`self.data`).  `run()` = local (N/G)-point transform + twiddle/pack (`pm_ntt_dist_local`), one
+    `all_to_all_single` of equal blocks over NCCL/NVLink, G-point combine (`pm_ntt_dist_combine`).  The result
+    `self.out` holds X[k] for k = rank (mod world) at local index (k - rank)/world.  Everything is enqueued on
+    torch's current stream.  `exchange` can be replaced (the single-GPU tests emulate the ranks in one process).
+    """
+
+    def __init__(self, log_n: int, rank: int, world: int, group=None, device=None):
+        import torch
+        self.lib = _lib()
+        bind(self.lib)
+        assert world in (1, 2, 4, 8) and log_n >= 2 * (world.bit_length() - 1)
+        self.log_n, self.rank, self.world, self.group = log_n, rank, world, group
+        self.log_g = world.bit_length() - 1
+        self.local_elems = (1 << log_n) // world
+        device = device or torch.device("cuda", torch.cuda.current_device())
+        nbytes = self.local_elems * 32
+        self.data = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        self.send = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        self.recv = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        self.out = torch.empty(nbytes, dtype=torch.uint8, device=device)
+
+    def local_step(self, inverse=False):
+        import torch
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        check(self.lib.pm_ntt_dist_local(C.c_void_p(self.data.data_ptr()), C.c_void_p(self.send.data_ptr()), self.log_n,
+                                         self.log_g, self.rank, 1 if inverse else 0, stream))
+
+    def exchange(self):
+        ntt_exchange(self.send, self.recv, self.world, self.group)
+
+    def combine_step(self, inverse=False):
+        import torch
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        check(self.lib.pm_ntt_dist_combine(C.c_void_p(self.recv.data_ptr()), C.c_void_p(self.out.data_ptr()), self.log_n,
+                                           self.log_g, 1 if inverse else 0, stream))
+
+    def run(self, inverse=False):
+        self.local_step(inverse)
+        self.exchange()
+        self.combine_step(inverse)
+        return self.out
 
 
 def host_sum_partials(parts: bytes, count: int, stride: int = 192):

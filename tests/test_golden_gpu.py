@@ -83,7 +83,10 @@ class _Challenges:
         return x2, c_at_x1
 
 
-@pytest.mark.parametrize("log_n", [14, 17])
+_LARGE = [int(v) for v in os.environ.get("PM_TEST_LARGE", "").split(",") if v]   # e.g. PM_TEST_LARGE=22,24 (minutes)
+
+
+@pytest.mark.parametrize("log_n", [14, 17] + _LARGE)
 def test_large_synthetic_circuit_verifies(pmlib, log_n):
     """S-mimc(2^log_n): setup + prove entirely on the device, then the oracle's pairing
     check must accept — the property the reference's own tests assert.  2^17 exercises the fixed-base tables."""

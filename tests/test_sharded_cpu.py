@@ -100,3 +100,57 @@ def test_host_sum_partials_matches_oracle():
     one = lambda p: b"".join(codec.fq_to_wire(v) for v in (p[0], p[1], 1, 1))
     assert sharded.host_sum_partials(one(pt) + one(curve.g1_neg(pt)), 2) is None
     assert sharded.host_sum_partials(one(pt) + one(pt), 2) == curve.g1_mul(curve.G1_GEN, 18)
+
+
+def _ntt_worker(rank, world, port, q, log_n, inverse):
+    try:
+        sys.path.insert(0, ROOT)
+        os.environ["MASTER_ADDR"] = "127.0.0.1"
+        os.environ["MASTER_PORT"] = str(port)
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        from oracle import poly
+        from oracle.fields import R_MOD
+        from polymath_b200 import codec, sharded
+        n = 1 << log_n
+        rnd = random.Random(99)
+        x = [rnd.randrange(R_MOD) for _ in range(n)]
+        dom, sub = poly.Domain(n), poly.Domain(n // world)
+        w = pow(dom.group_gen, R_MOD - 2, R_MOD) if inverse else dom.group_gen
+        # local transform of the interleaved subsequence (the GPU does this with pm_ntt_dist_local) ...
+        mine = x[rank::world]
+        y = sub.ifft(mine) if inverse else sub.fft(mine)
+        # ... twiddled and packed in the product's send order
+        order = sharded.ntt_send_order(log_n, world)
+        send = torch.frombuffer(bytearray(codec.frs_to_wire([y[k2] * pow(w, rank * k2, R_MOD) % R_MOD for k2 in order])),
+                                dtype=torch.uint8)
+        recv = torch.empty_like(send)
+        sharded.ntt_exchange(send, recv, world)
+        got = codec.frs_from_wire(recv.numpy().tobytes())
+        per = n // world // world
+        wg = pow(w, n // world, R_MOD)
+        scale = pow(world, R_MOD - 2, R_MOD) if inverse else 1
+        out = [sum(got[g * per + b] * pow(wg, g * k1, R_MOD) for g in range(world)) * scale % R_MOD
+               for k1 in range(world) for b in range(per)]
+        full = dom.ifft(x) if inverse else dom.fft(x)
+        q.put((rank, out == full[rank::world]))
+        dist.destroy_process_group()
+    except Exception as e:  # pragma: no cover
+        q.put((rank, repr(e)))
+
+
+@pytest.mark.parametrize("log_n,inverse", [(6, False), (7, True)])
+def test_sharded_ntt_exchange_over_gloo_world2(log_n, inverse):
+    """The decomposition behind pm_ntt_dist_local / all-to-all / pm_ntt_dist_combine, on CPU: oracle transforms for
+    the local step, the product's send order and exchange, checked against the oracle's full transform."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_ntt_worker, args=(r, world, port, q, log_n, inverse)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, ok in sorted(results):
+        assert ok is True, results

@@ -68,3 +68,34 @@ def test_virtual_ranks_reproduce_the_oracle_proof(pmlib, world):
     assert opm.verify_proof(pk_or.vk, want, inst[1:])
     for h in ctxs:
         lib.pm_ctx_destroy(h)
+
+
+@pytest.mark.parametrize("log_n,world", [(2, 2), (4, 4), (6, 8), (9, 2), (12, 4), (13, 8), (20, 8)])
+@pytest.mark.parametrize("inverse", [False, True])
+def test_sharded_ntt_virtual_ranks(pmlib, log_n, world, inverse):
+    """pm_ntt_dist_local / pm_ntt_dist_combine with `world` virtual ranks on one GPU (the all-to-all is emulated by
+    slicing): every rank must hold the interleaved slice of the full transform.  Bit-exact."""
+    import random
+    import torch
+    from oracle import poly
+    from polymath_b200 import codec, kernels, sharded
+    n = 1 << log_n
+    rnd = random.Random(log_n * 10 + world)
+    seeds = [rnd.randrange(R_MOD) for _ in range(61)]
+    x = [seeds[i % 61] * (i + 1) % R_MOD for i in range(n)]
+    if log_n <= 13:
+        dom = poly.Domain(n)
+        full = dom.ifft(x) if inverse else dom.fft(x)
+    else:
+        full = kernels.ntt_fr(x, inverse=inverse)        # checked against the oracle in test_kernels_gpu.py
+    ranks = [sharded.ShardedNtt(log_n, r, world) for r in range(world)]
+    for r, sn in enumerate(ranks):
+        sn.data.copy_(torch.frombuffer(bytearray(codec.frs_to_wire(x[r::world])), dtype=torch.uint8))
+        sn.local_step(inverse)
+    blk = (n // world // world) * 32
+    for h, sn in enumerate(ranks):
+        sn.recv.copy_(torch.cat([src.send[h * blk:(h + 1) * blk] for src in ranks]))
+        sn.combine_step(inverse)
+    torch.cuda.synchronize()
+    for h, sn in enumerate(ranks):
+        assert codec.frs_from_wire(sn.out.cpu().numpy().tobytes()) == full[h::world]
