@@ -125,23 +125,32 @@ class ClockSampler:
         self.thread = None
 
     def _run(self):
-        while not self.stop_flag.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                parts = [p.strip() for p in out.strip().split(",")]
+        # one long-running nvidia-smi in loop mode (spawning a process per sample perturbs launch-bound phases)
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "250"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                parts = [p.strip() for p in line.strip().split(",")]
                 if len(parts) >= 6:
                     self.samples.append(parts)
-            except Exception:
-                pass
-            self.stop_flag.wait(0.2)
+                if self.stop_flag.is_set():
+                    break
+        except Exception:
+            pass
 
     def start(self):
+        self.proc = None
         self.thread = threading.Thread(target=self._run, daemon=True)
         self.thread.start()
 
     def stop(self):
         self.stop_flag.set()
+        if getattr(self, "proc", None) is not None:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
         if self.thread:
             self.thread.join(timeout=6)
         if not self.samples:
@@ -225,9 +234,10 @@ def run_ours(args):
         prove_resident()
     check(lib.pm_bench_set_kernel_timing(1))
     launches0 = lib.pm_kernel_launches()
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     barrier()
-    sampler.start()
+    if sampler:
+        sampler.start()
     check(lib.pm_timer_start())
     wall0 = time.perf_counter()
     acc_ms, bwd_ms, msm_geom = [], [], (0, 0)
@@ -260,7 +270,7 @@ def run_ours(args):
         prove_e2e()
     check(lib.pm_timer_stop(C.byref(ms)))
     barrier()
-    clocks = sampler.stop()          # sampled over both timed legs (resident + e2e)
+    clocks = sampler.stop() if sampler else None          # rank 0, sampled over both timed legs (resident + e2e)
     e2e_ms = ms.value
     if world > 1:
         t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)

@@ -777,7 +777,17 @@ MsmEngine::Shape MsmEngine::run(const G1Affine* bases, const Fr* scalars, size_t
     uint32_t lev_m[16];
     int nlev = 0;
     uint32_t m_top = nb;
-    while (m_top > kTopMax) {
+    for (;;) {
+        if (m_top <= 512) break;
+        if (m_top <= kTopMax) {
+            // The masked sums make log2(m) half-empty passes over the array (~16 k pipe cycles per warp addition on
+            // 592 schedulers), another 16-ary level costs ~0.35 ms of latency: descend while that is cheaper
+            // (many bucket sets of a few thousand buckets: the shards of a multi-GPU prove).
+            int bits = 0;
+            while ((1u << bits) < m_top) bits++;
+            const double masked_ms = (double)ngroups * (bits + 1) * (m_top / 32.0 + 12.0) * 16e3 / 592.0 / 1.9e6;
+            if (masked_ms <= 0.35) break;
+        }
         lev_m[nlev++] = m_top;
         m_top = (m_top + kRedK - 1) / kRedK;
     }
