@@ -211,7 +211,13 @@ void ProverCtx::phase1_partial(const uint8_t* ra, uint8_t* partials_out) {
         const char* v = getenv("PM_P1_ROUNDS_BIAS");
         p1_bias = v ? atoi(v) : 1;
     }
-    MsmConfig cfg_a;
+    // the a-side bases are a prefix of bases_c: its fixed-base table serves both MSMs
+    static int a_tables = -1;
+    if (a_tables < 0) {
+        const char* v = getenv("PM_A_TABLES");
+        a_tables = v ? atoi(v) : 1;
+    }
+    MsmConfig cfg_a = a_tables ? cfg_c() : MsmConfig();
     cfg_a.rounds_bias = p1_bias;
     MsmConfig cfg_cs = cfg_c();
     cfg_cs.rounds_bias = p1_bias;
