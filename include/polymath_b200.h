@@ -45,6 +45,7 @@ enum {
 #define PM_FR_BYTES 32
 #define PM_FQ_BYTES 48
 #define PM_G1_BYTES 96
+#define PM_G1_COMPRESSED_BYTES 48 /* zcash / ark-bls12-381 compressed G1 */
 #define PM_XYZZ_BYTES 192 /* (X, Y, ZZ, ZZZ) partial sum of a sharded MSM; x = X/ZZ, y = Y/ZZZ */
 
 const char* pm_last_error(void);
@@ -103,6 +104,15 @@ int pm_msm_g1_levels(const uint8_t* bases, size_t base_stride, const uint8_t* sc
  * Results never depend on it; test and sweep hook. */
 int pm_msm_set_tuning(int rounds);
 
+/* G1 point (de)compression on the device: the 48-byte zcash encoding ark-bls12-381 uses for `CanonicalSerialize`
+ * (big-endian x; byte 0: 0x80 compressed, 0x40 infinity, 0x20 y is the larger root).  Replaces the per-point work of
+ * `ProvingKey::{deserialize_compressed, serialize_compressed}` (src/data_structures.rs:55-73): one Fq square root per
+ * decoded point.  in/out: n x 48 bytes <-> n x 96 bytes (Montgomery affine, (0,0) = infinity).
+ * validate != 0 also checks the prime-order subgroup (`deserialize_compressed`); 0 stops at the on-curve check
+ * (a superset of `deserialize_compressed_unchecked`).  A bad encoding fails with PM_ERR_ARG naming the first index. */
+int pm_g1_decompress_batch(const uint8_t* in, size_t n, int validate, uint8_t* out);
+int pm_g1_compress_batch(const uint8_t* in, size_t n, uint8_t* out);
+
 /* out[i] = scalars[i] * G (G = the BLS12-381 G1 generator), canonical affine.
  * Replaces `generate()` (src/generator.rs:169-177). */
 int pm_fixed_base_mul(const uint8_t* scalars, size_t n, uint8_t* out);
@@ -122,7 +132,9 @@ typedef struct {
     const uint64_t* c_row_ptr; const uint32_t* c_col; const uint8_t* c_val;
 } pm_r1cs_view;
 
-/* Borrowed view of a `ProvingKey` (src/data_structures.rs:56-73).  All point arrays share `point_stride`. */
+/* Borrowed view of a `ProvingKey` (src/data_structures.rs:56-73).  All point arrays share `point_stride`:
+ * 96 (packed Montgomery affine), >= 104 (arkworks' in-memory `Affine{x,y,infinity}`) or 48 = the compressed
+ * encoding of `serialize_compressed` (decoded on the device while uploading; on-curve checked). */
 typedef struct {
     pm_r1cs_view r1cs;                    /* pk.sap_matrices */
     uint64_t n;                           /* pk.vk.n  (domain size) */
@@ -248,6 +260,8 @@ int pm_bench_imad_peak(double* mads_per_s);
 int pm_bench_field_mul(int field, double* muls_per_s);
 /* Average milliseconds of `iters` size-2^log_n transforms on resident data (after one warm-up). */
 int pm_bench_ntt(unsigned log_n, int inverse, int iters, double* ms_avg);
+/* Milliseconds of one device-resident decompression / compression of n synthetic G1 points. */
+int pm_bench_g1_codec(size_t n, double* ms_decompress, double* ms_compress);
 /* Average milliseconds of `iters` n-point MSMs on resident synthetic bases/scalars (after one warm-up);
  * ms_accumulate (nullable) receives the average time of the bucket-accumulation kernel alone. */
 int pm_bench_msm(size_t n, int window_bits, int iters, double* ms_avg, double* ms_accumulate);

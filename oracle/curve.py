@@ -257,6 +257,42 @@ def g1_compress(pt) -> bytes:
     return bytes(b)
 
 
+def g1_decompress(b: bytes, validate: bool = True):
+    """ark-bls12-381 `read_g1_compressed` + `get_point_from_x_unchecked` [mem] (third-party crate, not under
+    /root/reference; call sites: derive(CanonicalDeserialize) on src/data_structures.rs:10-73).  Raises ValueError
+    where arkworks returns a SerializationError.  validate=True adds `deserialize_compressed`'s subgroup check."""
+    assert len(b) == 48
+    flags = b[0]
+    if not flags & 0x80:
+        raise ValueError("UnexpectedFlags: not a compressed encoding")
+    if flags & 0x40:
+        return None
+    x = int.from_bytes(bytes([b[0] & 0x1F]) + b[1:], "big")
+    if x >= P:
+        raise ValueError("InvalidData: x >= q")
+    rhs = (x * x * x + 4) % P
+    y = pow(rhs, (P + 1) // 4, P)
+    if y * y % P != rhs:
+        raise ValueError("InvalidData: not on the curve")
+    small, large = (y, P - y) if y < P - y else (P - y, y)
+    pt = (x, large if flags & 0x20 else small)
+    if validate and not g1_in_subgroup(pt):
+        raise ValueError("InvalidData: not in the prime-order subgroup")
+    return pt
+
+
+def g1_in_subgroup(pt) -> bool:
+    """[r]P == O (what `is_in_correct_subgroup_assuming_on_curve` decides), by the plain ladder (no reduction of r)."""
+    if pt is None:
+        return True
+    acc = JINF
+    for bit in bin(R_MOD)[2:]:
+        acc = jac_double(acc)
+        if bit == "1":
+            acc = jac_add_affine(acc, pt)
+    return acc[2] == 0
+
+
 def _fq2_lex_largest(y) -> bool:
     # zcash: compare c1 first, then c0
     half = (P - 1) // 2

@@ -183,6 +183,8 @@ class ProvingKey:
         buf = C.create_string_buffer(max(ln * stride, 1))
         check(self._lib.pm_ctx_export_key(self._h, which, buf, stride))
         raw = buf.raw[:ln * stride]
+        if stride == 48:
+            return raw                       # `serialize_compressed` bytes of the vector, without the length prefix
         if stride == 96:
             return codec.g1s_from_wire(raw)
         out = []
@@ -254,7 +256,10 @@ class Polymath:
         keep = []
         for name in KEY_NAMES:
             pts = vectors[name]
-            if stride == 96:
+            if stride == 48:
+                raw = pts if isinstance(pts, (bytes, bytearray)) else b"".join(pts)   # compressed encodings
+                pts = range(len(raw) // 48)
+            elif stride == 96:
                 raw = codec.g1s_to_wire(pts)
             else:
                 raw = b"".join(codec.g1_to_wire(p) + (b"\x01" if p is None else b"\x00") + bytes(stride - 97) for p in pts)

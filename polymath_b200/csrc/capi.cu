@@ -8,6 +8,7 @@
 #include "common.cuh"
 #include "field_kernels.cuh"
 #include "fixed_base.cuh"
+#include "g1_codec.cuh"
 #include "msm.cuh"
 #include "ntt.cuh"
 #include "runtime.cuh"
@@ -195,6 +196,45 @@ int pm_msm_g1(const uint8_t* bases, size_t base_stride, const uint8_t* scalars, 
     return pm_msm_g1_window(bases, base_stride, scalars, n, 0, 0, out);
 }
 
+int pm_g1_decompress_batch(const uint8_t* in, size_t n, int validate, uint8_t* out) {
+    return guarded([&] {
+        if (n == 0) return;
+        if (!in || !out) throw StatusError(PM_ERR_ARG, "null buffer");
+        Runtime& rt = runtime();
+        DevBuf din, dout, dbad;
+        uint8_t* pi = din.as<uint8_t>(n * 48);
+        G1Affine* po = dout.as<G1Affine>(n);
+        unsigned long long* bad = dbad.as<unsigned long long>(1);
+        PM_CUDA(cudaMemcpyAsync(pi, in, n * 48, cudaMemcpyHostToDevice, rt.stream));
+        PM_CUDA(cudaMemsetAsync(bad, 0xff, sizeof(unsigned long long), rt.stream));
+        launch_g1_decompress(pi, n, validate != 0, po, bad, rt.stream);
+        rt.extra_launches++;
+        unsigned long long hbad = 0;
+        PM_CUDA(cudaMemcpyAsync(&hbad, bad, sizeof hbad, cudaMemcpyDeviceToHost, rt.stream));
+        PM_CUDA(cudaMemcpyAsync(out, po, n * sizeof(G1Affine), cudaMemcpyDeviceToHost, rt.stream));
+        PM_CUDA(cudaStreamSynchronize(rt.stream));
+        if (hbad != ~0ull)
+            throw StatusError(PM_ERR_ARG, "invalid compressed G1 point at index " + std::to_string(hbad >> 3) + ": " +
+                                              g1_decode_status_name((unsigned)(hbad & 7)));
+    });
+}
+
+int pm_g1_compress_batch(const uint8_t* in, size_t n, uint8_t* out) {
+    return guarded([&] {
+        if (n == 0) return;
+        if (!in || !out) throw StatusError(PM_ERR_ARG, "null buffer");
+        Runtime& rt = runtime();
+        DevBuf din, dout;
+        G1Affine* pi = din.as<G1Affine>(n);
+        uint8_t* po = dout.as<uint8_t>(n * 48);
+        PM_CUDA(cudaMemcpyAsync(pi, in, n * sizeof(G1Affine), cudaMemcpyHostToDevice, rt.stream));
+        launch_g1_compress(pi, n, po, rt.stream);
+        rt.extra_launches++;
+        PM_CUDA(cudaMemcpyAsync(out, po, n * 48, cudaMemcpyDeviceToHost, rt.stream));
+        PM_CUDA(cudaStreamSynchronize(rt.stream));
+    });
+}
+
 int pm_fixed_base_mul(const uint8_t* scalars, size_t n, uint8_t* out) {
     return guarded([&] {
         if (n == 0) return;
@@ -294,6 +334,39 @@ int pm_bench_ntt(unsigned log_n, int inverse, int iters, double* ms_avg) {
         cudaEventDestroy(e0);
         cudaEventDestroy(e1);
         *ms_avg = ms / iters;
+    });
+}
+
+int pm_bench_g1_codec(size_t n, double* ms_decompress, double* ms_compress) {
+    return guarded([&] {
+        if (n == 0 || !ms_decompress || !ms_compress) throw StatusError(PM_ERR_ARG, "bad bench arguments");
+        Runtime& rt = runtime();
+        DevBuf ds, dp, dc, dbad;
+        Fr* ps = ds.as<Fr>(n);
+        G1Affine* pp = dp.as<G1Affine>(n);
+        uint8_t* pc = dc.as<uint8_t>(n * 48);
+        unsigned long long* bad = dbad.as<unsigned long long>(1);
+        launch_fill_fr(ps, n, 0xc0dec, rt.stream);
+        rt.fixed_base.run(ps, n, pp, rt.stream);       // points = [s_i]G
+        cudaEvent_t e0, e1, e2;
+        PM_CUDA(cudaEventCreate(&e0)); PM_CUDA(cudaEventCreate(&e1)); PM_CUDA(cudaEventCreate(&e2));
+        launch_g1_compress(pp, n, pc, rt.stream);      // warm-up
+        PM_CUDA(cudaMemsetAsync(bad, 0xff, sizeof(unsigned long long), rt.stream));
+        PM_CUDA(cudaEventRecord(e0, rt.stream));
+        launch_g1_compress(pp, n, pc, rt.stream);
+        PM_CUDA(cudaEventRecord(e1, rt.stream));
+        launch_g1_decompress(pc, n, false, pp, bad, rt.stream);
+        PM_CUDA(cudaEventRecord(e2, rt.stream));
+        PM_CUDA(cudaEventSynchronize(e2));
+        float fc = 0, fd = 0;
+        PM_CUDA(cudaEventElapsedTime(&fc, e0, e1));
+        PM_CUDA(cudaEventElapsedTime(&fd, e1, e2));
+        unsigned long long hbad = 0;
+        PM_CUDA(cudaMemcpy(&hbad, bad, sizeof hbad, cudaMemcpyDeviceToHost));
+        cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+        if (hbad != ~0ull) throw StatusError(PM_ERR_STATE, "codec bench: round trip failed");
+        *ms_compress = fc;
+        *ms_decompress = fd;
     });
 }
 

@@ -13,6 +13,7 @@
 #include <cstdlib>
 
 #include "host/g1_host.hpp"
+#include "g1_codec.cuh"
 #include "msm.cuh"
 #include "ntt.cuh"
 
@@ -363,6 +364,33 @@ void upload_points(const ProverCtx& c, G1Affine* dst_base, uint64_t global_off, 
     }
     // first global index >= global_off owned by this rank
     uint64_t g0 = global_off + ((uint64_t)c.rank + c.world - global_off % c.world) % c.world;
+    if (stride == PM_G1_COMPRESSED_BYTES) {
+        // compressed key vector (`serialize_compressed` bytes without the length prefix): decode on the device
+        std::vector<uint8_t> packed;
+        const uint8_t* first = src + (g0 - global_off) * 48;
+        uint64_t cnt = g0 < global_off + len ? (global_off + len - g0 + c.world - 1) / c.world : 0;
+        if (c.world > 1) {
+            packed.reserve(cnt * 48);
+            for (uint64_t g = g0; g < global_off + len; g += c.world) packed.insert(packed.end(), src + (g - global_off) * 48, src + (g - global_off) * 48 + 48);
+            first = packed.data();
+        }
+        if (cnt) {
+            DevBuf din, dbad;
+            uint8_t* pi = din.as<uint8_t>(cnt * 48);
+            unsigned long long* bad = dbad.as<unsigned long long>(1);
+            PM_CUDA(cudaMemcpyAsync(pi, first, cnt * 48, cudaMemcpyHostToDevice, rt.stream));
+            PM_CUDA(cudaMemsetAsync(bad, 0xff, sizeof(unsigned long long), rt.stream));
+            launch_g1_decompress(pi, cnt, false, dst_base + g0 / c.world, bad, rt.stream);
+            rt.extra_launches++;
+            unsigned long long hbad = 0;
+            PM_CUDA(cudaMemcpyAsync(&hbad, bad, sizeof hbad, cudaMemcpyDeviceToHost, rt.stream));
+            PM_CUDA(cudaStreamSynchronize(rt.stream));
+            if (hbad != ~0ull)
+                throw StatusError(PM_ERR_ARG, std::string("invalid compressed point in ") + name + ": " +
+                                                  g1_decode_status_name((unsigned)(hbad & 7)));
+        }
+        return;
+    }
     std::vector<uint8_t> packed;
     for (uint64_t g = g0; g < global_off + len; g += c.world) {
         const uint8_t* p = src + (g - global_off) * stride;
@@ -398,7 +426,8 @@ int pm_ctx_create(const pm_pk_view* pk, pm_ctx** out) { return pm_ctx_create_sha
 int pm_ctx_create_sharded(const pm_pk_view* pk, int rank, int world, pm_ctx** out) {
     return guarded([&] {
         if (!pk || !out) throw StatusError(PM_ERR_ARG, "null argument");
-        if (pk->point_stride < PM_G1_BYTES) throw StatusError(PM_ERR_ARG, "point stride < 96");
+        if (pk->point_stride < PM_G1_BYTES && pk->point_stride != PM_G1_COMPRESSED_BYTES)
+            throw StatusError(PM_ERR_ARG, "point stride must be >= 96, or 48 for compressed points");
         if (world < 1 || rank < 0 || rank >= world) throw StatusError(PM_ERR_ARG, "bad rank/world");
         runtime();
         std::unique_ptr<pm_ctx> h(new pm_ctx());
@@ -493,12 +522,20 @@ int pm_ctx_key_len(const pm_ctx* ctx, int which, uint64_t* len) {
 
 int pm_ctx_export_key(const pm_ctx* ctx, int which, uint8_t* out, size_t stride) {
     return guarded([&] {
-        if (!ctx || !out || stride < PM_G1_BYTES) throw StatusError(PM_ERR_ARG, "bad export arguments");
+        if (!ctx || !out || (stride < PM_G1_BYTES && stride != PM_G1_COMPRESSED_BYTES)) throw StatusError(PM_ERR_ARG, "bad export arguments");
         const ProverCtx& c = ctx->impl;
         if (c.world != 1) throw StatusError(PM_ERR_STATE, "key export needs an unsharded context");
         KeySlice ks = key_slice(c, which);
         const G1Affine* src = (ks.in_d ? c.bases_d.get<G1Affine>() : c.bases_c.get<G1Affine>()) + ks.off;
         Runtime& rt = runtime();
+        if (stride == PM_G1_COMPRESSED_BYTES) {
+            DevBuf dout;
+            uint8_t* po = dout.as<uint8_t>(ks.len * 48 + 16);
+            launch_g1_compress(src, ks.len, po, rt.stream);
+            PM_CUDA(cudaMemcpyAsync(out, po, ks.len * 48, cudaMemcpyDeviceToHost, rt.stream));
+            PM_CUDA(cudaStreamSynchronize(rt.stream));
+            return;
+        }
         if (stride == PM_G1_BYTES) {
             PM_CUDA(cudaMemcpyAsync(out, src, ks.len * sizeof(G1Affine), cudaMemcpyDeviceToHost, rt.stream));
             PM_CUDA(cudaStreamSynchronize(rt.stream));

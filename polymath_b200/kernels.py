@@ -82,6 +82,24 @@ def msm_set_tuning(rounds=-1):
     check(lib.pm_msm_set_tuning(rounds))
 
 
+def g1_decompress_batch(encodings: bytes, validate=False):
+    """48-byte compressed encodings -> list of affine points / None (`deserialize_compressed[_unchecked]`)."""
+    lib = require_device()
+    n = len(encodings) // 48
+    out = C.create_string_buffer(max(n * 96, 1))
+    check(lib.pm_g1_decompress_batch(bytes(encodings), n, 1 if validate else 0, out))
+    return codec.g1s_from_wire(out.raw[:n * 96])
+
+
+def g1_compress_batch(points) -> bytes:
+    """Affine points / None -> concatenated 48-byte compressed encodings (`serialize_compressed`)."""
+    lib = require_device()
+    n = len(points)
+    out = C.create_string_buffer(max(n * 48, 1))
+    check(lib.pm_g1_compress_batch(codec.g1s_to_wire(points), n, out))
+    return out.raw[:n * 48]
+
+
 def fixed_base_mul(scalars):
     lib = require_device()
     out = C.create_string_buffer(len(scalars) * 96)

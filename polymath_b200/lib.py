@@ -48,12 +48,18 @@ def load():
     lib.pm_msm_g1_levels.restype = C.c_int
     lib.pm_msm_set_tuning.argtypes = [C.c_int]
     lib.pm_msm_set_tuning.restype = C.c_int
+    lib.pm_g1_decompress_batch.argtypes = [u8p, sz, C.c_int, u8p]
+    lib.pm_g1_decompress_batch.restype = C.c_int
+    lib.pm_g1_compress_batch.argtypes = [u8p, sz, u8p]
+    lib.pm_g1_compress_batch.restype = C.c_int
     lib.pm_fixed_base_mul.argtypes = [u8p, sz, u8p]
     lib.pm_fixed_base_mul.restype = C.c_int
     dp = C.POINTER(C.c_double)
     lib.pm_bench_imad_peak.argtypes = [dp]
     lib.pm_bench_field_mul.argtypes = [C.c_int, dp]
     lib.pm_bench_ntt.argtypes = [C.c_uint, C.c_int, C.c_int, dp]
+    lib.pm_bench_g1_codec.argtypes = [sz, dp, dp]
+    lib.pm_bench_g1_codec.restype = C.c_int
     lib.pm_bench_last_msm.argtypes = [dp]
     lib.pm_bench_last_msm.restype = C.c_int
     lib.pm_bench_msm.argtypes = [sz, C.c_int, C.c_int, dp, dp]

@@ -83,6 +83,45 @@ def test_ntt_coset(pmlib):
     assert kernels.ntt_fr(ev, inverse=True, coset_gen=g) == vals
 
 
+def test_g1_compression_roundtrip_and_rejects(pmlib):
+    """Device (de)compression against the oracle's restatement of ark-bls12-381's zcash encoding."""
+    from polymath_b200 import kernels
+    from polymath_b200.lib import PolymathB200Error
+    rnd = random.Random(21)
+    pts = [curve.G1_GEN, None, curve.g1_neg(curve.G1_GEN)] + _bases(200, rnd)
+    pts += [curve.g1_neg(p) for p in pts[3:40]]
+    enc = b"".join(curve.g1_compress(p) for p in pts)
+    assert kernels.g1_compress_batch(pts) == enc
+    assert kernels.g1_decompress_batch(enc) == pts
+    assert kernels.g1_decompress_batch(enc[:48 * 20], validate=True) == pts[:20]
+    # infinity flag wins over the remaining bits (ark-bls12-381 returns zero right away)
+    assert kernels.g1_decompress_batch(bytes([0xC0]) + b"\x01" * 47) == [None]
+    # a curve point outside the prime-order subgroup
+    x = 1
+    while True:
+        rhs = (x ** 3 + 4) % Q_MOD
+        y = pow(rhs, (Q_MOD + 1) // 4, Q_MOD)
+        if y * y % Q_MOD == rhs and not curve.g1_in_subgroup((x, y)):
+            break
+        x += 1
+    off = curve.g1_compress((x, y))
+    assert kernels.g1_decompress_batch(enc[:96] + off) == pts[:2] + [(x, y)]
+    bad_cases = {
+        "prime-order subgroup": (enc[:96] + off, True),
+        "compression flag": (enc[:48] + bytes(48), False),
+        "field modulus": (bytes([0x9F]) + b"\xff" * 47, False),
+    }
+    nr = 1
+    while pow((nr ** 3 + 4) % Q_MOD, (Q_MOD - 1) // 2, Q_MOD) == 1:
+        nr += 1
+    bad_cases["curve point"] = (enc[:144] + bytes([0x80]) + nr.to_bytes(47, "big"), False)
+    for needle, (data, validate) in bad_cases.items():
+        with pytest.raises(PolymathB200Error) as ei:
+            kernels.g1_decompress_batch(data, validate=validate)
+        assert needle in str(ei.value), (needle, str(ei.value))
+    assert "index 3" in str(ei.value)
+
+
 def _bases(k, rnd):
     tbl = curve.FixedBaseTable(curve.G1_GEN, window=8)
     return tbl.mul_many([rnd.randrange(1, R_MOD) for _ in range(k)])

@@ -171,3 +171,39 @@ def test_golden_fixtures_are_reproduced():
     assert proof.serialize_compressed().hex() == g["proof_hex"]
     assert pk.vk.serialize_compressed().hex() == g["vk_hex"]
     assert pub == int(g["public_input"])
+
+
+def test_g1_decompress_restatement():
+    """g1_decompress inverts g1_compress on the pinned generator encoding and on random subgroup points; rejects
+    x >= q, non-residues, missing compression flag and (validating) points outside the prime-order subgroup."""
+    import random
+    from oracle.fields import Q_MOD
+    rnd = random.Random(11)
+    assert curve.g1_decompress(curve.g1_compress(curve.G1_GEN)) == curve.G1_GEN
+    assert curve.g1_decompress(curve.g1_compress(None)) is None
+    for _ in range(6):
+        p = curve.g1_mul(curve.G1_GEN, rnd.randrange(1, R_MOD))
+        for q in (p, curve.g1_neg(p)):
+            assert curve.g1_decompress(curve.g1_compress(q)) == q
+    with pytest.raises(ValueError):
+        curve.g1_decompress(bytes(48))                                   # compression flag missing
+    with pytest.raises(ValueError):
+        curve.g1_decompress(bytes([0x9F]) + b"\xff" * 47)                # x >= q
+    # a curve point outside the subgroup: accepted unchecked, rejected when validating
+    x = 1
+    while True:
+        rhs = (x ** 3 + 4) % Q_MOD
+        y = pow(rhs, (Q_MOD + 1) // 4, Q_MOD)
+        if y * y % Q_MOD == rhs and not curve.g1_in_subgroup((x, y)):
+            break
+        x += 1
+    enc = curve.g1_compress((x, y))
+    assert curve.g1_decompress(enc, validate=False) == (x, y)
+    with pytest.raises(ValueError):
+        curve.g1_decompress(enc, validate=True)
+    # a non-residue abscissa
+    x = 1
+    while pow((x ** 3 + 4) % Q_MOD, (Q_MOD - 1) // 2, Q_MOD) == 1:
+        x += 1
+    with pytest.raises(ValueError):
+        curve.g1_decompress(bytes([0x80 | (x >> 376)]) + (x % (1 << 376)).to_bytes(47, "big"), validate=False)

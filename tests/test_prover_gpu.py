@@ -141,8 +141,15 @@ def test_load_host_key_matches_device_setup(pmlib):
         pk = Polymath.load_key(_r1cs_from_cs(cs), pk_or.vk.n, pk_or.vk.sigma, vectors, stride=stride)
         proofs.append(Polymath.prove(pk, pcs.instance_assignment, pcs.witness_assignment, StdRng.seed_from_u64(2)))
         pk.close()
+    # compressed key vectors (`serialize_compressed` bytes): decoded on the device; exported again they are identical
+    comp = {name: b"".join(curve.g1_compress(p) for p in vectors[name]) for name in KEY_NAMES}
+    pk = Polymath.load_key(_r1cs_from_cs(cs), pk_or.vk.n, pk_or.vk.sigma, comp, stride=48)
+    proofs.append(Polymath.prove(pk, pcs.instance_assignment, pcs.witness_assignment, StdRng.seed_from_u64(2)))
+    for which, name in enumerate(KEY_NAMES):
+        assert pk.export_key(which, stride=48) == comp[name]
+    pk.close()
     want = opm.create_proof_with_assignment(pk_or, pcs.instance_assignment, pcs.witness_assignment, OStdRng.seed_from_u64(2))
-    assert proofs[0] == proofs[1] == want.serialize_compressed()
+    assert proofs[0] == proofs[1] == proofs[2] == want.serialize_compressed()
 
 
 def test_setup_g2_and_trapdoor_api(pmlib):

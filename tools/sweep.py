@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--levels", default="1", help="comma list; 0 = as many levels as windows")
     ap.add_argument("--rounds", default="-1", help="comma list of pair-round settings (-1 = automatic, 0 = XYZZ walk only)")
     ap.add_argument("--skip-basics", action="store_true")
+    ap.add_argument("--codec", default="", help="comma list of log2 sizes for the G1 (de)compression kernels")
     a = ap.parse_args()
     lib = require_device()
     d = C.c_double()
@@ -38,6 +39,10 @@ def main():
             print(json.dumps({"kernel": "ntt_fr", "log_n": lg, "inverse": inv, "ms": d.value,
                               "gelem_per_s": n / d.value / 1e6, "algo_gb_per_s": 64 * n / d.value / 1e6,
                               "butterfly_muls_per_s": (n / 2) * lg / (d.value * 1e-3)}), flush=True)
+    for lg in [int(x) for x in a.codec.split(",") if x]:
+        check(lib.pm_bench_g1_codec(1 << lg, C.byref(d), C.byref(acc := C.c_double())))
+        print(json.dumps({"kernel": "g1_decompress", "log_n": lg, "ms": d.value, "mpts_per_s": (1 << lg) / d.value / 1e3,
+                          "compress_ms": acc.value}), flush=True)
     acc = C.c_double()
     for lg in [float(x) for x in a.msm.split(",") if x]:
         for w in [int(x) for x in a.windows.split(",")]:
