@@ -40,10 +40,12 @@ __device__ __forceinline__ uint32_t window_bits(const uint32_t* s, int pos, int 
     return (uint32_t)(v >> off) & ((1u << c) - 1u);
 }
 
+// Only the windows of the bucket sets [set_begin, set_end) are emitted (one pass of a large MSM); the signed-digit
+// carry still runs through all lower windows.
 template <bool SCATTER>
 __global__ void __launch_bounds__(256) k_digits(const G1Affine* __restrict__ bases, const Fr* __restrict__ scalars,
                                                 size_t n, size_t sc_stride, size_t sc_offset, int c, int nwin, uint32_t nb,
-                                                int levels, uint32_t level_stride,
+                                                int levels, uint32_t level_stride, int set_begin, int set_end,
                                                 uint32_t* __restrict__ counters, uint32_t* __restrict__ sorted) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -65,18 +67,19 @@ __global__ void __launch_bounds__(256) k_digits(const G1Affine* __restrict__ bas
     const uint32_t half = 1u << (c - 1);
     uint32_t carry = 0;
     // windows in batches of four: the four atomics of a batch are in flight together
-    for (int w0 = 0; w0 < nwin; w0 += 4) {
+    const int w_end = min(nwin, set_end * levels);
+    for (int w0 = 0; w0 < w_end; w0 += 4) {
         uint32_t slot[4], val[4];
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             const int w = w0 + k;
             slot[k] = 0xffffffffu;
-            if (w < nwin) {
+            if (w < w_end) {
                 uint32_t d = window_bits(limbs, w * c, c) + carry;
                 uint32_t neg = 0;
                 if (d > half) { d = (1u << c) - d; neg = 1; carry = 1; } else { carry = 0; }
-                if (d != 0) {
-                    slot[k] = (uint32_t)(w / levels) * nb + (d - 1);
+                if (d != 0 && w / levels >= set_begin) {
+                    slot[k] = (uint32_t)(w / levels - set_begin) * nb + (d - 1);
                     val[k] = ((uint32_t)(w % levels) * level_stride + (uint32_t)i) | (neg << 31);
                 }
             }
@@ -842,55 +845,90 @@ MsmEngine::Shape MsmEngine::run(const G1Affine* bases, const Fr* scalars, size_t
             if (rounds < 0) rounds = 0;
         }
         if (rounds > kMaxRounds) rounds = kMaxRounds;
-        // padded list / workspace must stay addressable and fit into the device memory that is still free (plus what
-        // this engine already holds for the purpose), else use the XYZZ walk only
-        while (rounds > 0) {
-            const size_t slots = entries + (size_t)total * ((1u << rounds) - 1);
-            const size_t need = (slots / 2 + 2) * (sizeof(G1Affine) + sizeof(Fq)) + (slots / 4 + 2) * sizeof(G1Affine) + slots * 4;
-            const size_t held = pairs_a_.cap + pairs_b_.cap + prefix_.cap + sorted_.cap;
-            bool fits = forced_rounds >= 0 || need <= held;
-            if (!fits) {
-                size_t free_b = 0, total_b = 0;
-                PM_CUDA(cudaMemGetInfo(&free_b, &total_b));
-                fits = need <= held + free_b / 10 * 8;
-            }
-            if (slots < ((size_t)1 << 32) - 4096 && fits) break;
-            rounds = 0;
+        // The bucket sets are independent: a large MSM runs them in passes of `sets_per_pass`, so that the padded list
+        // stays addressable (32-bit offsets) and the pair-round workspace fits into the device memory that is still
+        // free (plus what this engine already holds for the purpose).  If not even one set fits: XYZZ walk only.
+    }
+    int sets_per_pass = ngroups;
+    {
+        const size_t per_set = n * (size_t)levels;      // entries of one bucket set (upper bound)
+        auto workspace = [&](int sets, int r) {
+            const size_t slots = per_set * sets + (size_t)nb * sets * ((1u << r) - 1);
+            return r ? (slots / 2 + 2) * (sizeof(G1Affine) + sizeof(Fq)) + (slots / 4 + 2) * sizeof(G1Affine) + slots * 4 : slots * 4;
+        };
+        auto addressable = [&](int sets, int r) {
+            return per_set * sets + (size_t)nb * sets * ((1u << r) - 1) < ((size_t)1 << 32) - 4096;
+        };
+        const size_t held = pairs_a_.cap + pairs_b_.cap + prefix_.cap + sorted_.cap;
+        size_t budget = held;
+        if (forced_rounds < 0 && workspace(ngroups, rounds) > held) {
+            size_t free_b = 0, total_b = 0;
+            PM_CUDA(cudaMemGetInfo(&free_b, &total_b));
+            budget = held + free_b / 10 * 8;
+        } else if (forced_rounds >= 0) {
+            budget = ~(size_t)0;
         }
+        int forced_sets = cfg.sets_per_pass;
+        if (forced_sets <= 0) {
+            const char* v = getenv("PM_MSM_SETS_PER_PASS");      // test hook, read on every call
+            if (v) forced_sets = atoi(v);
+        }
+        if (forced_sets > 0) sets_per_pass = forced_sets < ngroups ? forced_sets : ngroups;
+        while (sets_per_pass > 1 && forced_sets <= 0 &&
+               (!addressable(sets_per_pass, rounds) || workspace(sets_per_pass, rounds) > budget))
+            sets_per_pass = (sets_per_pass + 1) / 2;
+        if (rounds > 0 && (!addressable(sets_per_pass, rounds) || workspace(sets_per_pass, rounds) > budget)) rounds = 0;
+        while (sets_per_pass > 1 && !addressable(sets_per_pass, rounds)) sets_per_pass = (sets_per_pass + 1) / 2;
+        if (!addressable(sets_per_pass, rounds)) throw CudaError("msm: too many points per bucket set");
     }
     const uint32_t pad_mask = (1u << rounds) - 1u;
-    const size_t slots_max = (entries + (size_t)total * pad_mask + 1) & ~(size_t)1;   // upper bound of S_0
+    const uint32_t pass_total = (uint32_t)sets_per_pass * nb;           // buckets of one pass
+    const size_t pass_entries = n * (size_t)levels * sets_per_pass;
+    const size_t slots_max = (pass_entries + (size_t)pass_total * pad_mask + 1) & ~(size_t)1;   // upper bound of S_0
+    const uint32_t pass_tiles = (pass_total + kScanTile - 1) / kScanTile;
 
-    uint32_t* counts = counts_.as<uint32_t>(total + 1);
-    uint32_t* offsets = offsets_.as<uint32_t>(total + 1);
-    uint32_t* cursors = cursors_.as<uint32_t>((size_t)total + 1 + ntiles + 1);
-    uint32_t* tile_sums = cursors + total + 1;
+    uint32_t* counts = counts_.as<uint32_t>(pass_total + 1);
+    uint32_t* offsets = offsets_.as<uint32_t>(pass_total + 1);
+    uint32_t* cursors = cursors_.as<uint32_t>((size_t)pass_total + 1 + pass_tiles + 1);
+    uint32_t* tile_sums = cursors + pass_total + 1;
     uint32_t* sorted = sorted_.as<uint32_t>(slots_max + 2);
-    G1XYZZ* buckets = buckets_.as<G1XYZZ>(total);
+    G1XYZZ* all_buckets = buckets_.as<G1XYZZ>(total);
     G1XYZZ* segs = segs_.as<G1XYZZ>(2 * seg_total + (size_t)ngroups * 256 + 64);
-    uint32_t* order = order_.as<uint32_t>((size_t)total + kLenBins);
-    uint32_t* len_hist = order + total;
+    uint32_t* order = order_.as<uint32_t>((size_t)pass_total + kLenBins);
+    uint32_t* len_hist = order + pass_total;
     HeavyLists hl;
     {
         // one allocation: [tasks uint2 | heavy uint4 | partials]
-        size_t bytes = max_tasks * sizeof(uint2) + (size_t)total * sizeof(uint4) + max_tasks * sizeof(G1XYZZ) + 64;
+        size_t bytes = max_tasks * sizeof(uint2) + (size_t)pass_total * sizeof(uint4) + max_tasks * sizeof(G1XYZZ) + 64;
         uint8_t* base = heavy_list_.as<uint8_t>(bytes);
         hl.heavy = reinterpret_cast<uint4*>(base);
-        hl.partials = reinterpret_cast<G1XYZZ*>(base + (size_t)total * sizeof(uint4));
-        hl.tasks = reinterpret_cast<uint2*>(base + (size_t)total * sizeof(uint4) + max_tasks * sizeof(G1XYZZ));
+        hl.partials = reinterpret_cast<G1XYZZ*>(base + (size_t)pass_total * sizeof(uint4));
+        hl.tasks = reinterpret_cast<uint2*>(base + (size_t)pass_total * sizeof(uint4) + max_tasks * sizeof(G1XYZZ));
         hl.counters = heavy_count_.as<uint32_t>(2);
     }
+    if (time_accumulate && !ev_acc_begin) {
+        PM_CUDA(cudaEventCreate(&ev_acc_begin)); PM_CUDA(cudaEventCreate(&ev_acc_end));
+        PM_CUDA(cudaEventCreate(&ev_bwd_begin)); PM_CUDA(cudaEventCreate(&ev_bwd_end));
+    }
+    last_rounds = rounds;
+    last_entries = pass_entries;
 
+    for (int set_begin = 0; set_begin < ngroups; set_begin += sets_per_pass) {
+    const int set_end = set_begin + sets_per_pass < ngroups ? set_begin + sets_per_pass : ngroups;
+    const uint32_t total = (uint32_t)(set_end - set_begin) * nb;      // buckets of this pass (shadows the MSM total)
+    const uint32_t ntiles = (total + kScanTile - 1) / kScanTile;
+    G1XYZZ* buckets = all_buckets + (size_t)set_begin * nb;
+    const bool timed = time_accumulate && set_begin == 0;             // the hooks time the first pass
     PM_CUDA(cudaMemsetAsync(counts, 0, (total + 1) * sizeof(uint32_t), stream));
     PM_CUDA(cudaMemsetAsync(hl.counters, 0, 2 * sizeof(uint32_t), stream));
     const unsigned dgrid = ceil_div(n, 256);
-    k_digits<false><<<dgrid, 256, 0, stream>>>(bases, scalars, n, scalar_stride, scalar_offset, c, nwin, nb, levels, (uint32_t)cfg.level_stride, counts, nullptr);
+    k_digits<false><<<dgrid, 256, 0, stream>>>(bases, scalars, n, scalar_stride, scalar_offset, c, nwin, nb, levels, (uint32_t)cfg.level_stride, set_begin, set_end, counts, nullptr);
     PM_LAUNCH_CHECK();
     k_scan_tiles<<<ntiles, 1024, 0, stream>>>(counts, total, pad_mask, offsets, tile_sums);
     k_scan_tile_sums<<<1, 1024, 0, stream>>>(tile_sums, ntiles);
     k_scan_apply<<<ntiles, 1024, 0, stream>>>(total, tile_sums, ntiles, offsets, cursors);
     PM_LAUNCH_CHECK();
-    k_digits<true><<<dgrid, 256, 0, stream>>>(bases, scalars, n, scalar_stride, scalar_offset, c, nwin, nb, levels, (uint32_t)cfg.level_stride, cursors, sorted);
+    k_digits<true><<<dgrid, 256, 0, stream>>>(bases, scalars, n, scalar_stride, scalar_offset, c, nwin, nb, levels, (uint32_t)cfg.level_stride, set_begin, set_end, cursors, sorted);
     PM_LAUNCH_CHECK();
     if (rounds > 0) {
         k_pad_runs<<<ceil_div(total, 256), 256, 0, stream>>>(counts, offsets, total, sorted);
@@ -902,15 +940,7 @@ MsmEngine::Shape MsmEngine::run(const G1Affine* bases, const Fr* scalars, size_t
     k_len_scan<<<1, 1024, 0, stream>>>(len_hist);
     k_len_scatter<<<ceil_div(total, 256), 256, 0, stream>>>(offsets, total, rounds, len_hist, order);
     PM_LAUNCH_CHECK();
-    if (time_accumulate) {
-        if (!ev_acc_begin) {
-            PM_CUDA(cudaEventCreate(&ev_acc_begin)); PM_CUDA(cudaEventCreate(&ev_acc_end));
-            PM_CUDA(cudaEventCreate(&ev_bwd_begin)); PM_CUDA(cudaEventCreate(&ev_bwd_end));
-        }
-        PM_CUDA(cudaEventRecord(ev_acc_begin, stream));
-    }
-    last_rounds = rounds;
-    last_entries = entries;
+    if (timed) PM_CUDA(cudaEventRecord(ev_acc_begin, stream));
     PointPlanes run_pts{nullptr, 0};
     if (rounds > 0) {
         const size_t cap_a = slots_max / 2 + 2, cap_b = slots_max / 4 + 2;
@@ -949,9 +979,9 @@ MsmEngine::Shape MsmEngine::run(const G1Affine* bases, const Fr* scalars, size_t
                 PairSource<true> src{bases, sorted, run_pts};
                 k_pairs_forward<true><<<g, 128, 0, stream>>>(src, slots0, r, prefix, tvals);
                 invert();
-                if (time_accumulate) PM_CUDA(cudaEventRecord(ev_bwd_begin, stream));
+                if (timed) PM_CUDA(cudaEventRecord(ev_bwd_begin, stream));
                 k_pairs_backward<true><<<g, 128, 0, stream>>>(src, slots0, r, prefix, tvals, dst);
-                if (time_accumulate) PM_CUDA(cudaEventRecord(ev_bwd_end, stream));
+                if (timed) PM_CUDA(cudaEventRecord(ev_bwd_end, stream));
             } else {
                 PairSource<false> src{bases, sorted, run_pts};
                 k_pairs_forward<false><<<g, 128, 0, stream>>>(src, slots0, r, prefix, tvals);
@@ -977,7 +1007,7 @@ MsmEngine::Shape MsmEngine::run(const G1Affine* bases, const Fr* scalars, size_t
         else k_accumulate<4, MulCall><<<g, 128, 0, stream>>>(bases, sorted, offsets, order, buckets, total, heavy_thr, hl);
         PM_LAUNCH_CHECK();
     }
-    if (time_accumulate) PM_CUDA(cudaEventRecord(ev_acc_end, stream));
+    if (timed) PM_CUDA(cudaEventRecord(ev_acc_end, stream));
     {
         static bool attr_set = false;
         const int smem = 256 * (int)sizeof(G1XYZZ);
@@ -992,8 +1022,10 @@ MsmEngine::Shape MsmEngine::run(const G1Affine* bases, const Fr* scalars, size_t
         k_heavy_finish<<<2 * sm_count(), 128, 0, stream>>>(buckets, hl);
         PM_LAUNCH_CHECK();
     }
+    launches += 9;
+    }   // passes over the bucket sets
     {
-        const G1XYZZ* X = buckets;
+        const G1XYZZ* X = all_buckets;
         G1XYZZ* cursor = segs;
         G1XYZZ* scratch = segs + 2 * seg_total;     // [ngroups][64] slice partials
         const int nsum = shape.nsum;
@@ -1030,7 +1062,6 @@ MsmEngine::Shape MsmEngine::run(const G1Affine* bases, const Fr* scalars, size_t
         PM_LAUNCH_CHECK();
         launches++;
     }
-    launches += 9;
     return shape;
 }
 

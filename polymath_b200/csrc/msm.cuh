@@ -18,6 +18,8 @@ struct MsmConfig {
     // another one on a second stream hides the fixed per-round latency and can afford one more round).
     int rounds = -1;
     int rounds_bias = 0;
+    // Bucket sets handled per pass (0 = as many as address space and free device memory allow); test hook.
+    int sets_per_pass = 0;
 };
 
 // Reusable workspace + launch sequence.  One engine per context / stream.

@@ -215,6 +215,25 @@ def test_msm_pair_rounds(msm_tuning, n, c, rounds):
         assert kernels.msm_g1(bases, scalars, window_bits=c, levels=3) == want
 
 
+@pytest.mark.parametrize("sets,rounds", [(1, 0), (1, 3), (3, 2), (5, 0)])
+def test_msm_bucket_set_passes(msm_tuning, monkeypatch, sets, rounds):
+    """Large MSMs run their bucket sets in several passes (address space / workspace): forced on a small one."""
+    from polymath_b200 import kernels
+    monkeypatch.setenv("PM_MSM_SETS_PER_PASS", str(sets))
+    rnd = random.Random(500 + sets)
+    n = 1200
+    bases = _bases(n, rnd)
+    bases[3] = None
+    hot = rnd.randrange(R_MOD)
+    scalars = [hot if i % 4 == 0 else rnd.randrange(R_MOD) for i in range(n)]
+    want = poly.msm_pippenger(scalars, bases)
+    msm_tuning(rounds)
+    assert kernels.msm_g1(bases, scalars, window_bits=7) == want                       # 37 bucket sets
+    assert kernels.msm_g1(bases, scalars, window_bits=7, heavy_threshold=16) == want
+    assert kernels.msm_g1(bases, scalars, window_bits=9, levels=4) == want              # 8 sets of 4 levels
+    assert kernels.msm_g1(bases, scalars, window_bits=9, levels=29) == want             # one set
+
+
 @pytest.mark.parametrize("rounds", [1, 2, 3, 5, 8])
 def test_msm_pair_rounds_exceptional_pairs(msm_tuning, rounds):
     """P + P, P + (-P), infinity operands and results inside the pair rounds; heavy buckets skipped by them."""
