@@ -877,7 +877,10 @@ MsmEngine::Shape MsmEngine::run(const G1Affine* bases, const Fr* scalars, size_t
         while (sets_per_pass > 1 && forced_sets <= 0 &&
                (!addressable(sets_per_pass, rounds) || workspace(sets_per_pass, rounds) > budget))
             sets_per_pass = (sets_per_pass + 1) / 2;
-        if (rounds > 0 && (!addressable(sets_per_pass, rounds) || workspace(sets_per_pass, rounds) > budget)) rounds = 0;
+        if (rounds > 0 && (!addressable(sets_per_pass, rounds) || workspace(sets_per_pass, rounds) > budget)) {
+            rounds = 0;                                   // not even one set fits: one XYZZ walk over as many sets as possible
+            if (forced_sets <= 0) sets_per_pass = ngroups;
+        }
         while (sets_per_pass > 1 && !addressable(sets_per_pass, rounds)) sets_per_pass = (sets_per_pass + 1) / 2;
         if (!addressable(sets_per_pass, rounds)) throw CudaError("msm: too many points per bucket set");
     }
