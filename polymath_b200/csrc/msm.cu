@@ -809,10 +809,11 @@ MsmEngine::Shape MsmEngine::run(const G1Affine* bases, const Fr* scalars, size_t
     size_t seg_total = 0;   // T and R arrays of all levels
     for (int j = 0; j < nlev; j++) seg_total += (size_t)((lev_m[j] + kRedK - 1) / kRedK) * ngroups;
     const uint32_t ntiles = (total + kScanTile - 1) / kScanTile;
-    // A bucket is split only when walking it serially would approach the whole kernel's duration:
-    // buckets run longest-first, so a run up to 1/8192 of all entries still hides behind the rest.
-    size_t share = n * (size_t)nwin / 8192;
-    uint32_t heavy_thr = cfg.heavy ? (uint32_t)cfg.heavy : (uint32_t)(share > 512 ? share : 512);
+    // A run is cut into chunked tasks when walking it serially would approach the whole kernel's duration: one
+    // thread adds a point every ~6.4 us, the whole GPU ~2.8 G points/s, so a run of E / 18000 entries already takes
+    // as long as everything else together; split from E / 32768 (skewed witnesses: repeated values).
+    size_t share = n * (size_t)nwin / 32768;
+    uint32_t heavy_thr = cfg.heavy ? (uint32_t)cfg.heavy : (uint32_t)(share > 128 ? share : 128);
     const size_t max_tasks = n * (size_t)nwin / kHeavyChunk + total + 16;
     const size_t entries = n * (size_t)nwin;   // upper bound of the sorted list
 
@@ -997,7 +998,7 @@ MsmEngine::Shape MsmEngine::run(const G1Affine* bases, const Fr* scalars, size_t
         }
     }
     // runs are cut into chunked tasks only when walking them serially would approach the kernel's duration
-    const uint32_t walk_heavy_thr = rounds > 0 && !cfg.heavy ? (heavy_thr >> rounds > 64 ? heavy_thr >> rounds : 64) : heavy_thr;
+    const uint32_t walk_heavy_thr = rounds > 0 && !cfg.heavy ? (heavy_thr >> rounds > 32 ? heavy_thr >> rounds : 32) : heavy_thr;
     {
         static int variant = -1;
         if (variant < 0) {
