@@ -918,115 +918,115 @@ MsmEngine::Shape MsmEngine::run(const G1Affine* bases, const Fr* scalars, size_t
     last_entries = pass_entries;
 
     for (int set_begin = 0; set_begin < ngroups; set_begin += sets_per_pass) {
-    const int set_end = set_begin + sets_per_pass < ngroups ? set_begin + sets_per_pass : ngroups;
-    const uint32_t total = (uint32_t)(set_end - set_begin) * nb;      // buckets of this pass (shadows the MSM total)
-    const uint32_t ntiles = (total + kScanTile - 1) / kScanTile;
-    G1XYZZ* buckets = all_buckets + (size_t)set_begin * nb;
-    const bool timed = time_accumulate && set_begin == 0;             // the hooks time the first pass
-    PM_CUDA(cudaMemsetAsync(counts, 0, (total + 1) * sizeof(uint32_t), stream));
-    PM_CUDA(cudaMemsetAsync(hl.counters, 0, 2 * sizeof(uint32_t), stream));
-    const unsigned dgrid = ceil_div(n, 256);
-    k_digits<false><<<dgrid, 256, 0, stream>>>(bases, scalars, n, scalar_stride, scalar_offset, c, nwin, nb, levels, (uint32_t)cfg.level_stride, set_begin, set_end, counts, nullptr);
-    PM_LAUNCH_CHECK();
-    k_scan_tiles<<<ntiles, 1024, 0, stream>>>(counts, total, pad_mask, offsets, tile_sums);
-    k_scan_tile_sums<<<1, 1024, 0, stream>>>(tile_sums, ntiles);
-    k_scan_apply<<<ntiles, 1024, 0, stream>>>(total, tile_sums, ntiles, offsets, cursors);
-    PM_LAUNCH_CHECK();
-    k_digits<true><<<dgrid, 256, 0, stream>>>(bases, scalars, n, scalar_stride, scalar_offset, c, nwin, nb, levels, (uint32_t)cfg.level_stride, set_begin, set_end, cursors, sorted);
-    PM_LAUNCH_CHECK();
-    if (rounds > 0) {
-        k_pad_runs<<<ceil_div(total, 256), 256, 0, stream>>>(counts, offsets, total, sorted);
+        const int set_end = set_begin + sets_per_pass < ngroups ? set_begin + sets_per_pass : ngroups;
+        const uint32_t total = (uint32_t)(set_end - set_begin) * nb;      // buckets of this pass (shadows the MSM total)
+        const uint32_t ntiles = (total + kScanTile - 1) / kScanTile;
+        G1XYZZ* buckets = all_buckets + (size_t)set_begin * nb;
+        const bool timed = time_accumulate && set_begin == 0;             // the hooks time the first pass
+        PM_CUDA(cudaMemsetAsync(counts, 0, (total + 1) * sizeof(uint32_t), stream));
+        PM_CUDA(cudaMemsetAsync(hl.counters, 0, 2 * sizeof(uint32_t), stream));
+        const unsigned dgrid = ceil_div(n, 256);
+        k_digits<false><<<dgrid, 256, 0, stream>>>(bases, scalars, n, scalar_stride, scalar_offset, c, nwin, nb, levels, (uint32_t)cfg.level_stride, set_begin, set_end, counts, nullptr);
         PM_LAUNCH_CHECK();
-    }
-    // walk order: by the run length the XYZZ walk will see (after the pair rounds)
-    PM_CUDA(cudaMemsetAsync(len_hist, 0, kLenBins * sizeof(uint32_t), stream));
-    k_len_hist<<<ceil_div(total, 256), 256, 0, stream>>>(offsets, total, rounds, len_hist);
-    k_len_scan<<<1, 1024, 0, stream>>>(len_hist);
-    k_len_scatter<<<ceil_div(total, 256), 256, 0, stream>>>(offsets, total, rounds, len_hist, order);
-    PM_LAUNCH_CHECK();
-    if (timed) PM_CUDA(cudaEventRecord(ev_acc_begin, stream));
-    PointPlanes run_pts{nullptr, 0};
-    if (rounds > 0) {
-        const size_t cap_a = slots_max / 2 + 2, cap_b = slots_max / 4 + 2;
-        PointPlanes ping{pairs_a_.as<uint4>(6 * cap_a), cap_a};
-        PointPlanes pong{rounds > 1 ? pairs_b_.as<uint4>(6 * cap_b) : nullptr, cap_b};
-        FqPlanes prefix{prefix_.as<uint4>(3 * cap_a), cap_a};
-        // thread totals and the levels of the inversion tree above them: [T_0 | T_1 | T_2], prefixes [pre_0 | pre_1]
-        size_t lvl[kInvLevels + 1];
-        lvl[0] = (slots_max / 2 + kPairTile - 1) / kPairTile * 128 + 128;
-        for (int l = 0; l < kInvLevels; l++) lvl[l + 1] = (lvl[l] + kInvFan - 1) / kInvFan + 1;
-        Fq* tlev[kInvLevels + 1];
-        Fq* plev[kInvLevels];
-        tlev[0] = tvals_.as<Fq>(lvl[0] + lvl[1] + lvl[2]);
-        plev[0] = tpre_.as<Fq>(lvl[0] + lvl[1]);
-        for (int l = 0; l < kInvLevels; l++) tlev[l + 1] = tlev[l] + lvl[l];
-        plev[1] = plev[0] + lvl[0];
-        Fq* tvals = tlev[0];
-        const uint32_t* slots0 = offsets + total;
-        for (int r = 0; r < rounds; r++) {
-            const size_t pairs_max = (slots_max >> r) >> 1;
-            const unsigned g = ceil_div(pairs_max, kPairTile);
-            if (g == 0) break;
-            PointPlanes dst = (r & 1) ? pong : ping;
-            // level sizes for the grids (upper bounds; the kernels derive the exact ones from slots0)
-            size_t nl[kInvLevels + 1];
-            nl[0] = (size_t)g * 128;
-            for (int l = 0; l < kInvLevels; l++) nl[l + 1] = (nl[l] + kInvFan - 1) / kInvFan;
-            auto invert = [&]() {
-                for (int l = 0; l < kInvLevels; l++)
-                    k_invert_up<<<ceil_div(nl[l + 1], 128), 128, 0, stream>>>(tlev[l], plev[l], tlev[l + 1], slots0, r, l);
-                k_invert_top<<<ceil_div(nl[kInvLevels], 128), 128, 0, stream>>>(tlev[kInvLevels], slots0, r, kInvLevels);
-                for (int l = kInvLevels; l-- > 0;)
-                    k_invert_down<<<ceil_div(nl[l + 1], 128), 128, 0, stream>>>(tlev[l], plev[l], tlev[l + 1], slots0, r, l);
-            };
-            if (r == 0) {
-                PairSource<true> src{bases, sorted, run_pts};
-                k_pairs_forward<true><<<g, 128, 0, stream>>>(src, slots0, r, prefix, tvals);
-                invert();
-                if (timed) PM_CUDA(cudaEventRecord(ev_bwd_begin, stream));
-                k_pairs_backward<true><<<g, 128, 0, stream>>>(src, slots0, r, prefix, tvals, dst);
-                if (timed) PM_CUDA(cudaEventRecord(ev_bwd_end, stream));
-            } else {
-                PairSource<false> src{bases, sorted, run_pts};
-                k_pairs_forward<false><<<g, 128, 0, stream>>>(src, slots0, r, prefix, tvals);
-                invert();
-                k_pairs_backward<false><<<g, 128, 0, stream>>>(src, slots0, r, prefix, tvals, dst);
-            }
+        k_scan_tiles<<<ntiles, 1024, 0, stream>>>(counts, total, pad_mask, offsets, tile_sums);
+        k_scan_tile_sums<<<1, 1024, 0, stream>>>(tile_sums, ntiles);
+        k_scan_apply<<<ntiles, 1024, 0, stream>>>(total, tile_sums, ntiles, offsets, cursors);
+        PM_LAUNCH_CHECK();
+        k_digits<true><<<dgrid, 256, 0, stream>>>(bases, scalars, n, scalar_stride, scalar_offset, c, nwin, nb, levels, (uint32_t)cfg.level_stride, set_begin, set_end, cursors, sorted);
+        PM_LAUNCH_CHECK();
+        if (rounds > 0) {
+            k_pad_runs<<<ceil_div(total, 256), 256, 0, stream>>>(counts, offsets, total, sorted);
             PM_LAUNCH_CHECK();
-            run_pts = dst;
-            launches += 3 + 2 * kInvLevels;
         }
-    }
-    // runs are cut into chunked tasks only when walking them serially would approach the kernel's duration
-    const uint32_t walk_heavy_thr = rounds > 0 && !cfg.heavy ? (heavy_thr >> rounds > 32 ? heavy_thr >> rounds : 32) : heavy_thr;
-    {
-        static int variant = -1;
-        if (variant < 0) {
-            const char* v = getenv("PM_ACC_VARIANT");
-            variant = v ? atoi(v) : 24;
+        // walk order: by the run length the XYZZ walk will see (after the pair rounds)
+        PM_CUDA(cudaMemsetAsync(len_hist, 0, kLenBins * sizeof(uint32_t), stream));
+        k_len_hist<<<ceil_div(total, 256), 256, 0, stream>>>(offsets, total, rounds, len_hist);
+        k_len_scan<<<1, 1024, 0, stream>>>(len_hist);
+        k_len_scatter<<<ceil_div(total, 256), 256, 0, stream>>>(offsets, total, rounds, len_hist, order);
+        PM_LAUNCH_CHECK();
+        if (timed) PM_CUDA(cudaEventRecord(ev_acc_begin, stream));
+        PointPlanes run_pts{nullptr, 0};
+        if (rounds > 0) {
+            const size_t cap_a = slots_max / 2 + 2, cap_b = slots_max / 4 + 2;
+            PointPlanes ping{pairs_a_.as<uint4>(6 * cap_a), cap_a};
+            PointPlanes pong{rounds > 1 ? pairs_b_.as<uint4>(6 * cap_b) : nullptr, cap_b};
+            FqPlanes prefix{prefix_.as<uint4>(3 * cap_a), cap_a};
+            // thread totals and the levels of the inversion tree above them: [T_0 | T_1 | T_2], prefixes [pre_0 | pre_1]
+            size_t lvl[kInvLevels + 1];
+            lvl[0] = (slots_max / 2 + kPairTile - 1) / kPairTile * 128 + 128;
+            for (int l = 0; l < kInvLevels; l++) lvl[l + 1] = (lvl[l] + kInvFan - 1) / kInvFan + 1;
+            Fq* tlev[kInvLevels + 1];
+            Fq* plev[kInvLevels];
+            tlev[0] = tvals_.as<Fq>(lvl[0] + lvl[1] + lvl[2]);
+            plev[0] = tpre_.as<Fq>(lvl[0] + lvl[1]);
+            for (int l = 0; l < kInvLevels; l++) tlev[l + 1] = tlev[l] + lvl[l];
+            plev[1] = plev[0] + lvl[0];
+            Fq* tvals = tlev[0];
+            const uint32_t* slots0 = offsets + total;
+            for (int r = 0; r < rounds; r++) {
+                const size_t pairs_max = (slots_max >> r) >> 1;
+                const unsigned g = ceil_div(pairs_max, kPairTile);
+                if (g == 0) break;
+                PointPlanes dst = (r & 1) ? pong : ping;
+                // level sizes for the grids (upper bounds; the kernels derive the exact ones from slots0)
+                size_t nl[kInvLevels + 1];
+                nl[0] = (size_t)g * 128;
+                for (int l = 0; l < kInvLevels; l++) nl[l + 1] = (nl[l] + kInvFan - 1) / kInvFan;
+                auto invert = [&]() {
+                    for (int l = 0; l < kInvLevels; l++)
+                        k_invert_up<<<ceil_div(nl[l + 1], 128), 128, 0, stream>>>(tlev[l], plev[l], tlev[l + 1], slots0, r, l);
+                    k_invert_top<<<ceil_div(nl[kInvLevels], 128), 128, 0, stream>>>(tlev[kInvLevels], slots0, r, kInvLevels);
+                    for (int l = kInvLevels; l-- > 0;)
+                        k_invert_down<<<ceil_div(nl[l + 1], 128), 128, 0, stream>>>(tlev[l], plev[l], tlev[l + 1], slots0, r, l);
+                };
+                if (r == 0) {
+                    PairSource<true> src{bases, sorted, run_pts};
+                    k_pairs_forward<true><<<g, 128, 0, stream>>>(src, slots0, r, prefix, tvals);
+                    invert();
+                    if (timed) PM_CUDA(cudaEventRecord(ev_bwd_begin, stream));
+                    k_pairs_backward<true><<<g, 128, 0, stream>>>(src, slots0, r, prefix, tvals, dst);
+                    if (timed) PM_CUDA(cudaEventRecord(ev_bwd_end, stream));
+                } else {
+                    PairSource<false> src{bases, sorted, run_pts};
+                    k_pairs_forward<false><<<g, 128, 0, stream>>>(src, slots0, r, prefix, tvals);
+                    invert();
+                    k_pairs_backward<false><<<g, 128, 0, stream>>>(src, slots0, r, prefix, tvals, dst);
+                }
+                PM_LAUNCH_CHECK();
+                run_pts = dst;
+                launches += 3 + 2 * kInvLevels;
+            }
         }
-        const unsigned g = ceil_div(total, 128);
-        if (rounds > 0) k_accumulate_rounds<<<g, 128, 0, stream>>>(run_pts, offsets, order, rounds, buckets, total, walk_heavy_thr, hl);
-        else if (variant == 3) k_accumulate<3, MulInline><<<g, 128, 0, stream>>>(bases, sorted, offsets, order, buckets, total, heavy_thr, hl);
-        else k_accumulate<4, MulCall><<<g, 128, 0, stream>>>(bases, sorted, offsets, order, buckets, total, heavy_thr, hl);
-        PM_LAUNCH_CHECK();
-    }
-    if (timed) PM_CUDA(cudaEventRecord(ev_acc_end, stream));
-    {
-        static bool attr_set = false;
-        const int smem = 256 * (int)sizeof(G1XYZZ);
-        if (!attr_set) {
-            PM_CUDA(cudaFuncSetAttribute(k_accumulate_heavy<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            PM_CUDA(cudaFuncSetAttribute(k_accumulate_heavy<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            attr_set = true;
+        // runs are cut into chunked tasks only when walking them serially would approach the kernel's duration
+        const uint32_t walk_heavy_thr = rounds > 0 && !cfg.heavy ? (heavy_thr >> rounds > 32 ? heavy_thr >> rounds : 32) : heavy_thr;
+        {
+            static int variant = -1;
+            if (variant < 0) {
+                const char* v = getenv("PM_ACC_VARIANT");
+                variant = v ? atoi(v) : 24;
+            }
+            const unsigned g = ceil_div(total, 128);
+            if (rounds > 0) k_accumulate_rounds<<<g, 128, 0, stream>>>(run_pts, offsets, order, rounds, buckets, total, walk_heavy_thr, hl);
+            else if (variant == 3) k_accumulate<3, MulInline><<<g, 128, 0, stream>>>(bases, sorted, offsets, order, buckets, total, heavy_thr, hl);
+            else k_accumulate<4, MulCall><<<g, 128, 0, stream>>>(bases, sorted, offsets, order, buckets, total, heavy_thr, hl);
+            PM_LAUNCH_CHECK();
         }
-        if (rounds > 0) k_accumulate_heavy<true><<<4 * sm_count(), 256, smem, stream>>>(bases, sorted, run_pts, rounds, offsets, hl);
-        else k_accumulate_heavy<false><<<4 * sm_count(), 256, smem, stream>>>(bases, sorted, run_pts, 0, offsets, hl);
-        PM_LAUNCH_CHECK();
-        k_heavy_finish<<<2 * sm_count(), 128, 0, stream>>>(buckets, hl);
-        PM_LAUNCH_CHECK();
-    }
-    launches += 9;
+        if (timed) PM_CUDA(cudaEventRecord(ev_acc_end, stream));
+        {
+            static bool attr_set = false;
+            const int smem = 256 * (int)sizeof(G1XYZZ);
+            if (!attr_set) {
+                PM_CUDA(cudaFuncSetAttribute(k_accumulate_heavy<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+                PM_CUDA(cudaFuncSetAttribute(k_accumulate_heavy<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+                attr_set = true;
+            }
+            if (rounds > 0) k_accumulate_heavy<true><<<4 * sm_count(), 256, smem, stream>>>(bases, sorted, run_pts, rounds, offsets, hl);
+            else k_accumulate_heavy<false><<<4 * sm_count(), 256, smem, stream>>>(bases, sorted, run_pts, 0, offsets, hl);
+            PM_LAUNCH_CHECK();
+            k_heavy_finish<<<2 * sm_count(), 128, 0, stream>>>(buckets, hl);
+            PM_LAUNCH_CHECK();
+        }
+        launches += 9;
     }   // passes over the bucket sets
     {
         const G1XYZZ* X = all_buckets;

@@ -17,10 +17,17 @@ def main():
     ap.add_argument("--log-n", type=int, default=20)
     ap.add_argument("--world", type=int, default=1)
     ap.add_argument("--iters", type=int, default=2)
+    ap.add_argument("--dummy", action="store_true", help="S-dummy (benches/bench.rs shape) instead of S-mimc")
     a = ap.parse_args()
     lib = _lib()
     sharded.bind(lib)
-    r1cs, inst, wit, rng = circuits.synthetic_mimc(1 << a.log_n, seed=1)
+    if a.dummy:
+        rng = StdRng.seed_from_u64(0)
+        av, bv = rng.fr_rand(), rng.fr_rand()
+        nv = nc = (1 << (a.log_n - 1)) - 2          # SAP rows = 2 (m0 + n_r) = 2^log_n
+        r1cs, inst, wit = circuits.bench_dummy(nv, nc, av, bv)
+    else:
+        r1cs, inst, wit, rng = circuits.synthetic_mimc(1 << a.log_n, seed=1)
     x, z = rng.fr_rand(), rng.fr_rand()
     h = C.c_void_p()
     xg2, zg2 = C.create_string_buffer(192), C.create_string_buffer(192)
