@@ -16,7 +16,7 @@ LIB = os.path.join(ROOT, "polymath_b200", "libpolymath_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-    "-Xcompiler", "-fPIC,-O2", "--expt-relaxed-constexpr", "-I", os.path.join(ROOT, "include"),
+    "-Xcompiler", "-fPIC,-O3", "--expt-relaxed-constexpr", "-I", os.path.join(ROOT, "include"),
 ]
 
 

@@ -235,6 +235,27 @@ int pm_polymath_setup(const pm_r1cs_view* r1cs, pm_rng* rng, pm_ctx** ctx_out, u
  * (176 bytes, src/data_structures.rs:10-19). */
 int pm_polymath_prove(pm_ctx* ctx, const uint8_t* instance, const uint8_t* witness, pm_rng* rng, uint8_t proof_out[176]);
 
+/* `Polymath::verify` / `verify_proof` (src/verifier.rs:19-62) on the HOST — no device work (BASELINE north_star:
+ * pairing-based verification stays on the host): deserialises the compressed VerifyingKey (392 bytes) and Proof
+ * (176 bytes) with ark-serialize's validation (on curve, prime-order subgroup, canonical scalars), recomputes
+ * x1, c(x1), x2 through the Merlin transcript and checks
+ *   e([a]_1 + x2 [c]_1 - (a(x1) + x2 c(x1)) [1]_1, [z]_2) * e(-[d]_1, [x]_2 - x1 [1]_2) == 1.
+ * public_inputs: num_public x 32 bytes (Montgomery), WITHOUT the leading one (the verifier prepends it,
+ * src/verifier.rs:26).  *accepted = 1 / 0 = the reference's Ok(true) / Ok(false); a key or proof that does not
+ * deserialise fails with PM_ERR_ARG (the reference's SerializationError). */
+int pm_polymath_verify(const uint8_t vk[392], const uint8_t* public_inputs, size_t num_public, const uint8_t proof[176],
+                       int* accepted);
+/* Batch form: `count` proofs under one key, proof i with the public inputs
+ * public_inputs[i * num_public ..].  The pairing equations are combined with 128-bit coefficients drawn from
+ * rand `StdRng::from_seed(seed)` (r_0 = 1) into ONE product of three pairings:
+ *   e(sum r_i L_i, [z]_2) * e(-sum r_i [d_i]_1, [x]_2) * e(sum r_i x1_i [d_i]_1, [1]_2) == 1.
+ * *accepted = 1 iff the combined check holds (all proofs valid, up to 2^-128 soundness error from the caller's seed). */
+int pm_polymath_verify_batch(const uint8_t vk[392], size_t count, const uint8_t* public_inputs, size_t num_public,
+                             const uint8_t* proofs, const uint8_t seed[32], int* accepted);
+/* Host-only test hook: prod_i e(P_i, Q_i) == 1 for `count` pairs of affine points (G1: 96 bytes, G2: 192 bytes
+ * x.c0, x.c1, y.c0, y.c1; Montgomery; all-zero = infinity).  `E::multi_pairing(..).0.is_one()` (src/verifier.rs:50-61). */
+int pm_host_pairing_product_is_one(const uint8_t* g1_points, const uint8_t* g2_points, int count, int* is_one);
+
 /* Collective supplied by the caller for the sharded flow: gather `bytes` from every rank into
  * recv (world * bytes, rank order).  Returns 0 on success. */
 typedef int (*pm_allgather_fn)(void* user, const uint8_t* send, size_t bytes, uint8_t* recv);

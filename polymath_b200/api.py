@@ -5,7 +5,8 @@
 matrices (`cs.to_matrices()`, generator.rs:46) and the instance / witness assignments
 (prover.rs:53-58) that the caller's circuit produces.  All computation happens in
 libpolymath_b200.so (CUDA); this file only marshals bytes.  Verification (pairing check) stays
-on the host and is not part of this backend (BASELINE.json north_star).
+on the host (BASELINE.json north_star): `Polymath.verify` / `verify_batch` call the library's host-only
+verifier (`pm_polymath_verify`, src/verifier.rs:19-62) and need no GPU.
 """
 import ctypes as C
 
@@ -73,6 +74,9 @@ def _bind(lib):
     lib.pm_polymath_setup.argtypes = [C.POINTER(R1CSView), vp, C.POINTER(vp), u8p]
     lib.pm_polymath_prove.argtypes = [vp, u8p, u8p, vp, u8p]
     lib.pm_polymath_prove_resident.argtypes = [vp, u8p, vp, u8p]
+    lib.pm_polymath_verify.argtypes = [u8p, u8p, C.c_size_t, u8p, C.POINTER(C.c_int)]
+    lib.pm_polymath_verify_batch.argtypes = [u8p, C.c_size_t, u8p, C.c_size_t, u8p, u8p, C.POINTER(C.c_int)]
+    lib.pm_host_pairing_product_is_one.argtypes = [u8p, u8p, C.c_int, C.POINTER(C.c_int)]
     lib.pm_timer_start.argtypes = []
     lib.pm_timer_stop.argtypes = [C.POINTER(C.c_double)]
     lib.pm_bench_set_kernel_timing.argtypes = [C.c_int]
@@ -299,3 +303,31 @@ class Polymath:
         d = C.create_string_buffer(96)
         check(lib.pm_prove_phase3(pk._h, codec.fr_to_wire(x2), codec.fr_to_wire(c_at_x1), d))
         return a_pt, c_pt, a_at_x1, codec.g1_from_wire(d.raw)
+
+    @staticmethod
+    def verify(vk_bytes: bytes, public_inputs, proof_bytes: bytes) -> bool:
+        """`verify` (lib.rs:80-91 -> verifier.rs:19-62) on the host: compressed VerifyingKey (392 B), the public
+        inputs WITHOUT the leading one, compressed Proof (176 B).  No GPU involved."""
+        lib = load()
+        _bind(lib)
+        if len(vk_bytes) != 392 or len(proof_bytes) != 176:
+            raise ValueError("vk must be 392 bytes and the proof 176 bytes")
+        ok = C.c_int(0)
+        pub = codec.frs_to_wire(public_inputs)
+        check(lib.pm_polymath_verify(vk_bytes, pub, len(public_inputs), proof_bytes, C.byref(ok)))
+        return bool(ok.value)
+
+    @staticmethod
+    def verify_batch(vk_bytes: bytes, public_inputs_list, proofs, seed: bytes) -> bool:
+        """Many proofs under one key with ONE product of three pairings (random linear combination)."""
+        lib = load()
+        _bind(lib)
+        if len(public_inputs_list) != len(proofs):
+            raise ValueError("one public-input list per proof")
+        k = len(public_inputs_list[0]) if proofs else 0
+        if any(len(p) != k for p in public_inputs_list) or any(len(p) != 176 for p in proofs) or len(seed) != 32:
+            raise ValueError("ragged public inputs / bad proof or seed length")
+        ok = C.c_int(0)
+        pub = b"".join(codec.frs_to_wire(p) for p in public_inputs_list)
+        check(lib.pm_polymath_verify_batch(vk_bytes, len(proofs), pub, k, b"".join(proofs), seed, C.byref(ok)))
+        return bool(ok.value)

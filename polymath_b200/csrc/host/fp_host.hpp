@@ -59,12 +59,15 @@ struct FpH {
     FpH operator*(const FpH& b) const {
         uint64_t t[N + 2];
         memset(t, 0, sizeof t);
+#pragma GCC unroll 8
         for (int i = 0; i < N; i++) {
             u128 c = 0;
+#pragma GCC unroll 8
             for (int j = 0; j < N; j++) { c += (u128)v[j] * b.v[i] + t[j]; t[j] = (uint64_t)c; c >>= 64; }
             c += t[N]; t[N] = (uint64_t)c; t[N + 1] = (uint64_t)(c >> 64);
             uint64_t m = t[0] * P.inv;
             c = (u128)m * P.mod[0] + t[0]; c >>= 64;
+#pragma GCC unroll 8
             for (int j = 1; j < N; j++) { c += (u128)m * P.mod[j] + t[j]; t[j - 1] = (uint64_t)c; c >>= 64; }
             c += t[N]; t[N - 1] = (uint64_t)c; t[N] = t[N + 1] + (uint64_t)(c >> 64);
         }
@@ -82,11 +85,37 @@ struct FpH {
         return acc;
     }
     FpH pow_u64(uint64_t e) const { return pow(&e, 1); }
-    FpH inv() const {   // Fermat; inverse of zero is zero (callers check)
-        uint64_t e[N]; memcpy(e, P.mod, sizeof e);
-        u128 borrow = 2;
-        for (int i = 0; i < N && borrow; i++) { u128 t = (u128)e[i] - (uint64_t)borrow; e[i] = (uint64_t)t; borrow = (t >> 64) & 1; }
-        return pow(e, N);
+    // binary extended Euclid on the raw limbs (aR)^-1 = a^-1 R^-1, then one Montgomery product by R^3;
+    // inverse of zero is zero (callers check).  ~10x cheaper than the Fermat chain: the Miller loop of the host
+    // verifier inverts once per step.
+    FpH inv() const {
+        if (is_zero()) return zero();
+        uint64_t u[N], w[N], x1[N], x2[N];
+        memcpy(u, v, sizeof u);
+        memcpy(w, P.mod, sizeof w);
+        memset(x1, 0, sizeof x1); x1[0] = 1;
+        memset(x2, 0, sizeof x2);
+        auto is_one = [](const uint64_t* a) { uint64_t o = a[0] ^ 1; for (int i = 1; i < N; i++) o |= a[i]; return o == 0; };
+        auto shr1 = [](uint64_t* a, uint64_t top) { for (int i = 0; i < N; i++) a[i] = (a[i] >> 1) | ((i + 1 < N ? a[i + 1] : top) << 63); };
+        auto halve = [&](uint64_t* a) {          // a / 2 mod p
+            uint64_t top = 0;
+            if (a[0] & 1) { u128 c = 0; for (int i = 0; i < N; i++) { c += (u128)a[i] + P.mod[i]; a[i] = (uint64_t)c; c >>= 64; } top = (uint64_t)c; }
+            shr1(a, top);
+        };
+        auto geq = [](const uint64_t* a, const uint64_t* b) { for (int i = N - 1; i >= 0; i--) if (a[i] != b[i]) return a[i] > b[i]; return true; };
+        auto sub = [](uint64_t* a, const uint64_t* b) { u128 br = 0; for (int i = 0; i < N; i++) { u128 t = (u128)a[i] - b[i] - (uint64_t)br; a[i] = (uint64_t)t; br = (t >> 64) & 1; } return (uint64_t)br; };
+        auto sub_modp = [&](uint64_t* a, const uint64_t* b) {   // a - b mod p, a, b < p
+            if (sub(a, b)) { u128 c = 0; for (int i = 0; i < N; i++) { c += (u128)a[i] + P.mod[i]; a[i] = (uint64_t)c; c >>= 64; } }
+        };
+        while (!is_one(u) && !is_one(w)) {
+            while (!(u[0] & 1)) { shr1(u, 0); halve(x1); }
+            while (!(w[0] & 1)) { shr1(w, 0); halve(x2); }
+            if (geq(u, w)) { sub(u, w); sub_modp(x1, x2); } else { sub(w, u); sub_modp(x2, x1); }
+        }
+        FpH r, r2;
+        memcpy(r.v, is_one(u) ? x1 : x2, sizeof r.v);
+        memcpy(r2.v, P.r2, sizeof r2.v);
+        return r * (r2 * r2);
     }
     // canonical value > (p-1)/2 ?   (zcash "lexicographically largest" flag)
     bool canonical_gt_half() const {

@@ -14,6 +14,7 @@
 #include "../../../include/polymath_b200.h"
 #include "../common.cuh"
 #include "transcript_host.hpp"
+#include "pairing_host.hpp"
 
 using namespace pm::host;
 
@@ -248,6 +249,169 @@ static int prove_impl(pm_ctx* ctx, const uint8_t* instance, const uint8_t* witne
     ser_fr(proof, a_at_x1);
     ser_g1_compressed(proof, d_g1);
     memcpy(proof_out, proof.data(), 176);
+    return PM_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------
+// `Polymath::verify` on the host (src/verifier.rs:19-62) — no device work
+// ---------------------------------------------------------------------------------------
+namespace {
+
+uint64_t rd_u64(const uint8_t* b) { uint64_t v = 0; for (int i = 0; i < 8; i++) v |= (uint64_t)b[i] << (8 * i); return v; }
+
+struct VkH {       // VerifyingKey, data_structures.rs:25-50
+    G1H one_g1;
+    G2H one_g2, x_g2, z_g2;
+    uint64_t n, m0, sigma;
+    FrH omega;
+};
+struct ProofH {    // Proof, data_structures.rs:10-19
+    G1H a, c, d;
+    FrH a_at_x1;
+};
+
+// `VerifyingKey::deserialize_compressed`: points validated (on curve, prime-order subgroup), scalars canonical
+bool parse_vk(const uint8_t vk[392], VkH& out) {
+    if (!g1_decompress(vk, out.one_g1)) return false;
+    if (!g2_decompress(vk + 48, out.one_g2)) return false;
+    if (!g2_decompress(vk + 144, out.x_g2)) return false;
+    if (!g2_decompress(vk + 240, out.z_g2)) return false;
+    out.n = rd_u64(vk + 336);
+    out.m0 = rd_u64(vk + 344);
+    out.sigma = rd_u64(vk + 352);
+    return fr_from_canonical(vk + 360, out.omega);
+}
+bool parse_proof(const uint8_t p[176], ProofH& out) {
+    return g1_decompress(p, out.a) && g1_decompress(p + 48, out.c) && fr_from_canonical(p + 96, out.a_at_x1) &&
+           g1_decompress(p + 128, out.d);
+}
+void g1_wire(const G1H& p, uint8_t out[96]) {
+    if (p.inf) { memset(out, 0, 96); return; }
+    p.x.to_wire(out);
+    p.y.to_wire(out + 48);
+}
+
+struct Challenges { FrH x1, x2, c_at_x1; };
+
+// verifier.rs:24-42: the transcript is fed exactly like the prover's (common.rs:21-37)
+Challenges derive_challenges(const VkH& vk, const std::vector<FrH>& pub, const ProofH& pr) {
+    MerlinFieldTranscript t(B_POLYMATH);
+    std::vector<uint8_t> msg;
+    ser_u64(msg, pub.size());
+    for (auto& v : pub) ser_fr(msg, v);
+    t.append_message("public_inputs", msg);
+    msg.clear();
+    uint8_t w[96];
+    ser_u64(msg, 2);
+    g1_wire(pr.a, w);
+    ser_g1_compressed(msg, w);
+    g1_wire(pr.c, w);
+    ser_g1_compressed(msg, w);
+    t.append_message("commitments", msg);
+    Challenges ch;
+    ch.x1 = t.challenge("x1");
+    FrH y1 = ch.x1.pow_u64(vk.sigma);
+    FrH y1_gamma = neg_power(y1, MINUS_GAMMA);
+    FrH pi_at_x1 = compute_pi_at_x1(vk.n, vk.omega, pub, ch.x1, y1_gamma);
+    FrH y1_alpha = neg_power(y1, MINUS_ALPHA);
+    ch.c_at_x1 = ((pr.a_at_x1 + y1_gamma) * pr.a_at_x1 - pi_at_x1) * y1_alpha.inv();   // common.rs:73-75
+    msg.clear();
+    ser_fr(msg, ch.x1);
+    t.append_message("x1", msg);
+    msg.clear();
+    ser_u64(msg, 2);
+    ser_fr(msg, pr.a_at_x1);
+    ser_fr(msg, ch.c_at_x1);
+    t.append_message("values", msg);
+    ch.x2 = t.challenge("x2");
+    return ch;
+}
+
+// [a]_1 + x2 [c]_1 - (a(x1) + x2 c(x1)) [1]_1     (verifier.rs:44-47)
+G1H commitments_minus_evals(const VkH& vk, const ProofH& pr, const Challenges& ch) {
+    G1H acc = aff_add(pr.a, jac_to_affine(scalar_mul(pr.c, ch.x2)));
+    FrH ev = (pr.a_at_x1 + ch.x2 * ch.c_at_x1).neg();
+    return aff_add(acc, jac_to_affine(scalar_mul(vk.one_g1, ev)));
+}
+
+std::vector<FrH> public_with_one(const uint8_t* public_inputs, size_t num_public) {
+    std::vector<FrH> pub(num_public + 1);
+    pub[0] = FrH::one();                                  // verifier.rs:26
+    for (size_t i = 0; i < num_public; i++) pub[i + 1] = FrH::from_wire(public_inputs + 32 * i);
+    return pub;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pm_polymath_verify(const uint8_t vk[392], const uint8_t* public_inputs, size_t num_public, const uint8_t proof[176],
+                       int* accepted) {
+    if (!vk || !proof || !accepted || (num_public && !public_inputs)) { pm::set_last_error("null argument"); return PM_ERR_ARG; }
+    *accepted = 0;
+    VkH k;
+    ProofH pr;
+    if (!parse_vk(vk, k)) { pm::set_last_error("verifying key does not deserialise (ark-serialize SerializationError)"); return PM_ERR_ARG; }
+    if (!parse_proof(proof, pr)) { pm::set_last_error("proof does not deserialise (ark-serialize SerializationError)"); return PM_ERR_ARG; }
+    std::vector<FrH> pub = public_with_one(public_inputs, num_public);
+    Challenges ch = derive_challenges(k, pub, pr);
+    G1H lhs = commitments_minus_evals(k, pr, ch);
+    G2H x_minus_x1 = aff_add(k.x_g2, jac_to_affine(scalar_mul(k.one_g2, ch.x1.neg())));   // verifier.rs:48
+    PairingTerm terms[2] = {{lhs, k.z_g2}, {pr.d.neg(), x_minus_x1}};                      // verifier.rs:50-59
+    *accepted = pairing_product_is_one(terms, 2) ? 1 : 0;
+    return PM_OK;
+}
+
+int pm_polymath_verify_batch(const uint8_t vk[392], size_t count, const uint8_t* public_inputs, size_t num_public,
+                             const uint8_t* proofs, const uint8_t seed[32], int* accepted) {
+    if (!vk || !accepted || (count && (!proofs || !seed)) || (count && num_public && !public_inputs)) {
+        pm::set_last_error("null argument");
+        return PM_ERR_ARG;
+    }
+    *accepted = 0;
+    VkH k;
+    if (!parse_vk(vk, k)) { pm::set_last_error("verifying key does not deserialise"); return PM_ERR_ARG; }
+    // sum_i r_i * (check_i): e(sum r_i L_i, [z]_2) * e(-sum r_i d_i, [x]_2) * e(sum r_i x1_i d_i, [1]_2) == 1,
+    // r_0 = 1 and r_i = 128-bit values drawn from StdRng(seed): three pairings for any number of proofs
+    StdRng rng(seed);
+    JacH<FqH> sum_l = JacH<FqH>::infinity(), sum_d = JacH<FqH>::infinity(), sum_dx = JacH<FqH>::infinity();
+    for (size_t i = 0; i < count; i++) {
+        ProofH pr;
+        if (!parse_proof(proofs + 176 * i, pr)) { pm::set_last_error("proof " + std::to_string(i) + " does not deserialise"); return PM_ERR_ARG; }
+        std::vector<FrH> pub = public_with_one(public_inputs ? public_inputs + 32 * num_public * i : nullptr, num_public);
+        Challenges ch = derive_challenges(k, pub, pr);
+        FrH r = FrH::one();
+        if (i) {
+            FrH c = FrH::zero();
+            c.v[0] = rng.next_u64();
+            c.v[1] = rng.next_u64();
+            r = c.to_mont();
+        }
+        jac_add_affine(sum_l, jac_to_affine(scalar_mul(commitments_minus_evals(k, pr, ch), r)));
+        jac_add_affine(sum_d, jac_to_affine(scalar_mul(pr.d, r)));
+        jac_add_affine(sum_dx, jac_to_affine(scalar_mul(pr.d, r * ch.x1)));
+    }
+    PairingTerm terms[3] = {{jac_to_affine(sum_l), k.z_g2}, {jac_to_affine(sum_d).neg(), k.x_g2}, {jac_to_affine(sum_dx), k.one_g2}};
+    *accepted = pairing_product_is_one(terms, 3) ? 1 : 0;
+    return PM_OK;
+}
+
+int pm_host_pairing_product_is_one(const uint8_t* g1_points, const uint8_t* g2_points, int count, int* is_one) {
+    if (count < 0 || !is_one || (count && (!g1_points || !g2_points))) { pm::set_last_error("bad argument"); return PM_ERR_ARG; }
+    std::vector<PairingTerm> terms(count);
+    static const uint8_t zero[192] = {0};
+    for (int i = 0; i < count; i++) {
+        const uint8_t* p = g1_points + 96 * (size_t)i;
+        const uint8_t* q = g2_points + 192 * (size_t)i;
+        terms[i].p = memcmp(p, zero, 96) == 0 ? G1H::infinity() : G1H{FqH::from_wire(p), FqH::from_wire(p + 48), false};
+        terms[i].q = memcmp(q, zero, 192) == 0
+                         ? G2H::infinity()
+                         : G2H{{FqH::from_wire(q), FqH::from_wire(q + 48)}, {FqH::from_wire(q + 96), FqH::from_wire(q + 144)}, false};
+        if (!g1_on_curve(terms[i].p) || !g2_on_curve(terms[i].q)) { pm::set_last_error("point not on the curve"); return PM_ERR_ARG; }
+    }
+    *is_one = pairing_product_is_one(terms.data(), count) ? 1 : 0;
     return PM_OK;
 }
 

@@ -62,6 +62,9 @@ def _run_flow(make_circuit_setup, make_circuit_prove, seed, proofs=1, compare_tr
             assert pk_dev.debug_read(6) == trace["d_coeffs"]
         assert proof_dev == proof_or.serialize_compressed()
         assert opm.verify_proof(pk_or.vk, proof_or, public)
+        # the host verifier of the library (verifier.rs:19-62) agrees with the oracle's: accept, and reject a wrong input
+        assert Polymath.verify(vk_bytes, public, proof_dev)
+        assert not Polymath.verify(vk_bytes, [(public[0] + 1) % R_MOD] + list(public[1:]), proof_dev)
         # the RNG streams stay aligned after the proof
         assert drng.next_u64() == orng.next_u64()
     pk_dev.close()

@@ -1,0 +1,128 @@
+"""Host verifier of the C++ mirror (`pm_polymath_verify`, /root/reference/src/verifier.rs:19-62) against the oracle.
+
+No GPU: the pairing check stays on the host (BASELINE.json north_star).  The oracle (oracle/pairing.py,
+oracle/polymath.py) is the checker; the golden proofs were produced by the oracle prover
+(tests/golden/make_golden.py) and are accepted by the oracle verifier in tests/test_oracle.py.
+"""
+import ctypes as C
+import json
+import os
+import random
+
+import pytest
+
+from oracle import curve as oc
+from oracle import pairing as opair
+from oracle.fields import R_MOD
+from polymath_b200 import codec
+from polymath_b200.api import Polymath, _bind
+from polymath_b200.lib import PolymathB200Error, load
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _golden(name):
+    d = json.load(open(os.path.join(GOLDEN, name)))
+    pub = [int(d["public_input"])] if "public_input" in d else [int(d["image"])]
+    return bytes.fromhex(d["vk_hex"]), pub, bytes.fromhex(d["proof_hex"])
+
+
+def _g2_wire(q):
+    if q is None:
+        return bytes(192)
+    (x0, x1), (y0, y1) = q
+    return b"".join(codec.fq_to_wire(v) for v in (x0, x1, y0, y1))
+
+
+def _pairing_is_one(pairs):
+    lib = load()
+    _bind(lib)
+    ok = C.c_int(-1)
+    g1 = b"".join(codec.g1_to_wire(p) for p, _ in pairs)
+    g2 = b"".join(_g2_wire(q) for _, q in pairs)
+    rc = lib.pm_host_pairing_product_is_one(g1, g2, len(pairs), C.byref(ok))
+    assert rc == 0, lib.pm_last_error()
+    return bool(ok.value)
+
+
+def test_pairing_bilinearity_matches_oracle():
+    rnd = random.Random(11)
+    g1, g2 = oc.G1_GEN, oc.G2_GEN
+    for _ in range(3):
+        a, b = rnd.randrange(1, R_MOD), rnd.randrange(1, R_MOD)
+        pa, qb = oc.g1_mul(g1, a), oc.g2_mul(g2, b)
+        pab = oc.g1_mul(g1, a * b % R_MOD)
+        # e(aP, bQ) * e(-abP, Q) == 1
+        good = [(pa, qb), (oc.g1_neg(pab), g2)]
+        bad = [(pa, qb), (oc.g1_neg(oc.g1_mul(g1, (a * b + 1) % R_MOD)), g2)]
+        assert _pairing_is_one(good)
+        assert not _pairing_is_one(bad)
+    # infinity operands contribute the factor one; the oracle agrees on a small case
+    assert _pairing_is_one([(None, g2), (g1, None)])
+    small = [(oc.g1_mul(g1, 5), oc.g2_mul(g2, 7)), (oc.g1_neg(oc.g1_mul(g1, 35)), g2)]
+    assert _pairing_is_one(small) == opair.pairing_product_is_one(small) is True
+    assert not _pairing_is_one([(g1, g2)])
+
+
+@pytest.mark.parametrize("name", ["dummy_seed0.json", "mimc8_seed7.json", "mimc322_seed1.json"])
+def test_verify_accepts_golden_proofs_and_rejects_tampering(name):
+    vk, pub, proof = _golden(name)
+    assert Polymath.verify(vk, pub, proof) is True
+    # wrong public input (the reference has no negative test; the oracle verifier rejects the same way)
+    assert Polymath.verify(vk, [(pub[0] + 1) % R_MOD], proof) is False
+    # a(x1) changed: still canonical, must be rejected
+    a_at = int.from_bytes(proof[96:128], "little")
+    bad = proof[:96] + ((a_at + 1) % R_MOD).to_bytes(32, "little") + proof[128:]
+    assert Polymath.verify(vk, pub, bad) is False
+    # [a]_1 and [c]_1 swapped: valid points, wrong proof
+    assert Polymath.verify(vk, pub, proof[48:96] + proof[:48] + proof[96:]) is False
+
+
+def test_verify_rejects_malformed_encodings():
+    vk, pub, proof = _golden("dummy_seed0.json")
+    # non-canonical scalar (>= r)
+    bad = proof[:96] + (R_MOD).to_bytes(32, "little") + proof[128:]
+    with pytest.raises(PolymathB200Error):
+        Polymath.verify(vk, pub, bad)
+    # compression flag cleared
+    with pytest.raises(PolymathB200Error):
+        Polymath.verify(vk, pub, bytes([proof[0] & 0x7F]) + proof[1:])
+    # x coordinate not on the curve: search a few single-byte perturbations for one that fails to decode
+    hit = False
+    for delta in range(1, 40):
+        cand = proof[:47] + bytes([(proof[47] + delta) & 0xFF]) + proof[48:]
+        try:
+            assert Polymath.verify(vk, pub, cand) is False      # decodes to another subgroup point: plain reject
+        except PolymathB200Error:
+            hit = True
+            break
+    assert hit, "expected at least one perturbed x without a curve/subgroup point"
+    # truncated G2 flag in the key
+    with pytest.raises(PolymathB200Error):
+        Polymath.verify(vk[:48] + bytes([vk[48] & 0x7F]) + vk[49:], pub, proof)
+
+
+def test_verify_matches_oracle_verifier_on_fresh_proofs():
+    """Oracle prover -> product verifier and oracle verifier agree (accept and reject)."""
+    from oracle import polymath as opm, r1cs as orc
+    from oracle.rng import StdRng as ORng, fr_rand
+    rng = ORng.seed_from_u64(99)
+    pk = opm.generate_proving_key(orc.DummyCircuit(), rng)
+    vk_bytes = pk.vk.serialize_compressed()
+    proofs, pubs = [], []
+    for _ in range(3):
+        x, y = fr_rand(rng), fr_rand(rng)
+        cs = orc.synthesize(orc.DummyCircuit(x, y), setup_mode=False)
+        pr = opm.create_proof_with_assignment(pk, cs.instance_assignment, cs.witness_assignment, rng)
+        pub = [x * y % R_MOD]
+        assert opm.verify_proof(pk.vk, pr, pub)
+        assert Polymath.verify(vk_bytes, pub, pr.serialize_compressed())
+        proofs.append(pr.serialize_compressed())
+        pubs.append(pub)
+    # batch: all good -> accept; one public input off -> reject; proofs permuted against inputs -> reject
+    seed = bytes(range(32))
+    assert Polymath.verify_batch(vk_bytes, pubs, proofs, seed) is True
+    assert Polymath.verify_batch(vk_bytes, pubs[:1], proofs[:1], seed) is True
+    assert Polymath.verify_batch(vk_bytes, [pubs[0], [(pubs[1][0] + 1) % R_MOD], pubs[2]], proofs, seed) is False
+    assert Polymath.verify_batch(vk_bytes, pubs, [proofs[1], proofs[0], proofs[2]], seed) is False
+    assert Polymath.verify_batch(vk_bytes, [], [], seed) is True
