@@ -139,7 +139,17 @@ class ClockSampler:
         except Exception:
             pass
 
+    def wait_first(self, timeout):
+        t0 = time.perf_counter()
+        while not self.samples and time.perf_counter() - t0 < timeout:
+            time.sleep(0.02)
+
+    def mark(self):
+        """Start of the timed region: earlier samples (warm-up) are only used if none arrives later."""
+        self.first = len(self.samples)
+
     def start(self):
+        self.first = 0
         self.proc = None
         self.thread = threading.Thread(target=self._run, daemon=True)
         self.thread.start()
@@ -155,12 +165,14 @@ class ClockSampler:
             self.thread.join(timeout=6)
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
-        mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
+        timed = self.samples[self.first:]
+        use = timed if timed else self.samples[-1:]      # a run shorter than the sampling period: last warm-up sample
+        sm = sorted(int(s[0]) for s in use if s[0].isdigit())
+        mx = [int(s[1]) for s in use if s[1].isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for s in self.samples for i in range(4) if s[2 + i].lower().startswith("active")})
+        reasons = sorted({names[i] for s in use for i in range(4) if s[2 + i].lower().startswith("active")})
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(self.samples)}
+                "samples": len(timed), "samples_incl_warmup": len(self.samples)}
 
 
 # --------------------------------------------------------------------------------------------
@@ -231,14 +243,19 @@ def run_ours(args):
         prover.set_assignment(p_inst, p_wit)
     else:
         check(lib.pm_ctx_set_assignment(pk._h, p_inst, p_wit))
+    # nvidia-smi is started BEFORE the warm-up: its start-up (NVML initialisation) contends with CUDA calls for the
+    # driver, which would otherwise fall into the timed region of a short run; only samples taken after the mark count
+    sampler = ClockSampler(local_rank) if (rank == 0 and not os.environ.get("PM_BENCH_NO_CLOCKS")) else None
+    if sampler:
+        sampler.start()
+        sampler.wait_first(5.0)
     for _ in range(args.warmup):
         prove_resident()
     check(lib.pm_bench_set_kernel_timing(1))
     launches0 = lib.pm_kernel_launches()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     barrier()
     if sampler:
-        sampler.start()
+        sampler.mark()
     check(lib.pm_timer_start())
     wall0 = time.perf_counter()
     acc_ms, bwd_ms, msm_geom = [], [], (0, 0)

@@ -23,6 +23,7 @@
 // Points at infinity ((0,0)) and zero scalars are skipped in step 1/3.
 #include "msm.cuh"
 
+#include <cstdio>
 #include <cstdlib>
 
 namespace pm {
@@ -884,6 +885,16 @@ MsmEngine::Shape MsmEngine::run(const G1Affine* bases, const Fr* scalars, size_t
         }
         while (sets_per_pass > 1 && !addressable(sets_per_pass, rounds)) sets_per_pass = (sets_per_pass + 1) / 2;
         if (!addressable(sets_per_pass, rounds)) throw CudaError("msm: too many points per bucket set");
+    }
+    {
+        static int debug = -1;
+        if (debug < 0) { const char* v = getenv("PM_MSM_DEBUG"); debug = v ? atoi(v) : 0; }
+        if (debug) {
+            size_t free_b = 0, total_b = 0;
+            cudaMemGetInfo(&free_b, &total_b);
+            fprintf(stderr, "[msm] n=%zu c=%d windows=%d levels=%d sets=%d sets_per_pass=%d rounds=%d free=%.1f GB\n", n, c, nwin,
+                    levels, ngroups, sets_per_pass, rounds, free_b / 1e9);
+        }
     }
     const uint32_t pad_mask = (1u << rounds) - 1u;
     const uint32_t pass_total = (uint32_t)sets_per_pass * nb;           // buckets of one pass
