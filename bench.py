@@ -115,29 +115,74 @@ def run_reference(args):
 # clocks sampling
 # --------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region.
+
+    In-process NVML (pynvml: one handle, two light queries per sample) — a looping `nvidia-smi` process costs
+    milliseconds of driver time per query and showed up as +6.5 ms per prove at n = 2^16 (profiles/r1_h_summary.md);
+    nvidia-smi is only the fallback when pynvml is missing.  The sampler starts before the warm-up; `mark()` is called
+    at the start of the timed region and only later samples count.
+    """
     FIELDS = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
-    def __init__(self, index):
+    def __init__(self, index, period_s=0.1):
         self.index = index
-        self.samples = []
+        self.period = period_s
+        self.samples = []          # (sm_mhz, sm_max_mhz, [reason names])
+        self.first = 0
         self.stop_flag = threading.Event()
         self.thread = None
+        self.proc = None
+        self.source = None
+
+    def _run_nvml(self):
+        import pynvml as nv
+        nv.nvmlInit()
+        # LOCAL_RANK indexes the visible devices; NVML indexes the physical ones
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = self.index
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if self.index < len(ids) and ids[self.index].isdigit():
+                idx = int(ids[self.index])
+        h = nv.nvmlDeviceGetHandleByIndex(idx)
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        bits = [(nv.nvmlClocksEventReasonHwSlowdown, 0), (nv.nvmlClocksEventReasonHwThermalSlowdown, 1),
+                (nv.nvmlClocksEventReasonSwThermalSlowdown, 2), (nv.nvmlClocksEventReasonSwPowerCap, 3)]
+        self.source = "nvml"
+        while not self.stop_flag.is_set():
+            sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+            self.samples.append((int(sm), int(mx), [self.NAMES[i] for b, i in bits if r & b]))
+            self.stop_flag.wait(self.period)
+        nv.nvmlShutdown()
+
+    def _run_smi(self):
+        self.source = "nvidia-smi"
+        self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                                      "--format=csv,noheader,nounits", "-lms", "500"],
+                                     stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.strip().split(",")]
+            if len(parts) >= 6 and parts[0].isdigit() and parts[1].isdigit():
+                self.samples.append((int(parts[0]), int(parts[1]),
+                                     [self.NAMES[i] for i in range(4) if parts[2 + i].lower().startswith("active")]))
+            if self.stop_flag.is_set():
+                break
 
     def _run(self):
-        # one long-running nvidia-smi in loop mode (spawning a process per sample perturbs launch-bound phases)
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
-                                          "--format=csv,noheader,nounits", "-lms", "250"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            for line in self.proc.stdout:
-                parts = [p.strip() for p in line.strip().split(",")]
-                if len(parts) >= 6:
-                    self.samples.append(parts)
-                if self.stop_flag.is_set():
-                    break
+            self._run_nvml()
         except Exception:
-            pass
+            try:
+                self._run_smi()
+            except Exception:
+                pass
+
+    def start(self):
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
 
     def wait_first(self, timeout):
         t0 = time.perf_counter()
@@ -148,15 +193,9 @@ class ClockSampler:
         """Start of the timed region: earlier samples (warm-up) are only used if none arrives later."""
         self.first = len(self.samples)
 
-    def start(self):
-        self.first = 0
-        self.proc = None
-        self.thread = threading.Thread(target=self._run, daemon=True)
-        self.thread.start()
-
     def stop(self):
         self.stop_flag.set()
-        if getattr(self, "proc", None) is not None:
+        if self.proc is not None:
             try:
                 self.proc.terminate()
             except Exception:
@@ -164,15 +203,13 @@ class ClockSampler:
         if self.thread:
             self.thread.join(timeout=6)
         if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": self.source}
         timed = self.samples[self.first:]
         use = timed if timed else self.samples[-1:]      # a run shorter than the sampling period: last warm-up sample
-        sm = sorted(int(s[0]) for s in use if s[0].isdigit())
-        mx = [int(s[1]) for s in use if s[1].isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for s in use for i in range(4) if s[2 + i].lower().startswith("active")})
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(timed), "samples_incl_warmup": len(self.samples)}
+        sm = sorted(s[0] for s in use)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(s[1] for s in use),
+                "reasons": sorted({r for s in use for r in s[2]}), "samples": len(timed),
+                "samples_incl_warmup": len(self.samples), "source": self.source}
 
 
 # --------------------------------------------------------------------------------------------

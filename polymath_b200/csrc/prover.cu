@@ -10,6 +10,7 @@
 #include "prover.cuh"
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 
 #include "host/g1_host.hpp"
@@ -96,35 +97,74 @@ void ProverCtx::upload_matrix(DevMatrix& dst, const uint64_t* row_ptr, const uin
     PM_CUDA(cudaStreamSynchronize(rt.stream));  // host vectors die here
 }
 
+// Fixed-base tables of one base array: window bits and the largest level count the 31-bit point index allows.
+// The level count is then cut down jointly for both arrays by plan_tables().
 static ProverCtx::MsmPlan plan_for(uint64_t count) {
     ProverCtx::MsmPlan p;
     p.stride = count ? count : 1;
     const char* env = getenv("PM_MSM_PRECOMP");
     const bool enabled = !(env && atoi(env) == 0);
     const char* envmin = getenv("PM_MSM_PRECOMP_MIN");             // test hook: minimum size that gets tables
-    const uint64_t min_count = envmin ? (uint64_t)atoll(envmin) : ((uint64_t)1 << 20);
+    const uint64_t min_count = envmin ? (uint64_t)atoll(envmin) : ((uint64_t)1 << 14);
     if (!enabled || count < min_count) return p;                   // small MSMs: plain windows (c chosen per call)
-    p.c = count >= 6000000 ? 22 : 20;
+    // All windows of a table share ONE bucket set: the host combines a single group of partial sums instead of
+    // 16-22 (7 ms -> 0.1 ms of host time per proof at n = 2^16, profiles/r1_h_summary.md), and the window can be
+    // wide.  It must leave >= 2^15 buckets (walk / reduction parallelism) with tens of entries each:
+    // measured 2^16: c = 14 / 16 / 18 -> 29.7 / 34.3 / 11.5 ms per proof.
+    p.c = count >= 6000000 ? 22 : count >= ((uint64_t)1 << 20) ? 20 : count >= ((uint64_t)1 << 17) ? 18 : 16;
     if (env && atoi(env) >= 8) p.c = atoi(env);                // tuning hook: PM_MSM_PRECOMP=<window bits>
     const int nwin = (256 + p.c - 1) / p.c;
-    size_t free_b = 0, total_b = 0;
-    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) free_b = 0;
-    // keep the tables of one array under a third of what is free; fall back to fewer shared levels
+    p.levels = 1;
     for (int div = 1; div <= nwin; div++) {
         int lv = (nwin + div - 1) / div;
-        if ((double)lv * (double)p.stride * sizeof(G1Affine) <= 0.33 * (double)free_b &&
-            (uint64_t)lv * p.stride < ((uint64_t)1 << 31)) {
-            p.levels = lv;
-            break;
-        }
+        if ((uint64_t)lv * p.stride < ((uint64_t)1 << 31)) { p.levels = lv; break; }
     }
     if (p.levels <= 1) { p.levels = 1; p.c = 0; }
     return p;
 }
 
+// Next smaller level count that still divides the windows into fewer-level bucket sets (12 -> 6 -> 4 -> 3 -> 2 -> 1).
+static int fewer_levels(int c, int levels) {
+    const int nwin = (256 + c - 1) / c;
+    for (int div = 1; div <= nwin; div++) {
+        int lv = (nwin + div - 1) / div;
+        if (lv < levels) return lv;
+    }
+    return 1;
+}
+
+// Tables and the batched-affine pair rounds compete for HBM: a table costs levels x count x 96 B, the pair-round
+// workspace of ONE bucket set (the MSM engine runs the sets in passes) ~100 B per sorted entry = levels x count x 100 B.
+// Without the rounds the accumulation falls back to the XYZZ walk (10 instead of 6 Fq products per addition), which
+// costs far more than a few extra bucket sets: shrink the tables until tables + workspaces fit the free memory.
+// The c-side and [d]_1 MSMs share one engine (max of their workspaces), the a-side MSM runs beside the c-side on its own.
 void ProverCtx::plan_tables() {
-    plan_c = plan_for(local_count(len_c()));
-    plan_d = plan_for(local_count(len_d()));
+    const uint64_t cnt_c = local_count(len_c()), cnt_d = local_count(len_d()), cnt_a = local_count(n + 4);
+    plan_c = plan_for(cnt_c);
+    plan_d = plan_for(cnt_d);
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) free_b = 0;
+    const double budget = 0.85 * (double)free_b;
+    auto table = [](uint64_t count, int levels) { return (double)count * levels * sizeof(G1Affine); };
+    auto work = [](uint64_t count, int levels) { return (double)count * levels * 100.0 + 1.5e9; };
+    auto footprint = [&]() {
+        const double wc = work(cnt_c, plan_c.levels), wd = work(cnt_d, plan_d.levels);
+        return table(cnt_c, plan_c.levels) + table(cnt_d, plan_d.levels) + (wc > wd ? wc : wd) + work(cnt_a, plan_c.levels);
+    };
+    while (footprint() > budget && (plan_c.levels > 1 || plan_d.levels > 1)) {
+        // shrink the array whose levels currently cost the most
+        const double cost_c = plan_c.levels > 1 ? table(cnt_c, plan_c.levels) + work(cnt_c, plan_c.levels) + work(cnt_a, plan_c.levels) : -1;
+        const double cost_d = plan_d.levels > 1 ? table(cnt_d, plan_d.levels) + work(cnt_d, plan_d.levels) : -1;
+        MsmPlan& p = cost_d >= cost_c ? plan_d : plan_c;
+        p.levels = fewer_levels(p.c, p.levels);
+        // one level = no table: plain windows, width chosen per call (measured: 16 bits up to 2^26 points,
+        // profiles/sweep_r1_h_windows.jsonl — wider windows pay more in sort and reduction than they save in additions)
+        if (p.levels <= 1) { p.levels = 1; p.c = 0; }
+    }
+    if (getenv("PM_MSM_DEBUG"))
+        fprintf(stderr, "[plan] free=%.1f GB c-side: %llu pts c=%d levels=%d | d: %llu pts c=%d levels=%d | footprint %.1f GB\n",
+                free_b / 1e9, (unsigned long long)cnt_c, plan_c.c, plan_c.levels, (unsigned long long)cnt_d, plan_d.c, plan_d.levels,
+                footprint() / 1e9);
 }
 
 void ProverCtx::build_tables() {
@@ -218,7 +258,7 @@ void ProverCtx::phase1_partial(const uint8_t* ra, uint8_t* partials_out) {
         const char* v = getenv("PM_A_TABLES");
         a_tables = v ? atoi(v) : 1;
     }
-    MsmConfig cfg_a = a_tables ? cfg_c() : MsmConfig();
+    MsmConfig cfg_a = (a_tables && plan_c.levels > 1) ? cfg_c() : MsmConfig();   // no table: its own (narrower) windows
     cfg_a.rounds_bias = p1_bias;
     MsmConfig cfg_cs = cfg_c();
     cfg_cs.rounds_bias = p1_bias;
