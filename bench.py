@@ -462,7 +462,9 @@ def run_ours(args):
                                "Polymath prove, proving key resident on the device" % (log_n, n // 4 - 1),
                    "log_n": log_n, "msm_points_per_prove": 14 * n + 31,
                    "l2": "inputs larger than L2: key %.2f GB, MSM workspace > 0.7 GB per launch" % ((14 * n + 29) * 96 / 1e9),
-                   "parallelism": "1 GPU" if world == 1 else "MSM split by point range over %d GPUs, all-gather of partial sums" % world},
+                   "parallelism": "1 GPU" if world == 1 else "MSM split by point range over %d GPUs, all-gather of partial sums (%s)" % (
+                       world, "ncclAllGather on device buffers inside the phases" if getattr(prover, "collective", "") == "nccl"
+                       else "torch.distributed callback")},
         "e2e": {"value": e2e_value, "unit": "ms", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches), "clocks": clocks,
         "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu,

@@ -201,6 +201,20 @@ int pm_prove_phase1_finish(pm_ctx* ctx, const uint8_t* gathered, int count, uint
 int pm_prove_phase3_partial(pm_ctx* ctx, const uint8_t x2[PM_FR_BYTES], const uint8_t c_at_x1[PM_FR_BYTES],
                             uint8_t partial_out[PM_XYZZ_BYTES]);
 int pm_prove_phase3_finish(pm_ctx* ctx, const uint8_t* gathered, int count, uint8_t d_out[PM_G1_BYTES]);
+/* The same exchange INSIDE the phase: with an NCCL communicator attached to the sharded context, the per-rank sums of
+ * each MSM are all-gathered on the device (ncclAllGather over NVLink, enqueued on the library's stream right behind
+ * the MSM kernels: no host round trip between compute and collective) and every rank finishes on its host.
+ * NCCL is bound at run time: `libnccl_path` names the libnccl.so.2 the process already uses (NULL = "libnccl.so.2"
+ * from the loader path).  Rank 0 calls pm_nccl_unique_id and distributes the 128 bytes (any transport); every rank
+ * then calls pm_ctx_attach_nccl (collective: returns when all ranks of the context's world have joined).
+ * pm_prove_phase{1,3}_collective replace the *_partial / all-gather / *_finish triple. */
+int pm_nccl_unique_id(const char* libnccl_path, uint8_t id_out[128]);
+int pm_ctx_attach_nccl(pm_ctx* ctx, const char* libnccl_path, const uint8_t id[128]);
+int pm_ctx_has_collective(const pm_ctx* ctx);
+int pm_prove_phase1_collective(pm_ctx* ctx, const uint8_t r_a[2 * PM_FR_BYTES], uint8_t a_out[PM_G1_BYTES],
+                               uint8_t c_out[PM_G1_BYTES]);
+int pm_prove_phase3_collective(pm_ctx* ctx, const uint8_t x2[PM_FR_BYTES], const uint8_t c_at_x1[PM_FR_BYTES],
+                               uint8_t d_out[PM_G1_BYTES]);
 /* Host-only helper (no device needed): canonical affine sum of `count` XYZZ records spaced `stride` bytes. */
 int pm_host_sum_partials(const uint8_t* parts, int count, size_t stride, uint8_t out[PM_G1_BYTES]);
 
@@ -260,7 +274,8 @@ int pm_host_pairing_product_is_one(const uint8_t* g1_points, const uint8_t* g2_p
  * recv (world * bytes, rank order).  Returns 0 on success. */
 typedef int (*pm_allgather_fn)(void* user, const uint8_t* send, size_t bytes, uint8_t* recv);
 /* Sharded variants: every rank calls them with the same arguments and its own sharded context; all
- * ranks obtain identical vk / proof bytes.  `upload` = 0 reuses the resident assignment. */
+ * ranks obtain identical vk / proof bytes.  `upload` = 0 reuses the resident assignment.  `allgather` may be NULL
+ * when the context has an NCCL communicator (pm_ctx_attach_nccl): the phases then run their own collective. */
 int pm_polymath_setup_sharded(const pm_r1cs_view* r1cs, pm_rng* rng, int rank, int world, pm_ctx** ctx_out,
                               uint8_t vk_out[392]);
 int pm_polymath_prove_sharded(pm_ctx* ctx, const uint8_t* instance, const uint8_t* witness, int upload, pm_rng* rng,

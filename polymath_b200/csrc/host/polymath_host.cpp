@@ -153,7 +153,11 @@ static int prove_impl(pm_ctx* ctx, const uint8_t* instance, const uint8_t* witne
     if (!ctx || !instance || !rng || !proof_out) { pm::set_last_error("null argument"); return PM_ERR_ARG; }
     int rank = 0, world = 1;
     if (pm_ctx_shard(ctx, &rank, &world) != PM_OK) return PM_ERR_ARG;
-    if (world > 1 && !allgather) { pm::set_last_error("sharded context needs an all-gather callback"); return PM_ERR_ARG; }
+    const bool collective = !allgather && pm_ctx_has_collective(ctx);    // NCCL all-gather inside the phases
+    if (world > 1 && !allgather && !collective) {
+        pm::set_last_error("sharded context needs an all-gather callback or an attached communicator (pm_ctx_attach_nccl)");
+        return PM_ERR_ARG;
+    }
     // gather `bytes` from every rank (identity when unsharded)
     auto gather = [&](const uint8_t* send, size_t bytes, std::vector<uint8_t>& recv) -> int {
         recv.resize(bytes * world);
@@ -182,13 +186,18 @@ static int prove_impl(pm_ctx* ctx, const uint8_t* instance, const uint8_t* witne
     uint8_t ra[64], a_g1[96], c_g1[96];
     rng->rng.fr_rand().to_wire(ra);         // r_a coefficient 0
     rng->rng.fr_rand().to_wire(ra + 32);    // r_a coefficient 1
-    uint8_t part1[2 * PM_XYZZ_BYTES];
-    rc = pm_prove_phase1_partial(ctx, ra, part1);
-    if (rc != PM_OK) return rc;
-    rc = gather(part1, sizeof part1, gathered);
-    if (rc != PM_OK) return rc;
-    rc = pm_prove_phase1_finish(ctx, gathered.data(), world, a_g1, c_g1);
-    if (rc != PM_OK) return rc;
+    if (collective) {
+        rc = pm_prove_phase1_collective(ctx, ra, a_g1, c_g1);
+        if (rc != PM_OK) return rc;
+    } else {
+        uint8_t part1[2 * PM_XYZZ_BYTES];
+        rc = pm_prove_phase1_partial(ctx, ra, part1);
+        if (rc != PM_OK) return rc;
+        rc = gather(part1, sizeof part1, gathered);
+        if (rc != PM_OK) return rc;
+        rc = pm_prove_phase1_finish(ctx, gathered.data(), world, a_g1, c_g1);
+        if (rc != PM_OK) return rc;
+    }
 
     std::vector<FrH> pub(m0);
     for (uint64_t i = 0; i < m0; i++) pub[i] = FrH::from_wire(instance + 32 * i);
@@ -234,13 +243,18 @@ static int prove_impl(pm_ctx* ctx, const uint8_t* instance, const uint8_t* witne
     uint8_t x2b[32], cb[32], d_g1[96];
     x2.to_wire(x2b);
     c_at_x1.to_wire(cb);
-    uint8_t part3[PM_XYZZ_BYTES];
-    rc = pm_prove_phase3_partial(ctx, x2b, cb, part3);   // prover.rs:142-229
-    if (rc != PM_OK) return rc;
-    rc = gather(part3, sizeof part3, gathered);
-    if (rc != PM_OK) return rc;
-    rc = pm_prove_phase3_finish(ctx, gathered.data(), world, d_g1);
-    if (rc != PM_OK) return rc;
+    if (collective) {
+        rc = pm_prove_phase3_collective(ctx, x2b, cb, d_g1);   // prover.rs:142-229
+        if (rc != PM_OK) return rc;
+    } else {
+        uint8_t part3[PM_XYZZ_BYTES];
+        rc = pm_prove_phase3_partial(ctx, x2b, cb, part3);   // prover.rs:142-229
+        if (rc != PM_OK) return rc;
+        rc = gather(part3, sizeof part3, gathered);
+        if (rc != PM_OK) return rc;
+        rc = pm_prove_phase3_finish(ctx, gathered.data(), world, d_g1);
+        if (rc != PM_OK) return rc;
+    }
 
     // Proof, compressed (data_structures.rs:10-19): a_g1, c_g1, a_at_x1, d_g1
     std::vector<uint8_t> proof;

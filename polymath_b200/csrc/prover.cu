@@ -16,6 +16,7 @@
 #include "host/g1_host.hpp"
 #include "g1_codec.cuh"
 #include "msm.cuh"
+#include "nccl_dyn.cuh"
 #include "ntt.cuh"
 
 namespace pm {
@@ -44,6 +45,8 @@ int log2_exact(uint64_t v) {
 }  // namespace
 
 ProverCtx::~ProverCtx() {
+    if (nccl_comm && nccl_api().CommDestroy) nccl_api().CommDestroy(nccl_comm);
+    if (host_gather) cudaFreeHost(host_gather);
     if (host_stage) cudaFreeHost(host_stage);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
@@ -211,11 +214,11 @@ static void check_status(uint32_t st) {
     if (st & ST_OPENING_REMAINDER) throw StatusError(PM_ERR_REMAINDER, "opening numerator does not vanish at x1 (prover.rs:221)");
 }
 
-void ProverCtx::phase1_partial(const uint8_t* ra, uint8_t* partials_out) {
+ProverCtx::Phase1Shapes ProverCtx::phase1_enqueue(const uint8_t* ra) {
     Runtime& rt = runtime();
     cudaStream_t s = rt.stream;
     if (!assignment_set) throw StatusError(PM_ERR_STATE, "phase 1 needs an assignment");
-    if (!ra || !partials_out) throw StatusError(PM_ERR_ARG, "null phase-1 argument");
+    if (!ra) throw StatusError(PM_ERR_ARG, "null phase-1 argument");
     phase = 0;
     Fr* sm = small.get<Fr>();
     uint32_t* st = status.get<uint32_t>();
@@ -243,7 +246,6 @@ void ProverCtx::phase1_partial(const uint8_t* ra, uint8_t* partials_out) {
     // compute_a_g1 (prover.rs:330-338) and c_g1 (prover.rs:116-123) over this rank's share of the bases.
     // The two MSMs are independent: the a-side runs on the side stream with its own workspace so that its
     // sort / reduction tail hides behind the c-side bucket accumulation.
-    uint8_t* hs = static_cast<uint8_t*>(host_stage);
     PM_CUDA(cudaEventRecord(rt.ev_fork, s));
     PM_CUDA(cudaStreamWaitEvent(rt.stream2, rt.ev_fork, 0));
     // beside each other on two streams the MSMs hide their latency-bound inversion passes: one more pair round pays
@@ -262,12 +264,29 @@ void ProverCtx::phase1_partial(const uint8_t* ra, uint8_t* partials_out) {
     cfg_a.rounds_bias = p1_bias;
     MsmConfig cfg_cs = cfg_c();
     cfg_cs.rounds_bias = p1_bias;
-    MsmEngine::Shape sa = rt.msm2.run(bc, scal_a.get<Fr>(), local_count(n + 4), ac, rt.stream2, cfg_a, world, rank);
-    PM_CUDA(cudaMemcpyAsync(hs, ac, sa.count() * sizeof(G1XYZZ), cudaMemcpyDeviceToHost, rt.stream2));
+    // every rank of a sharded proof must produce the same layout of partial sums (they are gathered and decoded with
+    // one Shape): without a table the window follows the per-rank share of the GLOBAL count, not the local count
+    if (world > 1 && cfg_a.c == 0) cfg_a.c = MsmEngine::choose_window((n + 4) / world);
+    if (world > 1 && cfg_cs.c == 0) cfg_cs.c = MsmEngine::choose_window(len_c() / world);
+    Phase1Shapes sh;
+    sh.sa = rt.msm2.run(bc, scal_a.get<Fr>(), local_count(n + 4), ac, rt.stream2, cfg_a, world, rank);
     PM_CUDA(cudaEventRecord(rt.ev_join, rt.stream2));
-    MsmEngine::Shape sc = rt.msm.run(bc, scal_c.get<Fr>(), local_count(len_c()), ac + kMaxMsmSums, s, cfg_cs, world, rank);
-    PM_CUDA(cudaMemcpyAsync(hs + kStageWin, ac + kMaxMsmSums, sc.count() * sizeof(G1XYZZ), cudaMemcpyDeviceToHost, s));
+    sh.sc = rt.msm.run(bc, scal_c.get<Fr>(), local_count(len_c()), ac + kMaxMsmSums, s, cfg_cs, world, rank);
     PM_CUDA(cudaStreamWaitEvent(s, rt.ev_join, 0));
+    return sh;
+}
+
+void ProverCtx::phase1_partial(const uint8_t* ra, uint8_t* partials_out) {
+    Runtime& rt = runtime();
+    cudaStream_t s = rt.stream;
+    if (!partials_out) throw StatusError(PM_ERR_ARG, "null phase-1 argument");
+    Phase1Shapes sh = phase1_enqueue(ra);
+    const MsmEngine::Shape &sa = sh.sa, &sc = sh.sc;
+    G1XYZZ* ac = acc.get<G1XYZZ>();
+    uint32_t* st = status.get<uint32_t>();
+    uint8_t* hs = static_cast<uint8_t*>(host_stage);
+    PM_CUDA(cudaMemcpyAsync(hs, ac, sa.count() * sizeof(G1XYZZ), cudaMemcpyDeviceToHost, s));
+    PM_CUDA(cudaMemcpyAsync(hs + kStageWin, ac + kMaxMsmSums, sc.count() * sizeof(G1XYZZ), cudaMemcpyDeviceToHost, s));
     PM_CUDA(cudaMemcpyAsync(hs + kStageStatus, st, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     PM_CUDA(cudaEventRecord(ev1, s));
     PM_CUDA(cudaStreamSynchronize(s));
@@ -280,6 +299,69 @@ void ProverCtx::phase1_partial(const uint8_t* ra, uint8_t* partials_out) {
     host::combine_shifted(hs, sa.nwin, sa.c, sa.nsum, sa.shift).to_wire(partials_out);
     host::combine_shifted(hs + kStageWin, sc.nwin, sc.c, sc.nsum, sc.shift).to_wire(partials_out + sizeof(G1XYZZ));
     phase = 10;   // partial done, waiting for finish
+}
+
+// ---- sharded flow with the collective inside the phase (NCCL all-gather on the device, stream-ordered) ----
+uint8_t* ProverCtx::gather_stage(size_t bytes) {
+    if (bytes > host_gather_bytes) {
+        if (host_gather) PM_CUDA(cudaFreeHost(host_gather));
+        host_gather = nullptr;
+        host_gather_bytes = 0;
+        PM_CUDA(cudaMallocHost(&host_gather, bytes));
+        host_gather_bytes = bytes;
+    }
+    return static_cast<uint8_t*>(host_gather);
+}
+
+void ProverCtx::attach_nccl(const char* libnccl_path, const uint8_t id[128]) {
+    if (nccl_comm) throw StatusError(PM_ERR_STATE, "context already has a communicator");
+    if (!id) throw StatusError(PM_ERR_ARG, "null NCCL id");
+    NcclApi& api = nccl_api();
+    api.load(libnccl_path);
+    NcclUniqueId uid;
+    memcpy(uid.internal, id, sizeof uid.internal);
+    void* comm = nullptr;
+    api.check(api.CommInitRank(&comm, world, uid, rank), "ncclCommInitRank");
+    nccl_comm = comm;
+}
+
+void ProverCtx::phase1_collective(const uint8_t* ra, uint8_t* a_out, uint8_t* c_out) {
+    Runtime& rt = runtime();
+    cudaStream_t s = rt.stream;
+    if (!nccl_comm) throw StatusError(PM_ERR_STATE, "no communicator attached (pm_ctx_attach_nccl)");
+    if (!a_out || !c_out) throw StatusError(PM_ERR_ARG, "null phase-1 argument");
+    Phase1Shapes sh = phase1_enqueue(ra);
+    const MsmEngine::Shape &sa = sh.sa, &sc = sh.sc;
+    const size_t ba = sa.count() * sizeof(G1XYZZ), bc_ = sc.count() * sizeof(G1XYZZ);
+    G1XYZZ* ac = acc.get<G1XYZZ>();
+    uint32_t* st = status.get<uint32_t>();
+    // gathered = [rank][a sums] then [rank][c sums]
+    uint8_t* g = gathered.as<uint8_t>((size_t)world * (ba + bc_) + 256);
+    NcclApi& api = nccl_api();
+    api.check(api.GroupStart(), "ncclGroupStart");
+    api.check(api.AllGather(ac, g, ba, NcclApi::kUint8, nccl_comm, s), "ncclAllGather");
+    api.check(api.AllGather(ac + kMaxMsmSums, g + (size_t)world * ba, bc_, NcclApi::kUint8, nccl_comm, s), "ncclAllGather");
+    api.check(api.GroupEnd(), "ncclGroupEnd");
+    uint8_t* hg = gather_stage((size_t)world * (ba + bc_) + 256);
+    uint8_t* hs = static_cast<uint8_t*>(host_stage);
+    PM_CUDA(cudaMemcpyAsync(hg, g, (size_t)world * (ba + bc_), cudaMemcpyDeviceToHost, s));
+    PM_CUDA(cudaMemcpyAsync(hs + kStageStatus, st, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    PM_CUDA(cudaEventRecord(ev1, s));
+    PM_CUDA(cudaStreamSynchronize(s));
+    float ms = 0;
+    PM_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+    phase_ms[0] = ms;
+    uint32_t stv;
+    memcpy(&stv, hs + kStageStatus, 4);
+    check_status(stv);     // the polynomial work is replicated: every rank sees the same status
+    host::XyzzH sum_a = host::XyzzH::inf(), sum_c = host::XyzzH::inf();
+    for (int r = 0; r < world; r++) {
+        host::xyzz_add(sum_a, host::combine_shifted(hg + (size_t)r * ba, sa.nwin, sa.c, sa.nsum, sa.shift));
+        host::xyzz_add(sum_c, host::combine_shifted(hg + (size_t)world * ba + (size_t)r * bc_, sc.nwin, sc.c, sc.nsum, sc.shift));
+    }
+    host::xyzz_to_affine_wire(sum_a, a_out);
+    host::xyzz_to_affine_wire(sum_c, c_out);
+    phase = 1;
 }
 
 void ProverCtx::phase1_finish(const uint8_t* gathered, int count, uint8_t* a_out, uint8_t* c_out) {
@@ -330,11 +412,11 @@ NumeratorSrc ProverCtx::numerator_src() const {
     return src;
 }
 
-void ProverCtx::phase3_partial(const uint8_t* x2, const uint8_t* c_at_x1, uint8_t* partial_out) {
+MsmEngine::Shape ProverCtx::phase3_enqueue(const uint8_t* x2, const uint8_t* c_at_x1) {
     Runtime& rt = runtime();
     cudaStream_t s = rt.stream;
     if (phase != 2) throw StatusError(PM_ERR_STATE, "phase 3 must follow phase 2");
-    if (!x2 || !c_at_x1 || !partial_out) throw StatusError(PM_ERR_ARG, "null phase-3 argument");
+    if (!x2 || !c_at_x1) throw StatusError(PM_ERR_ARG, "null phase-3 argument");
     Fr* sm = small.get<Fr>();
     uint32_t* st = status.get<uint32_t>();
     PM_CUDA(cudaEventRecord(ev0, s));
@@ -345,7 +427,18 @@ void ProverCtx::phase3_partial(const uint8_t* x2, const uint8_t* c_at_x1, uint8_
     NumeratorSrc src = numerator_src();
     rt.extra_launches += 1 + launch_divide_numerator(src, sm + S_X1, q.get<Fr>(), chunk_vals.get<Fr>(), st, s);   // prover.rs:211-225
     G1XYZZ* ac = acc.get<G1XYZZ>() + 2 * kMaxMsmSums;
-    MsmEngine::Shape sd = rt.msm.run(bases_d.get<G1Affine>(), q.get<Fr>(), local_count(src.len - 1), ac, s, cfg_d(), world, rank);  // prover.rs:229
+    MsmConfig cfg = cfg_d();
+    if (world > 1 && cfg.c == 0) cfg.c = MsmEngine::choose_window((src.len - 1) / world);   // same Shape on every rank
+    return rt.msm.run(bases_d.get<G1Affine>(), q.get<Fr>(), local_count(src.len - 1), ac, s, cfg, world, rank);  // prover.rs:229
+}
+
+void ProverCtx::phase3_partial(const uint8_t* x2, const uint8_t* c_at_x1, uint8_t* partial_out) {
+    Runtime& rt = runtime();
+    cudaStream_t s = rt.stream;
+    if (!partial_out) throw StatusError(PM_ERR_ARG, "null phase-3 argument");
+    MsmEngine::Shape sd = phase3_enqueue(x2, c_at_x1);
+    G1XYZZ* ac = acc.get<G1XYZZ>() + 2 * kMaxMsmSums;
+    uint32_t* st = status.get<uint32_t>();
     uint8_t* hs = static_cast<uint8_t*>(host_stage);
     PM_CUDA(cudaMemcpyAsync(hs, ac, sd.count() * sizeof(G1XYZZ), cudaMemcpyDeviceToHost, s));
     PM_CUDA(cudaMemcpyAsync(hs + kStageStatus, st, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
@@ -359,6 +452,36 @@ void ProverCtx::phase3_partial(const uint8_t* x2, const uint8_t* c_at_x1, uint8_
     check_status(stv);
     host::combine_shifted(hs, sd.nwin, sd.c, sd.nsum, sd.shift).to_wire(partial_out);
     phase = 30;
+}
+
+void ProverCtx::phase3_collective(const uint8_t* x2, const uint8_t* c_at_x1, uint8_t* d_out) {
+    Runtime& rt = runtime();
+    cudaStream_t s = rt.stream;
+    if (!nccl_comm) throw StatusError(PM_ERR_STATE, "no communicator attached (pm_ctx_attach_nccl)");
+    if (!d_out) throw StatusError(PM_ERR_ARG, "null phase-3 argument");
+    MsmEngine::Shape sd = phase3_enqueue(x2, c_at_x1);
+    const size_t bd = sd.count() * sizeof(G1XYZZ);
+    G1XYZZ* ac = acc.get<G1XYZZ>() + 2 * kMaxMsmSums;
+    uint32_t* st = status.get<uint32_t>();
+    uint8_t* g = gathered.as<uint8_t>((size_t)world * bd + 256);
+    NcclApi& api = nccl_api();
+    api.check(api.AllGather(ac, g, bd, NcclApi::kUint8, nccl_comm, s), "ncclAllGather");
+    uint8_t* hg = gather_stage((size_t)world * bd + 256);
+    uint8_t* hs = static_cast<uint8_t*>(host_stage);
+    PM_CUDA(cudaMemcpyAsync(hg, g, (size_t)world * bd, cudaMemcpyDeviceToHost, s));
+    PM_CUDA(cudaMemcpyAsync(hs + kStageStatus, st, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    PM_CUDA(cudaEventRecord(ev1, s));
+    PM_CUDA(cudaStreamSynchronize(s));
+    float ms = 0;
+    PM_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+    phase_ms[2] = ms;
+    uint32_t stv;
+    memcpy(&stv, hs + kStageStatus, 4);
+    check_status(stv);
+    host::XyzzH sum_d = host::XyzzH::inf();
+    for (int r = 0; r < world; r++) host::xyzz_add(sum_d, host::combine_shifted(hg + (size_t)r * bd, sd.nwin, sd.c, sd.nsum, sd.shift));
+    host::xyzz_to_affine_wire(sum_d, d_out);
+    phase = 0;
 }
 
 void ProverCtx::phase3_finish(const uint8_t* gathered, int count, uint8_t* d_out) {
@@ -638,6 +761,35 @@ int pm_prove_phase3_finish(pm_ctx* ctx, const uint8_t* gathered, int count, uint
     return guarded([&] {
         if (!ctx) throw StatusError(PM_ERR_ARG, "null context");
         ctx->impl.phase3_finish(gathered, count, d_out);
+    });
+}
+int pm_nccl_unique_id(const char* libnccl_path, uint8_t id_out[128]) {
+    return guarded([&] {
+        if (!id_out) throw StatusError(PM_ERR_ARG, "null argument");
+        NcclApi& api = nccl_api();
+        api.load(libnccl_path);
+        NcclUniqueId uid;
+        api.check(api.GetUniqueId(&uid), "ncclGetUniqueId");
+        memcpy(id_out, uid.internal, sizeof uid.internal);
+    });
+}
+int pm_ctx_attach_nccl(pm_ctx* ctx, const char* libnccl_path, const uint8_t id[128]) {
+    return guarded([&] {
+        if (!ctx) throw StatusError(PM_ERR_ARG, "null context");
+        ctx->impl.attach_nccl(libnccl_path, id);
+    });
+}
+int pm_ctx_has_collective(const pm_ctx* ctx) { return ctx && ctx->impl.nccl_comm ? 1 : 0; }
+int pm_prove_phase1_collective(pm_ctx* ctx, const uint8_t r_a[2 * PM_FR_BYTES], uint8_t a_out[PM_G1_BYTES], uint8_t c_out[PM_G1_BYTES]) {
+    return guarded([&] {
+        if (!ctx) throw StatusError(PM_ERR_ARG, "null context");
+        ctx->impl.phase1_collective(r_a, a_out, c_out);
+    });
+}
+int pm_prove_phase3_collective(pm_ctx* ctx, const uint8_t x2[PM_FR_BYTES], const uint8_t c_at_x1[PM_FR_BYTES], uint8_t d_out[PM_G1_BYTES]) {
+    return guarded([&] {
+        if (!ctx) throw StatusError(PM_ERR_ARG, "null context");
+        ctx->impl.phase3_collective(x2, c_at_x1, d_out);
     });
 }
 int pm_ctx_shard(const pm_ctx* ctx, int* rank, int* world) {

@@ -48,6 +48,16 @@ struct ProverCtx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double phase_ms[3] = {0, 0, 0};
 
+    // Optional NCCL communicator of the sharded flow (nccl_dyn.cuh): with it the per-rank partial sums are
+    // all-gathered on the device, stream-ordered behind the MSM kernels, and every rank finishes on its host.
+    void* nccl_comm = nullptr;
+    DevBuf gathered;              // [rank][sums] receive buffers of the all-gathers
+    void* host_gather = nullptr;  // pinned copy of `gathered`
+    size_t host_gather_bytes = 0;
+    void attach_nccl(const char* libnccl_path, const uint8_t id[128]);
+    void phase1_collective(const uint8_t* ra, uint8_t* a_out, uint8_t* c_out);
+    void phase3_collective(const uint8_t* x2, const uint8_t* c_at_x1, uint8_t* d_out);
+
     ~ProverCtx();
     void allocate_work();
     void upload_matrix(DevMatrix& dst, const uint64_t* row_ptr, const uint32_t* col, const uint8_t* val, bool want_csc);
@@ -59,6 +69,13 @@ struct ProverCtx {
     void phase3_partial(const uint8_t* x2, const uint8_t* c_at_x1, uint8_t* partial_out);
     void phase3_finish(const uint8_t* gathered, int count, uint8_t* d_out);
     NumeratorSrc numerator_src() const;
+
+private:
+    struct Phase1Shapes { MsmEngine::Shape sa, sc; };
+    // device work of a phase up to and including its MSM launches, joined on the main stream; nothing synchronised
+    Phase1Shapes phase1_enqueue(const uint8_t* ra);
+    MsmEngine::Shape phase3_enqueue(const uint8_t* x2, const uint8_t* c_at_x1);
+    uint8_t* gather_stage(size_t bytes);
 };
 
 // setup.cu: fill bases_c / bases_d of a context whose matrices are uploaded (with CSC), and the G2 images.

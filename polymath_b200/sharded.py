@@ -1,11 +1,17 @@
 """Multi-GPU proving: one process per GPU, MSMs split by point range.
 
 Every rank holds the points g = k*world + rank of the proving key, runs the (small) polynomial work
-redundantly and its share of each MSM; the per-rank XYZZ partial sums (2 x 192 B in phase 1, 192 B in
-phase 3) are exchanged with one `all_gather` each — NCCL over NVLink when the process group is NCCL,
-gloo in the CPU tests — and added on the host by every rank (group addition is not an NCCL reduction).
-The protocol flow itself stays in the C++ host mirror (`pm_polymath_prove_sharded`); this module only
-supplies the collective as a callback.
+redundantly and its share of each MSM; the per-rank partial sums are exchanged with one all-gather per
+MSM phase and added on the host by every rank (group addition is not an NCCL reduction).  Two transports:
+
+* "nccl" (default on an NCCL process group): the library owns an NCCL communicator (`attach_nccl` ->
+  `pm_ctx_attach_nccl`, NCCL bound with dlopen to the libnccl the process already uses) and the phases
+  all-gather the raw per-window sums on the DEVICE, stream-ordered right behind the MSM kernels
+  (`pm_prove_phase{1,3}_collective`): no host round trip between compute and collective;
+* "callback": the host-side 192-byte partial sums travel through a `torch.distributed` all-gather
+  supplied as a C callback (gloo in the CPU tests).
+
+The protocol flow itself stays in the C++ host mirror (`pm_polymath_prove_sharded`).
 """
 import ctypes as C
 import os
@@ -85,9 +91,51 @@ def bind(lib):
     lib.pm_prove_phase3_partial.argtypes = [vp, u8p, u8p, u8p]
     lib.pm_prove_phase3_finish.argtypes = [vp, u8p, C.c_int, u8p]
     lib.pm_host_sum_partials.argtypes = [u8p, C.c_int, C.c_size_t, u8p]
+    lib.pm_nccl_unique_id.argtypes = [u8p, u8p]
+    lib.pm_ctx_attach_nccl.argtypes = [vp, u8p, u8p]
+    lib.pm_ctx_has_collective.argtypes = [vp]
+    lib.pm_prove_phase1_collective.argtypes = [vp, u8p, u8p, u8p]
+    lib.pm_prove_phase3_collective.argtypes = [vp, u8p, u8p, u8p]
     lib.pm_ntt_dist_local.argtypes = [vp, vp, C.c_uint, C.c_uint, C.c_uint, C.c_int, vp]
     lib.pm_ntt_dist_combine.argtypes = [vp, vp, C.c_uint, C.c_uint, C.c_int, vp]
     lib._sharded_bound = True
+
+
+def loaded_nccl_path():
+    """Path of the libnccl this process already has mapped (torch's bundled one), so that one NCCL serves the process."""
+    try:
+        with open("/proc/self/maps") as fh:
+            for line in fh:
+                if "libnccl.so" in line:
+                    return line.split()[-1]
+    except OSError:
+        pass
+    try:
+        import nvidia.nccl as n
+        cand = os.path.join(list(n.__path__)[0], "lib", "libnccl.so.2")
+        if os.path.exists(cand):
+            return cand
+    except Exception:
+        pass
+    return None
+
+
+def attach_nccl(lib, ctx_handle, rank: int, world: int, group=None):
+    """Give a sharded context its own NCCL communicator (`pm_ctx_attach_nccl`): rank 0 creates the id, the bytes travel
+    through the torch process group, every rank joins.  Afterwards the phases all-gather their partial sums on the
+    device (`pm_prove_phase{1,3}_collective`) and `pm_polymath_prove_sharded` needs no callback."""
+    import torch
+    import torch.distributed as dist
+    path = loaded_nccl_path()
+    pb = path.encode() if path else None
+    buf = C.create_string_buffer(128)
+    if rank == 0:
+        check(lib.pm_nccl_unique_id(pb, buf))
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    t = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).to(dev)
+    dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    ident = bytes(t.cpu().numpy().tobytes())
+    check(lib.pm_ctx_attach_nccl(ctx_handle, pb, ident))
 
 
 def ntt_send_order(log_n: int, world: int):
@@ -167,11 +215,19 @@ def host_sum_partials(parts: bytes, count: int, stride: int = 192):
 class ShardedProver:
     """`Polymath::setup` + `prove` across `world` processes (one GPU each)."""
 
-    def __init__(self, r1cs: R1CS, rng: StdRng, rank: int, world: int, group=None):
+    def __init__(self, r1cs: R1CS, rng: StdRng, rank: int, world: int, group=None, collective="auto"):
+        """collective: "nccl" = the library's own NCCL all-gather inside the phases (device buffers, stream-ordered);
+        "callback" = host partial sums exchanged by a torch.distributed callback (works on gloo: the CPU tests);
+        "auto" = nccl when the process group is NCCL, else callback."""
+        import torch.distributed as dist
         self.lib = _lib()
         bind(self.lib)
         self.rank, self.world = rank, world
-        self._cb = make_allgather(group) if world > 1 else ALLGATHER_FN(lambda *_: 1)
+        if collective == "auto":
+            collective = os.environ.get("PM_SHARDED_COLLECTIVE") or \
+                ("nccl" if world > 1 and dist.is_initialized() and dist.get_backend(group) == "nccl" else "callback")
+        self.collective = collective
+        self._cb = make_allgather(group) if (world > 1 and collective == "callback") else ALLGATHER_FN(lambda *_: 1)
         h = C.c_void_p()
         vk = C.create_string_buffer(392)
         check(self.lib.pm_polymath_setup_sharded(C.byref(r1cs.view), rng._h, rank, world, C.byref(h), vk))
@@ -179,6 +235,9 @@ class ShardedProver:
         self.pk._r1cs = r1cs
         self.vk_bytes = vk.raw
         self._proof = C.create_string_buffer(176)
+        if collective == "nccl":
+            attach_nccl(self.lib, self.pk._h, rank, world, group)
+            self._cb = C.cast(None, ALLGATHER_FN)      # NULL: the phases run their own collective
 
     def set_assignment(self, instance_ptr, witness_ptr):
         check(self.lib.pm_ctx_set_assignment(self.pk._h, instance_ptr, witness_ptr))

@@ -99,3 +99,42 @@ def test_sharded_ntt_virtual_ranks(pmlib, log_n, world, inverse):
     torch.cuda.synchronize()
     for h, sn in enumerate(ranks):
         assert codec.frs_from_wire(sn.out.cpu().numpy().tobytes()) == full[h::world]
+
+
+def test_collective_phases_with_a_one_rank_communicator(pmlib):
+    """pm_ctx_attach_nccl + pm_prove_phase{1,3}_collective (NCCL all-gather on the device inside the phases) on a
+    communicator of ONE rank: the plumbing (dlopen'd NCCL, gather buffers, per-rank decoding of the partial sums)
+    must reproduce the oracle's proof bytes.  The multi-rank exchange itself is covered by bench.py --gpus N
+    (proof_verified) and, for the host logic, by the gloo tests."""
+    from polymath_b200 import codec, sharded
+    from polymath_b200.api import R1CS, StdRng, _lib
+    from polymath_b200.lib import check
+    lib = _lib()
+    sharded.bind(lib)
+    consts = [3, 1, 4, 1, 5, 9, 2, 6]
+    circ = orc.MiMCDemo(None, None, consts)
+    cs = orc.synthesize(circ, setup_mode=True)
+    a, b, c = cs.to_matrices()
+    seed = 4242
+    orng, drng = ORng.seed_from_u64(seed), StdRng.seed_from_u64(seed)
+    pk_or = opm.generate_proving_key(circ, orng)
+    r1cs = R1CS(cs.num_instance_variables, cs.num_witness_variables, a, b, c)
+    h = C.c_void_p()
+    vk = C.create_string_buffer(392)
+    check(lib.pm_polymath_setup_sharded(C.byref(r1cs.view), drng._h, 0, 1, C.byref(h), vk))
+    assert vk.raw == pk_or.vk.serialize_compressed()
+    path = sharded.loaded_nccl_path()
+    pb = path.encode() if path else None
+    ident = C.create_string_buffer(128)
+    check(lib.pm_nccl_unique_id(pb, ident))
+    check(lib.pm_ctx_attach_nccl(h, pb, ident.raw))
+    assert lib.pm_ctx_has_collective(h) == 1
+    pcs = orc.synthesize(orc.MiMCDemo(7, 8, consts), setup_mode=False)
+    inst, wit = pcs.instance_assignment, pcs.witness_assignment
+    want = opm.create_proof_with_assignment(pk_or, inst, wit, orng)
+    got = C.create_string_buffer(176)
+    null_cb = C.cast(None, sharded.ALLGATHER_FN)
+    # `drng` has consumed exactly the setup draws, like `orng` had before its proof
+    check(lib.pm_polymath_prove_sharded(h, codec.frs_to_wire(inst), codec.frs_to_wire(wit), 1, drng._h, null_cb, None, got))
+    assert got.raw == want.serialize_compressed()
+    lib.pm_ctx_destroy(h)
