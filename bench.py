@@ -224,6 +224,12 @@ def run_ours(args):
     if world != args.gpus:
         if world == 1 and args.gpus > 1:
             raise SystemExit("launch with torch.distributed.run --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
+    lmem_flag = None
+    if not os.environ.get("PM_BENCH_NO_LMEM_FLAG"):
+        from polymath_b200.lib import load as _load
+        _l = _load()
+        _l.pm_runtime_configure.argtypes = [C.c_int]
+        lmem_flag = _l.pm_runtime_configure(local_rank)       # before torch creates the device's primary context
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl")
@@ -466,7 +472,7 @@ def run_ours(args):
                        world, "ncclAllGather on device buffers inside the phases" if getattr(prover, "collective", "") == "nccl"
                        else "torch.distributed callback")},
         "e2e": {"value": e2e_value, "unit": "ms", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-        "gpu_launches": int(launches), "clocks": clocks,
+        "gpu_launches": int(launches), "clocks": clocks, "lmem_resize_to_max": lmem_flag,
         "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu,
         "phase_ms": {"phase1": phase_ms[0], "phase2": phase_ms[1], "phase3": phase_ms[2]},
         "wall_ms_per_step": wall_resident / args.steps, "setup_s": setup_s,

@@ -51,6 +51,11 @@ enum {
 const char* pm_last_error(void);
 /* ABI version of this header; bumped on any incompatible change. */
 int pm_abi_version(void);
+/* Optional, before the first CUDA call of the process on `device` (-1 = current): sets cudaDeviceLmemResizeToMax so
+ * that the driver keeps the local-memory pool of the context at its high-water mark instead of shrinking and regrowing
+ * it between kernels with different stack frames (a device-wide synchronisation inside a phase).  Returns 1 when the
+ * flag is in place, 0 when the context already existed without it, < 0 on error. */
+int pm_runtime_configure(int device);
 /* Number of CUDA devices visible; <= 0 means the library cannot run (no CPU fallback exists). */
 int pm_device_count(void);
 /* Kernels launched by this library on the current device since load (bench accounting). */

@@ -85,6 +85,23 @@ extern "C" {
 
 const char* pm_last_error(void) { return last_error().c_str(); }
 int pm_abi_version(void) { return 1; }
+// Keep the context's local-memory pool at its high-water mark (cudaDeviceLmemResizeToMax): several kernels here run
+// with stack frames of up to 384 bytes per thread, and by default the driver may shrink the pool after such a kernel
+// and grow it again at a later launch — a device-wide synchronisation plus reallocation in the middle of a phase.
+// Must run before the device's primary context is created (first CUDA call of the process on that device); later
+// it can only report whether the flag is in place.  Returns 1 if the flag is set, 0 if not, < 0 on error.
+int pm_runtime_configure(int device) {
+    unsigned flags = 0;
+    int dev = device;
+    if (dev < 0 && cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    // runtime API first; when the primary context is already active the driver-level call below still applies
+    cudaError_t e = cudaSetDevice(dev) == cudaSuccess ? cudaSetDeviceFlags(cudaDeviceLmemResizeToMax) : cudaErrorInvalidDevice;
+    (void)e;
+    cudaGetLastError();
+    if (cudaGetDeviceFlags(&flags) != cudaSuccess) { cudaGetLastError(); return -1; }
+    return (flags & cudaDeviceLmemResizeToMax) ? 1 : 0;
+}
+
 int pm_device_count(void) {
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess) return 0;

@@ -25,6 +25,8 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <map>
+#include <tuple>
 
 namespace pm {
 
@@ -821,6 +823,26 @@ MsmEngine::Shape MsmEngine::run(const G1Affine* bases, const Fr* scalars, size_t
     // ---- batched-affine pair rounds (see k_pairs_forward): choose R from the mean run length ----
     const int forced_rounds = cfg.rounds >= 0 ? cfg.rounds : g_tuning_rounds;
     int rounds = 0;
+    // The plan (pair rounds, bucket sets per pass) of a shape is computed once per engine: a proving context issues the
+    // same few MSM shapes for every proof, its buffers only grow, and planning may query the free device memory.
+    int forced_sets_env = 0;
+    {
+        const char* v = getenv("PM_MSM_SETS_PER_PASS");      // test hook, read on every call
+        if (v) forced_sets_env = atoi(v);
+    }
+    static int rounds_bias_env = -100;
+    if (rounds_bias_env == -100) {
+        const char* v = getenv("PM_MSM_ROUNDS_BIAS");
+        rounds_bias_env = v ? atoi(v) : 0;
+    }
+    const PlanKey plan_key{n, c, levels, forced_rounds, cfg.rounds_bias + rounds_bias_env,
+                           cfg.sets_per_pass > 0 ? cfg.sets_per_pass : forced_sets_env};
+    const auto cached_plan = plans_.find(plan_key);
+    int sets_per_pass = ngroups;
+    if (cached_plan != plans_.end()) {
+        rounds = cached_plan->second.first;
+        sets_per_pass = cached_plan->second.second;
+    } else {
     {
         const double lambda = (double)entries / (double)total;
         if (forced_rounds >= 0) {
@@ -837,13 +859,7 @@ MsmEngine::Shape MsmEngine::run(const G1Affine* bases, const Fr* scalars, size_t
                 if (r == 0) cost = 0.365 * (lambda > 1 ? lambda - 1 : 0);
                 if (cost < best) { best = cost; rounds = r; }
             }
-            rounds += cfg.rounds_bias;
-            static int bias = -100;
-            if (bias == -100) {
-                const char* v = getenv("PM_MSM_ROUNDS_BIAS");
-                bias = v ? atoi(v) : 0;
-            }
-            rounds += bias;
+            rounds += cfg.rounds_bias + rounds_bias_env;
             if (rounds < 0) rounds = 0;
         }
         if (rounds > kMaxRounds) rounds = kMaxRounds;
@@ -851,7 +867,6 @@ MsmEngine::Shape MsmEngine::run(const G1Affine* bases, const Fr* scalars, size_t
         // stays addressable (32-bit offsets) and the pair-round workspace fits into the device memory that is still
         // free (plus what this engine already holds for the purpose).  If not even one set fits: XYZZ walk only.
     }
-    int sets_per_pass = ngroups;
     {
         const size_t per_set = n * (size_t)levels;      // entries of one bucket set (upper bound)
         auto workspace = [&](int sets, int r) {
@@ -862,19 +877,29 @@ MsmEngine::Shape MsmEngine::run(const G1Affine* bases, const Fr* scalars, size_t
             return per_set * sets + (size_t)nb * sets * ((1u << r) - 1) < ((size_t)1 << 32) - 4096;
         };
         const size_t held = pairs_a_.cap + pairs_b_.cap + prefix_.cap + sorted_.cap;
+        // does the plan fit the buffers this engine already holds?  (per buffer: one round needs no second ping-pong
+        // array.)  Then nothing is queried: cudaMemGetInfo on a busy device blocks the host for up to tens of
+        // milliseconds (measured: 5-60 ms in 1 of 5 proofs while the NTT kernels of the phase were running).
+        auto fits_held = [&](int sets, int r) {
+            const size_t slots = per_set * sets + (size_t)nb * sets * ((1u << r) - 1);
+            const size_t smax = (slots + 1) & ~(size_t)1, cap_a = smax / 2 + 2, cap_b = smax / 4 + 2;
+            return sorted_.cap >= (smax + 2) * 4 &&
+                   (r == 0 || (pairs_a_.cap >= cap_a * sizeof(G1Affine) && prefix_.cap >= cap_a * sizeof(Fq))) &&
+                   (r <= 1 || pairs_b_.cap >= cap_b * sizeof(G1Affine));
+        };
         size_t budget = held;
-        if (forced_rounds < 0 && workspace(ngroups, rounds) > held) {
+        if (forced_rounds >= 0) {
+            budget = ~(size_t)0;
+        } else if (fits_held(ngroups, rounds)) {
+            const size_t w = workspace(ngroups, rounds);
+            budget = w > held ? w : held;
+        } else {
             size_t free_b = 0, total_b = 0;
             PM_CUDA(cudaMemGetInfo(&free_b, &total_b));
             budget = held + free_b / 10 * 8;
-        } else if (forced_rounds >= 0) {
-            budget = ~(size_t)0;
         }
         int forced_sets = cfg.sets_per_pass;
-        if (forced_sets <= 0) {
-            const char* v = getenv("PM_MSM_SETS_PER_PASS");      // test hook, read on every call
-            if (v) forced_sets = atoi(v);
-        }
+        if (forced_sets <= 0) forced_sets = forced_sets_env;
         if (forced_sets > 0) sets_per_pass = forced_sets < ngroups ? forced_sets : ngroups;
         while (sets_per_pass > 1 && forced_sets <= 0 &&
                (!addressable(sets_per_pass, rounds) || workspace(sets_per_pass, rounds) > budget))
@@ -886,6 +911,8 @@ MsmEngine::Shape MsmEngine::run(const G1Affine* bases, const Fr* scalars, size_t
         while (sets_per_pass > 1 && !addressable(sets_per_pass, rounds)) sets_per_pass = (sets_per_pass + 1) / 2;
         if (!addressable(sets_per_pass, rounds)) throw CudaError("msm: too many points per bucket set");
     }
+        plans_[plan_key] = std::make_pair(rounds, sets_per_pass);
+    }   // plan not cached
     {
         static int debug = -1;
         if (debug < 0) { const char* v = getenv("PM_MSM_DEBUG"); debug = v ? atoi(v) : 0; }

@@ -1,5 +1,8 @@
 // K4 — G1 Pippenger MSM engine (interface).  See msm.cu.
 #pragma once
+#include <map>
+#include <tuple>
+#include <utility>
 #include "common.cuh"
 #include "ec.cuh"
 
@@ -55,6 +58,9 @@ public:
     ~MsmEngine();
 
 private:
+    // (n, c, levels, forced rounds, rounds bias, forced sets) -> (pair rounds, bucket sets per pass)
+    using PlanKey = std::tuple<size_t, int, int, int, int, int>;
+    std::map<PlanKey, std::pair<int, int>> plans_;
     DevBuf counts_, offsets_, cursors_, sorted_, buckets_, segs_, heavy_list_, heavy_count_, order_;
     DevBuf pairs_a_, pairs_b_, prefix_, tvals_, tpre_;   // pair rounds
 };

@@ -10,6 +10,7 @@
 #include "prover.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 
@@ -114,7 +115,10 @@ static ProverCtx::MsmPlan plan_for(uint64_t count) {
     // 16-22 (7 ms -> 0.1 ms of host time per proof at n = 2^16, profiles/r1_h_summary.md), and the window can be
     // wide.  It must leave >= 2^15 buckets (walk / reduction parallelism) with tens of entries each:
     // measured 2^16: c = 14 / 16 / 18 -> 29.7 / 34.3 / 11.5 ms per proof.
-    p.c = count >= 6000000 ? 22 : count >= ((uint64_t)1 << 20) ? 20 : count >= ((uint64_t)1 << 17) ? 18 : 16;
+    // Table sweep (profiles/sweep_r1_j_tables.jsonl, all levels): c = 20 wins from 0.4 M to 10.5 M points (10.5 M:
+    // 44.7 ms vs 47.8 ms at c = 22 — the wider window saves 5 % of the additions but doubles sort and reduction);
+    // the additions only outweigh that above ~32 M points.
+    p.c = count >= ((uint64_t)1 << 25) ? 22 : count >= ((uint64_t)1 << 18) ? 20 : count >= ((uint64_t)1 << 16) ? 18 : 16;
     if (env && atoi(env) >= 8) p.c = atoi(env);                // tuning hook: PM_MSM_PRECOMP=<window bits>
     const int nwin = (256 + p.c - 1) / p.c;
     p.levels = 1;
@@ -222,8 +226,15 @@ ProverCtx::Phase1Shapes ProverCtx::phase1_enqueue(const uint8_t* ra) {
     phase = 0;
     Fr* sm = small.get<Fr>();
     uint32_t* st = status.get<uint32_t>();
+    static const bool dbg = getenv("PM_PHASE_DEBUG") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms_since = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+        return std::chrono::duration<double, std::milli>(b - a).count();
+    };
+    const auto tp0 = now();
     PM_CUDA(cudaEventRecord(ev0, s));
     PM_CUDA(cudaMemcpyAsync(sm + S_RA, ra, 2 * sizeof(Fr), cudaMemcpyHostToDevice, s));
+    const auto tp1 = now();
     PM_CUDA(cudaMemsetAsync(st, 0, 4 * sizeof(uint32_t), s));
     launch_ra_square(sm + S_RA, s);
     SapDims d{(uint32_t)m0, (uint32_t)mw, (uint32_t)nr, n};
@@ -241,6 +252,7 @@ ProverCtx::Phase1Shapes ProverCtx::phase1_enqueue(const uint8_t* ra) {
     launch_quotient_checks(pu2, pw, n, st, s);   // prover.rs:104-108
     launch_assemble_phase1_scalars(pu, pu2, ztail.get<Fr>(), cols - m0, sm + S_RA, n, scal_a.get<Fr>(), scal_c.get<Fr>(), s);
     rt.extra_launches += 9;
+    const auto tp2 = now();
     G1XYZZ* ac = acc.get<G1XYZZ>();
     const G1Affine* bc = bases_c.get<G1Affine>();
     // compute_a_g1 (prover.rs:330-338) and c_g1 (prover.rs:116-123) over this rank's share of the bases.
@@ -270,9 +282,14 @@ ProverCtx::Phase1Shapes ProverCtx::phase1_enqueue(const uint8_t* ra) {
     if (world > 1 && cfg_cs.c == 0) cfg_cs.c = MsmEngine::choose_window(len_c() / world);
     Phase1Shapes sh;
     sh.sa = rt.msm2.run(bc, scal_a.get<Fr>(), local_count(n + 4), ac, rt.stream2, cfg_a, world, rank);
+    const auto tp3 = now();
     PM_CUDA(cudaEventRecord(rt.ev_join, rt.stream2));
     sh.sc = rt.msm.run(bc, scal_c.get<Fr>(), local_count(len_c()), ac + kMaxMsmSums, s, cfg_cs, world, rank);
     PM_CUDA(cudaStreamWaitEvent(s, rt.ev_join, 0));
+    const auto tp4 = now();
+    if (dbg && ms_since(tp0, tp4) > 5.0)
+        fprintf(stderr, "[phase1-enqueue] ra copy %.3f | poly %.3f | fork+a-side msm %.3f | c-side msm %.3f ms\n", ms_since(tp0, tp1),
+                ms_since(tp1, tp2), ms_since(tp2, tp3), ms_since(tp3, tp4));
     return sh;
 }
 
@@ -280,7 +297,9 @@ void ProverCtx::phase1_partial(const uint8_t* ra, uint8_t* partials_out) {
     Runtime& rt = runtime();
     cudaStream_t s = rt.stream;
     if (!partials_out) throw StatusError(PM_ERR_ARG, "null phase-1 argument");
+    const auto t_host0 = std::chrono::steady_clock::now();
     Phase1Shapes sh = phase1_enqueue(ra);
+    const auto t_host1 = std::chrono::steady_clock::now();
     const MsmEngine::Shape &sa = sh.sa, &sc = sh.sc;
     G1XYZZ* ac = acc.get<G1XYZZ>();
     uint32_t* st = status.get<uint32_t>();
@@ -293,6 +312,10 @@ void ProverCtx::phase1_partial(const uint8_t* ra, uint8_t* partials_out) {
     float ms = 0;
     PM_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
     phase_ms[0] = ms;
+    if (getenv("PM_PHASE_DEBUG"))
+        fprintf(stderr, "[phase1] device %.3f ms, host enqueue %.3f ms, enqueue+sync %.3f ms\n", ms,
+                std::chrono::duration<double, std::milli>(t_host1 - t_host0).count(),
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_host0).count());
     uint32_t stv;
     memcpy(&stv, hs + kStageStatus, 4);
     check_status(stv);
