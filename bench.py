@@ -26,7 +26,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC_FMT = "prove_ms_2p{log_n}_sap_constraints"
-TRAFFIC_BWD = 34.59e9   # dram__bytes_read.sum + dram__bytes_write.sum of that launch, ncu --set full (profiles/r1_e_summary.md)
+TRAFFIC_BWD = 37.20e9   # dram__bytes_read.sum + dram__bytes_write.sum of that launch (30.34 + 6.85 GB), ncu --set full (profiles/prof_bwd_r1_k_details.csv)
 
 
 # --------------------------------------------------------------------------------------------
