@@ -63,11 +63,10 @@ inline void fq_exp_q_minus1_div6(uint64_t e[6]) {  // (q - 1) / 6: Frobenius con
 }
 
 // square root in Fq; false when v is not a square
+struct FqExp { uint64_t w[6]; };
 inline bool fq_sqrt(const FqH& v, FqH& out) {
-    static uint64_t e[6];
-    static bool init = false;
-    if (!init) { fq_exp_q_plus1_div4(e); init = true; }
-    FqH s = v.pow(e, 6);
+    static const FqExp e = [] { FqExp x; fq_exp_q_plus1_div4(x.w); return x; }();   // thread-safe one-time init
+    FqH s = v.pow(e.w, 6);
     if (!(s.sqr() == v)) return false;
     out = s;
     return true;
@@ -273,19 +272,19 @@ struct Fq12H {
         for (int i = 1; i < 6; i += 2) r.c[i] = r.c[i].neg();
         return r;
     }
+    struct Gammas { Fq2H g[6]; };
     static const Fq2H* frob_gamma() {   // gamma_i = xi^(i (q - 1)/6): w^(i q) = gamma_i w^i
-        static Fq2H g[6];
-        static bool init = false;
-        if (!init) {
+        static const Gammas t = [] {       // thread-safe one-time init
+            Gammas x;
             uint64_t e[6];
             fq_exp_q_minus1_div6(e);
             Fq2H xi{FqH::one(), FqH::one()};
-            g[0] = Fq2H::one();
-            g[1] = xi.pow(e, 6);
-            for (int i = 2; i < 6; i++) g[i] = g[i - 1] * g[1];
-            init = true;
-        }
-        return g;
+            x.g[0] = Fq2H::one();
+            x.g[1] = xi.pow(e, 6);
+            for (int i = 2; i < 6; i++) x.g[i] = x.g[i - 1] * x.g[1];
+            return x;
+        }();
+        return t.g;
     }
     Fq12H frobenius() const {
         const Fq2H* g = frob_gamma();
