@@ -103,10 +103,11 @@ void ProverCtx::upload_matrix(DevMatrix& dst, const uint64_t* row_ptr, const uin
 
 // Fixed-base tables of one base array: window bits and the largest level count the 31-bit point index allows.
 // The level count is then cut down jointly for both arrays by plan_tables().
-static ProverCtx::MsmPlan plan_for(uint64_t count) {
+static ProverCtx::MsmPlan plan_for(uint64_t count, const char* env_name, bool serves_a_side) {
     ProverCtx::MsmPlan p;
     p.stride = count ? count : 1;
-    const char* env = getenv("PM_MSM_PRECOMP");
+    const char* env = getenv(env_name);
+    if (!env) env = getenv("PM_MSM_PRECOMP");
     const bool enabled = !(env && atoi(env) == 0);
     const char* envmin = getenv("PM_MSM_PRECOMP_MIN");             // test hook: minimum size that gets tables
     const uint64_t min_count = envmin ? (uint64_t)atoll(envmin) : ((uint64_t)1 << 14);
@@ -118,7 +119,10 @@ static ProverCtx::MsmPlan plan_for(uint64_t count) {
     // Table sweep (profiles/sweep_r1_j_tables.jsonl, all levels): c = 20 wins from 0.4 M to 10.5 M points (10.5 M:
     // 44.7 ms vs 47.8 ms at c = 22 — the wider window saves 5 % of the additions but doubles sort and reduction);
     // the additions only outweigh that above ~32 M points.
-    p.c = count >= ((uint64_t)1 << 25) ? 22 : count >= ((uint64_t)1 << 18) ? 20 : count >= ((uint64_t)1 << 16) ? 18 : 16;
+    // The c-side table also serves the a-side MSM (a third of its points, running beside it): there the narrower window
+    // wins up to ~1 M points (phase 1 at 0.39 M / 0.79 M points: c = 18 -> 5.4 / 8.3 ms, c = 20 -> 6.2 / 8.5 ms).
+    const uint64_t c20_from = serves_a_side ? ((uint64_t)1 << 20) : ((uint64_t)1 << 18);
+    p.c = count >= ((uint64_t)1 << 25) ? 22 : count >= c20_from ? 20 : count >= ((uint64_t)1 << 16) ? 18 : 16;
     if (env && atoi(env) >= 8) p.c = atoi(env);                // tuning hook: PM_MSM_PRECOMP=<window bits>
     const int nwin = (256 + p.c - 1) / p.c;
     p.levels = 1;
@@ -147,8 +151,8 @@ static int fewer_levels(int c, int levels) {
 // The c-side and [d]_1 MSMs share one engine (max of their workspaces), the a-side MSM runs beside the c-side on its own.
 void ProverCtx::plan_tables() {
     const uint64_t cnt_c = local_count(len_c()), cnt_d = local_count(len_d()), cnt_a = local_count(n + 4);
-    plan_c = plan_for(cnt_c);
-    plan_d = plan_for(cnt_d);
+    plan_c = plan_for(cnt_c, "PM_MSM_PRECOMP_C", true);     // tuning hooks: window bits per array
+    plan_d = plan_for(cnt_d, "PM_MSM_PRECOMP_D", false);
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) free_b = 0;
     const double budget = 0.85 * (double)free_b;
