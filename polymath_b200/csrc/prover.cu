@@ -36,6 +36,17 @@ constexpr size_t kStageWin = (size_t)kMaxMsmSums * sizeof(G1XYZZ);   // one MSM'
 constexpr size_t kStageBytes = 3 * kStageWin + 256;
 constexpr size_t kStageStatus = 3 * kStageWin;
 
+// loc[j] = data[j * G + r]: this rank's interleaved slice of a replicated array
+__global__ void k_take_stride(const Fr* __restrict__ data, Fr* __restrict__ loc, size_t count, uint32_t g, uint32_t r) {
+    size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < count) loc[j] = data[j * g + r];
+}
+// data[r + G * i] = gathered[r * per + i]: the all-gathered slices back in natural order
+__global__ void k_interleave(const Fr* __restrict__ gathered, Fr* __restrict__ data, size_t total, size_t per, uint32_t g) {
+    size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < total) data[k] = gathered[(k % g) * per + k / g];
+}
+
 int log2_exact(uint64_t v) {
     int l = 0;
     while (((uint64_t)1 << l) < v) l++;
@@ -244,15 +255,16 @@ ProverCtx::Phase1Shapes ProverCtx::phase1_enqueue(const uint8_t* ra) {
     SapDims d{(uint32_t)m0, (uint32_t)mw, (uint32_t)nr, n};
     Fr *pu = u.get<Fr>(), *pw = w.get<Fr>(), *pwu = wu.get<Fr>(), *pu2 = u2.get<Fr>();
     launch_sap_evals(d, A.csr(), B.csr(), C.csr(), ztail.get<Fr>(), pu, pw, pwu, s);
-    rt.ntt.run(pu, log_n, true, s);    // poly_coeffs, prover.rs:94
-    rt.ntt.run(pw, log_n, true, s);    // prover.rs:96
-    rt.ntt.run(pwu, log_n, true, s);   // prover.rs:161 (witness_w == w: prover.rs:165 is not recomputed)
+    // ntt_full: replicated transform, or the sharded one (one NCCL all-to-all + all-gather) for large domains
+    ntt_full(pu, log_n, true, s);    // poly_coeffs, prover.rs:94
+    ntt_full(pw, log_n, true, s);    // prover.rs:96
+    ntt_full(pwu, log_n, true, s);   // prover.rs:161 (witness_w == w: prover.rs:165 is not recomputed)
     // square_polynomial, prover.rs:315-328
     PM_CUDA(cudaMemcpyAsync(pu2, pu, n * sizeof(Fr), cudaMemcpyDeviceToDevice, s));
     PM_CUDA(cudaMemsetAsync(pu2 + n, 0, n * sizeof(Fr), s));
-    rt.ntt.run(pu2, log_n + 1, false, s);
+    ntt_full(pu2, log_n + 1, false, s);
     launch_square(pu2, 2 * n, s);
-    rt.ntt.run(pu2, log_n + 1, true, s);
+    ntt_full(pu2, log_n + 1, true, s);
     launch_quotient_checks(pu2, pw, n, st, s);   // prover.rs:104-108
     launch_assemble_phase1_scalars(pu, pu2, ztail.get<Fr>(), cols - m0, sm + S_RA, n, scal_a.get<Fr>(), scal_c.get<Fr>(), s);
     rt.extra_launches += 9;
@@ -340,6 +352,38 @@ uint8_t* ProverCtx::gather_stage(size_t bytes) {
     return static_cast<uint8_t*>(host_gather);
 }
 
+void ProverCtx::ntt_full(Fr* data, int lg, bool inverse, cudaStream_t s) {
+    Runtime& rt = runtime();
+    int log_g = 0;
+    while ((1 << log_g) < world) log_g++;
+    const bool pow2 = (1 << log_g) == world;
+    if (world == 1 || !nccl_comm || !pow2 || log_g > 3 || lg < sharded_ntt_min_log || lg < 2 * log_g) {
+        rt.ntt.run(data, lg, inverse, s);
+        return;
+    }
+    const size_t total = (size_t)1 << lg, per = total >> log_g, blk = per >> log_g;
+    Fr* loc = ntt_loc.as<Fr>(per);
+    Fr* send = ntt_send.as<Fr>(per);
+    Fr* recv = ntt_recv.as<Fr>(per);
+    Fr* gath = ntt_gather.as<Fr>(total);
+    k_take_stride<<<ceil_div(per, 256), 256, 0, s>>>(data, loc, per, (uint32_t)world, (uint32_t)rank);
+    PM_LAUNCH_CHECK();
+    rt.ntt.dist_local(loc, send, lg, log_g, (uint32_t)rank, inverse, s);
+    NcclApi& api = nccl_api();
+    // the one exchange of the four-step transform: block h of `send` goes to rank h (NVLink all-to-all)
+    api.check(api.GroupStart(), "ncclGroupStart");
+    for (int h = 0; h < world; h++) {
+        api.check(api.Send(send + (size_t)h * blk, blk * sizeof(Fr), NcclApi::kUint8, h, nccl_comm, s), "ncclSend");
+        api.check(api.Recv(recv + (size_t)h * blk, blk * sizeof(Fr), NcclApi::kUint8, h, nccl_comm, s), "ncclRecv");
+    }
+    api.check(api.GroupEnd(), "ncclGroupEnd");
+    rt.ntt.dist_combine(recv, loc, lg, log_g, inverse, s);      // loc[i] = X[rank + G * i]
+    api.check(api.AllGather(loc, gath, per * sizeof(Fr), NcclApi::kUint8, nccl_comm, s), "ncclAllGather");
+    k_interleave<<<ceil_div(total, 256), 256, 0, s>>>(gath, data, total, per, (uint32_t)world);
+    PM_LAUNCH_CHECK();
+    rt.extra_launches += 2;
+}
+
 void ProverCtx::attach_nccl(const char* libnccl_path, const uint8_t id[128]) {
     if (nccl_comm) throw StatusError(PM_ERR_STATE, "context already has a communicator");
     if (!id) throw StatusError(PM_ERR_ARG, "null NCCL id");
@@ -350,6 +394,7 @@ void ProverCtx::attach_nccl(const char* libnccl_path, const uint8_t id[128]) {
     void* comm = nullptr;
     api.check(api.CommInitRank(&comm, world, uid, rank), "ncclCommInitRank");
     nccl_comm = comm;
+    if (const char* v = getenv("PM_SHARDED_NTT_MIN_LOG")) sharded_ntt_min_log = atoi(v);   // tuning / test hook
 }
 
 void ProverCtx::phase1_collective(const uint8_t* ra, uint8_t* a_out, uint8_t* c_out) {

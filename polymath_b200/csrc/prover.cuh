@@ -55,6 +55,13 @@ struct ProverCtx {
     void* host_gather = nullptr;  // pinned copy of `gathered`
     size_t host_gather_bytes = 0;
     void attach_nccl(const char* libnccl_path, const uint8_t id[128]);
+    // Transform of a replicated array through the SHARDED NTT: every rank transforms its interleaved
+    // slice (local (N/G)-point NTT, twiddle/pack, ONE all-to-all over NCCL, G-point combine) and the slices are
+    // all-gathered back into the full array.  Used for domains of at least 2^sharded_ntt_min_log elements when a
+    // communicator is attached; smaller ones run replicated (the exchange latency would exceed the saving).
+    DevBuf ntt_loc, ntt_send, ntt_recv, ntt_gather;
+    int sharded_ntt_min_log = 22;
+    void ntt_full(Fr* data, int log_size, bool inverse, cudaStream_t s);
     void phase1_collective(const uint8_t* ra, uint8_t* a_out, uint8_t* c_out);
     void phase3_collective(const uint8_t* x2, const uint8_t* c_at_x1, uint8_t* d_out);
 
