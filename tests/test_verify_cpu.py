@@ -126,3 +126,32 @@ def test_verify_matches_oracle_verifier_on_fresh_proofs():
     assert Polymath.verify_batch(vk_bytes, [pubs[0], [(pubs[1][0] + 1) % R_MOD], pubs[2]], proofs, seed) is False
     assert Polymath.verify_batch(vk_bytes, pubs, [proofs[1], proofs[0], proofs[2]], seed) is False
     assert Polymath.verify_batch(vk_bytes, [], [], seed) is True
+
+
+def test_verify_edge_encodings():
+    """Infinity commitments, a zero evaluation, a proof from another statement: decoded like ark-serialize, rejected
+    without a crash or a false accept."""
+    vk_bytes, pub, proof = _golden("mimc8_seed7.json")
+    inf = bytes([0xC0]) + bytes(47)
+    cases = [
+        inf + proof[48:],                                   # [a]_1 = O
+        proof[:48] + inf + proof[96:],                      # [c]_1 = O
+        proof[:128] + inf,                                  # [d]_1 = O
+        inf + inf + bytes(32) + inf,                        # everything trivial
+        proof[:96] + bytes(32) + proof[128:],               # a(x1) = 0
+    ]
+    for cand in cases:
+        got = Polymath.verify(vk_bytes, pub, cand)
+        assert got is False
+    # infinity with stray bits must not decode
+    with pytest.raises(PolymathB200Error):
+        Polymath.verify(vk_bytes, pub, bytes([0xC0]) + bytes(46) + b"\x01" + proof[48:])
+    with pytest.raises(PolymathB200Error):
+        Polymath.verify(vk_bytes, pub, bytes([0xE0]) + bytes(47) + proof[48:])     # infinity + sort flag
+    # a valid proof of ANOTHER key/statement is rejected under this key
+    vk2, pub2, proof2 = _golden("dummy_seed0.json")
+    assert Polymath.verify(vk_bytes, pub, proof2) is False
+    assert Polymath.verify(vk2, pub2, proof) is False
+    # more / fewer public inputs than the key expects: plain reject, like the reference (no length check there)
+    assert Polymath.verify(vk_bytes, pub + [5], proof) is False
+    assert Polymath.verify(vk_bytes, [], proof) is False
