@@ -192,7 +192,7 @@ inline bool fq_from_be(const uint8_t* b, uint8_t mask_top, FqH& out) {
     out = FqH::from_canonical_le(le);
     return true;
 }
-inline bool g1_decompress(const uint8_t b[48], G1H& out) {
+inline bool g1_decompress(const uint8_t b[48], G1H& out, bool check_subgroup = true) {
     if (!(b[0] & 0x80)) return false;                     // compressed form only
     if (b[0] & 0x40) {                                    // infinity: everything else zero
         if (b[0] & 0x3f) return false;
@@ -205,9 +205,9 @@ inline bool g1_decompress(const uint8_t b[48], G1H& out) {
     if (!fq_sqrt(x.sqr() * x + fq_from_u64(4), y)) return false;
     if (y.canonical_gt_half() != ((b[0] & 0x20) != 0)) y = y.neg();
     out = {x, y, false};
-    return in_subgroup(out);
+    return !check_subgroup || in_subgroup(out);
 }
-inline bool g2_decompress(const uint8_t b[96], G2H& out) {
+inline bool g2_decompress(const uint8_t b[96], G2H& out, bool check_subgroup = true) {
     if (!(b[0] & 0x80)) return false;
     if (b[0] & 0x40) {
         if (b[0] & 0x3f) return false;
@@ -221,7 +221,7 @@ inline bool g2_decompress(const uint8_t b[96], G2H& out) {
     if (!fq2_sqrt(x.sqr() * x + g2_b(), y)) return false;
     if (y.lex_largest() != ((b[0] & 0x20) != 0)) y = y.neg();
     out = {x, y, false};
-    return in_subgroup(out);
+    return !check_subgroup || in_subgroup(out);
 }
 // 32 little-endian bytes -> Fr; false when >= r (ark-serialize rejects non-canonical scalars)
 inline bool fr_from_canonical(const uint8_t b[32], FrH& out) {
@@ -252,7 +252,21 @@ struct Fq12H {
         for (int k = 6; k < 11; k++) r.c[k - 6] = r.c[k - 6] + t[k].mul_xi();
         return r;
     }
-    Fq12H sqr() const { return *this * *this; }
+    Fq12H sqr() const {   // symmetric schoolbook: 15 cross products (doubled) + 6 squares instead of 36 products
+        Fq2H t[11];
+        for (int k = 0; k < 11; k++) t[k] = Fq2H::zero();
+        for (int i = 0; i < 6; i++) {
+            t[2 * i] = t[2 * i] + c[i].sqr();
+            for (int j = i + 1; j < 6; j++) {
+                Fq2H p = c[i] * c[j];
+                t[i + j] = t[i + j] + p + p;
+            }
+        }
+        Fq12H r;
+        for (int k = 0; k < 6; k++) r.c[k] = t[k];
+        for (int k = 6; k < 11; k++) r.c[k - 6] = r.c[k - 6] + t[k].mul_xi();
+        return r;
+    }
     // * (l0 + l2 w^2 + l3 w^3), l3 in Fq: the Miller-loop line
     Fq12H mul_line(const Fq2H& l0, const Fq2H& l2, const FqH& l3) const {
         Fq2H t[9];
@@ -318,29 +332,52 @@ struct Fq12H {
 
 constexpr uint64_t kBlsXAbs = 0xd201000000010000ull;   // |u|; the BLS12-381 parameter u is negative
 
-// f_{|u|, Q}(P), conjugated because u < 0 (up to factors the final exponentiation removes)
-inline Fq12H miller_loop(const G1H& p, const G2H& q) {
-    Fq12H f = Fq12H::one();
-    if (p.inf || q.inf) return f;
-    Fq2H xt = q.x, yt = q.y;
+struct PairingTerm { G1H p; G2H q; };
+
+// prod_i f_{|u|, Q_i}(P_i), conjugated because u < 0 (up to factors the final exponentiation removes): one shared
+// accumulator, so the 63 squarings are paid once for all pairs.  Pairs with a point at infinity contribute 1.
+inline Fq12H multi_miller_loop(const PairingTerm* terms, int count) {
+    struct State { const PairingTerm* t; Fq2H xt, yt; };
+    State st[8];
+    int m = 0;
+    Fq12H f = Fq12H::one(), rest = Fq12H::one();
+    for (int i = 0; i < count; i++) {
+        if (terms[i].p.inf || terms[i].q.inf) continue;
+        if (m == 8) {   // more than eight live pairs: the remaining ones in a loop of their own
+            rest = multi_miller_loop(terms + i, count - i);
+            break;
+        }
+        st[m++] = {&terms[i], terms[i].q.x, terms[i].q.y};
+    }
+    if (m == 0) return f;
     for (int bit = 62; bit >= 0; bit--) {     // bit 63 is the leading one
-        // tangent at T
-        Fq2H xx = xt.sqr();
-        Fq2H lam = (xx + xx + xx) * (yt + yt).inv();
-        f = f.sqr().mul_line(lam * xt - yt, lam.scale(p.x).neg(), p.y);
-        Fq2H x3 = lam.sqr() - xt - xt;
-        yt = lam * (xt - x3) - yt;
-        xt = x3;
+        f = f.sqr();
+        for (int k = 0; k < m; k++) {         // tangent at T
+            State& s = st[k];
+            Fq2H xx = s.xt.sqr();
+            Fq2H lam = (xx + xx + xx) * (s.yt + s.yt).inv();
+            f = f.mul_line(lam * s.xt - s.yt, lam.scale(s.t->p.x).neg(), s.t->p.y);
+            Fq2H x3 = lam.sqr() - s.xt - s.xt;
+            s.yt = lam * (s.xt - x3) - s.yt;
+            s.xt = x3;
+        }
         if ((kBlsXAbs >> bit) & 1) {
-            // chord through T and Q
-            Fq2H lam2 = (q.y - yt) * (q.x - xt).inv();
-            f = f.mul_line(lam2 * xt - yt, lam2.scale(p.x).neg(), p.y);
-            Fq2H x4 = lam2.sqr() - xt - q.x;
-            yt = lam2 * (xt - x4) - yt;
-            xt = x4;
+            for (int k = 0; k < m; k++) {     // chord through T and Q
+                State& s = st[k];
+                const G2H& q = s.t->q;
+                Fq2H lam2 = (q.y - s.yt) * (q.x - s.xt).inv();
+                f = f.mul_line(lam2 * s.xt - s.yt, lam2.scale(s.t->p.x).neg(), s.t->p.y);
+                Fq2H x4 = lam2.sqr() - s.xt - q.x;
+                s.yt = lam2 * (s.xt - x4) - s.yt;
+                s.xt = x4;
+            }
         }
     }
-    return f.conj6();
+    return f.conj6() * rest;
+}
+inline Fq12H miller_loop(const G1H& p, const G2H& q) {
+    PairingTerm t{p, q};
+    return multi_miller_loop(&t, 1);
 }
 
 // g^u for g in the cyclotomic subgroup (inverse = conj6)
@@ -360,12 +397,9 @@ inline Fq12H final_exponentiation_cubed(const Fq12H& f) {
     return y3 * f2.sqr() * f2;                              // * f2^3
 }
 
-struct PairingTerm { G1H p; G2H q; };
 // prod_i e(P_i, Q_i) == 1 ?
 inline bool pairing_product_is_one(const PairingTerm* terms, int count) {
-    Fq12H f = Fq12H::one();
-    for (int i = 0; i < count; i++) f = f * miller_loop(terms[i].p, terms[i].q);
-    return final_exponentiation_cubed(f).is_one();
+    return final_exponentiation_cubed(multi_miller_loop(terms, count)).is_one();
 }
 
 }}  // namespace pm::host

@@ -55,6 +55,16 @@ FrH compute_pi_at_x1(uint64_t n, const FrH& omega, const std::vector<FrH>& pub, 
     return sum * y1_gamma;
 }
 
+// zcash encodings of the BLS12-381 generators (VerifyingKey.e.one_g1 / one_g2, data_structures.rs:27-29)
+const uint8_t G1_GEN_COMPRESSED[48] = {
+    0x97, 0xf1, 0xd3, 0xa7, 0x31, 0x97, 0xd7, 0x94, 0x26, 0x95, 0x63, 0x8c, 0x4f, 0xa9, 0xac, 0x0f, 0xc3, 0x68, 0x8c, 0x4f, 0x97, 0x74, 0xb9, 0x05,
+    0xa1, 0x4e, 0x3a, 0x3f, 0x17, 0x1b, 0xac, 0x58, 0x6c, 0x55, 0xe8, 0x3f, 0xf9, 0x7a, 0x1a, 0xef, 0xfb, 0x3a, 0xf0, 0x0a, 0xdb, 0x22, 0xc6, 0xbb};
+const uint8_t G2_GEN_COMPRESSED[96] = {
+    0x93, 0xe0, 0x2b, 0x60, 0x52, 0x71, 0x9f, 0x60, 0x7d, 0xac, 0xd3, 0xa0, 0x88, 0x27, 0x4f, 0x65, 0x59, 0x6b, 0xd0, 0xd0, 0x99, 0x20, 0xb6, 0x1a,
+    0xb5, 0xda, 0x61, 0xbb, 0xdc, 0x7f, 0x50, 0x49, 0x33, 0x4c, 0xf1, 0x12, 0x13, 0x94, 0x5d, 0x57, 0xe5, 0xac, 0x7d, 0x05, 0x5d, 0x04, 0x2b, 0x7e,
+    0x02, 0x4a, 0xa2, 0xb2, 0xf0, 0x8f, 0x0a, 0x91, 0x26, 0x08, 0x05, 0x27, 0x2d, 0xc5, 0x10, 0x51, 0xc6, 0xe4, 0x7a, 0xd4, 0xfa, 0x40, 0x3b, 0x02,
+    0xb4, 0x51, 0x0b, 0x64, 0x7a, 0xe3, 0xd1, 0x77, 0x0b, 0xac, 0x03, 0x26, 0xa8, 0x05, 0xbb, 0xef, 0xd4, 0x80, 0x56, 0xc8, 0xc1, 0x21, 0xbd, 0xb8};
+
 int log2_u64(uint64_t n) { int l = 0; while (((uint64_t)1 << l) < n) l++; return l; }
 
 }  // namespace
@@ -114,14 +124,6 @@ int pm_polymath_setup_sharded(const pm_r1cs_view* r1cs, pm_rng* rng, int rank, i
     if (rc != PM_OK) return rc;
     // VerifyingKey, compressed (data_structures.rs:25-50): e.one_g1, e.one_g2, e.x_g2, e.z_g2, n, m0, sigma, omega
     std::vector<uint8_t> vk;
-    static const uint8_t G1_GEN_COMPRESSED[48] = {
-        0x97, 0xf1, 0xd3, 0xa7, 0x31, 0x97, 0xd7, 0x94, 0x26, 0x95, 0x63, 0x8c, 0x4f, 0xa9, 0xac, 0x0f, 0xc3, 0x68, 0x8c, 0x4f, 0x97, 0x74, 0xb9, 0x05,
-        0xa1, 0x4e, 0x3a, 0x3f, 0x17, 0x1b, 0xac, 0x58, 0x6c, 0x55, 0xe8, 0x3f, 0xf9, 0x7a, 0x1a, 0xef, 0xfb, 0x3a, 0xf0, 0x0a, 0xdb, 0x22, 0xc6, 0xbb};
-    static const uint8_t G2_GEN_COMPRESSED[96] = {
-        0x93, 0xe0, 0x2b, 0x60, 0x52, 0x71, 0x9f, 0x60, 0x7d, 0xac, 0xd3, 0xa0, 0x88, 0x27, 0x4f, 0x65, 0x59, 0x6b, 0xd0, 0xd0, 0x99, 0x20, 0xb6, 0x1a,
-        0xb5, 0xda, 0x61, 0xbb, 0xdc, 0x7f, 0x50, 0x49, 0x33, 0x4c, 0xf1, 0x12, 0x13, 0x94, 0x5d, 0x57, 0xe5, 0xac, 0x7d, 0x05, 0x5d, 0x04, 0x2b, 0x7e,
-        0x02, 0x4a, 0xa2, 0xb2, 0xf0, 0x8f, 0x0a, 0x91, 0x26, 0x08, 0x05, 0x27, 0x2d, 0xc5, 0x10, 0x51, 0xc6, 0xe4, 0x7a, 0xd4, 0xfa, 0x40, 0x3b, 0x02,
-        0xb4, 0x51, 0x0b, 0x64, 0x7a, 0xe3, 0xd1, 0x77, 0x0b, 0xac, 0x03, 0x26, 0xa8, 0x05, 0xbb, 0xef, 0xd4, 0x80, 0x56, 0xc8, 0xc1, 0x21, 0xbd, 0xb8};
     vk.insert(vk.end(), G1_GEN_COMPRESSED, G1_GEN_COMPRESSED + 48);
     vk.insert(vk.end(), G2_GEN_COMPRESSED, G2_GEN_COMPRESSED + 96);
     ser_g2_compressed(vk, x_g2);
@@ -288,8 +290,9 @@ struct ProofH {    // Proof, data_structures.rs:10-19
 
 // `VerifyingKey::deserialize_compressed`: points validated (on curve, prime-order subgroup), scalars canonical
 bool parse_vk(const uint8_t vk[392], VkH& out) {
-    if (!g1_decompress(vk, out.one_g1)) return false;
-    if (!g2_decompress(vk + 48, out.one_g2)) return false;
+    // the standard generators (what `generate_proving_key` writes, generator.rs:141-143) need no subgroup check
+    if (!g1_decompress(vk, out.one_g1, memcmp(vk, G1_GEN_COMPRESSED, 48) != 0)) return false;
+    if (!g2_decompress(vk + 48, out.one_g2, memcmp(vk + 48, G2_GEN_COMPRESSED, 96) != 0)) return false;
     if (!g2_decompress(vk + 144, out.x_g2)) return false;
     if (!g2_decompress(vk + 240, out.z_g2)) return false;
     out.n = rd_u64(vk + 336);

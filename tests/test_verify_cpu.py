@@ -155,3 +155,16 @@ def test_verify_edge_encodings():
     # more / fewer public inputs than the key expects: plain reject, like the reference (no length check there)
     assert Polymath.verify(vk_bytes, pub + [5], proof) is False
     assert Polymath.verify(vk_bytes, [], proof) is False
+
+
+def test_pairing_product_with_many_pairs():
+    """More than eight live pairs (the shared Miller loop folds the rest): prod e(a_i P, Q) * e(-(sum a_i) P, Q) == 1."""
+    rnd = random.Random(5)
+    g1, g2 = oc.G1_GEN, oc.G2_GEN
+    coeffs = [rnd.randrange(1, 1 << 64) for _ in range(11)]
+    q = oc.g2_mul(g2, 9)
+    pairs = [(oc.g1_mul(g1, a), q) for a in coeffs] + [(oc.g1_neg(oc.g1_mul(g1, sum(coeffs) % R_MOD)), q)]
+    assert _pairing_is_one(pairs)
+    assert not _pairing_is_one(pairs[:-1] + [(oc.g1_neg(oc.g1_mul(g1, (sum(coeffs) + 1) % R_MOD)), q)])
+    # infinity entries interleaved do not disturb the product
+    assert _pairing_is_one(pairs[:5] + [(None, q), (g1, None)] + pairs[5:])
