@@ -843,74 +843,74 @@ MsmEngine::Shape MsmEngine::run(const G1Affine* bases, const Fr* scalars, size_t
         rounds = cached_plan->second.first;
         sets_per_pass = cached_plan->second.second;
     } else {
-    {
-        const double lambda = (double)entries / (double)total;
-        if (forced_rounds >= 0) {
-            rounds = forced_rounds;
-        } else if (entries >= ((size_t)1 << 20)) {
-            // Cost per bucket in ns, constants measured on B200 (profiles/r1_e_summary.md): a slot pair of the padded
-            // run costs 0.205 (backward) + 0.083 / 0.044 (forward: first round gathers, later rounds stream), an XYZZ
-            // addition of what is left 0.38, and every round a fixed ~0.55 ms (inversion tree, launches)
-            double best = 1e300;
-            for (int r = 0; r <= 6; r++) {
-                const double a = (double)(1u << r), lp = lambda + (a - 1) / 2, rest = lp / a;
-                double cost = (r ? 0.365 * 0 : 0) + 0.38 * (rest > 1 ? rest - 1 : 0) + r * 0.55e6 / (double)total;
-                for (int k = 0; k < r; k++) cost += lp / (double)(2u << k) * (0.205 + (k ? 0.044 : 0.083));
-                if (r == 0) cost = 0.365 * (lambda > 1 ? lambda - 1 : 0);
-                if (cost < best) { best = cost; rounds = r; }
+        {
+            const double lambda = (double)entries / (double)total;
+            if (forced_rounds >= 0) {
+                rounds = forced_rounds;
+            } else if (entries >= ((size_t)1 << 20)) {
+                // Cost per bucket in ns, constants measured on B200 (profiles/r1_e_summary.md): a slot pair of the padded
+                // run costs 0.205 (backward) + 0.083 / 0.044 (forward: first round gathers, later rounds stream), an XYZZ
+                // addition of what is left 0.38, and every round a fixed ~0.55 ms (inversion tree, launches)
+                double best = 1e300;
+                for (int r = 0; r <= 6; r++) {
+                    const double a = (double)(1u << r), lp = lambda + (a - 1) / 2, rest = lp / a;
+                    double cost = (r ? 0.365 * 0 : 0) + 0.38 * (rest > 1 ? rest - 1 : 0) + r * 0.55e6 / (double)total;
+                    for (int k = 0; k < r; k++) cost += lp / (double)(2u << k) * (0.205 + (k ? 0.044 : 0.083));
+                    if (r == 0) cost = 0.365 * (lambda > 1 ? lambda - 1 : 0);
+                    if (cost < best) { best = cost; rounds = r; }
+                }
+                rounds += cfg.rounds_bias + rounds_bias_env;
+                if (rounds < 0) rounds = 0;
             }
-            rounds += cfg.rounds_bias + rounds_bias_env;
-            if (rounds < 0) rounds = 0;
+            if (rounds > kMaxRounds) rounds = kMaxRounds;
+            // The bucket sets are independent: a large MSM runs them in passes of `sets_per_pass`, so that the padded list
+            // stays addressable (32-bit offsets) and the pair-round workspace fits into the device memory that is still
+            // free (plus what this engine already holds for the purpose).  If not even one set fits: XYZZ walk only.
         }
-        if (rounds > kMaxRounds) rounds = kMaxRounds;
-        // The bucket sets are independent: a large MSM runs them in passes of `sets_per_pass`, so that the padded list
-        // stays addressable (32-bit offsets) and the pair-round workspace fits into the device memory that is still
-        // free (plus what this engine already holds for the purpose).  If not even one set fits: XYZZ walk only.
-    }
-    {
-        const size_t per_set = n * (size_t)levels;      // entries of one bucket set (upper bound)
-        auto workspace = [&](int sets, int r) {
-            const size_t slots = per_set * sets + (size_t)nb * sets * ((1u << r) - 1);
-            return r ? (slots / 2 + 2) * (sizeof(G1Affine) + sizeof(Fq)) + (slots / 4 + 2) * sizeof(G1Affine) + slots * 4 : slots * 4;
-        };
-        auto addressable = [&](int sets, int r) {
-            return per_set * sets + (size_t)nb * sets * ((1u << r) - 1) < ((size_t)1 << 32) - 4096;
-        };
-        const size_t held = pairs_a_.cap + pairs_b_.cap + prefix_.cap + sorted_.cap;
-        // does the plan fit the buffers this engine already holds?  (per buffer: one round needs no second ping-pong
-        // array.)  Then nothing is queried: cudaMemGetInfo on a busy device blocks the host for up to tens of
-        // milliseconds (measured: 5-60 ms in 1 of 5 proofs while the NTT kernels of the phase were running).
-        auto fits_held = [&](int sets, int r) {
-            const size_t slots = per_set * sets + (size_t)nb * sets * ((1u << r) - 1);
-            const size_t smax = (slots + 1) & ~(size_t)1, cap_a = smax / 2 + 2, cap_b = smax / 4 + 2;
-            return sorted_.cap >= (smax + 2) * 4 &&
-                   (r == 0 || (pairs_a_.cap >= cap_a * sizeof(G1Affine) && prefix_.cap >= cap_a * sizeof(Fq))) &&
-                   (r <= 1 || pairs_b_.cap >= cap_b * sizeof(G1Affine));
-        };
-        size_t budget = held;
-        if (forced_rounds >= 0) {
-            budget = ~(size_t)0;
-        } else if (fits_held(ngroups, rounds)) {
-            const size_t w = workspace(ngroups, rounds);
-            budget = w > held ? w : held;
-        } else {
-            size_t free_b = 0, total_b = 0;
-            PM_CUDA(cudaMemGetInfo(&free_b, &total_b));
-            budget = held + free_b / 10 * 8;
+        {
+            const size_t per_set = n * (size_t)levels;      // entries of one bucket set (upper bound)
+            auto workspace = [&](int sets, int r) {
+                const size_t slots = per_set * sets + (size_t)nb * sets * ((1u << r) - 1);
+                return r ? (slots / 2 + 2) * (sizeof(G1Affine) + sizeof(Fq)) + (slots / 4 + 2) * sizeof(G1Affine) + slots * 4 : slots * 4;
+            };
+            auto addressable = [&](int sets, int r) {
+                return per_set * sets + (size_t)nb * sets * ((1u << r) - 1) < ((size_t)1 << 32) - 4096;
+            };
+            const size_t held = pairs_a_.cap + pairs_b_.cap + prefix_.cap + sorted_.cap;
+            // does the plan fit the buffers this engine already holds?  (per buffer: one round needs no second ping-pong
+            // array.)  Then nothing is queried: cudaMemGetInfo on a busy device blocks the host for up to tens of
+            // milliseconds (measured: 5-60 ms in 1 of 5 proofs while the NTT kernels of the phase were running).
+            auto fits_held = [&](int sets, int r) {
+                const size_t slots = per_set * sets + (size_t)nb * sets * ((1u << r) - 1);
+                const size_t smax = (slots + 1) & ~(size_t)1, cap_a = smax / 2 + 2, cap_b = smax / 4 + 2;
+                return sorted_.cap >= (smax + 2) * 4 &&
+                       (r == 0 || (pairs_a_.cap >= cap_a * sizeof(G1Affine) && prefix_.cap >= cap_a * sizeof(Fq))) &&
+                       (r <= 1 || pairs_b_.cap >= cap_b * sizeof(G1Affine));
+            };
+            size_t budget = held;
+            if (forced_rounds >= 0) {
+                budget = ~(size_t)0;
+            } else if (fits_held(ngroups, rounds)) {
+                const size_t w = workspace(ngroups, rounds);
+                budget = w > held ? w : held;
+            } else {
+                size_t free_b = 0, total_b = 0;
+                PM_CUDA(cudaMemGetInfo(&free_b, &total_b));
+                budget = held + free_b / 10 * 8;
+            }
+            int forced_sets = cfg.sets_per_pass;
+            if (forced_sets <= 0) forced_sets = forced_sets_env;
+            if (forced_sets > 0) sets_per_pass = forced_sets < ngroups ? forced_sets : ngroups;
+            while (sets_per_pass > 1 && forced_sets <= 0 &&
+                   (!addressable(sets_per_pass, rounds) || workspace(sets_per_pass, rounds) > budget))
+                sets_per_pass = (sets_per_pass + 1) / 2;
+            if (rounds > 0 && (!addressable(sets_per_pass, rounds) || workspace(sets_per_pass, rounds) > budget)) {
+                rounds = 0;                                   // not even one set fits: one XYZZ walk over as many sets as possible
+                if (forced_sets <= 0) sets_per_pass = ngroups;
+            }
+            while (sets_per_pass > 1 && !addressable(sets_per_pass, rounds)) sets_per_pass = (sets_per_pass + 1) / 2;
+            if (!addressable(sets_per_pass, rounds)) throw CudaError("msm: too many points per bucket set");
         }
-        int forced_sets = cfg.sets_per_pass;
-        if (forced_sets <= 0) forced_sets = forced_sets_env;
-        if (forced_sets > 0) sets_per_pass = forced_sets < ngroups ? forced_sets : ngroups;
-        while (sets_per_pass > 1 && forced_sets <= 0 &&
-               (!addressable(sets_per_pass, rounds) || workspace(sets_per_pass, rounds) > budget))
-            sets_per_pass = (sets_per_pass + 1) / 2;
-        if (rounds > 0 && (!addressable(sets_per_pass, rounds) || workspace(sets_per_pass, rounds) > budget)) {
-            rounds = 0;                                   // not even one set fits: one XYZZ walk over as many sets as possible
-            if (forced_sets <= 0) sets_per_pass = ngroups;
-        }
-        while (sets_per_pass > 1 && !addressable(sets_per_pass, rounds)) sets_per_pass = (sets_per_pass + 1) / 2;
-        if (!addressable(sets_per_pass, rounds)) throw CudaError("msm: too many points per bucket set");
-    }
         plans_[plan_key] = std::make_pair(rounds, sets_per_pass);
     }   // plan not cached
     {
