@@ -45,6 +45,7 @@ def cpu_baseline(log_n, msm_log=21, ntt_log=22):
     MSM cost is scaled by points x windows (arkworks window rule at each size); NTT by (N/2) log2 N.
     """
     from oracle import cpp
+    cpp.use_all_cores()          # torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm uses the host's cores
     n = 1 << log_n
     m = 1 << msm_log
     rnd = random.Random(7)

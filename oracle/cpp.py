@@ -39,6 +39,20 @@ def num_threads() -> int:
     return load().orc_num_threads()
 
 
+def use_all_cores() -> int:
+    """Run the OpenMP loops on every core this process may use (torchrun sets OMP_NUM_THREADS=1 for its workers)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    want = int(os.environ.get("PM_REF_THREADS", n))
+    lib = load()
+    lib.orc_set_num_threads.argtypes = [C.c_int]
+    lib.orc_set_num_threads.restype = None
+    lib.orc_set_num_threads(want)
+    return lib.orc_num_threads()
+
+
 def make_bases_wire(n: int) -> bytes:
     out = C.create_string_buffer(96 * n)
     load().orc_make_bases(n, out)

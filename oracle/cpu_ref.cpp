@@ -303,3 +303,5 @@ extern "C" int orc_fq_mul(const uint64_t* a, const uint64_t* b, uint64_t* out, s
     return 0;
 }
 extern "C" int orc_num_threads(void) { return omp_get_max_threads(); }
+// torchrun exports OMP_NUM_THREADS=1 to its workers: the CPU arm of bench.py asks for the host's cores explicitly
+extern "C" void orc_set_num_threads(int n) { if (n > 0) omp_set_num_threads(n); }
