@@ -453,7 +453,7 @@ def run_ours(args):
     msm_mpts = (1 << 22) / (d.value * 1e-3) / 1e6
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:       # the CPU arm is timed on rank 0 at N = 1 only
         try:
             cpu = cpu_baseline(log_n)
         except Exception as e:  # the oracle library is optional on the product path
