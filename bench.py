@@ -38,12 +38,18 @@ def ark_window(n):
     return ((n - 1).bit_length()) * 69 // 100 + 2
 
 
-def cpu_baseline(log_n, msm_log=21, ntt_log=22):
+def cpu_baseline(log_n, msm_log=None, ntt_log=None):
     """Time the C++/OpenMP port on a bounded sample and scale to one prove at n = 2^log_n.
 
     prove(n) = MSMs over ~14n + 29 points + 3 iNTT(n) + NTT(2n) + iNTT(2n).
     MSM cost is scaled by points x windows (arkworks window rule at each size); NTT by (N/2) log2 N.
     """
+    # sample sizes: 2^21-point MSM + 2^22 NTT (about 2-3 s on 16 threads); PM_REF_SAMPLE_LOG shrinks both (CPU tests)
+    shrink = os.environ.get("PM_REF_SAMPLE_LOG")
+    if msm_log is None:
+        msm_log = int(shrink) if shrink else 21
+    if ntt_log is None:
+        ntt_log = int(shrink) + 1 if shrink else 22
     from oracle import cpp
     cpp.use_all_cores()          # torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm uses the host's cores
     n = 1 << log_n
