@@ -264,6 +264,16 @@ int pm_polymath_prove(pm_ctx* ctx, const uint8_t* instance, const uint8_t* witne
  * deserialise fails with PM_ERR_ARG (the reference's SerializationError). */
 int pm_polymath_verify(const uint8_t vk[392], const uint8_t* public_inputs, size_t num_public, const uint8_t proof[176],
                        int* accepted);
+/* The reference's other two `Transcript` implementations (src/transcript/keccak256.rs, blake3.rs; exercised by
+ * tests/dummy.rs:76-80): same flows with the Fiat-Shamir challenges drawn from H(transcript || label) mod r.
+ * transcript: PM_TRANSCRIPT_MERLIN (what pm_polymath_prove / pm_polymath_verify use), _KECCAK256, _BLAKE3. */
+enum { PM_TRANSCRIPT_MERLIN = 0, PM_TRANSCRIPT_KECCAK256 = 1, PM_TRANSCRIPT_BLAKE3 = 2 };
+int pm_polymath_prove_transcript(pm_ctx* ctx, const uint8_t* instance, const uint8_t* witness, pm_rng* rng, int transcript,
+                                 uint8_t proof_out[176]);
+int pm_polymath_verify_transcript(const uint8_t vk[392], const uint8_t* public_inputs, size_t num_public,
+                                  const uint8_t proof[176], int transcript, int* accepted);
+/* Host-only test hook: out = Keccak-256 (kind 1, the `sha3` crate's Keccak256: original padding) or BLAKE3 (kind 2). */
+int pm_host_hash(int kind, const uint8_t* data, size_t len, uint8_t out[32]);
 /* Batch form: `count` proofs under one key, proof i with the public inputs
  * public_inputs[i * num_public ..].  The pairing equations are combined with 128-bit coefficients drawn from
  * rand `StdRng::from_seed(seed)` (r_0 = 1) into ONE product of three pairings:

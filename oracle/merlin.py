@@ -150,3 +150,55 @@ class MerlinFieldTranscript:
             r = fr_from_random_bytes(buf)
             if r is not None:
                 return r
+
+
+# ---------------------------------------------------------------------------
+# The reference's two hash transcripts (transcript/keccak256.rs:16-42, transcript/blake3.rs:16-42)
+# ---------------------------------------------------------------------------
+
+def keccak256(data: bytes) -> bytes:
+    """Keccak-256 with the ORIGINAL padding (0x01 ... 0x80), the `sha3` crate's `Keccak256` (not NIST SHA3-256)."""
+    rate = 136
+    st = bytearray(200)
+    padded = bytearray(data) + b"\x01"
+    padded += bytes((-len(padded)) % rate)
+    padded[-1] ^= 0x80
+    for off in range(0, len(padded), rate):
+        for i in range(rate):
+            st[i] ^= padded[off + i]
+        keccak_f1600(st)
+    return bytes(st[:32])
+
+
+def blake3_hash(data: bytes) -> bytes:
+    import blake3          # third-party module: an implementation independent of the product's C++ one
+    return blake3.blake3(data).digest()
+
+
+class _HashFieldTranscript:
+    """`new` ignores the name; messages are appended as label || message; a challenge is H(transcript || label) as a
+    big-endian integer mod r (`from_be_bytes_mod_order`), after which the transcript is the digest."""
+    hash_fn = None
+
+    def __init__(self, name: bytes):
+        self.transcript = b""
+
+    def append_message(self, label: bytes, message: bytes):
+        self.transcript += label + message
+
+    def challenge(self, label: bytes) -> int:
+        buf = type(self).hash_fn(self.transcript + label)
+        self.transcript = buf
+        return int.from_bytes(buf, "big") % R_MOD
+
+
+class Keccak256FieldTranscript(_HashFieldTranscript):
+    hash_fn = staticmethod(keccak256)
+
+
+class Blake3FieldTranscript(_HashFieldTranscript):
+    hash_fn = staticmethod(blake3_hash)
+
+
+TRANSCRIPTS = {"merlin": MerlinFieldTranscript, "keccak256": Keccak256FieldTranscript, "blake3": Blake3FieldTranscript}
+

@@ -483,7 +483,8 @@ def divide_by_linear(num, x1):
     return q, rem
 
 
-def create_proof_with_assignment(pk: ProvingKey, x, w, rng, literal=False, trace=None) -> Proof:
+def create_proof_with_assignment(pk: ProvingKey, x, w, rng, literal=False, trace=None,
+                                 transcript_cls=MerlinFieldTranscript) -> Proof:
     polys = prove_polys(pk, x, w, literal=literal)
     n, u, h = polys["n"], polys["u"], polys["h"]
     sigma = pk.vk.sigma
@@ -504,7 +505,7 @@ def create_proof_with_assignment(pk: ProvingKey, x, w, rng, literal=False, trace
     lcs_g1 = _msm(z_tail, pk.uj_wj_lcs_by_y_alpha_g1)
     c_g1 = g1_add(g1_add(lcs_g1, h_g1), r_g1)                                 # prover.rs:123
 
-    t = MerlinFieldTranscript(B_POLYMATH)
+    t = transcript_cls(B_POLYMATH)
     x1 = compute_x1(t, list(x), [a_g1, c_g1])                                 # prover.rs:125-126
     y1 = compute_y1(x1, sigma)
     y1_alpha = neg_power(y1, MINUS_ALPHA)
@@ -538,8 +539,8 @@ def create_proof(circuit, pk, rng, literal=False, trace=None):               # p
 # verify  (verifier.rs:19-62)
 # ---------------------------------------------------------------------------
 
-def verify_proof(vk: VerifyingKey, proof: Proof, public_inputs) -> bool:
-    t = MerlinFieldTranscript(B_POLYMATH)
+def verify_proof(vk: VerifyingKey, proof: Proof, public_inputs, transcript_cls=MerlinFieldTranscript) -> bool:
+    t = transcript_cls(B_POLYMATH)
     pub = [1] + [v % P for v in public_inputs]
     x1 = compute_x1(t, pub, [proof.a_g1, proof.c_g1])
     y1 = compute_y1(x1, vk.sigma)

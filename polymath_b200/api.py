@@ -38,6 +38,8 @@ class PKView(C.Structure):
     ]
 
 
+TRANSCRIPTS = {"merlin": 0, "keccak256": 1, "blake3": 2}     # PM_TRANSCRIPT_* (src/transcript/{merlin,keccak256,blake3}.rs)
+
 KEY_NAMES = ("x_powers_g1", "x_powers_y_alpha_g1", "x_powers_zh_by_y_alpha_g1", "x_powers_y_gamma_g1",
              "x_powers_y_gamma_z_g1", "uj_wj_lcs_by_y_alpha_g1")
 
@@ -75,6 +77,9 @@ def _bind(lib):
     lib.pm_polymath_prove.argtypes = [vp, u8p, u8p, vp, u8p]
     lib.pm_polymath_prove_resident.argtypes = [vp, u8p, vp, u8p]
     lib.pm_polymath_verify.argtypes = [u8p, u8p, C.c_size_t, u8p, C.POINTER(C.c_int)]
+    lib.pm_polymath_verify_transcript.argtypes = [u8p, u8p, C.c_size_t, u8p, C.c_int, C.POINTER(C.c_int)]
+    lib.pm_polymath_prove_transcript.argtypes = [vp, u8p, u8p, vp, C.c_int, u8p]
+    lib.pm_host_hash.argtypes = [C.c_int, u8p, C.c_size_t, u8p]
     lib.pm_polymath_verify_batch.argtypes = [u8p, C.c_size_t, u8p, C.c_size_t, u8p, u8p, C.POINTER(C.c_int)]
     lib.pm_host_pairing_product_is_one.argtypes = [u8p, u8p, C.c_int, C.POINTER(C.c_int)]
     lib.pm_timer_start.argtypes = []
@@ -278,12 +283,13 @@ class Polymath:
         return pk
 
     @staticmethod
-    def prove(pk: ProvingKey, instance, witness, rng: StdRng) -> bytes:
+    def prove(pk: ProvingKey, instance, witness, rng: StdRng, transcript="merlin") -> bytes:
         """`prove` (lib.rs:72-78) below synthesis: instance = [1, public...], witness values; returns the
-        176-byte compressed Proof."""
+        176-byte compressed Proof.  `transcript`: "merlin" (the north-star type), "keccak256" or "blake3"."""
         lib = _lib()
         out = C.create_string_buffer(176)
-        check(lib.pm_polymath_prove(pk._h, codec.frs_to_wire(instance), codec.frs_to_wire(witness), rng._h, out))
+        check(lib.pm_polymath_prove_transcript(pk._h, codec.frs_to_wire(instance), codec.frs_to_wire(witness), rng._h,
+                                               TRANSCRIPTS[transcript], out))
         return out.raw
 
     @staticmethod
@@ -305,7 +311,7 @@ class Polymath:
         return a_pt, c_pt, a_at_x1, codec.g1_from_wire(d.raw)
 
     @staticmethod
-    def verify(vk_bytes: bytes, public_inputs, proof_bytes: bytes) -> bool:
+    def verify(vk_bytes: bytes, public_inputs, proof_bytes: bytes, transcript="merlin") -> bool:
         """`verify` (lib.rs:80-91 -> verifier.rs:19-62) on the host: compressed VerifyingKey (392 B), the public
         inputs WITHOUT the leading one, compressed Proof (176 B).  No GPU involved."""
         lib = load()
@@ -314,7 +320,8 @@ class Polymath:
             raise ValueError("vk must be 392 bytes and the proof 176 bytes")
         ok = C.c_int(0)
         pub = codec.frs_to_wire(public_inputs)
-        check(lib.pm_polymath_verify(vk_bytes, pub, len(public_inputs), proof_bytes, C.byref(ok)))
+        check(lib.pm_polymath_verify_transcript(vk_bytes, pub, len(public_inputs), proof_bytes, TRANSCRIPTS[transcript],
+                                                C.byref(ok)))
         return bool(ok.value)
 
     @staticmethod

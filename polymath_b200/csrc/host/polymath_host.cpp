@@ -137,7 +137,7 @@ int pm_polymath_setup_sharded(const pm_r1cs_view* r1cs, pm_rng* rng, int rank, i
 }
 
 static int prove_impl(pm_ctx* ctx, const uint8_t* instance, const uint8_t* witness, bool upload, pm_rng* rng,
-                      pm_allgather_fn allgather, void* user, uint8_t proof_out[176]);
+                      pm_allgather_fn allgather, void* user, uint8_t proof_out[176], int transcript = kTranscriptMerlin);
 
 int pm_polymath_prove(pm_ctx* ctx, const uint8_t* instance, const uint8_t* witness, pm_rng* rng, uint8_t proof_out[176]) {
     return prove_impl(ctx, instance, witness, true, rng, nullptr, nullptr, proof_out);
@@ -145,14 +145,19 @@ int pm_polymath_prove(pm_ctx* ctx, const uint8_t* instance, const uint8_t* witne
 int pm_polymath_prove_resident(pm_ctx* ctx, const uint8_t* instance, pm_rng* rng, uint8_t proof_out[176]) {
     return prove_impl(ctx, instance, nullptr, false, rng, nullptr, nullptr, proof_out);
 }
+int pm_polymath_prove_transcript(pm_ctx* ctx, const uint8_t* instance, const uint8_t* witness, pm_rng* rng, int transcript,
+                                 uint8_t proof_out[176]) {
+    return prove_impl(ctx, instance, witness, true, rng, nullptr, nullptr, proof_out, transcript);
+}
 int pm_polymath_prove_sharded(pm_ctx* ctx, const uint8_t* instance, const uint8_t* witness, int upload, pm_rng* rng,
                               pm_allgather_fn allgather, void* user, uint8_t proof_out[176]) {
     return prove_impl(ctx, instance, witness, upload != 0, rng, allgather, user, proof_out);
 }
 
 static int prove_impl(pm_ctx* ctx, const uint8_t* instance, const uint8_t* witness, bool upload, pm_rng* rng,
-                      pm_allgather_fn allgather, void* user, uint8_t proof_out[176]) {
+                      pm_allgather_fn allgather, void* user, uint8_t proof_out[176], int transcript) {
     if (!ctx || !instance || !rng || !proof_out) { pm::set_last_error("null argument"); return PM_ERR_ARG; }
+    if (transcript < kTranscriptMerlin || transcript > kTranscriptBlake3) { pm::set_last_error("unknown transcript"); return PM_ERR_ARG; }
     int rank = 0, world = 1;
     if (pm_ctx_shard(ctx, &rank, &world) != PM_OK) return PM_ERR_ARG;
     const bool collective = !allgather && pm_ctx_has_collective(ctx);    // NCCL all-gather inside the phases
@@ -205,7 +210,7 @@ static int prove_impl(pm_ctx* ctx, const uint8_t* instance, const uint8_t* witne
     for (uint64_t i = 0; i < m0; i++) pub[i] = FrH::from_wire(instance + 32 * i);
 
     // compute_x1, common.rs:21-30
-    MerlinFieldTranscript t(B_POLYMATH);
+    FieldTranscript t(transcript, B_POLYMATH);
     std::vector<uint8_t> msg;
     ser_u64(msg, m0);
     for (auto& v : pub) ser_fr(msg, v);
@@ -313,8 +318,8 @@ void g1_wire(const G1H& p, uint8_t out[96]) {
 struct Challenges { FrH x1, x2, c_at_x1; };
 
 // verifier.rs:24-42: the transcript is fed exactly like the prover's (common.rs:21-37)
-Challenges derive_challenges(const VkH& vk, const std::vector<FrH>& pub, const ProofH& pr) {
-    MerlinFieldTranscript t(B_POLYMATH);
+Challenges derive_challenges(const VkH& vk, const std::vector<FrH>& pub, const ProofH& pr, int transcript = kTranscriptMerlin) {
+    FieldTranscript t(transcript, B_POLYMATH);
     std::vector<uint8_t> msg;
     ser_u64(msg, pub.size());
     for (auto& v : pub) ser_fr(msg, v);
@@ -366,14 +371,29 @@ extern "C" {
 
 int pm_polymath_verify(const uint8_t vk[392], const uint8_t* public_inputs, size_t num_public, const uint8_t proof[176],
                        int* accepted) {
+    return pm_polymath_verify_transcript(vk, public_inputs, num_public, proof, kTranscriptMerlin, accepted);
+}
+
+int pm_host_hash(int kind, const uint8_t* data, size_t len, uint8_t out[32]) {
+    if ((len && !data) || !out) { pm::set_last_error("null argument"); return PM_ERR_ARG; }
+    static const uint8_t none = 0;
+    if (kind == kTranscriptKeccak256) keccak256(data ? data : &none, len, out);
+    else if (kind == kTranscriptBlake3) blake3_hash(data ? data : &none, len, out);
+    else { pm::set_last_error("unknown hash"); return PM_ERR_ARG; }
+    return PM_OK;
+}
+
+int pm_polymath_verify_transcript(const uint8_t vk[392], const uint8_t* public_inputs, size_t num_public, const uint8_t proof[176],
+                                  int transcript, int* accepted) {
     if (!vk || !proof || !accepted || (num_public && !public_inputs)) { pm::set_last_error("null argument"); return PM_ERR_ARG; }
+    if (transcript < kTranscriptMerlin || transcript > kTranscriptBlake3) { pm::set_last_error("unknown transcript"); return PM_ERR_ARG; }
     *accepted = 0;
     VkH k;
     ProofH pr;
     if (!parse_vk(vk, k)) { pm::set_last_error("verifying key does not deserialise (ark-serialize SerializationError)"); return PM_ERR_ARG; }
     if (!parse_proof(proof, pr)) { pm::set_last_error("proof does not deserialise (ark-serialize SerializationError)"); return PM_ERR_ARG; }
     std::vector<FrH> pub = public_with_one(public_inputs, num_public);
-    Challenges ch = derive_challenges(k, pub, pr);
+    Challenges ch = derive_challenges(k, pub, pr, transcript);
     G1H lhs = commitments_minus_evals(k, pr, ch);
     G2H x_minus_x1 = aff_add(k.x_g2, jac_to_affine(scalar_mul(k.one_g2, ch.x1.neg())));   // verifier.rs:48
     PairingTerm terms[2] = {{lhs, k.z_g2}, {pr.d.neg(), x_minus_x1}};                      // verifier.rs:50-59

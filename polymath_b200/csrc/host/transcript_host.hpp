@@ -152,6 +152,135 @@ private:
     MerlinTranscript t_;
 };
 
+// ---- Keccak-256 (original padding, as the `sha3` crate's Keccak256) and BLAKE3 ------------------------------
+// for the reference's two hash transcripts (transcript/keccak256.rs:16-42, transcript/blake3.rs:16-42)
+inline void keccak256(const uint8_t* data, size_t len, uint8_t out[32]) {
+    constexpr size_t kRate = 136;
+    uint64_t st[25];
+    memset(st, 0, sizeof st);
+    uint8_t block[kRate];
+    auto absorb_block = [&](const uint8_t* b) {
+        for (size_t i = 0; i < kRate / 8; i++) { uint64_t w; memcpy(&w, b + 8 * i, 8); st[i] ^= w; }   // little-endian host
+        keccak_f1600(st);
+    };
+    while (len >= kRate) { absorb_block(data); data += kRate; len -= kRate; }
+    memset(block, 0, sizeof block);
+    memcpy(block, data, len);
+    block[len] ^= 0x01;
+    block[kRate - 1] ^= 0x80;
+    absorb_block(block);
+    memcpy(out, st, 32);
+}
+
+namespace blake3_detail {
+constexpr uint32_t IV[8] = {0x6A09E667u, 0xBB67AE85u, 0x3C6EF372u, 0xA54FF53Au, 0x510E527Fu, 0x9B05688Cu, 0x1F83D9ABu, 0x5BE0CD19u};
+constexpr int PERM[16] = {2, 6, 3, 10, 7, 0, 4, 13, 1, 11, 12, 5, 9, 14, 15, 8};
+enum : uint32_t { CHUNK_START = 1, CHUNK_END = 2, PARENT = 4, ROOT = 8 };
+inline uint32_t rotr(uint32_t x, int n) { return (x >> n) | (x << (32 - n)); }
+inline void g(uint32_t* v, int a, int b, int c, int d, uint32_t mx, uint32_t my) {
+    v[a] = v[a] + v[b] + mx; v[d] = rotr(v[d] ^ v[a], 16);
+    v[c] = v[c] + v[d];      v[b] = rotr(v[b] ^ v[c], 12);
+    v[a] = v[a] + v[b] + my; v[d] = rotr(v[d] ^ v[a], 8);
+    v[c] = v[c] + v[d];      v[b] = rotr(v[b] ^ v[c], 7);
+}
+// compression function; out = the first eight words (the chaining value / first half of the root output)
+inline void compress(const uint32_t cv[8], const uint8_t block[64], uint64_t counter, uint32_t block_len, uint32_t flags, uint32_t out[8]) {
+    uint32_t m[16], v[16];
+    for (int i = 0; i < 16; i++) memcpy(&m[i], block + 4 * i, 4);   // little-endian host
+    for (int i = 0; i < 8; i++) v[i] = cv[i];
+    for (int i = 0; i < 4; i++) v[8 + i] = IV[i];
+    v[12] = (uint32_t)counter; v[13] = (uint32_t)(counter >> 32); v[14] = block_len; v[15] = flags;
+    for (int round = 0; round < 7; round++) {
+        g(v, 0, 4, 8, 12, m[0], m[1]);   g(v, 1, 5, 9, 13, m[2], m[3]);
+        g(v, 2, 6, 10, 14, m[4], m[5]);  g(v, 3, 7, 11, 15, m[6], m[7]);
+        g(v, 0, 5, 10, 15, m[8], m[9]);  g(v, 1, 6, 11, 12, m[10], m[11]);
+        g(v, 2, 7, 8, 13, m[12], m[13]); g(v, 3, 4, 9, 14, m[14], m[15]);
+        uint32_t p[16];
+        for (int i = 0; i < 16; i++) p[i] = m[PERM[i]];
+        memcpy(m, p, sizeof m);
+    }
+    for (int i = 0; i < 8; i++) out[i] = v[i] ^ v[i + 8];
+}
+// one chunk (<= 1024 bytes): chained block compressions; `root` marks a single-chunk input
+inline void chunk_cv(const uint8_t* data, size_t len, uint64_t chunk_index, bool root, uint32_t out[8]) {
+    uint32_t cv[8];
+    memcpy(cv, IV, sizeof cv);
+    const size_t nblocks = len == 0 ? 1 : (len + 63) / 64;
+    for (size_t b = 0; b < nblocks; b++) {
+        uint8_t block[64];
+        memset(block, 0, sizeof block);
+        const size_t off = b * 64, take = len - off < 64 ? len - off : 64;
+        memcpy(block, data + off, take);
+        uint32_t flags = (b == 0 ? CHUNK_START : 0) | (b + 1 == nblocks ? CHUNK_END | (root ? ROOT : 0) : 0);
+        uint32_t next[8];
+        compress(cv, block, chunk_index, (uint32_t)take, flags, next);
+        memcpy(cv, next, sizeof cv);
+    }
+    memcpy(out, cv, sizeof cv);
+}
+inline void parent_cv(const uint32_t l[8], const uint32_t r[8], bool root, uint32_t out[8]) {
+    uint8_t block[64];
+    memcpy(block, l, 32);
+    memcpy(block + 32, r, 32);
+    compress(IV, block, 0, 64, PARENT | (root ? ROOT : 0), out);
+}
+// left subtree = the largest power-of-two number of whole chunks that leaves at least one byte on the right
+inline size_t left_len(size_t len) {
+    size_t chunks = (len - 1) / 1024, p = 1;
+    while (p * 2 <= chunks) p *= 2;
+    return p * 1024;
+}
+inline void subtree_cv(const uint8_t* data, size_t len, uint64_t chunk_index, bool root, uint32_t out[8]) {
+    if (len <= 1024) { chunk_cv(data, len, chunk_index, root, out); return; }
+    const size_t ll = left_len(len);
+    uint32_t l[8], r[8];
+    subtree_cv(data, ll, chunk_index, false, l);
+    subtree_cv(data + ll, len - ll, chunk_index + ll / 1024, false, r);
+    parent_cv(l, r, root, out);
+}
+}  // namespace blake3_detail
+
+inline void blake3_hash(const uint8_t* data, size_t len, uint8_t out[32]) {
+    uint32_t cv[8];
+    blake3_detail::subtree_cv(data, len, 0, true, cv);
+    memcpy(out, cv, 32);   // little-endian words
+}
+
+enum TranscriptKind { kTranscriptMerlin = 0, kTranscriptKeccak256 = 1, kTranscriptBlake3 = 2 };
+
+// The reference's `Transcript` trait (transcript/mod.rs:17-29) over its three implementations.  The two hash
+// transcripts ignore the name, keep label || message bytes, and answer H(transcript || label) reduced mod r
+// (`from_be_bytes_mod_order`), after which the transcript IS the digest (keccak256.rs:26-41, blake3.rs:26-41).
+class FieldTranscript {
+public:
+    FieldTranscript(int kind, const std::string& name) : kind_(kind), merlin_(name) {}
+    void append_message(const char* label, const std::vector<uint8_t>& msg) {
+        if (kind_ == kTranscriptMerlin) { merlin_.append_message(label, msg); return; }
+        buf_.insert(buf_.end(), label, label + strlen(label));
+        buf_.insert(buf_.end(), msg.begin(), msg.end());
+    }
+    FrH challenge(const char* label) {
+        if (kind_ == kTranscriptMerlin) return merlin_.challenge(label);
+        std::vector<uint8_t> in(buf_);
+        in.insert(in.end(), label, label + strlen(label));
+        uint8_t digest[32];
+        if (kind_ == kTranscriptKeccak256) keccak256(in.data(), in.size(), digest);
+        else blake3_hash(in.data(), in.size(), digest);
+        buf_.assign(digest, digest + 32);
+        // from_be_bytes_mod_order: the 256-bit big-endian integer mod r (a Montgomery product by R^2 reduces it)
+        FrH v;
+        uint8_t le[32];
+        for (int i = 0; i < 32; i++) le[i] = digest[31 - i];
+        memcpy(v.v, le, 32);
+        return v.to_mont();
+    }
+
+private:
+    int kind_;
+    MerlinFieldTranscript merlin_;
+    std::vector<uint8_t> buf_;
+};
+
 // ---- rand 0.8 StdRng ------------------------------------------------------------------
 class StdRng {
 public:

@@ -202,3 +202,30 @@ def test_prover_with_pair_rounds(pmlib, rounds):
         _run_flow(mk_setup, mk_prove, seed=77 + rounds, proofs=1)
     finally:
         kernels.msm_set_tuning(-1)
+
+
+@pytest.mark.parametrize("name", ["keccak256", "blake3"])
+def test_dummy_circuit_with_the_hash_transcripts(pmlib, name):
+    """tests/dummy.rs:76-80: the same flow with `Keccak256Transcript` / `Blake3Transcript`; the device phases are the same,
+    only the host-side challenges differ.  Proof bytes must equal the oracle's and both verifiers must accept."""
+    from oracle import merlin as om
+    from polymath_b200.api import Polymath, StdRng
+    cls = om.TRANSCRIPTS[name]
+    seed = 606
+    orng, drng = OStdRng.seed_from_u64(seed), StdRng.seed_from_u64(seed)
+    cs = orc.synthesize(orc.DummyCircuit(), setup_mode=True)
+    pk_or = opm.generate_proving_key(orc.DummyCircuit(), orng)
+    pk_dev, vk_bytes = Polymath.setup(_r1cs_from_cs(cs), drng)
+    assert vk_bytes == pk_or.vk.serialize_compressed()
+    for _ in range(2):
+        a, b = o_fr_rand(orng), o_fr_rand(orng)
+        drng.fr_rand(); drng.fr_rand()
+        pcs = orc.synthesize(orc.DummyCircuit(a, b), setup_mode=False)
+        want = opm.create_proof_with_assignment(pk_or, pcs.instance_assignment, pcs.witness_assignment, orng, transcript_cls=cls)
+        got = Polymath.prove(pk_dev, pcs.instance_assignment, pcs.witness_assignment, drng, transcript=name)
+        assert got == want.serialize_compressed()
+        pub = [a * b % R_MOD]
+        assert opm.verify_proof(pk_or.vk, want, pub, transcript_cls=cls)
+        assert Polymath.verify(vk_bytes, pub, got, transcript=name)
+        assert not Polymath.verify(vk_bytes, pub, got, transcript="merlin")
+    pk_dev.close()

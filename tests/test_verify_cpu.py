@@ -168,3 +168,51 @@ def test_pairing_product_with_many_pairs():
     assert not _pairing_is_one(pairs[:-1] + [(oc.g1_neg(oc.g1_mul(g1, (sum(coeffs) + 1) % R_MOD)), q)])
     # infinity entries interleaved do not disturb the product
     assert _pairing_is_one(pairs[:5] + [(None, q), (g1, None)] + pairs[5:])
+
+
+def _host_hash(kind, data):
+    lib = load()
+    _bind(lib)
+    out = C.create_string_buffer(32)
+    assert lib.pm_host_hash(kind, data, len(data), out) == 0
+    return out.raw
+
+
+def test_keccak256_and_blake3_match_known_answers_and_the_oracle():
+    import hashlib
+    import blake3
+    from oracle import merlin as om
+    # Keccak-256 known answers (original padding, not SHA3-256)
+    assert om.keccak256(b"").hex() == "c5d2460186f7233c927e7db2dcc703c0e500b653ca82273b7bfad8045d85a470"
+    assert om.keccak256(b"abc").hex() == "4e03657aea45a94fc7d47ba826c8d667c0d1e6e33a64a036ec44f58fa12d6c45"
+    assert om.keccak256(b"abc") != hashlib.sha3_256(b"abc").digest()
+    # BLAKE3 known answer for the empty input (official test vector)
+    assert blake3.blake3(b"").hexdigest() == "af1349b9f5f9a1a6a0404dea36dcc9499bcb25c9adc112b7cc9a93cae41f3262"
+    rnd = random.Random(3)
+    for ln in [0, 1, 2, 63, 64, 65, 135, 136, 137, 271, 272, 1023, 1024, 1025, 2047, 2048, 2049, 3072, 3073, 4096, 5000,
+               7 * 1024, 8 * 1024 + 1, 20000]:
+        data = bytes(rnd.randrange(256) for _ in range(ln))
+        assert _host_hash(1, data) == om.keccak256(data), ln
+        assert _host_hash(2, data) == blake3.blake3(data).digest(), ln
+
+
+@pytest.mark.parametrize("name", ["merlin", "keccak256", "blake3"])
+def test_verify_with_each_transcript_like_tests_dummy_rs(name):
+    """tests/dummy.rs:76-80 runs setup -> prove -> verify with all three transcripts: oracle prover, product verifier."""
+    from oracle import polymath as opm, r1cs as orc
+    from oracle import merlin as om
+    from oracle.rng import StdRng as ORng, fr_rand
+    cls = om.TRANSCRIPTS[name]
+    rng = ORng.seed_from_u64(31)
+    pk = opm.generate_proving_key(orc.DummyCircuit(), rng)
+    x, y = fr_rand(rng), fr_rand(rng)
+    cs = orc.synthesize(orc.DummyCircuit(x, y), setup_mode=False)
+    pr = opm.create_proof_with_assignment(pk, cs.instance_assignment, cs.witness_assignment, rng, transcript_cls=cls)
+    pub = [x * y % R_MOD]
+    assert opm.verify_proof(pk.vk, pr, pub, transcript_cls=cls)
+    vk_bytes, proof = pk.vk.serialize_compressed(), pr.serialize_compressed()
+    assert Polymath.verify(vk_bytes, pub, proof, transcript=name) is True
+    for other in om.TRANSCRIPTS:
+        if other != name:
+            assert Polymath.verify(vk_bytes, pub, proof, transcript=other) is False
+            assert not opm.verify_proof(pk.vk, pr, pub, transcript_cls=om.TRANSCRIPTS[other])
