@@ -156,7 +156,9 @@ typedef struct {
 typedef struct pm_ctx pm_ctx;
 
 /* Upload (and repack) a proving key once; later `prove` calls reuse the device copy
- * (`prove(&pk, ..)` borrows the key on every call, src/lib.rs:72-78). */
+ * (`prove(&pk, ..)` borrows the key on every call, src/lib.rs:72-78).  Compressed vectors (point_stride 48) are
+ * validated like `ProvingKey::deserialize_compressed`: canonical x, flags, on the curve AND in the prime-order
+ * subgroup; pm_ctx_create_unchecked (below) skips the subgroup check only, like `deserialize_compressed_unchecked`. */
 int pm_ctx_create(const pm_pk_view* pk, pm_ctx** out);
 void pm_ctx_destroy(pm_ctx* ctx);
 
@@ -199,6 +201,9 @@ int pm_prove_phase3(pm_ctx* ctx, const uint8_t x2[PM_FR_BYTES], const uint8_t c_
 int pm_setup_sharded(const pm_r1cs_view* r1cs, const uint8_t x[PM_FR_BYTES], const uint8_t z[PM_FR_BYTES], int rank,
                      int world, pm_ctx** out, uint8_t x_g2[192], uint8_t z_g2[192]);
 int pm_ctx_create_sharded(const pm_pk_view* pk, int rank, int world, pm_ctx** out);
+/* Opt-in `deserialize_compressed_unchecked`: no prime-order-subgroup check of compressed key vectors (rank 0, world 1
+ * for an unsharded context).  Encoding and on-curve checks still run. */
+int pm_ctx_create_unchecked(const pm_pk_view* pk, int rank, int world, pm_ctx** out);
 int pm_ctx_shard(const pm_ctx* ctx, int* rank, int* world);
 int pm_prove_phase1_partial(pm_ctx* ctx, const uint8_t r_a[2 * PM_FR_BYTES], uint8_t partials_out[2 * PM_XYZZ_BYTES]);
 int pm_prove_phase1_finish(pm_ctx* ctx, const uint8_t* gathered, int count, uint8_t a_out[PM_G1_BYTES],
@@ -251,7 +256,10 @@ int pm_polymath_setup(const pm_r1cs_view* r1cs, pm_rng* rng, pm_ctx** ctx_out, u
 /* `create_proof_with_assignment` (src/prover.rs:66-237): instance = m0 values (leading 1 first),
  * witness = mw values, both Montgomery; draws r_a from `rng`; runs the Merlin transcript
  * (src/common.rs:21-37) on the host between the device phases; writes the compressed Proof
- * (176 bytes, src/data_structures.rs:10-19). */
+ * (176 bytes, src/data_structures.rs:10-19).  Instance values must be reduced (limbs < r), else PM_ERR_ARG.
+ * RNG: r_a is drawn before the device work starts; when phase 1 fails (PM_ERR_UNSATISFIED / PM_ERR_DEGENERATE: the
+ * reference panics at src/prover.rs:107-108, BEFORE `F::rand` at :110) the generator is restored, so after a failed
+ * proof the caller's stream has not advanced, exactly like the reference's. */
 int pm_polymath_prove(pm_ctx* ctx, const uint8_t* instance, const uint8_t* witness, pm_rng* rng, uint8_t proof_out[176]);
 
 /* `Polymath::verify` / `verify_proof` (src/verifier.rs:19-62) on the HOST — no device work (BASELINE north_star:
@@ -261,7 +269,9 @@ int pm_polymath_prove(pm_ctx* ctx, const uint8_t* instance, const uint8_t* witne
  *   e([a]_1 + x2 [c]_1 - (a(x1) + x2 c(x1)) [1]_1, [z]_2) * e(-[d]_1, [x]_2 - x1 [1]_2) == 1.
  * public_inputs: num_public x 32 bytes (Montgomery), WITHOUT the leading one (the verifier prepends it,
  * src/verifier.rs:26).  *accepted = 1 / 0 = the reference's Ok(true) / Ok(false); a key or proof that does not
- * deserialise fails with PM_ERR_ARG (the reference's SerializationError). */
+ * deserialise fails with PM_ERR_ARG (the reference's SerializationError).  A public input whose limbs are not
+ * below r fails with PM_ERR_ARG as well: raw limbs are never reduced, so x and x + r cannot alias (the reference
+ * takes typed field elements). */
 int pm_polymath_verify(const uint8_t vk[392], const uint8_t* public_inputs, size_t num_public, const uint8_t proof[176],
                        int* accepted);
 /* The reference's other two `Transcript` implementations (src/transcript/keccak256.rs, blake3.rs; exercised by
@@ -275,10 +285,12 @@ int pm_polymath_verify_transcript(const uint8_t vk[392], const uint8_t* public_i
 /* Host-only test hook: out = Keccak-256 (kind 1, the `sha3` crate's Keccak256: original padding) or BLAKE3 (kind 2). */
 int pm_host_hash(int kind, const uint8_t* data, size_t len, uint8_t out[32]);
 /* Batch form: `count` proofs under one key, proof i with the public inputs
- * public_inputs[i * num_public ..].  The pairing equations are combined with 128-bit coefficients drawn from
- * rand `StdRng::from_seed(seed)` (r_0 = 1) into ONE product of three pairings:
+ * public_inputs[i * num_public ..].  The pairing equations are combined with 128-bit coefficients (r_0 = 1) drawn
+ * from rand `StdRng::from_seed(BLAKE3(seed | vk | proofs | public inputs))` — bound to the statements, so knowing
+ * the caller's seed in advance does not help to craft proofs whose errors cancel — into ONE product of three pairings:
  *   e(sum r_i L_i, [z]_2) * e(-sum r_i [d_i]_1, [x]_2) * e(sum r_i x1_i [d_i]_1, [1]_2) == 1.
- * *accepted = 1 iff the combined check holds (all proofs valid, up to 2^-128 soundness error from the caller's seed). */
+ * *accepted = 1 iff the combined check holds (all proofs valid, up to 2^-128 soundness error); count == 0 accepts
+ * (seed may then be NULL).  The seed should still be fresh per call. */
 int pm_polymath_verify_batch(const uint8_t vk[392], size_t count, const uint8_t* public_inputs, size_t num_public,
                              const uint8_t* proofs, const uint8_t seed[32], int* accepted);
 /* Host-only test hook: prod_i e(P_i, Q_i) == 1 for `count` pairs of affine points (G1: 96 bytes, G2: 192 bytes

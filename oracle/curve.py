@@ -266,6 +266,10 @@ def g1_decompress(b: bytes, validate: bool = True):
     if not flags & 0x80:
         raise ValueError("UnexpectedFlags: not a compressed encoding")
     if flags & 0x40:
+        # arkworks algebra master (the snapshot the reference patches to, Cargo.toml:84-101) rejects an infinity
+        # encoding that carries the sort flag or a non-zero x; ark-bls12-381 0.4.0 returned zero right away
+        if flags != 0xC0 or any(b[1:]):
+            raise ValueError("InvalidData: infinity flag on a non-zero encoding")
         return None
     x = int.from_bytes(bytes([b[0] & 0x1F]) + b[1:], "big")
     if x >= P:

@@ -226,6 +226,16 @@ class ProvingKey:
             pass
 
 
+def _checked_frs(vals, what):
+    """Field elements as Montgomery wire bytes; values outside [0, r) are refused, never reduced (the reference
+    takes typed `F` values, lib.rs:72-86, and so cannot alias x with x + r)."""
+    vals = list(vals)
+    for v in vals:
+        if not 0 <= v < codec.R_MOD:
+            raise ValueError("%s: %d is not a reduced BLS12-381 scalar (0 <= v < r)" % (what, v))
+    return codec.frs_to_wire(vals)
+
+
 class Polymath:
     """`Polymath::<Bls12_381, MerlinFieldTranscript<Fr>>` (src/lib.rs:44-98), proving side."""
 
@@ -288,8 +298,8 @@ class Polymath:
         176-byte compressed Proof.  `transcript`: "merlin" (the north-star type), "keccak256" or "blake3"."""
         lib = _lib()
         out = C.create_string_buffer(176)
-        check(lib.pm_polymath_prove_transcript(pk._h, codec.frs_to_wire(instance), codec.frs_to_wire(witness), rng._h,
-                                               TRANSCRIPTS[transcript], out))
+        check(lib.pm_polymath_prove_transcript(pk._h, _checked_frs(instance, "instance"), _checked_frs(witness, "witness"),
+                                               rng._h, TRANSCRIPTS[transcript], out))
         return out.raw
 
     @staticmethod
@@ -319,7 +329,7 @@ class Polymath:
         if len(vk_bytes) != 392 or len(proof_bytes) != 176:
             raise ValueError("vk must be 392 bytes and the proof 176 bytes")
         ok = C.c_int(0)
-        pub = codec.frs_to_wire(public_inputs)
+        pub = _checked_frs(public_inputs, "public input")
         check(lib.pm_polymath_verify_transcript(vk_bytes, pub, len(public_inputs), proof_bytes, TRANSCRIPTS[transcript],
                                                 C.byref(ok)))
         return bool(ok.value)
@@ -335,6 +345,6 @@ class Polymath:
         if any(len(p) != k for p in public_inputs_list) or any(len(p) != 176 for p in proofs) or len(seed) != 32:
             raise ValueError("ragged public inputs / bad proof or seed length")
         ok = C.c_int(0)
-        pub = b"".join(codec.frs_to_wire(p) for p in public_inputs_list)
+        pub = b"".join(_checked_frs(p, "public input") for p in public_inputs_list)
         check(lib.pm_polymath_verify_batch(vk_bytes, len(proofs), pub, k, b"".join(proofs), seed, C.byref(ok)))
         return bool(ok.value)

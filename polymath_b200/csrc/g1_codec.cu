@@ -48,7 +48,9 @@ __device__ __forceinline__ bool fq_is_largest(const Fq& y_mont) {
     return borrow == 0;
 }
 
-// status: 0 = ok, 1 = compression flag missing, 2 = x >= q, 3 = not on the curve, 4 = not in the prime-order subgroup
+// status: 0 = ok, 1 = compression flag missing, 2 = x >= q, 3 = not on the curve, 4 = not in the prime-order subgroup,
+// 5 = infinity flag with the sort flag or a non-zero payload (ark-bls12-381 `read_g1_compressed` and the host codec
+// accept exactly 0xc0 00 .. 00 as the point at infinity)
 __global__ void __launch_bounds__(128) k_g1_decompress(const uint8_t* __restrict__ in, size_t n, int validate,
                                                        G1Affine* __restrict__ out, unsigned long long* __restrict__ first_bad) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -59,7 +61,11 @@ __global__ void __launch_bounds__(128) k_g1_decompress(const uint8_t* __restrict
     G1Affine p = G1Affine::inf();
     if (!(flags & 0x80)) {
         status = 1;
-    } else if (!(flags & 0x40)) {
+    } else if (flags & 0x40) {
+        uint32_t rest = flags & 0x3fu;
+        for (int j = 1; j < 48; j++) rest |= b[j];
+        if (rest) status = 5;
+    } else {
         Fq x;
 #pragma unroll
         for (int j = 0; j < 12; j++) {
@@ -145,6 +151,7 @@ const char* g1_decode_status_name(unsigned status) {
         case 2: return "x coordinate not below the field modulus";
         case 3: return "x is not the abscissa of a curve point";
         case 4: return "point is not in the prime-order subgroup";
+        case 5: return "infinity flag set on a non-zero encoding";
         default: return "ok";
     }
 }

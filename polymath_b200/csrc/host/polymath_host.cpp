@@ -184,22 +184,30 @@ static int prove_impl(pm_ctx* ctx, const uint8_t* instance, const uint8_t* witne
         m0 = cols - lcs_len;
     }
     (void)rank;
-    // the device work of phase 1 needs r_a, which the reference draws after the polynomial
-    // work (prover.rs:110) — nothing else consumes the RNG in between, so the stream is identical.
+    // The device work of phase 1 needs r_a, which the reference draws after the polynomial work and after
+    // its divisibility / degree asserts (prover.rs:107-110).  Nothing else consumes the RNG in between, so
+    // the stream is identical when the proof succeeds; when phase 1 fails (the reference would have panicked
+    // BEFORE `F::rand`) the caller's generator is put back to where it was, so it has not advanced either.
+    for (uint64_t i = 0; i < m0; i++) {
+        uint64_t limbs[4];
+        memcpy(limbs, instance + 32 * i, 32);
+        if (FrH::geq_mod(limbs)) { pm::set_last_error("instance value is not a reduced field element"); return PM_ERR_ARG; }
+    }
     if (upload) {
         rc = pm_ctx_set_assignment(ctx, instance, witness);
         if (rc != PM_OK) return rc;
     }
     uint8_t ra[64], a_g1[96], c_g1[96];
+    const StdRng rng_before = rng->rng;
     rng->rng.fr_rand().to_wire(ra);         // r_a coefficient 0
     rng->rng.fr_rand().to_wire(ra + 32);    // r_a coefficient 1
     if (collective) {
         rc = pm_prove_phase1_collective(ctx, ra, a_g1, c_g1);
-        if (rc != PM_OK) return rc;
+        if (rc != PM_OK) { rng->rng = rng_before; return rc; }
     } else {
         uint8_t part1[2 * PM_XYZZ_BYTES];
         rc = pm_prove_phase1_partial(ctx, ra, part1);
-        if (rc != PM_OK) return rc;
+        if (rc != PM_OK) { rng->rng = rng_before; return rc; }
         rc = gather(part1, sizeof part1, gathered);
         if (rc != PM_OK) return rc;
         rc = pm_prove_phase1_finish(ctx, gathered.data(), world, a_g1, c_g1);
@@ -358,11 +366,34 @@ G1H commitments_minus_evals(const VkH& vk, const ProofH& pr, const Challenges& c
     return aff_add(acc, jac_to_affine(scalar_mul(vk.one_g1, ev)));
 }
 
-std::vector<FrH> public_with_one(const uint8_t* public_inputs, size_t num_public) {
-    std::vector<FrH> pub(num_public + 1);
-    pub[0] = FrH::one();                                  // verifier.rs:26
-    for (size_t i = 0; i < num_public; i++) pub[i + 1] = FrH::from_wire(public_inputs + 32 * i);
-    return pub;
+// The reference takes typed field elements (`&[F]`, lib.rs:80-86) and cannot alias x with x + r; raw limb
+// vectors can, so anything that is not a reduced Montgomery representative is refused (no silent reduction).
+bool public_with_one(const uint8_t* public_inputs, size_t num_public, std::vector<FrH>& pub) {
+    pub.assign(num_public + 1, FrH::one());               // verifier.rs:26
+    for (size_t i = 0; i < num_public; i++) {
+        uint64_t limbs[4];
+        memcpy(limbs, public_inputs + 32 * i, 32);
+        if (FrH::geq_mod(limbs)) return false;
+        pub[i + 1] = FrH::from_wire(public_inputs + 32 * i);
+    }
+    return true;
+}
+
+// exceptions (std::bad_alloc, ...) must not cross the C ABI
+template <class F>
+int host_guarded(F&& f) {
+    try {
+        return f();
+    } catch (const std::bad_alloc&) {
+        pm::set_last_error("out of host memory");
+        return PM_ERR_STATE;
+    } catch (const std::exception& e) {
+        pm::set_last_error(e.what());
+        return PM_ERR_STATE;
+    } catch (...) {
+        pm::set_last_error("unknown exception");
+        return PM_ERR_STATE;
+    }
 }
 
 }  // namespace
@@ -388,17 +419,20 @@ int pm_polymath_verify_transcript(const uint8_t vk[392], const uint8_t* public_i
     if (!vk || !proof || !accepted || (num_public && !public_inputs)) { pm::set_last_error("null argument"); return PM_ERR_ARG; }
     if (transcript < kTranscriptMerlin || transcript > kTranscriptBlake3) { pm::set_last_error("unknown transcript"); return PM_ERR_ARG; }
     *accepted = 0;
-    VkH k;
-    ProofH pr;
-    if (!parse_vk(vk, k)) { pm::set_last_error("verifying key does not deserialise (ark-serialize SerializationError)"); return PM_ERR_ARG; }
-    if (!parse_proof(proof, pr)) { pm::set_last_error("proof does not deserialise (ark-serialize SerializationError)"); return PM_ERR_ARG; }
-    std::vector<FrH> pub = public_with_one(public_inputs, num_public);
-    Challenges ch = derive_challenges(k, pub, pr, transcript);
-    G1H lhs = commitments_minus_evals(k, pr, ch);
-    G2H x_minus_x1 = aff_add(k.x_g2, jac_to_affine(scalar_mul(k.one_g2, ch.x1.neg())));   // verifier.rs:48
-    PairingTerm terms[2] = {{lhs, k.z_g2}, {pr.d.neg(), x_minus_x1}};                      // verifier.rs:50-59
-    *accepted = pairing_product_is_one(terms, 2) ? 1 : 0;
-    return PM_OK;
+    return host_guarded([&]() -> int {
+        VkH k;
+        ProofH pr;
+        if (!parse_vk(vk, k)) { pm::set_last_error("verifying key does not deserialise (ark-serialize SerializationError)"); return PM_ERR_ARG; }
+        if (!parse_proof(proof, pr)) { pm::set_last_error("proof does not deserialise (ark-serialize SerializationError)"); return PM_ERR_ARG; }
+        std::vector<FrH> pub;
+        if (!public_with_one(public_inputs, num_public, pub)) { pm::set_last_error("public input is not a reduced field element"); return PM_ERR_ARG; }
+        Challenges ch = derive_challenges(k, pub, pr, transcript);
+        G1H lhs = commitments_minus_evals(k, pr, ch);
+        G2H x_minus_x1 = aff_add(k.x_g2, jac_to_affine(scalar_mul(k.one_g2, ch.x1.neg())));   // verifier.rs:48
+        PairingTerm terms[2] = {{lhs, k.z_g2}, {pr.d.neg(), x_minus_x1}};                      // verifier.rs:50-59
+        *accepted = pairing_product_is_one(terms, 2) ? 1 : 0;
+        return PM_OK;
+    });
 }
 
 int pm_polymath_verify_batch(const uint8_t vk[392], size_t count, const uint8_t* public_inputs, size_t num_public,
@@ -408,31 +442,50 @@ int pm_polymath_verify_batch(const uint8_t vk[392], size_t count, const uint8_t*
         return PM_ERR_ARG;
     }
     *accepted = 0;
-    VkH k;
-    if (!parse_vk(vk, k)) { pm::set_last_error("verifying key does not deserialise"); return PM_ERR_ARG; }
-    // sum_i r_i * (check_i): e(sum r_i L_i, [z]_2) * e(-sum r_i d_i, [x]_2) * e(sum r_i x1_i d_i, [1]_2) == 1,
-    // r_0 = 1 and r_i = 128-bit values drawn from StdRng(seed): three pairings for any number of proofs
-    StdRng rng(seed);
-    JacH<FqH> sum_l = JacH<FqH>::infinity(), sum_d = JacH<FqH>::infinity(), sum_dx = JacH<FqH>::infinity();
-    for (size_t i = 0; i < count; i++) {
-        ProofH pr;
-        if (!parse_proof(proofs + 176 * i, pr)) { pm::set_last_error("proof " + std::to_string(i) + " does not deserialise"); return PM_ERR_ARG; }
-        std::vector<FrH> pub = public_with_one(public_inputs ? public_inputs + 32 * num_public * i : nullptr, num_public);
-        Challenges ch = derive_challenges(k, pub, pr);
-        FrH r = FrH::one();
-        if (i) {
-            FrH c = FrH::zero();
-            c.v[0] = rng.next_u64();
-            c.v[1] = rng.next_u64();
-            r = c.to_mont();
+    return host_guarded([&]() -> int {
+        VkH k;
+        if (!parse_vk(vk, k)) { pm::set_last_error("verifying key does not deserialise"); return PM_ERR_ARG; }
+        if (count == 0) { *accepted = 1; return PM_OK; }      // the empty conjunction; no seed needed
+        // sum_i r_i * (check_i): e(sum r_i L_i, [z]_2) * e(-sum r_i d_i, [x]_2) * e(sum r_i x1_i d_i, [1]_2) == 1: three
+        // pairings for any number of proofs.  r_0 = 1 and r_i = 128-bit values from StdRng keyed by
+        // BLAKE3(seed | vk | proofs | public inputs): the coefficients are bound to the statements, so a party
+        // that knows (or fixes) the caller's seed still cannot choose proofs against known coefficients.
+        uint8_t key[32];
+        {
+            std::vector<uint8_t> bind;
+            bind.reserve(32 + 392 + count * (176 + 32 * num_public));
+            bind.insert(bind.end(), seed, seed + 32);
+            bind.insert(bind.end(), vk, vk + 392);
+            bind.insert(bind.end(), proofs, proofs + 176 * count);
+            if (num_public) bind.insert(bind.end(), public_inputs, public_inputs + 32 * num_public * count);
+            blake3_hash(bind.data(), bind.size(), key);
         }
-        jac_add_affine(sum_l, jac_to_affine(scalar_mul(commitments_minus_evals(k, pr, ch), r)));
-        jac_add_affine(sum_d, jac_to_affine(scalar_mul(pr.d, r)));
-        jac_add_affine(sum_dx, jac_to_affine(scalar_mul(pr.d, r * ch.x1)));
-    }
-    PairingTerm terms[3] = {{jac_to_affine(sum_l), k.z_g2}, {jac_to_affine(sum_d).neg(), k.x_g2}, {jac_to_affine(sum_dx), k.one_g2}};
-    *accepted = pairing_product_is_one(terms, 3) ? 1 : 0;
-    return PM_OK;
+        StdRng rng(key);
+        JacH<FqH> sum_l = JacH<FqH>::infinity(), sum_d = JacH<FqH>::infinity(), sum_dx = JacH<FqH>::infinity();
+        for (size_t i = 0; i < count; i++) {
+            ProofH pr;
+            if (!parse_proof(proofs + 176 * i, pr)) { pm::set_last_error("proof " + std::to_string(i) + " does not deserialise"); return PM_ERR_ARG; }
+            std::vector<FrH> pub;
+            if (!public_with_one(public_inputs ? public_inputs + 32 * num_public * i : nullptr, num_public, pub)) {
+                pm::set_last_error("public input of proof " + std::to_string(i) + " is not a reduced field element");
+                return PM_ERR_ARG;
+            }
+            Challenges ch = derive_challenges(k, pub, pr);
+            FrH r = FrH::one();
+            if (i) {
+                FrH c = FrH::zero();
+                c.v[0] = rng.next_u64();
+                c.v[1] = rng.next_u64();
+                r = c.to_mont();
+            }
+            jac_add_affine(sum_l, jac_to_affine(scalar_mul(commitments_minus_evals(k, pr, ch), r)));
+            jac_add_affine(sum_d, jac_to_affine(scalar_mul(pr.d, r)));
+            jac_add_affine(sum_dx, jac_to_affine(scalar_mul(pr.d, r * ch.x1)));
+        }
+        PairingTerm terms[3] = {{jac_to_affine(sum_l), k.z_g2}, {jac_to_affine(sum_d).neg(), k.x_g2}, {jac_to_affine(sum_dx), k.one_g2}};
+        *accepted = pairing_product_is_one(terms, 3) ? 1 : 0;
+        return PM_OK;
+    });
 }
 
 int pm_host_pairing_product_is_one(const uint8_t* g1_points, const uint8_t* g2_points, int count, int* is_one) {

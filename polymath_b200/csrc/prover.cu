@@ -161,11 +161,18 @@ static int fewer_levels(int c, int levels) {
 // costs far more than a few extra bucket sets: shrink the tables until tables + workspaces fit the free memory.
 // The c-side and [d]_1 MSMs share one engine (max of their workspaces), the a-side MSM runs beside the c-side on its own.
 void ProverCtx::plan_tables() {
-    const uint64_t cnt_c = local_count(len_c()), cnt_d = local_count(len_d()), cnt_a = local_count(n + 4);
+    // Every rank of a sharded proof must arrive at the SAME plan: the per-window sums are all-gathered raw and decoded
+    // with the local Shape (phase{1,3}_collective).  So the plan is derived from rank-independent inputs only — the
+    // largest shard ceil(total / world) (the table stride: ranks with one point less leave the last slot unused), and
+    // the free memory quantised down to 4 GiB steps; attach_nccl() then compares the plans of all ranks and refuses
+    // to continue on a mismatch (e.g. another process occupying one of the GPUs) instead of hanging in the collective.
+    auto shard = [&](uint64_t total) { return (total + (uint64_t)world - 1) / (uint64_t)world; };
+    const uint64_t cnt_c = shard(len_c()), cnt_d = shard(len_d()), cnt_a = shard(n + 4);
     plan_c = plan_for(cnt_c, "PM_MSM_PRECOMP_C", true);     // tuning hooks: window bits per array
     plan_d = plan_for(cnt_d, "PM_MSM_PRECOMP_D", false);
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) free_b = 0;
+    if (world > 1) free_b &= ~(((size_t)1 << 32) - 1);
     const double budget = 0.85 * (double)free_b;
     auto table = [](uint64_t count, int levels) { return (double)count * levels * sizeof(G1Affine); };
     auto work = [](uint64_t count, int levels) { return (double)count * levels * 100.0 + 1.5e9; };
@@ -193,6 +200,7 @@ void ProverCtx::build_tables() {
     Runtime& rt = runtime();
     launch_build_levels(bases_c.get<G1Affine>(), local_count(len_c()), plan_c.levels, plan_c.stride, plan_c.c, rt.stream);
     launch_build_levels(bases_d.get<G1Affine>(), local_count(len_d()), plan_d.levels, plan_d.stride, plan_d.c, rt.stream);
+    // (the stride is the largest shard; local_count() <= stride on every rank)
 }
 
 void ProverCtx::allocate_work() {
@@ -395,6 +403,30 @@ void ProverCtx::attach_nccl(const char* libnccl_path, const uint8_t id[128]) {
     api.check(api.CommInitRank(&comm, world, uid, rank), "ncclCommInitRank");
     nccl_comm = comm;
     if (const char* v = getenv("PM_SHARDED_NTT_MIN_LOG")) sharded_ntt_min_log = atoi(v);   // tuning / test hook
+    // All ranks must decode each other's raw per-window sums with one Shape: compare the table plans now, where a
+    // mismatch is an error message, not a hang or a silently wrong proof inside phase{1,3}_collective.
+    {
+        Runtime& rt = runtime();
+        const uint64_t mine[8] = {(uint64_t)plan_c.c, (uint64_t)plan_c.levels, (uint64_t)plan_d.c, (uint64_t)plan_d.levels,
+                                  n, (uint64_t)world, cols, (uint64_t)sharded_ntt_min_log};
+        uint64_t* dev = reinterpret_cast<uint64_t*>(gathered.as<uint8_t>((size_t)(world + 1) * sizeof mine + 256));
+        std::vector<uint64_t> all((size_t)world * 8);
+        PM_CUDA(cudaMemcpyAsync(dev + (size_t)world * 8, mine, sizeof mine, cudaMemcpyHostToDevice, rt.stream));
+        api.check(api.AllGather(dev + (size_t)world * 8, dev, sizeof mine, NcclApi::kUint8, nccl_comm, rt.stream), "ncclAllGather");
+        PM_CUDA(cudaMemcpyAsync(all.data(), dev, all.size() * sizeof(uint64_t), cudaMemcpyDeviceToHost, rt.stream));
+        PM_CUDA(cudaStreamSynchronize(rt.stream));
+        for (int r = 0; r < world; r++)
+            if (memcmp(all.data() + (size_t)r * 8, mine, sizeof mine) != 0) {
+                char msg[256];
+                snprintf(msg, sizeof msg,
+                         "rank %d planned (c-side c=%llu levels=%llu, d c=%llu levels=%llu), rank %d planned (c=%llu levels=%llu, c=%llu "
+                         "levels=%llu): the ranks of a sharded context must see the same free device memory and settings",
+                         rank, (unsigned long long)mine[0], (unsigned long long)mine[1], (unsigned long long)mine[2],
+                         (unsigned long long)mine[3], r, (unsigned long long)all[(size_t)r * 8], (unsigned long long)all[(size_t)r * 8 + 1],
+                         (unsigned long long)all[(size_t)r * 8 + 2], (unsigned long long)all[(size_t)r * 8 + 3]);
+                throw StatusError(PM_ERR_STATE, msg);
+            }
+    }
 }
 
 void ProverCtx::phase1_collective(const uint8_t* ra, uint8_t* a_out, uint8_t* c_out) {
@@ -615,7 +647,7 @@ void upload_points(const ProverCtx& c, G1Affine* dst_base, uint64_t global_off, 
             unsigned long long* bad = dbad.as<unsigned long long>(1);
             PM_CUDA(cudaMemcpyAsync(pi, first, cnt * 48, cudaMemcpyHostToDevice, rt.stream));
             PM_CUDA(cudaMemsetAsync(bad, 0xff, sizeof(unsigned long long), rt.stream));
-            launch_g1_decompress(pi, cnt, false, dst_base + g0 / c.world, bad, rt.stream);
+            launch_g1_decompress(pi, cnt, c.validate_key, dst_base + g0 / c.world, bad, rt.stream);
             rt.extra_launches++;
             unsigned long long hbad = 0;
             PM_CUDA(cudaMemcpyAsync(&hbad, bad, sizeof hbad, cudaMemcpyDeviceToHost, rt.stream));
@@ -658,7 +690,11 @@ extern "C" {
 
 int pm_ctx_create(const pm_pk_view* pk, pm_ctx** out) { return pm_ctx_create_sharded(pk, 0, 1, out); }
 
-int pm_ctx_create_sharded(const pm_pk_view* pk, int rank, int world, pm_ctx** out) {
+static int ctx_create_impl(const pm_pk_view* pk, int rank, int world, bool validate_key, pm_ctx** out);
+int pm_ctx_create_sharded(const pm_pk_view* pk, int rank, int world, pm_ctx** out) { return ctx_create_impl(pk, rank, world, true, out); }
+int pm_ctx_create_unchecked(const pm_pk_view* pk, int rank, int world, pm_ctx** out) { return ctx_create_impl(pk, rank, world, false, out); }
+
+static int ctx_create_impl(const pm_pk_view* pk, int rank, int world, bool validate_key, pm_ctx** out) {
     return guarded([&] {
         if (!pk || !out) throw StatusError(PM_ERR_ARG, "null argument");
         if (pk->point_stride < PM_G1_BYTES && pk->point_stride != PM_G1_COMPRESSED_BYTES)
@@ -669,6 +705,7 @@ int pm_ctx_create_sharded(const pm_pk_view* pk, int rank, int world, pm_ctx** ou
         ProverCtx& c = h->impl;
         c.rank = rank;
         c.world = world;
+        c.validate_key = validate_key;
         init_dims(c, pk->r1cs);
         c.n = pk->n;
         c.sigma = pk->sigma;

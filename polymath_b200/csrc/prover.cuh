@@ -24,6 +24,9 @@ struct ProverCtx {
     // MSM sharding: this process holds the points g = k*world + rank of both base
     // arrays; the polynomial work is replicated.  world == 1: the whole key.
     int rank = 0, world = 1;
+    // compressed key vectors (point_stride 48): subgroup-checked like `deserialize_compressed` unless the caller opts
+    // out (`deserialize_compressed_unchecked`); the on-curve and encoding checks always run
+    bool validate_key = true;
     uint64_t local_count(uint64_t total) const { return total > (uint64_t)rank ? (total - rank + world - 1) / world : 0; }
     // Fixed-base tables for the big MSMs: each base array is [levels][stride] with level l = 2^(c*l) * P
     // (msm.cuh MsmConfig); levels == 1 means no precomputation.  Chosen from the size and free memory.

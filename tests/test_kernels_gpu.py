@@ -94,8 +94,13 @@ def test_g1_compression_roundtrip_and_rejects(pmlib):
     assert kernels.g1_compress_batch(pts) == enc
     assert kernels.g1_decompress_batch(enc) == pts
     assert kernels.g1_decompress_batch(enc[:48 * 20], validate=True) == pts[:20]
-    # infinity flag wins over the remaining bits (ark-bls12-381 returns zero right away)
-    assert kernels.g1_decompress_batch(bytes([0xC0]) + b"\x01" * 47) == [None]
+    # an infinity flag on a non-zero payload / with the sort flag is refused, as by the host codec and the oracle
+    for bad_inf in (bytes([0xC0]) + b"\x01" * 47, bytes([0xE0]) + bytes(47), bytes([0xC1]) + bytes(47)):
+        with pytest.raises(PolymathB200Error) as ei:
+            kernels.g1_decompress_batch(enc[:48] + bad_inf)
+        assert "infinity flag" in str(ei.value) and "index 1" in str(ei.value)
+        with pytest.raises(ValueError):
+            curve.g1_decompress(bad_inf)
     # a curve point outside the prime-order subgroup
     x = 1
     while True:

@@ -127,6 +127,15 @@ def test_unsatisfied_witness_is_rejected(pmlib):
     # and the context is still usable afterwards
     proof = Polymath.prove(pk, [1, 6], [2, 3], StdRng.seed_from_u64(4))
     assert len(proof) == 176
+    # the reference panics (prover.rs:107-108) BEFORE it draws r_a (prover.rs:110): after a refused witness the
+    # caller's generator must stand where it stood
+    rng, fresh = StdRng.seed_from_u64(4), StdRng.seed_from_u64(4)
+    with pytest.raises(PolymathB200Error):
+        Polymath.prove(pk, [1, 7], [2, 3], rng)
+    assert rng.next_u64() == fresh.next_u64()
+    # values outside [0, r) are refused, not reduced
+    with pytest.raises(ValueError):
+        Polymath.prove(pk, [1, 6 + R_MOD], [2, 3], StdRng.seed_from_u64(4))
     pk.close()
 
 

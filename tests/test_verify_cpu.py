@@ -128,6 +128,52 @@ def test_verify_matches_oracle_verifier_on_fresh_proofs():
     assert Polymath.verify_batch(vk_bytes, [], [], seed) is True
 
 
+def test_public_inputs_are_never_reduced():
+    """x and x + r must not alias.  The Python binding refuses values outside [0, r); the C ABI refuses raw
+    limb vectors >= r (PM_ERR_ARG) instead of running unreduced arithmetic on them."""
+    import ctypes as C
+    from polymath_b200.api import _bind
+    from polymath_b200.lib import load
+    vk_bytes, pub, proof = _golden("mimc8_seed7.json")
+    assert Polymath.verify(vk_bytes, pub, proof) is True
+    with pytest.raises(ValueError):
+        Polymath.verify(vk_bytes, [pub[0] + R_MOD], proof)
+    with pytest.raises(ValueError):
+        Polymath.verify(vk_bytes, [-1], proof)
+    with pytest.raises(ValueError):
+        Polymath.verify_batch(vk_bytes, [[pub[0] + R_MOD]], [proof], bytes(32))
+    lib = load()
+    _bind(lib)
+    ok = C.c_int(7)
+    # Montgomery limbs of the valid input plus r: still < 2^256 for most values, never < r
+    from polymath_b200 import codec
+    limbs = int.from_bytes(codec.fr_to_wire(pub[0]), "little") + R_MOD
+    if limbs < 1 << 256:
+        rc = lib.pm_polymath_verify(vk_bytes, limbs.to_bytes(32, "little"), 1, proof, C.byref(ok))
+        assert rc == 2 and ok.value == 0
+    rc = lib.pm_polymath_verify(vk_bytes, b"\xff" * 32, 1, proof, C.byref(ok))
+    assert rc == 2 and ok.value == 0
+    rc = lib.pm_polymath_verify_batch(vk_bytes, 1, b"\xff" * 32, 1, proof, bytes(32), C.byref(ok))
+    assert rc == 2 and ok.value == 0
+
+
+def test_verify_batch_empty_needs_no_seed():
+    """count == 0 accepts without touching the seed (NULL allowed); coefficients are bound to the statements, so the
+    verdict does not depend on the seed value."""
+    import ctypes as C
+    from polymath_b200.api import _bind
+    from polymath_b200.lib import load
+    vk_bytes, pub, proof = _golden("mimc8_seed7.json")
+    lib = load()
+    _bind(lib)
+    ok = C.c_int(0)
+    assert lib.pm_polymath_verify_batch(vk_bytes, 0, None, 1, None, None, C.byref(ok)) == 0 and ok.value == 1
+    for seed in (bytes(32), bytes(range(32)), b"\xaa" * 32):
+        assert Polymath.verify_batch(vk_bytes, [pub, pub], [proof, proof], seed) is True
+        bad = proof[:96] + bytes(32) + proof[128:]
+        assert Polymath.verify_batch(vk_bytes, [pub, pub], [proof, bad], seed) is False
+
+
 def test_verify_edge_encodings():
     """Infinity commitments, a zero evaluation, a proof from another statement: decoded like ark-serialize, rejected
     without a crash or a false accept."""
