@@ -26,38 +26,6 @@ struct alignas(16) G1XYZZ {
     }
 };
 
-// acc = 2 * p (p affine, not infinity)   EFD mdbl-2008-s-1
-static __device__ __noinline__ G1XYZZ xyzz_dbl_affine(const G1Affine& p) {
-    G1XYZZ r;
-    Fq u = p.y.dbl();
-    Fq v = u.sqr();
-    Fq w = u * v;
-    Fq s = p.x * v;
-    Fq xx = p.x.sqr();
-    Fq m = xx.dbl() + xx;
-    r.x = m.sqr() - s.dbl();
-    r.y = m * (s - r.x) - w * p.y;
-    r.zz = v;
-    r.zzz = w;
-    return r;
-}
-
-// acc = 2 * acc   EFD dbl-2008-s-1 (a = 0)
-static __device__ __noinline__ void xyzz_dbl(G1XYZZ& a) {
-    if (a.is_inf()) return;
-    Fq u = a.y.dbl();
-    Fq v = u.sqr();
-    Fq w = u * v;
-    Fq s = a.x * v;
-    Fq xx = a.x.sqr();
-    Fq m = xx.dbl() + xx;
-    Fq x3 = m.sqr() - s.dbl();
-    a.y = m * (s - x3) - w * a.y;
-    a.x = x3;
-    a.zz = v * a.zz;
-    a.zzz = w * a.zzz;
-}
-
 // Multiplication policies for the hot loop: fully inlined products, or one shared out-of-line copy
 // of the Fq product (keeps the loop body inside the instruction caches).
 struct MulInline {
@@ -67,6 +35,43 @@ static __device__ __noinline__ Fq fq_mul_call(Fq a, Fq b) { return a * b; }
 struct MulCall {
     static __device__ __forceinline__ Fq mul(const Fq& a, const Fq& b) { return fq_mul_call(a, b); }
 };
+
+// The general-purpose group operations below (full addition, doubling) go through the ONE out-of-line product too:
+// with every product inlined a single xyzz_add is ~100 KB of SASS, and the latency-bound kernels that call it from a
+// few warps per SM (bucket reduction, slice sums) stalled on instruction fetch rather than on the multiplier.
+
+// acc = 2 * p (p affine, not infinity)   EFD mdbl-2008-s-1
+static __device__ __noinline__ G1XYZZ xyzz_dbl_affine(const G1Affine& p) {
+    G1XYZZ r;
+    Fq u = p.y.dbl();
+    Fq v = fq_mul_call(u, u);
+    Fq w = fq_mul_call(u, v);
+    Fq s = fq_mul_call(p.x, v);
+    Fq xx = fq_mul_call(p.x, p.x);
+    Fq m = xx.dbl() + xx;
+    r.x = fq_mul_call(m, m) - s.dbl();
+    r.y = fq_mul_call(m, s - r.x) - fq_mul_call(w, p.y);
+    r.zz = v;
+    r.zzz = w;
+    return r;
+}
+
+// acc = 2 * acc   EFD dbl-2008-s-1 (a = 0)
+static __device__ __noinline__ void xyzz_dbl(G1XYZZ& a) {
+    if (a.is_inf()) return;
+    Fq u = a.y.dbl();
+    Fq v = fq_mul_call(u, u);
+    Fq w = fq_mul_call(u, v);
+    Fq s = fq_mul_call(a.x, v);
+    Fq xx = fq_mul_call(a.x, a.x);
+    Fq m = xx.dbl() + xx;
+    Fq x3 = fq_mul_call(m, m) - s.dbl();
+    a.y = fq_mul_call(m, s - x3) - fq_mul_call(w, a.y);
+    a.x = x3;
+    a.zz = fq_mul_call(v, a.zz);
+    a.zzz = fq_mul_call(w, a.zzz);
+}
+
 
 // acc += p (p affine; `neg` adds -p)   EFD madd-2008-s, products through policy M
 template <class M>
@@ -135,10 +140,10 @@ __device__ __forceinline__ void xyzz_madd(G1XYZZ& a, const G1Affine& p_in, bool 
 static __device__ __noinline__ void xyzz_add(G1XYZZ& a, const G1XYZZ& b) {
     if (b.is_inf()) return;
     if (a.is_inf()) { a = b; return; }
-    Fq u1 = a.x * b.zz;
-    Fq u2 = b.x * a.zz;
-    Fq s1 = a.y * b.zzz;
-    Fq s2 = b.y * a.zzz;
+    Fq u1 = fq_mul_call(a.x, b.zz);
+    Fq u2 = fq_mul_call(b.x, a.zz);
+    Fq s1 = fq_mul_call(a.y, b.zzz);
+    Fq s2 = fq_mul_call(b.y, a.zzz);
     Fq p = u2 - u1;
     Fq r = s2 - s1;
     if (p.is_zero()) {
@@ -146,23 +151,23 @@ static __device__ __noinline__ void xyzz_add(G1XYZZ& a, const G1XYZZ& b) {
         else a = G1XYZZ::inf();
         return;
     }
-    Fq pp = p.sqr();
-    Fq ppp = p * pp;
-    Fq q = u1 * pp;
-    Fq x3 = r.sqr() - ppp - q.dbl();
-    a.y = r * (q - x3) - s1 * ppp;
+    Fq pp = fq_mul_call(p, p);
+    Fq ppp = fq_mul_call(p, pp);
+    Fq q = fq_mul_call(u1, pp);
+    Fq x3 = fq_mul_call(r, r) - ppp - q.dbl();
+    a.y = fq_mul_call(r, q - x3) - fq_mul_call(s1, ppp);
     a.x = x3;
-    a.zz = a.zz * b.zz * pp;
-    a.zzz = a.zzz * b.zzz * ppp;
+    a.zz = fq_mul_call(fq_mul_call(a.zz, b.zz), pp);
+    a.zzz = fq_mul_call(fq_mul_call(a.zzz, b.zzz), ppp);
 }
 
 // canonical affine image: x = X/ZZ, y = Y/ZZZ with 1/ZZ = (ZZ/ZZZ)^2
 static __device__ __noinline__ G1Affine xyzz_to_affine(const G1XYZZ& a) {
     if (a.is_inf()) return G1Affine::inf();
     Fq izzz = a.zzz.inv();
-    Fq t = a.zz * izzz;
-    Fq izz = t.sqr();
-    return {a.x * izz, a.y * izzz};
+    Fq t = fq_mul_call(a.zz, izzz);
+    Fq izz = fq_mul_call(t, t);
+    return {fq_mul_call(a.x, izz), fq_mul_call(a.y, izzz)};
 }
 
 // acc = k * acc for a small unsigned k (double-and-add, MSB first)

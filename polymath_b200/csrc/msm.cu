@@ -192,8 +192,10 @@ __device__ __forceinline__ void defer_heavy(const HeavyLists& hl, uint32_t t, ui
 // Per slot pair: 1 + 5 Fq products (+ 3/kPairsPerThread for the second level), against 10 for an XYZZ
 // mixed addition.  Exceptional pairs (an operand at infinity — all padding —, P + P, P + (-P)) are classified
 // identically in both passes (pair_kind) and contribute no denominator, or 2y for a doubling.
-constexpr int kPairsPerThread = 32;
-constexpr uint32_t kPairTile = 128 * kPairsPerThread;   // slot pairs per CTA
+// Slot pairs per thread: chosen per round on the host (16..128, a power of two) so that the round still launches a few
+// waves of CTAs while the number of thread totals — the input of the latency-bound inversion tree — stays small.
+constexpr int kMinPairsPerThread = 16, kMaxPairsPerThread = 128;
+__host__ __device__ constexpr uint32_t pair_tile(int ppt) { return 128u * (uint32_t)ppt; }   // slot pairs per CTA
 constexpr uint32_t kPadEntry = 0xffffffffu;             // sorted-list sentinel: the point at infinity
 
 struct FqPlanes {      // n field elements as three planes of 16-byte chunks
@@ -262,10 +264,14 @@ struct PairSource {
     const G1Affine* table;
     const uint32_t* sorted;
     PointPlanes in;
+    // the two (index | sign) entries of slot pair p (FIRST only; later rounds have none)
+    __device__ __forceinline__ uint2 load_e(size_t p) const {
+        if (FIRST) return __ldg(reinterpret_cast<const uint2*>(sorted + 2 * p));
+        return make_uint2(0u, 0u);
+    }
     // x coordinates only; returns false when an operand is padding (FIRST only)
-    __device__ __forceinline__ bool load_x(size_t p, uint2& e, Fq& x1, Fq& x2) const {
+    __device__ __forceinline__ bool gather_x(size_t p, const uint2& e, Fq& x1, Fq& x2) const {
         if (FIRST) {
-            e = *reinterpret_cast<const uint2*>(sorted + 2 * p);
             if (e.x == kPadEntry || e.y == kPadEntry) return false;
             x1 = load_fq(&table[e.x & 0x7fffffffu].x);
             x2 = load_fq(&table[e.y & 0x7fffffffu].x);
@@ -309,19 +315,35 @@ struct PairSource {
 // slot pairs of round r: (S_0 >> r) / 2 with S_0 = *slots0
 __device__ __forceinline__ size_t round_pairs(const uint32_t* __restrict__ slots0, int r) { return (size_t)(*slots0 >> r) >> 1; }
 
+// Software-pipelined: the (index | sign) entries are fetched two pairs ahead and the x coordinates one pair ahead of
+// the product chain, so the two dependent memory latencies of the first round (entry -> table gather, random 96-byte
+// records of a multi-GB table) overlap the multiplication of the previous pair instead of serialising with it.
 template <bool FIRST>
-__global__ void __launch_bounds__(128) k_pairs_forward(PairSource<FIRST> src, const uint32_t* __restrict__ slots0, int r,
+__global__ void __launch_bounds__(128) k_pairs_forward(PairSource<FIRST> src, const uint32_t* __restrict__ slots0, int r, int ppt,
                                                        FqPlanes prefix, Fq* __restrict__ T) {
     const size_t npairs = round_pairs(slots0, r);
-    const size_t base = (size_t)blockIdx.x * kPairTile;
+    const size_t base = (size_t)blockIdx.x * pair_tile(ppt);
     if (base >= npairs) return;
+    const size_t p0 = base + threadIdx.x;
+    auto pair_at = [&](int i) { return p0 + (size_t)i * 128; };
+    auto live = [&](int i) { return i < ppt && pair_at(i) < npairs; };
     Fq acc = Fq::one();
-    for (int i = 0; i < kPairsPerThread; i++) {
-        const size_t p = base + (size_t)i * 128 + threadIdx.x;
+    uint2 e_cur = make_uint2(0u, 0u), e_nxt = make_uint2(0u, 0u);
+    Fq x1, x2;
+    bool has = false;
+    if (live(0)) e_cur = src.load_e(pair_at(0));
+    if (live(1)) e_nxt = src.load_e(pair_at(1));
+    if (live(0)) has = src.gather_x(pair_at(0), e_cur, x1, x2);
+    for (int i = 0; i < ppt; i++) {
+        const size_t p = pair_at(i);
         if (p >= npairs) break;
-        uint2 e = make_uint2(0u, 0u);
-        Fq x1, x2, d;
-        bool has = src.load_x(p, e, x1, x2);
+        // issue the loads of the following pairs before touching the multiplier
+        uint2 e_nn = make_uint2(0u, 0u);
+        if (live(i + 2)) e_nn = src.load_e(pair_at(i + 2));
+        Fq nx1, nx2;
+        bool nhas = false;
+        if (live(i + 1)) nhas = src.gather_x(pair_at(i + 1), e_nxt, nx1, nx2);
+        Fq d;
         if (has) {
             d = x2 - x1;
             if (d.is_zero() || x1.is_zero() || x2.is_zero()) {
@@ -329,7 +351,7 @@ __global__ void __launch_bounds__(128) k_pairs_forward(PairSource<FIRST> src, co
                 G1Affine a, b;
                 a.x = x1;
                 b.x = x2;
-                src.load_y(p, e, a.y, b.y);
+                src.load_y(p, e_cur, a.y, b.y);
                 const int kind = pair_kind(a, b);
                 if (kind == kPairDouble) d = a.y.dbl();
                 else if (kind != kPairAdd) has = false;
@@ -337,64 +359,185 @@ __global__ void __launch_bounds__(128) k_pairs_forward(PairSource<FIRST> src, co
         }
         prefix.store(p, acc);
         if (has) acc = fq_mul_call(acc, d);
+        e_cur = e_nxt;
+        e_nxt = e_nn;
+        x1 = nx1;
+        x2 = nx2;
+        has = nhas;
     }
     store_fq(T + (size_t)blockIdx.x * 128 + threadIdx.x, acc);
 }
 
-// ---- inversion of the thread totals T of round r (all non-zero), Montgomery's trick over a small tree ----
-// Level sizes: n_0 = thread totals of k_pairs_forward, n_{l+1} = ceil(n_l / kInvFan).  k_invert_up multiplies
-// kInvFan strided elements of level l into one element of level l+1 (exclusive prefixes kept), k_invert_top
-// takes the Fermat inverse of the few top elements, k_invert_down walks back.  3 products per element and
-// level; the serial Fermat chains (~570 products) run in a few thousand threads only.
-constexpr uint32_t kInvFan = 32;
-constexpr int kInvLevels = 2;
-__device__ __forceinline__ size_t invert_level_size(const uint32_t* __restrict__ slots0, int r, int level) {
-    size_t n = (round_pairs(slots0, r) + kPairTile - 1) / kPairTile * 128;
-    for (int l = 0; l < level; l++) n = (n + kInvFan - 1) / kInvFan;
+// ---- inversion of the thread totals T of round r (all non-zero), Montgomery's trick over block trees ----
+// Level sizes: n_0 = thread totals of k_pairs_forward, n_{l+1} = ceil(n_l / kInvTile).  One CTA owns a tile of
+// kInvTile = 512 threads x 4 elements, held in REGISTERS (loaded up front, so no serial chain of dependent global
+// loads), and multiplies it down to one product through an 8 x 8 x 8 tree in shared memory (exclusive prefixes
+// kept per tree level):  k_inv_up writes the tile products of level l as level l+1,  k_inv_top (one CTA, the last
+// level: <= kInvTile elements) inverts its tile product with ONE binary extended-Euclid inverse and walks its tree
+// back down,  k_inv_down does the same for the tiles of a lower level with the inverse of its tile product taken
+// from the level above.  Serial depth per kernel ~30 / ~85 Fq products instead of five latency-bound kernels of
+// 32-element global-memory chains (420 us per round under ncu, profiles/launches_r1_h_bench_2p20.csv).
+constexpr int kInvThreads = 512;
+constexpr int kInvPer = 4;
+constexpr uint32_t kInvTile = kInvThreads * kInvPer;
+constexpr int kInvMaxLevels = 4;      // 2048^3 tiles of 128 thread totals: far beyond 2^32 slots
+__device__ __forceinline__ size_t invert_level_size(const uint32_t* __restrict__ slots0, int r, int ppt, int level) {
+    size_t n = (round_pairs(slots0, r) + pair_tile(ppt) - 1) / pair_tile(ppt) * 128;
+    for (int l = 0; l < level; l++) n = (n + kInvTile - 1) / kInvTile;
     return n;
 }
-__global__ void __launch_bounds__(128) k_invert_up(const Fq* __restrict__ lo, Fq* __restrict__ pre, Fq* __restrict__ hi,
-                                                   const uint32_t* __restrict__ slots0, int r, int level) {
-    const size_t n = invert_level_size(slots0, r, level), m = (n + kInvFan - 1) / kInvFan;
-    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= m) return;
-    Fq acc = Fq::one();
-    for (size_t idx = j; idx < n; idx += m) {
-        store_fq(pre + idx, acc);
-        acc = fq_mul_call(acc, load_fq(lo + idx));
+
+struct InvTree {             // shared memory of one tile: values and exclusive prefixes of the three tree levels
+    Fq v0[kInvThreads], p0[kInvThreads];   // thread products, prefix inside groups of 8
+    Fq v1[64], p1[64];                     // group products, prefix inside groups of 8
+    Fq v2[8], p2[8];                       // 8 top products, prefix
+};
+
+// tile product -> returned in thread 0 (other threads: undefined)
+__device__ __forceinline__ Fq inv_tree_up(InvTree& t, const Fq& mine) {
+    const int tid = threadIdx.x;
+    t.v0[tid] = mine;
+    __syncthreads();
+    if (tid < 64) {
+        Fq acc = Fq::one();
+#pragma unroll 1
+        for (int k = 0; k < 8; k++) {
+            t.p0[tid * 8 + k] = acc;
+            acc = fq_mul_call(acc, t.v0[tid * 8 + k]);
+        }
+        t.v1[tid] = acc;
     }
-    store_fq(hi + j, acc);
+    __syncthreads();
+    if (tid < 8) {
+        Fq acc = Fq::one();
+#pragma unroll 1
+        for (int k = 0; k < 8; k++) {
+            t.p1[tid * 8 + k] = acc;
+            acc = fq_mul_call(acc, t.v1[tid * 8 + k]);
+        }
+        t.v2[tid] = acc;
+    }
+    __syncthreads();
+    Fq total = Fq::one();
+    if (tid == 0) {
+#pragma unroll 1
+        for (int k = 0; k < 8; k++) {
+            t.p2[k] = total;
+            total = fq_mul_call(total, t.v2[k]);
+        }
+    }
+    return total;
 }
-__global__ void __launch_bounds__(128) k_invert_top(Fq* __restrict__ top, const uint32_t* __restrict__ slots0, int r, int level) {
-    const size_t n = invert_level_size(slots0, r, level);
-    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
-    store_fq(top + j, load_fq(top + j).inv());
+// thread 0 passes the inverse of the tile product; every thread gets the inverse of the value it gave to inv_tree_up
+__device__ __forceinline__ Fq inv_tree_down(InvTree& t, Fq inv_total) {
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+#pragma unroll 1
+        for (int k = 8; k-- > 0;) {
+            Fq val = t.v2[k];
+            t.v2[k] = fq_mul_call(inv_total, t.p2[k]);
+            inv_total = fq_mul_call(inv_total, val);
+        }
+    }
+    __syncthreads();
+    if (tid < 8) {
+        Fq inv = t.v2[tid];
+#pragma unroll 1
+        for (int k = 8; k-- > 0;) {
+            Fq val = t.v1[tid * 8 + k];
+            t.v1[tid * 8 + k] = fq_mul_call(inv, t.p1[tid * 8 + k]);
+            inv = fq_mul_call(inv, val);
+        }
+    }
+    __syncthreads();
+    if (tid < 64) {
+        Fq inv = t.v1[tid];
+#pragma unroll 1
+        for (int k = 8; k-- > 0;) {
+            Fq val = t.v0[tid * 8 + k];
+            t.v0[tid * 8 + k] = fq_mul_call(inv, t.p0[tid * 8 + k]);
+            inv = fq_mul_call(inv, val);
+        }
+    }
+    __syncthreads();
+    return t.v0[tid];
 }
-__global__ void __launch_bounds__(128) k_invert_down(Fq* __restrict__ lo, const Fq* __restrict__ pre, const Fq* __restrict__ hi,
-                                                     const uint32_t* __restrict__ slots0, int r, int level) {
-    const size_t n = invert_level_size(slots0, r, level), m = (n + kInvFan - 1) / kInvFan;
-    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= m) return;
-    Fq inv = load_fq(hi + j);
-    const size_t cnt = (n - j + m - 1) / m;
-    for (size_t k = cnt; k-- > 0;) {
-        const size_t idx = j + k * m;
-        Fq t = load_fq(lo + idx);
-        store_fq(lo + idx, fq_mul_call(inv, load_fq(pre + idx)));
-        inv = fq_mul_call(inv, t);
+
+// the tile's elements of this thread (strided by the CTA: coalesced), ones beyond n
+__device__ __forceinline__ void inv_tile_load(const Fq* __restrict__ lo, size_t n, Fq vals[kInvPer]) {
+    const size_t base = (size_t)blockIdx.x * kInvTile + threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < kInvPer; k++) {
+        const size_t idx = base + (size_t)k * kInvThreads;
+        vals[k] = idx < n ? load_fq(lo + idx) : Fq::one();
+    }
+}
+__device__ __forceinline__ Fq inv_thread_product(const Fq vals[kInvPer]) {
+    Fq acc = vals[0];
+#pragma unroll
+    for (int k = 1; k < kInvPer; k++) acc = fq_mul_call(acc, vals[k]);
+    return acc;
+}
+// inverses of the thread's elements from the inverse of their product, stored in place
+__device__ __forceinline__ void inv_tile_store(Fq* __restrict__ lo, size_t n, const Fq vals[kInvPer], Fq inv) {
+    const size_t base = (size_t)blockIdx.x * kInvTile + threadIdx.x;
+    // exclusive prefixes again (cheaper than keeping them live across the tree)
+    Fq pre[kInvPer];
+    pre[0] = Fq::one();
+#pragma unroll
+    for (int k = 1; k < kInvPer; k++) pre[k] = k == 1 ? vals[0] : fq_mul_call(pre[k - 1], vals[k - 1]);
+#pragma unroll
+    for (int k = kInvPer; k-- > 0;) {
+        const size_t idx = base + (size_t)k * kInvThreads;
+        if (idx < n) store_fq(lo + idx, k == 0 ? inv : fq_mul_call(inv, pre[k]));
+        if (k) inv = fq_mul_call(inv, vals[k]);
     }
 }
 
+__global__ void __launch_bounds__(kInvThreads) k_inv_up(const Fq* __restrict__ lo, Fq* __restrict__ hi,
+                                                        const uint32_t* __restrict__ slots0, int r, int ppt, int level) {
+    extern __shared__ uint4 inv_smem[];
+    InvTree& tree = *reinterpret_cast<InvTree*>(inv_smem);
+    const size_t n = invert_level_size(slots0, r, ppt, level);
+    if ((size_t)blockIdx.x * kInvTile >= n) return;
+    Fq vals[kInvPer];
+    inv_tile_load(lo, n, vals);
+    const Fq total = inv_tree_up(tree, inv_thread_product(vals));
+    if (threadIdx.x == 0) store_fq(hi + blockIdx.x, total);
+}
+__global__ void __launch_bounds__(kInvThreads) k_inv_top(Fq* __restrict__ top, const uint32_t* __restrict__ slots0, int r, int ppt, int level) {
+    extern __shared__ uint4 inv_smem[];
+    InvTree& tree = *reinterpret_cast<InvTree*>(inv_smem);
+    const size_t n = invert_level_size(slots0, r, ppt, level);    // <= kInvTile by construction
+    Fq vals[kInvPer];
+    inv_tile_load(top, n, vals);
+    Fq total = inv_tree_up(tree, inv_thread_product(vals));
+    if (threadIdx.x == 0) total = total.inv();
+    inv_tile_store(top, n, vals, inv_tree_down(tree, total));
+}
+__global__ void __launch_bounds__(kInvThreads) k_inv_down(Fq* __restrict__ lo, const Fq* __restrict__ hi_inv,
+                                                          const uint32_t* __restrict__ slots0, int r, int ppt, int level) {
+    extern __shared__ uint4 inv_smem[];
+    InvTree& tree = *reinterpret_cast<InvTree*>(inv_smem);
+    const size_t n = invert_level_size(slots0, r, ppt, level);
+    if ((size_t)blockIdx.x * kInvTile >= n) return;
+    Fq vals[kInvPer];
+    inv_tile_load(lo, n, vals);
+    inv_tree_up(tree, inv_thread_product(vals));
+    Fq total_inv = Fq::one();
+    if (threadIdx.x == 0) total_inv = load_fq(hi_inv + blockIdx.x);
+    inv_tile_store(lo, n, vals, inv_tree_down(tree, total_inv));
+}
+
 template <bool FIRST>
-__global__ void __launch_bounds__(128, 4) k_pairs_backward(PairSource<FIRST> src, const uint32_t* __restrict__ slots0, int r,
+__global__ void __launch_bounds__(128, 4) k_pairs_backward(PairSource<FIRST> src, const uint32_t* __restrict__ slots0, int r, int ppt,
                                                            FqPlanes prefix, const Fq* __restrict__ Tinv, PointPlanes next) {
     const size_t npairs = round_pairs(slots0, r);
-    const size_t base = (size_t)blockIdx.x * kPairTile;
+    const size_t base = (size_t)blockIdx.x * pair_tile(ppt);
     if (base >= npairs) return;
     // threads of a partial last tile that own no pair hold T = 1
     Fq inv = load_fq(Tinv + (size_t)blockIdx.x * 128 + threadIdx.x);
-    for (int i = kPairsPerThread; i-- > 0;) {
+    for (int i = ppt; i-- > 0;) {
         const size_t p = base + (size_t)i * 128 + threadIdx.x;
         if (p >= npairs) continue;
         G1Affine a, b;
@@ -851,10 +994,16 @@ MsmEngine::Shape MsmEngine::run(const G1Affine* bases, const Fr* scalars, size_t
                 // Cost per bucket in ns, constants measured on B200 (profiles/r1_e_summary.md): a slot pair of the padded
                 // run costs 0.205 (backward) + 0.083 / 0.044 (forward: first round gathers, later rounds stream), an XYZZ
                 // addition of what is left 0.38, and every round a fixed ~0.55 ms (inversion tree, launches)
+                // (round 2: block-tree inversion over 16..128 pairs per thread, fixed cost ~0.35 ms instead of 0.55)
+                static double round_fixed_ns = -1;
+                if (round_fixed_ns < 0) {
+                    const char* v = getenv("PM_MSM_ROUND_FIXED_NS");
+                    round_fixed_ns = v ? atof(v) : 0.35e6;
+                }
                 double best = 1e300;
                 for (int r = 0; r <= 6; r++) {
                     const double a = (double)(1u << r), lp = lambda + (a - 1) / 2, rest = lp / a;
-                    double cost = (r ? 0.365 * 0 : 0) + 0.38 * (rest > 1 ? rest - 1 : 0) + r * 0.55e6 / (double)total;
+                    double cost = 0.38 * (rest > 1 ? rest - 1 : 0) + r * round_fixed_ns / (double)total;
                     for (int k = 0; k < r; k++) cost += lp / (double)(2u << k) * (0.205 + (k ? 0.044 : 0.083));
                     if (r == 0) cost = 0.365 * (lambda > 1 ? lambda - 1 : 0);
                     if (cost < best) { best = cost; rounds = r; }
@@ -989,50 +1138,72 @@ MsmEngine::Shape MsmEngine::run(const G1Affine* bases, const Fr* scalars, size_t
             PointPlanes ping{pairs_a_.as<uint4>(6 * cap_a), cap_a};
             PointPlanes pong{rounds > 1 ? pairs_b_.as<uint4>(6 * cap_b) : nullptr, cap_b};
             FqPlanes prefix{prefix_.as<uint4>(3 * cap_a), cap_a};
-            // thread totals and the levels of the inversion tree above them: [T_0 | T_1 | T_2], prefixes [pre_0 | pre_1]
-            size_t lvl[kInvLevels + 1];
-            lvl[0] = (slots_max / 2 + kPairTile - 1) / kPairTile * 128 + 128;
-            for (int l = 0; l < kInvLevels; l++) lvl[l + 1] = (lvl[l] + kInvFan - 1) / kInvFan + 1;
-            Fq* tlev[kInvLevels + 1];
-            Fq* plev[kInvLevels];
-            tlev[0] = tvals_.as<Fq>(lvl[0] + lvl[1] + lvl[2]);
-            plev[0] = tpre_.as<Fq>(lvl[0] + lvl[1]);
-            for (int l = 0; l < kInvLevels; l++) tlev[l + 1] = tlev[l] + lvl[l];
-            plev[1] = plev[0] + lvl[0];
+            // thread totals and the levels of the inversion tree above them: [T_0 | T_1 | ...], T_{l+1} = tile products of T_l
+            size_t lvl[kInvMaxLevels + 1];
+            int nlevels = 0;             // levels above T_0
+            lvl[0] = (slots_max / 2 + pair_tile(kMinPairsPerThread) - 1) / pair_tile(kMinPairsPerThread) * 128 + 128;
+            size_t lvl_total = lvl[0];
+            while (lvl[nlevels] > kInvTile) {
+                if (nlevels == kInvMaxLevels) throw CudaError("msm: inversion tree too deep");
+                lvl[nlevels + 1] = (lvl[nlevels] + kInvTile - 1) / kInvTile + 1;
+                lvl_total += lvl[++nlevels];
+            }
+            Fq* tlev[kInvMaxLevels + 1];
+            tlev[0] = tvals_.as<Fq>(lvl_total);
+            for (int l = 0; l < nlevels; l++) tlev[l + 1] = tlev[l] + lvl[l];
             Fq* tvals = tlev[0];
             const uint32_t* slots0 = offsets + total;
+            static int forced_ppt = -1;
+            if (forced_ppt < 0) {
+                const char* v = getenv("PM_MSM_PAIRS_PER_THREAD");      // tuning hook
+                forced_ppt = v ? atoi(v) : 0;
+            }
             for (int r = 0; r < rounds; r++) {
                 const size_t pairs_max = (slots_max >> r) >> 1;
-                const unsigned g = ceil_div(pairs_max, kPairTile);
+                // pairs per thread: keep >= ~4 waves of 128-thread CTAs (148 SMs x 4 resident) in the round
+                int ppt = kMinPairsPerThread;
+                while (ppt < kMaxPairsPerThread && pairs_max / (pair_tile(ppt) * 2) >= (size_t)sm_count() * 16) ppt *= 2;
+                if (forced_ppt >= kMinPairsPerThread && forced_ppt <= kMaxPairsPerThread) ppt = forced_ppt;
+                const unsigned g = ceil_div(pairs_max, pair_tile(ppt));
                 if (g == 0) break;
                 PointPlanes dst = (r & 1) ? pong : ping;
-                // level sizes for the grids (upper bounds; the kernels derive the exact ones from slots0)
-                size_t nl[kInvLevels + 1];
+                // level sizes for the grids (upper bounds; the kernels derive the exact ones from slots0).  The tree depth
+                // is fixed by the upper bound of the FIRST round, so a later, smaller round may find its top level with
+                // one element: k_inv_top handles any n <= kInvTile.
+                size_t nl[kInvMaxLevels + 1];
                 nl[0] = (size_t)g * 128;
-                for (int l = 0; l < kInvLevels; l++) nl[l + 1] = (nl[l] + kInvFan - 1) / kInvFan;
+                int top = 0;
+                while (nl[top] > kInvTile) { nl[top + 1] = (nl[top] + kInvTile - 1) / kInvTile; top++; }
+                constexpr int ism = (int)sizeof(InvTree);
+                static bool inv_attr_set = false;
+                if (!inv_attr_set) {
+                    PM_CUDA(cudaFuncSetAttribute(k_inv_up, cudaFuncAttributeMaxDynamicSharedMemorySize, ism));
+                    PM_CUDA(cudaFuncSetAttribute(k_inv_top, cudaFuncAttributeMaxDynamicSharedMemorySize, ism));
+                    PM_CUDA(cudaFuncSetAttribute(k_inv_down, cudaFuncAttributeMaxDynamicSharedMemorySize, ism));
+                    inv_attr_set = true;
+                }
                 auto invert = [&]() {
-                    for (int l = 0; l < kInvLevels; l++)
-                        k_invert_up<<<ceil_div(nl[l + 1], 128), 128, 0, stream>>>(tlev[l], plev[l], tlev[l + 1], slots0, r, l);
-                    k_invert_top<<<ceil_div(nl[kInvLevels], 128), 128, 0, stream>>>(tlev[kInvLevels], slots0, r, kInvLevels);
-                    for (int l = kInvLevels; l-- > 0;)
-                        k_invert_down<<<ceil_div(nl[l + 1], 128), 128, 0, stream>>>(tlev[l], plev[l], tlev[l + 1], slots0, r, l);
+                    for (int l = 0; l < top; l++) k_inv_up<<<(unsigned)nl[l + 1], kInvThreads, ism, stream>>>(tlev[l], tlev[l + 1], slots0, r, ppt, l);
+                    k_inv_top<<<1, kInvThreads, ism, stream>>>(tlev[top], slots0, r, ppt, top);
+                    for (int l = top; l-- > 0;) k_inv_down<<<(unsigned)nl[l + 1], kInvThreads, ism, stream>>>(tlev[l], tlev[l + 1], slots0, r, ppt, l);
+                    launches += 1 + 2 * (size_t)top;
                 };
                 if (r == 0) {
                     PairSource<true> src{bases, sorted, run_pts};
-                    k_pairs_forward<true><<<g, 128, 0, stream>>>(src, slots0, r, prefix, tvals);
+                    k_pairs_forward<true><<<g, 128, 0, stream>>>(src, slots0, r, ppt, prefix, tvals);
                     invert();
                     if (timed) PM_CUDA(cudaEventRecord(ev_bwd_begin, stream));
-                    k_pairs_backward<true><<<g, 128, 0, stream>>>(src, slots0, r, prefix, tvals, dst);
+                    k_pairs_backward<true><<<g, 128, 0, stream>>>(src, slots0, r, ppt, prefix, tvals, dst);
                     if (timed) PM_CUDA(cudaEventRecord(ev_bwd_end, stream));
                 } else {
                     PairSource<false> src{bases, sorted, run_pts};
-                    k_pairs_forward<false><<<g, 128, 0, stream>>>(src, slots0, r, prefix, tvals);
+                    k_pairs_forward<false><<<g, 128, 0, stream>>>(src, slots0, r, ppt, prefix, tvals);
                     invert();
-                    k_pairs_backward<false><<<g, 128, 0, stream>>>(src, slots0, r, prefix, tvals, dst);
+                    k_pairs_backward<false><<<g, 128, 0, stream>>>(src, slots0, r, ppt, prefix, tvals, dst);
                 }
                 PM_LAUNCH_CHECK();
                 run_pts = dst;
-                launches += 3 + 2 * kInvLevels;
+                launches += 2;
             }
         }
         // runs are cut into chunked tasks only when walking them serially would approach the kernel's duration

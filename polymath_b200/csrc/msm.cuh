@@ -62,7 +62,7 @@ private:
     using PlanKey = std::tuple<size_t, int, int, int, int, int>;
     std::map<PlanKey, std::pair<int, int>> plans_;
     DevBuf counts_, offsets_, cursors_, sorted_, buckets_, segs_, heavy_list_, heavy_count_, order_;
-    DevBuf pairs_a_, pairs_b_, prefix_, tvals_, tpre_;   // pair rounds
+    DevBuf pairs_a_, pairs_b_, prefix_, tvals_;   // pair rounds
 };
 
 constexpr int kMaxMsmWindows = 64;

@@ -8,13 +8,19 @@
 //   column pass(es): for every residue of the lower digits, an M-point sub-NTT over a
 //       strided digit, done entirely in shared memory by one CTA for a batch of B adjacent
 //       columns (B*32-byte contiguous chunks in HBM), then the inter-digit twiddle
-//       w^(low*k) is applied on the way out.  In place.
+//       w^(low*k) is applied on the way out.  The first column pass reads the caller's buffer and
+//       writes the engine's scratch buffer, later ones run in place there.
 //   row pass: contiguous M-point sub-NTTs; the store performs the digit-reversal transpose
-//       (B adjacent outputs per k), so the result lands in natural order.  Out of place.
-// Inside a CTA: 2048 elements, 256 threads, 8 elements per thread; radix-8 register rounds
-// (three butterfly stages between shared-memory exchanges), limb-plane layout padded one
-// slot per eight so strided rounds are bank-conflict free; the sub-NTT twiddles stay
-// resident in shared memory.
+//       (B adjacent outputs per k), so the result lands in natural order — written straight back into
+//       the caller's buffer (ping-pong: no copy after the transform).
+// Inside a CTA: a tile of 2^9..2^11 elements (2048 from 2^20 on; smaller transforms use smaller tiles so
+// that 2^16..2^19 still fill the 148 SMs), tile/8 threads, 8 elements per thread; radix-8 register rounds
+// (three butterfly stages between shared-memory exchanges).  Data and twiddles live in shared memory as
+// 16-byte limb planes with a multi-level skew (slot i -> i + i/8 + i/64 + i/512), which makes every
+// power-of-two stride conflict-free for the 8 lanes of a quarter-warp — the strided twiddle reads of the
+// previous layout (a contiguous Fr array) were 17.5 M of 25.3 M shared-memory wavefronts
+// (profiles/r1_c_summary.md).  Each distinct twiddle of a round is fetched once per thread (7 per
+// radix-8 round instead of 12).
 #include "ntt.cuh"
 #include "roots.cuh"
 
@@ -23,10 +29,14 @@ namespace pm {
 namespace {
 
 constexpr int kCoreBits = 11;
-constexpr int kElemsPerCta = 2048;
-constexpr int kThreads = 256;
+constexpr int kMaxTileBits = 11;
+constexpr int kMinTileBits = 9;
 constexpr int kTwBits = 11;
-constexpr int kPlane = kElemsPerCta + kElemsPerCta / 8;  // padded slots per plane
+
+__host__ __device__ constexpr int skew(int i) { return i + (i >> 3) + (i >> 6) + (i >> 9); }
+__host__ __device__ constexpr int data_plane(int log_tile) { return skew(1 << log_tile) + 8; }
+__host__ __device__ constexpr int tw_plane(int log_tile) { return skew(1 << (log_tile - 1)) + 8; }
+constexpr int smem_bytes(int log_tile) { return 2 * (data_plane(log_tile) + tw_plane(log_tile)) * (int)sizeof(uint4); }
 
 // table[k] = base^k for k < count, base = w_{2^log_size}^(2^shift)
 __global__ void k_build_table(Fr* table, int count, int log_size, int shift, bool inverse) {
@@ -52,14 +62,13 @@ struct PassArgs {
     int log_n;    // log2 of the full transform
     int log_s;    // column pass: log2 stride between sub-transform points
     int log_n1;   // row pass: bits of the most significant digit of the row index
+    int log_tile; // elements per CTA (blockDim.x = tile / 8)
     const Fr* core;
     const Fr* tw0;
     const Fr* tw1;
     const Fr* tw2;
     const Fr* scale;  // row pass: optional n^-1
 };
-
-__device__ __forceinline__ int phys(int i) { return i + (i >> 3); }
 
 __device__ __forceinline__ Fr sm_load(const uint4* lo, const uint4* hi, int slot) {
     Fr r;
@@ -73,44 +82,66 @@ __device__ __forceinline__ void sm_store(uint4* lo, uint4* hi, int slot, const F
     hi[slot] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
 }
 
+// One register round of R butterfly stages (s .. s+R-1) of an in-place M-point DIT on bit-reversed data.
+// A thread owns 8 slots: 2^(3-R) groups of 2^R (R < 3 only in the last round of a transform whose m is not a
+// multiple of three).  Stage q pairs j and j | 2^q; its twiddle w_M^e, e = (pos & (2^(s+q) - 1)) << (m-s-q-1),
+// depends on j only through its low q bits and its group, so each distinct twiddle is loaded once.
+template <int R>
+__device__ __forceinline__ void ntt_round(uint4* blo, uint4* bhi, const uint4* tlo, const uint4* thi, int m, int s, int tt) {
+    int pos[8];
+    Fr x[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const int vt = (tt << (3 - R)) + (j >> R);
+        const int jb = j & ((1 << R) - 1);
+        pos[j] = ((vt >> s) << (s + R)) | (jb << s) | (vt & ((1 << s) - 1));
+        x[j] = sm_load(blo, bhi, skew(pos[j]));
+    }
+#pragma unroll
+    for (int q = 0; q < R; q++) {
+        const int hb = s + q;  // half-size = 2^hb
+#pragma unroll
+        for (int v = 0; v < (1 << (3 - R)); v++) {
+#pragma unroll
+            for (int g = 0; g < (1 << q); g++) {
+                const int j0 = (v << R) | g;
+                const int e = (pos[j0] & ((1 << hb) - 1)) << (m - hb - 1);
+                Fr w;
+                if (e != 0) w = sm_load(tlo, thi, skew(e));
+#pragma unroll
+                for (int h = 0; h < (1 << (R - 1 - q)); h++) {
+                    const int j = j0 | (h << (q + 1));
+                    const int jj = j | (1 << q);
+                    Fr t = (e == 0) ? x[jj] : x[jj] * w;
+                    x[jj] = x[j] - t;
+                    x[j] = x[j] + t;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; j++) sm_store(blo, bhi, skew(pos[j]), x[j]);
+}
+
 // In-place M-point DIT butterflies on bit-reversed data for every sub-transform of the CTA.
-// Thread t owns 8 slots per round; a round covers up to three stages (s, s+1, s+2).
-__device__ __forceinline__ void core_ntt(uint4* lo, uint4* hi, const Fr* tw, int m, int tid) {
+__device__ __forceinline__ void core_ntt(uint4* lo, uint4* hi, const uint4* tlo, const uint4* thi, int m, int tid) {
     const int M = 1 << m;
-    const int mpad = M + (M >> 3);
+    const int mpad = skew(M);
     const int per_sub = M >> 3;          // threads per sub-transform
     const int b = tid / per_sub;
     const int tt = tid - b * per_sub;
     uint4* blo = lo + b * mpad;
     uint4* bhi = hi + b * mpad;
-    for (int s = 0; s < m; s += 3) {
-        const int r = (m - s) < 3 ? (m - s) : 3;
-        int pos[8];
-        Fr x[8];
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            int vt = (tt << (3 - r)) + (j >> r);
-            int jb = j & ((1 << r) - 1);
-            pos[j] = ((vt >> s) << (s + r)) | (jb << s) | (vt & ((1 << s) - 1));
-            x[j] = sm_load(blo, bhi, phys(pos[j]));
-        }
-#pragma unroll
-        for (int q = 0; q < 3; q++) {
-            if (q < r) {
-                const int hb = s + q;  // half-size = 2^hb
-#pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    if ((j >> q) & 1) continue;
-                    const int jj = j | (1 << q);
-                    int e = (pos[j] & ((1 << hb) - 1)) << (m - hb - 1);
-                    Fr v = (e == 0) ? x[jj] : x[jj] * tw[e];
-                    x[jj] = x[j] - v;
-                    x[j] = x[j] + v;
-                }
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < 8; j++) sm_store(blo, bhi, phys(pos[j]), x[j]);
+    int s = 0;
+    for (; s + 3 <= m; s += 3) {
+        ntt_round<3>(blo, bhi, tlo, thi, m, s, tt);
+        __syncthreads();
+    }
+    if (m - s == 2) {
+        ntt_round<2>(blo, bhi, tlo, thi, m, s, tt);
+        __syncthreads();
+    } else if (m - s == 1) {
+        ntt_round<1>(blo, bhi, tlo, thi, m, s, tt);
         __syncthreads();
     }
 }
@@ -122,45 +153,52 @@ __device__ __forceinline__ Fr interpass_twiddle(const PassArgs& a, uint64_t e) {
     return t;
 }
 
-__device__ __forceinline__ void load_core_twiddles(Fr* tw, const Fr* core, int m, int tid, int nthreads) {
+// w_M^k, k < M/2, from the resident table of w_2048^k into the skewed planes
+__device__ __forceinline__ void load_core_twiddles(uint4* tlo, uint4* thi, const Fr* core, int m, int tid, int nthreads) {
     const int half = 1 << (m - 1);
-    for (int k = tid; k < half; k += nthreads) tw[k] = core[(size_t)k << (kCoreBits - m)];
+    const uint4* c4 = reinterpret_cast<const uint4*>(core);
+    for (int u = tid; u < 2 * half; u += nthreads) {
+        const int k = u >> 1, hf = u & 1;
+        (hf ? thi : tlo)[skew(k)] = c4[(((size_t)k << (kCoreBits - m)) << 1) + hf];
+    }
 }
 
 // ---- column pass ----------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) k_ntt_columns(PassArgs a) {
+__global__ void __launch_bounds__(256, 2) k_ntt_columns(PassArgs a) {
     extern __shared__ uint4 smem[];
+    const int lt = a.log_tile, tile = 1 << lt;
     uint4* lo = smem;
-    uint4* hi = smem + kPlane;
-    Fr* tw = reinterpret_cast<Fr*>(smem + 2 * kPlane);
-    const int tid = threadIdx.x;
+    uint4* hi = lo + data_plane(lt);
+    uint4* tlo = hi + data_plane(lt);
+    uint4* thi = tlo + tw_plane(lt);
+    const int tid = threadIdx.x, nthreads = blockDim.x;
     const int m = a.m, M = 1 << m;
-    const int log_b = 11 - m;            // B = 2048 / M columns per CTA
+    const int log_b = lt - m;            // B = tile / M columns per CTA
     const int B = 1 << log_b;
-    const int mpad = M + (M >> 3);
+    const int mpad = skew(M);
     const uint64_t blocks_per_outer = (uint64_t)1 << (a.log_s - log_b);
     const uint64_t outer = blockIdx.x / blocks_per_outer;
     const uint64_t low0 = (blockIdx.x % blocks_per_outer) << log_b;
 
-    load_core_twiddles(tw, a.core, m, tid, kThreads);
+    load_core_twiddles(tlo, thi, a.core, m, tid, nthreads);
     const uint4* in4 = reinterpret_cast<const uint4*>(a.in);
-    for (int u = tid; u < 2 * kElemsPerCta; u += kThreads) {
+    for (int u = tid; u < 2 * tile; u += nthreads) {
         int el = u >> 1, half = u & 1;
         int c = el & (B - 1);
         int n1 = el >> log_b;
         uint64_t gi = ((((outer << m) + (uint64_t)n1) << a.log_s) + low0 + (uint64_t)c);
         uint4 val = in4[gi * 2 + half];
-        int slot = c * mpad + phys((int)(__brev((unsigned)n1) >> (32 - m)));
+        int slot = c * mpad + skew((int)(__brev((unsigned)n1) >> (32 - m)));
         (half ? hi : lo)[slot] = val;
     }
     __syncthreads();
-    core_ntt(lo, hi, tw, m, tid);
-    // twiddle by w_{M*S}^(low*k1) = w_N^(low*k1 * N/(M*S)) and store in place
+    core_ntt(lo, hi, tlo, thi, m, tid);
+    // twiddle by w_{M*S}^(low*k1) = w_N^(low*k1 * N/(M*S)) and store
     const int tw_shift = a.log_n - m - a.log_s;
-    for (int el = tid; el < kElemsPerCta; el += kThreads) {
+    for (int el = tid; el < tile; el += nthreads) {
         int c = el & (B - 1);
         int k1 = el >> log_b;
-        Fr v = sm_load(lo, hi, c * mpad + phys(k1));
+        Fr v = sm_load(lo, hi, c * mpad + skew(k1));
         uint64_t low = low0 + (uint64_t)c;
         uint64_t e = (low * (uint64_t)k1) << tw_shift;
         if (e != 0) v = v * interpass_twiddle(a, e);
@@ -170,19 +208,21 @@ __global__ void __launch_bounds__(kThreads) k_ntt_columns(PassArgs a) {
 }
 
 // ---- row pass (final; digit-reversal transpose on store) --------------------------------
-__global__ void __launch_bounds__(kThreads) k_ntt_rows(PassArgs a) {
+__global__ void __launch_bounds__(256, 2) k_ntt_rows(PassArgs a) {
     extern __shared__ uint4 smem[];
+    const int lt = a.log_tile;
     uint4* lo = smem;
-    uint4* hi = smem + kPlane;
-    Fr* tw = reinterpret_cast<Fr*>(smem + 2 * kPlane);
+    uint4* hi = lo + data_plane(lt);
+    uint4* tlo = hi + data_plane(lt);
+    uint4* thi = tlo + tw_plane(lt);
     const int tid = threadIdx.x;
     const int nthreads = blockDim.x;
     const int m = a.m, M = 1 << m;
     const int log_rows = a.log_n - m;
-    int log_b = 11 - m;
+    int log_b = lt - m;
     if (log_b > log_rows) log_b = log_rows;
     const int B = 1 << log_b;
-    const int mpad = M + (M >> 3);
+    const int mpad = skew(M);
     const int elems = B << m;
     // rows handled: k1 = k1_0 + b (most significant digit), rest = lower digits
     const int log_rest = log_rows - a.log_n1;
@@ -190,7 +230,7 @@ __global__ void __launch_bounds__(kThreads) k_ntt_rows(PassArgs a) {
     const uint64_t rest = blockIdx.x / blocks_per_rest;
     const uint64_t k1_0 = (blockIdx.x % blocks_per_rest) << log_b;
 
-    load_core_twiddles(tw, a.core, m, tid, nthreads);
+    load_core_twiddles(tlo, thi, a.core, m, tid, nthreads);
     const uint4* in4 = reinterpret_cast<const uint4*>(a.in);
     for (int u = tid; u < 2 * elems; u += nthreads) {
         int el = u >> 1, half = u & 1;
@@ -198,18 +238,18 @@ __global__ void __launch_bounds__(kThreads) k_ntt_rows(PassArgs a) {
         int b = el >> m;
         uint64_t row = ((k1_0 + (uint64_t)b) << log_rest) + rest;
         uint4 val = in4[((row << m) + (uint64_t)n) * 2 + half];
-        int slot = b * mpad + phys((int)(__brev((unsigned)n) >> (32 - m)));
+        int slot = b * mpad + skew((int)(__brev((unsigned)n) >> (32 - m)));
         (half ? hi : lo)[slot] = val;
     }
     __syncthreads();
-    core_ntt(lo, hi, tw, m, tid);
+    core_ntt(lo, hi, tlo, thi, m, tid);
     Fr scale;
     const bool do_scale = a.scale != nullptr;
     if (do_scale) scale = a.scale[0];
     for (int el = tid; el < elems; el += nthreads) {
         int b = el & (B - 1);
         int k = el >> log_b;
-        Fr v = sm_load(lo, hi, b * mpad + phys(k));
+        Fr v = sm_load(lo, hi, b * mpad + skew(k));
         if (do_scale) v = v * scale;
         uint64_t out_base = (k1_0 + (uint64_t)b) + (rest << a.log_n1);
         a.out[out_base + ((uint64_t)k << log_rows)] = v;
@@ -238,11 +278,21 @@ __global__ void k_ntt_tiny(Fr* data, int log_n, bool inverse) {
     for (int i = 0; i < n; i++) data[i] = out[i] * scale;
 }
 
-__global__ void k_scale_by_powers(Fr* data, size_t n, const Fr* g) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    Fr gi = g[0].pow_u64((uint64_t)i);
-    data[i] = data[i] * gi;
+// data[i] *= g^i.  A thread owns kPowPerThread elements strided by the CTA: one pow for its first exponent and the
+// CTA stride, then a running product (2 products per element instead of a 64-bit pow per element).
+constexpr int kPowPerThread = 16;
+__global__ void __launch_bounds__(256) k_scale_by_powers(Fr* data, size_t n, const Fr* g) {
+    const size_t base = (size_t)blockIdx.x * (256 * kPowPerThread) + threadIdx.x;
+    if (base >= n) return;
+    const Fr gen = g[0];
+    Fr gi = gen.pow_u64((uint64_t)base);
+    const Fr step = gen.pow_u64(256);
+    for (int k = 0; k < kPowPerThread; k++) {
+        const size_t i = base + (size_t)k * 256;
+        if (i >= n) break;
+        data[i] = data[i] * gi;
+        gi = gi * step;
+    }
 }
 
 // ---- sharded transform over G = 2^log_g ranks ("four-step, one all-to-all") -------------------
@@ -289,8 +339,6 @@ __global__ void __launch_bounds__(256) k_dist_combine(const Fr* __restrict__ rec
     }
 }
 
-constexpr int kSmemBytes = 2 * kPlane * (int)sizeof(uint4) + (1 << (kCoreBits - 1)) * (int)sizeof(Fr);
-
 }  // namespace
 
 NttEngine::~NttEngine() {
@@ -332,13 +380,12 @@ void NttEngine::run(Fr* data, int log_n, bool inverse, cudaStream_t stream) {
     }
     static bool attr_set = false;
     if (!attr_set) {
-        PM_CUDA(cudaFuncSetAttribute(k_ntt_columns, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        PM_CUDA(cudaFuncSetAttribute(k_ntt_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        PM_CUDA(cudaFuncSetAttribute(k_ntt_columns, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(kMaxTileBits)));
+        PM_CUDA(cudaFuncSetAttribute(k_ntt_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(kMaxTileBits)));
         attr_set = true;
     }
     const Tables& t = tables(log_n, stream);
     const size_t n = (size_t)1 << log_n;
-    Fr* scratch = scratch_.as<Fr>(n);
 
     // digit split: 1 pass up to 2^11, 2 passes up to 2^22, else 3; most significant digit first
     int npass = log_n <= kCoreBits ? 1 : (log_n <= 2 * kCoreBits ? 2 : 3);
@@ -350,8 +397,21 @@ void NttEngine::run(Fr* data, int log_n, bool inverse, cudaStream_t stream) {
             rem -= digits[p];
         }
     }
+    // Tile: 2048 elements per CTA from 2^20 on; below, the smallest tile that holds the largest digit (>= 512), so that
+    // 2^16 launches 128 CTAs instead of 32 on the 148 SMs
+    int log_tile = kMaxTileBits;
+    if (log_n < 20) {
+        log_tile = digits[0] > kMinTileBits ? digits[0] : kMinTileBits;
+        if (log_tile > kMaxTileBits) log_tile = kMaxTileBits;
+    }
+    if (const char* v = getenv("PM_NTT_TILE_BITS")) {       // tuning hook
+        const int f = atoi(v);
+        if (f >= digits[0] && f >= kMinTileBits && f <= kMaxTileBits) log_tile = f;
+    }
+    const int smem = smem_bytes(log_tile);
     PassArgs a{};
     a.log_n = log_n;
+    a.log_tile = log_tile;
     a.core = (inverse ? t.core_inv : t.core_fwd).get<Fr>();
     a.tw0 = (inverse ? t.tw_inv[0] : t.tw_fwd[0]).get<Fr>();
     a.tw1 = (inverse ? t.tw_inv[1] : t.tw_fwd[1]).get<Fr>();
@@ -360,38 +420,40 @@ void NttEngine::run(Fr* data, int log_n, bool inverse, cudaStream_t stream) {
         if (!ev_begin) { PM_CUDA(cudaEventCreate(&ev_begin)); PM_CUDA(cudaEventCreate(&ev_end)); }
         PM_CUDA(cudaEventRecord(ev_begin, stream));
     }
+    // ping-pong: caller's buffer -> scratch (first column pass), in place in scratch (second), scratch -> caller's
+    // buffer (row pass, which transposes and therefore cannot run in place).  A single-pass transform is one CTA that
+    // holds the whole array in shared memory between its loads and stores: in place.
+    Fr* scratch = npass > 1 ? scratch_.as<Fr>(n) : data;
     int consumed = 0;
     for (int p = 0; p < npass - 1; p++) {
-        a.in = data;
-        a.out = data;
+        a.in = p == 0 ? data : scratch;
+        a.out = scratch;
         a.m = digits[p];
         a.log_s = log_n - consumed - digits[p];
         a.scale = nullptr;
-        // sub-problem of size 2^(log_n - consumed): twiddle exponent scaled by 2^consumed via log_n - m - log_s
-        PassArgs c = a;
-        c.log_n = log_n;
-        k_ntt_columns<<<(unsigned)(n / kElemsPerCta), kThreads, kSmemBytes, stream>>>(c);
+        k_ntt_columns<<<(unsigned)(n >> log_tile), (1 << log_tile) / 8, smem, stream>>>(a);
         PM_LAUNCH_CHECK();
         launches++;
         consumed += digits[p];
     }
-    a.in = data;
-    a.out = scratch;
+    a.in = scratch;
+    a.out = data;
     a.m = digits[npass - 1];
     a.log_s = 0;
     a.log_n1 = npass == 1 ? 0 : digits[0];
     a.scale = inverse ? t.n_inv.get<Fr>() : nullptr;
     {
         const int log_rows = log_n - a.m;
-        int log_b = 11 - a.m;
+        int log_b = log_tile - a.m;
+        if (log_b < 0) throw CudaError("ntt: tile smaller than the row digit");
         if (log_b > log_rows) log_b = log_rows;
         const unsigned ctas = (unsigned)((size_t)1 << (log_rows - log_b));
-        const int threads = ((1 << log_b) << a.m) / 8;
-        k_ntt_rows<<<ctas, threads, kSmemBytes, stream>>>(a);
+        int threads = ((1 << log_b) << a.m) / 8;
+        if (threads < 1) threads = 1;
+        k_ntt_rows<<<ctas, threads, smem, stream>>>(a);
         PM_LAUNCH_CHECK();
         launches++;
     }
-    PM_CUDA(cudaMemcpyAsync(data, scratch, n * sizeof(Fr), cudaMemcpyDeviceToDevice, stream));
     if (time_passes) PM_CUDA(cudaEventRecord(ev_end, stream));
 }
 
@@ -430,7 +492,7 @@ void NttEngine::dist_combine(const Fr* recv, Fr* out, int log_n, int log_g, bool
 }
 
 void launch_scale_by_powers(Fr* data, size_t n, const Fr* g_dev, cudaStream_t stream) {
-    k_scale_by_powers<<<ceil_div(n, 256), 256, 0, stream>>>(data, n, g_dev);
+    k_scale_by_powers<<<ceil_div(n, 256 * kPowPerThread), 256, 0, stream>>>(data, n, g_dev);
     PM_LAUNCH_CHECK();
 }
 

@@ -14,6 +14,8 @@
 #include <cstdio>
 #include <cstdlib>
 
+#include <cuda_profiler_api.h>
+
 #include "host/g1_host.hpp"
 #include "g1_codec.cuh"
 #include "msm.cuh"
@@ -45,6 +47,32 @@ __global__ void k_take_stride(const Fr* __restrict__ data, Fr* __restrict__ loc,
 __global__ void k_interleave(const Fr* __restrict__ gathered, Fr* __restrict__ data, size_t total, size_t per, uint32_t g) {
     size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k < total) data[k] = gathered[(k % g) * per + k / g];
+}
+
+// PM_CUDA_PROFILER=phase1|phase3: cudaProfilerStart/Stop around the device work of that phase of the FIRST proof, so
+// that `ncu --profile-from-start off` captures exactly the kernels of one phase (profiles/: the --set full captures).
+int profiler_phase() {
+    static int which = -1;
+    if (which < 0) {
+        const char* v = getenv("PM_CUDA_PROFILER");
+        which = !v ? 0 : (strcmp(v, "phase1") == 0 ? 1 : strcmp(v, "phase3") == 0 ? 3 : 0);
+    }
+    return which;
+}
+bool g_profiler_running = false;
+void profiler_begin(int phase_id) {
+    static bool done[4] = {false, false, false, false};
+    if (profiler_phase() != phase_id || done[phase_id]) return;
+    done[phase_id] = true;
+    cudaDeviceSynchronize();
+    cudaProfilerStart();
+    g_profiler_running = true;
+}
+void profiler_end() {
+    if (!g_profiler_running) return;
+    cudaDeviceSynchronize();
+    cudaProfilerStop();
+    g_profiler_running = false;
 }
 
 int log2_exact(uint64_t v) {
@@ -255,6 +283,7 @@ ProverCtx::Phase1Shapes ProverCtx::phase1_enqueue(const uint8_t* ra) {
         return std::chrono::duration<double, std::milli>(b - a).count();
     };
     const auto tp0 = now();
+    profiler_begin(1);
     PM_CUDA(cudaEventRecord(ev0, s));
     PM_CUDA(cudaMemcpyAsync(sm + S_RA, ra, 2 * sizeof(Fr), cudaMemcpyHostToDevice, s));
     const auto tp1 = now();
@@ -333,6 +362,7 @@ void ProverCtx::phase1_partial(const uint8_t* ra, uint8_t* partials_out) {
     PM_CUDA(cudaMemcpyAsync(hs + kStageStatus, st, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     PM_CUDA(cudaEventRecord(ev1, s));
     PM_CUDA(cudaStreamSynchronize(s));
+    profiler_end();
     float ms = 0;
     PM_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
     phase_ms[0] = ms;
@@ -452,6 +482,7 @@ void ProverCtx::phase1_collective(const uint8_t* ra, uint8_t* a_out, uint8_t* c_
     PM_CUDA(cudaMemcpyAsync(hs + kStageStatus, st, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     PM_CUDA(cudaEventRecord(ev1, s));
     PM_CUDA(cudaStreamSynchronize(s));
+    profiler_end();
     float ms = 0;
     PM_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
     phase_ms[0] = ms;
@@ -523,6 +554,7 @@ MsmEngine::Shape ProverCtx::phase3_enqueue(const uint8_t* x2, const uint8_t* c_a
     if (!x2 || !c_at_x1) throw StatusError(PM_ERR_ARG, "null phase-3 argument");
     Fr* sm = small.get<Fr>();
     uint32_t* st = status.get<uint32_t>();
+    profiler_begin(3);
     PM_CUDA(cudaEventRecord(ev0, s));
     PM_CUDA(cudaMemcpyAsync(sm + S_X2, x2, sizeof(Fr), cudaMemcpyHostToDevice, s));
     PM_CUDA(cudaMemcpyAsync(sm + S_C_AT_X1, c_at_x1, sizeof(Fr), cudaMemcpyHostToDevice, s));
@@ -548,6 +580,7 @@ void ProverCtx::phase3_partial(const uint8_t* x2, const uint8_t* c_at_x1, uint8_
     PM_CUDA(cudaMemcpyAsync(hs + kStageStatus, st, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     PM_CUDA(cudaEventRecord(ev1, s));
     PM_CUDA(cudaStreamSynchronize(s));
+    profiler_end();
     float ms = 0;
     PM_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
     phase_ms[2] = ms;
@@ -576,6 +609,7 @@ void ProverCtx::phase3_collective(const uint8_t* x2, const uint8_t* c_at_x1, uin
     PM_CUDA(cudaMemcpyAsync(hs + kStageStatus, st, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     PM_CUDA(cudaEventRecord(ev1, s));
     PM_CUDA(cudaStreamSynchronize(s));
+    profiler_end();
     float ms = 0;
     PM_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
     phase_ms[2] = ms;
