@@ -325,6 +325,9 @@ int pm_bench_field_mul(int field, double* muls_per_s);
 int pm_bench_ntt(unsigned log_n, int inverse, int iters, double* ms_avg);
 /* Milliseconds of one device-resident decompression / compression of n synthetic G1 points. */
 int pm_bench_g1_codec(size_t n, double* ms_decompress, double* ms_compress);
+/* Average milliseconds of `iters` fixed-base batches of n scalar multiplications [s_i]G with the canonical-affine
+ * normalisation, resident scalars (after one warm-up): the generator's `generate()` (src/generator.rs:169-177). */
+int pm_bench_fixed_base(size_t n, int iters, double* ms_avg);
 /* Average milliseconds of `iters` n-point MSMs on resident synthetic bases/scalars (after one warm-up);
  * ms_accumulate (nullable) receives the average time of the bucket-accumulation kernel alone. */
 int pm_bench_msm(size_t n, int window_bits, int iters, double* ms_avg, double* ms_accumulate);

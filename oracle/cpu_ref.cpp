@@ -1,4 +1,7 @@
-// CPU restatement (C++/OpenMP) of the two heavy primitives of the Polymath proving path.
+// CPU restatement (C++/OpenMP) of the heavy steps of the Polymath proving path: NTT, MSM, the sparse SAP
+// evaluation, the opening-numerator assembly and the division by (X - x1) — everything
+// `create_proof_with_assignment` (/root/reference/src/prover.rs:66-237) spends time in.  oracle/fast.py drives
+// these into a complete CPU prove (transcript and serialisation stay in oracle/*.py).
 // TEST INFRASTRUCTURE / CPU BASELINE ONLY — never linked into libpolymath_b200.so.
 //
 // What it restates (un-vendored arkworks 0.4.x dependencies of /root/reference):
@@ -114,17 +117,31 @@ static Fr fr_root(int log_n, bool inverse) {
 extern "C" int orc_ntt(uint64_t* data, int log_n, int inverse) {
     const size_t n = (size_t)1 << log_n;
     Fr* a = reinterpret_cast<Fr*>(data);
-    // bit reversal
-    for (size_t i = 1, j = 0; i < n; i++) {
-        size_t bit = n >> 1;
-        for (; j & bit; bit >>= 1) j ^= bit;
-        j |= bit;
-        if (i < j) { Fr t = a[i]; a[i] = a[j]; a[j] = t; }
+    // bit reversal (each swap is owned by its smaller index)
+    if (log_n > 0) {
+#pragma omp parallel for schedule(static)
+        for (size_t i = 1; i < n; i++) {
+            size_t j = 0;
+            for (int b = 0; b < log_n; b++) j |= ((i >> b) & 1) << (log_n - 1 - b);
+            if (i < j) { Fr t = a[i]; a[i] = a[j]; a[j] = t; }
+        }
     }
     Fr w_n = fr_root(log_n, inverse != 0);
     std::vector<Fr> tw(n / 2 ? n / 2 : 1);
-    tw[0] = Fr::one();
-    for (size_t k = 1; k < n / 2; k++) tw[k] = tw[k - 1].mul(w_n);
+    {
+        // w^k for k < n/2: every thread starts its slice with one pow, then a running product
+        const size_t half_n = n / 2 ? n / 2 : 1;
+        const int nt = omp_get_max_threads();
+        const size_t per = (half_n + nt - 1) / nt;
+#pragma omp parallel for schedule(static, 1)
+        for (int t = 0; t < nt; t++) {
+            const size_t lo = (size_t)t * per, hi = lo + per < half_n ? lo + per : half_n;
+            if (lo >= hi) continue;
+            uint64_t e[1] = {lo};
+            Fr cur = w_n.pow(e, 1);
+            for (size_t k = lo; k < hi; k++) { tw[k] = cur; cur = cur.mul(w_n); }
+        }
+    }
     for (size_t len = 2; len <= n; len <<= 1) {
         const size_t half = len >> 1, step = n / len;
         if (len <= 1024 || n / len >= 8) {
@@ -235,18 +252,37 @@ extern "C" int orc_msm(const uint64_t* bases_raw, const uint64_t* scalars_raw, s
             digits[(size_t)w * n + i] = d;
         }
     }
-    std::vector<Jac> wsum(nwin);
+    // arkworks 0.4 runs one rayon task per window (15-17 tasks at these sizes); on a 16-32 thread host that leaves a
+    // third of the cores idle in the last round, so the points of a window are also cut into chunks: every
+    // (window, chunk) task fills and reduces its own bucket set, the chunk sums of a window are added afterwards.
+    int nchunk = 1;
+    {
+        const int nt = omp_get_max_threads();
+        if (n >= ((size_t)1 << 14)) nchunk = (2 * nt + nwin - 1) / nwin;
+        if (nchunk < 1) nchunk = 1;
+        // keep the running-sum reduction (2 * nb additions per task) below ~15 % of the task's mixed additions
+        while (nchunk > 1 && (n / nchunk) < 12 * nb) nchunk--;
+    }
+    std::vector<Jac> part((size_t)nwin * nchunk);
 #pragma omp parallel for schedule(dynamic, 1)
-    for (int w = 0; w < nwin; w++) {
+    for (int task = 0; task < nwin * nchunk; task++) {
+        const int w = task / nchunk, ch = task % nchunk;
+        const size_t lo = n * (size_t)ch / nchunk, hi = n * (size_t)(ch + 1) / nchunk;
         std::vector<Jac> buckets(nb, jac_inf());
         const int32_t* dw = &digits[(size_t)w * n];
-        for (size_t i = 0; i < n; i++) {
+        for (size_t i = lo; i < hi; i++) {
             int d = dw[i];
             if (d > 0) buckets[d - 1] = jac_madd(buckets[d - 1], bases[i], false);
             else if (d < 0) buckets[-d - 1] = jac_madd(buckets[-d - 1], bases[i], true);
         }
         Jac running = jac_inf(), acc = jac_inf();
         for (size_t b = nb; b-- > 0;) { running = jac_add(running, buckets[b]); acc = jac_add(acc, running); }
+        part[task] = acc;
+    }
+    std::vector<Jac> wsum(nwin);
+    for (int w = 0; w < nwin; w++) {
+        Jac acc = jac_inf();
+        for (int ch = 0; ch < nchunk; ch++) acc = jac_add(acc, part[(size_t)w * nchunk + ch]);
         wsum[w] = acc;
     }
     Jac total = jac_inf();
@@ -302,6 +338,210 @@ extern "C" int orc_fq_mul(const uint64_t* a, const uint64_t* b, uint64_t* out, s
     for (size_t i = 0; i < n; i++) o[i] = x[i].mul(y[i]);
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------
+// the remaining steps of create_proof_with_assignment (src/prover.rs:66-237), sparse closed form of SURVEY.md 8(a3)
+// ------------------------------------------------------------------------------------------
+// out[r] = sum_k val[k] * vec[col[k]] over row r of a CSR matrix (first-match duplicates are the caller's business:
+// ark-relations compacts rows, the product dedups at upload)
+extern "C" int orc_spmv(const uint64_t* row_ptr, const uint32_t* col, const uint64_t* val_raw, size_t nr, const uint64_t* vec_raw,
+                        uint64_t* out_raw) {
+    const Fr* val = reinterpret_cast<const Fr*>(val_raw);
+    const Fr* vec = reinterpret_cast<const Fr*>(vec_raw);
+    Fr* out = reinterpret_cast<Fr*>(out_raw);
+#pragma omp parallel for schedule(static)
+    for (size_t r = 0; r < nr; r++) {
+        Fr acc = Fr::zero();
+        for (uint64_t k = row_ptr[r]; k < row_ptr[r + 1]; k++) acc = acc.add(val[k].mul(vec[col[k]]));
+        out[r] = acc;
+    }
+    return 0;
+}
+
+// compute_y_vec (prover.rs:279-302) and U.z, W.z, witness-U.z (prover.rs:87-96,156-166) from A.z', B.z', C.z':
+//   y = [0] | (1 - x_j)^2 | (az - bz)^2;  rows i < m0: (1 + x_i, 4 x_i + y_i);  m0 + i: (1 - x_i, y_i);
+//   2 m0 + r: (az + bz, 4 cz + y_{m0+r});  2 m0 + nr + r: (az - bz, y_{m0+r});  rest 0;  wu = u with rows < 2 m0 zeroed
+extern "C" int orc_sap_evals(size_t m0, size_t nr, size_t n, const uint64_t* x_raw, const uint64_t* az_raw, const uint64_t* bz_raw,
+                             const uint64_t* cz_raw, uint64_t* y_raw, uint64_t* u_raw, uint64_t* w_raw, uint64_t* wu_raw) {
+    const Fr *x = reinterpret_cast<const Fr*>(x_raw), *az = reinterpret_cast<const Fr*>(az_raw),
+             *bz = reinterpret_cast<const Fr*>(bz_raw), *cz = reinterpret_cast<const Fr*>(cz_raw);
+    Fr *y = reinterpret_cast<Fr*>(y_raw), *u = reinterpret_cast<Fr*>(u_raw), *w = reinterpret_cast<Fr*>(w_raw),
+       *wu = reinterpret_cast<Fr*>(wu_raw);
+    if (2 * (m0 + nr) > n) return 1;
+    const Fr one = Fr::one();
+    y[0] = Fr::zero();
+    for (size_t j = 1; j < m0; j++) y[j] = one.sub(x[j]).sqr();
+#pragma omp parallel for schedule(static)
+    for (size_t r = 0; r < nr; r++) y[m0 + r] = az[r].sub(bz[r]).sqr();
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < n; i++) { u[i] = Fr::zero(); w[i] = Fr::zero(); wu[i] = Fr::zero(); }
+    for (size_t i = 0; i < m0; i++) {
+        u[i] = one.add(x[i]);
+        w[i] = x[i].dbl().dbl().add(y[i]);
+        u[m0 + i] = one.sub(x[i]);
+        w[m0 + i] = y[i];
+    }
+#pragma omp parallel for schedule(static)
+    for (size_t r = 0; r < nr; r++) {
+        u[2 * m0 + r] = az[r].add(bz[r]);
+        w[2 * m0 + r] = cz[r].dbl().dbl().add(y[m0 + r]);
+        u[2 * m0 + nr + r] = az[r].sub(bz[r]);
+        w[2 * m0 + nr + r] = y[m0 + r];
+        wu[2 * m0 + r] = u[2 * m0 + r];
+        wu[2 * m0 + nr + r] = u[2 * m0 + nr + r];
+    }
+    return 0;
+}
+
+// pointwise square (square_polynomial, prover.rs:321-323)
+extern "C" int orc_fr_square(uint64_t* a_raw, size_t n) {
+    Fr* a = reinterpret_cast<Fr*>(a_raw);
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < n; i++) a[i] = a[i].sqr();
+    return 0;
+}
+
+// h_num = u2 - w (2n coefficients), h = h_num[n..2n), remainder h_num[k] + h[k] (k < n) must vanish
+// (divide_by_vanishing_poly + the asserts of prover.rs:105-108).  Returns 0 ok, 3 remainder non-zero, 4 h zero / degree.
+extern "C" int orc_quotient(const uint64_t* u2_raw, const uint64_t* w_raw, size_t n, uint64_t* hnum_raw) {
+    const Fr *u2 = reinterpret_cast<const Fr*>(u2_raw), *w = reinterpret_cast<const Fr*>(w_raw);
+    Fr* hn = reinterpret_cast<Fr*>(hnum_raw);
+    int bad = 0, nonzero = 0;
+#pragma omp parallel for schedule(static) reduction(| : bad, nonzero)
+    for (size_t k = 0; k < n; k++) {
+        hn[k] = u2[k].sub(w[k]);
+        hn[n + k] = u2[n + k];
+        if (!hn[k].add(hn[n + k]).is_zero()) bad |= 1;
+        if (!hn[n + k].is_zero()) nonzero |= 1;
+    }
+    if (bad) return 3;
+    if (!nonzero || !hn[2 * n - 1].is_zero()) return 4;     // deg h <= n - 2
+    return 0;
+}
+
+// out[i] = 2 (ra0 u[i] + ra1 u[i-1]), i <= n   (compute_r_g1, prover.rs:340-347)
+extern "C" int orc_two_ra_u(const uint64_t* u_raw, size_t n, const uint64_t* ra_raw, uint64_t* out_raw) {
+    const Fr *u = reinterpret_cast<const Fr*>(u_raw), *ra = reinterpret_cast<const Fr*>(ra_raw);
+    Fr* out = reinterpret_cast<Fr*>(out_raw);
+    const Fr r0 = ra[0].dbl(), r1 = ra[1].dbl();
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i <= n; i++) {
+        Fr v = Fr::zero();
+        if (i < n) v = v.add(r0.mul(u[i]));
+        if (i > 0) v = v.add(r1.mul(u[i - 1]));
+        out[i] = v;
+    }
+    return 0;
+}
+
+// Horner evaluation (u_poly.evaluate(&x1), prover.rs:132); sequential like ark-poly's small case, chunked here
+extern "C" int orc_horner(const uint64_t* c_raw, size_t n, const uint64_t* x_raw, uint64_t* out_raw) {
+    const Fr* c = reinterpret_cast<const Fr*>(c_raw);
+    const Fr x = *reinterpret_cast<const Fr*>(x_raw);
+    const int nt = omp_get_max_threads();
+    const size_t per = (n + nt - 1) / (nt ? nt : 1);
+    std::vector<Fr> part(nt, Fr::zero());
+#pragma omp parallel for schedule(static, 1)
+    for (int t = 0; t < nt; t++) {
+        const size_t lo = (size_t)t * per, hi = lo + per < n ? lo + per : n;
+        Fr acc = Fr::zero();
+        for (size_t k = hi; k-- > lo;) acc = acc.mul(x).add(c[k]);
+        part[t] = acc;
+    }
+    uint64_t e[1] = {per};
+    const Fr xp = x.pow(e, 1);
+    Fr acc = Fr::zero();
+    for (int t = nt; t-- > 0;) acc = acc.mul(xp).add(part[t]);
+    *reinterpret_cast<Fr*>(out_raw) = acc;
+    return 0;
+}
+
+// Dense coefficients of A*Y^-gamma + x2*C*Y^-gamma - (a(x1) + x2*c(x1))*X^(5 sigma)  (prover.rs:142-209; the shifts
+// 2s, 3s, 5s, 8s with s = sigma), size 2(n-1) + 8 sigma + 1.  `consts` = [ra0, ra1, x2, a_at_x1, c_at_x1].
+extern "C" int orc_d_numerator(size_t n, size_t sigma, const uint64_t* u_raw, const uint64_t* wu_raw, const uint64_t* ww_raw,
+                               const uint64_t* hnum_raw, const uint64_t* consts_raw, uint64_t* out_raw) {
+    const Fr *u = reinterpret_cast<const Fr*>(u_raw), *wu = reinterpret_cast<const Fr*>(wu_raw),
+             *ww = reinterpret_cast<const Fr*>(ww_raw), *hn = reinterpret_cast<const Fr*>(hnum_raw),
+             *k = reinterpret_cast<const Fr*>(consts_raw);
+    Fr* num = reinterpret_cast<Fr*>(out_raw);
+    const size_t size = 2 * (n - 1) + 8 * sigma + 1;
+    const Fr ra0 = k[0], ra1 = k[1], x2 = k[2], a_at = k[3], c_at = k[4];
+    const size_t s_g = 5 * sigma, s_ga = 2 * sigma, s_a = 3 * sigma, s_ag = 8 * sigma;
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < size; i++) num[i] = Fr::zero();
+    // the supports [0,2) [2s,2s+3) [3s,3s+n) [5s,5s+n+1) [8s,8s+2n-1) are disjoint (sigma = n + 3): plain parallel loops
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < n; i++) {
+        num[s_g + i] = num[s_g + i].add(u[i]);                    // A: u * X^{5s}
+        num[s_a + i] = num[s_a + i].add(x2.mul(wu[i]));           // C: x2 * wu * X^{3s}
+    }
+    const Fr r0 = ra0.dbl(), r1 = ra1.dbl();
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i <= n; i++) {                             // x2 * two_ra_u * X^{5s}
+        Fr v = Fr::zero();
+        if (i < n) v = v.add(r0.mul(u[i]));
+        if (i > 0) v = v.add(r1.mul(u[i - 1]));
+        num[s_g + i] = num[s_g + i].add(x2.mul(v));
+    }
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < 2 * n; i++) {                          // x2 * (ww + h_num) * X^{8s}
+        Fr v = hn[i];
+        if (i < n) v = v.add(ww[i]);
+        if (s_ag + i < size) num[s_ag + i] = num[s_ag + i].add(x2.mul(v));
+    }
+    // r_a terms
+    num[s_ga] = num[s_ga].add(ra0);
+    num[s_ga + 1] = num[s_ga + 1].add(ra1);
+    const Fr sq[3] = {ra0.sqr(), ra0.mul(ra1).dbl(), ra1.sqr()};
+    for (int i = 0; i < 3; i++) num[s_ga + i] = num[s_ga + i].add(x2.mul(sq[i]));
+    num[0] = num[0].add(x2.mul(ra0));
+    num[1] = num[1].add(x2.mul(ra1));
+    num[s_g] = num[s_g].sub(a_at).sub(x2.mul(c_at));
+    return 0;
+}
+
+// divide_with_q_and_r by (X - x1): q_{k-1} = p_k + x1 q_k (prover.rs:211-220).  The reference's division is one
+// sequential recurrence; here every thread runs the recurrence of its coefficient range from a zero carry and the
+// carries are then propagated with powers of x1 (q is linear in the incoming carry).  rem_out = p_0 + x1 q_0.
+extern "C" int orc_divide_linear(const uint64_t* num_raw, size_t len, const uint64_t* x1_raw, uint64_t* q_raw, uint64_t* rem_out) {
+    const Fr* num = reinterpret_cast<const Fr*>(num_raw);
+    const Fr x1 = *reinterpret_cast<const Fr*>(x1_raw);
+    Fr* q = reinterpret_cast<Fr*>(q_raw);
+    if (len < 2) return 1;
+    const size_t m = len - 1;                                    // q has m coefficients: q[k-1] for k = m..1
+    const int nt = omp_get_max_threads();
+    const size_t per = (m + nt - 1) / nt;
+    std::vector<Fr> tail(nt, Fr::zero());
+#pragma omp parallel for schedule(static, 1)
+    for (int t = 0; t < nt; t++) {
+        const size_t lo = (size_t)t * per, hi = lo + per < m ? lo + per : m;     // q indices [lo, hi)
+        Fr carry = Fr::zero();
+        for (size_t j = hi; j-- > lo;) { carry = num[j + 1].add(x1.mul(carry)); q[j] = carry; }
+        tail[t] = carry;                                          // q[lo] with zero incoming carry
+    }
+    // incoming carry of range t = true q[hi_t] = q[lo_{t+1}]; adding carry c at hi changes q[j] by c * x1^(hi - j)
+    std::vector<Fr> incoming(nt, Fr::zero());
+    uint64_t e[1] = {per};
+    const Fr xper = x1.pow(e, 1);
+    for (int t = nt - 2; t >= 0; t--) {
+        const size_t lo_next = (size_t)(t + 1) * per;
+        if (lo_next >= m) continue;
+        const size_t hi_next = lo_next + per < m ? lo_next + per : m;
+        uint64_t e2[1] = {hi_next - lo_next};
+        const Fr xlen = (hi_next - lo_next == per) ? xper : x1.pow(e2, 1);
+        incoming[t] = tail[t + 1].add(incoming[t + 1].mul(xlen));
+    }
+#pragma omp parallel for schedule(static, 1)
+    for (int t = 0; t < nt; t++) {
+        const size_t lo = (size_t)t * per, hi = lo + per < m ? lo + per : m;
+        if (lo >= hi || incoming[t].is_zero()) continue;
+        Fr f = incoming[t];
+        for (size_t j = hi; j-- > lo;) { f = f.mul(x1); q[j] = q[j].add(f); }
+    }
+    *reinterpret_cast<Fr*>(rem_out) = num[0].add(x1.mul(q[0]));
+    return 0;
+}
+
 extern "C" int orc_num_threads(void) { return omp_get_max_threads(); }
 // torchrun exports OMP_NUM_THREADS=1 to its workers: the CPU arm of bench.py asks for the host's cores explicitly
 extern "C" void orc_set_num_threads(int n) { if (n > 0) omp_set_num_threads(n); }

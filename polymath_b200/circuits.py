@@ -62,9 +62,11 @@ def mimc_assignment(xl, xr, constants):
     return [1, image], wit
 
 
-def synthetic_mimc(n: int, seed: int = 1):
-    """S-mimc(n): constants and preimage from StdRng::seed_from_u64(seed) (SURVEY.md §8d)."""
-    rng = StdRng.seed_from_u64(seed)
+def synthetic_mimc(n: int, seed: int = 1, rng=None):
+    """S-mimc(n): constants and preimage from StdRng::seed_from_u64(seed) (SURVEY.md §8d).  `rng`: any object with
+    `fr_rand()` positioned at that seed (the CPU reference arm passes the oracle's generator, so that its process
+    never loads the CUDA library)."""
+    rng = rng or StdRng.seed_from_u64(seed)
     rounds = mimc_rounds_for_domain(n)
     constants = [rng.fr_rand() for _ in range(rounds)]
     r1cs = mimc_r1cs(constants)

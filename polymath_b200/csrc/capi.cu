@@ -387,6 +387,31 @@ int pm_bench_g1_codec(size_t n, double* ms_decompress, double* ms_compress) {
     });
 }
 
+int pm_bench_fixed_base(size_t n, int iters, double* ms_avg) {
+    return guarded([&] {
+        if (n == 0 || iters <= 0 || !ms_avg) throw StatusError(PM_ERR_ARG, "bad bench arguments");
+        Runtime& rt = runtime();
+        DevBuf ds, dp;
+        Fr* ps = ds.as<Fr>(n);
+        G1Affine* pp = dp.as<G1Affine>(n);
+        launch_fill_fr(ps, n, 0xf1bed, rt.stream);
+        rt.fixed_base.run(ps, n, pp, rt.stream);       // warm-up (builds the window table)
+        cudaEvent_t e0, e1;
+        PM_CUDA(cudaEventCreate(&e0));
+        PM_CUDA(cudaEventCreate(&e1));
+        PM_CUDA(cudaStreamSynchronize(rt.stream));
+        PM_CUDA(cudaEventRecord(e0, rt.stream));
+        for (int i = 0; i < iters; i++) rt.fixed_base.run(ps, n, pp, rt.stream);
+        PM_CUDA(cudaEventRecord(e1, rt.stream));
+        PM_CUDA(cudaEventSynchronize(e1));
+        float ms = 0;
+        PM_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        *ms_avg = ms / iters;
+    });
+}
+
 int pm_bench_msm(size_t n, int window_bits, int iters, double* ms_avg, double* ms_accumulate) {
     return pm_bench_msm_levels(n, window_bits, 1, iters, ms_avg, ms_accumulate);
 }

@@ -258,6 +258,27 @@ __global__ void k_pad_runs(const uint32_t* __restrict__ counts, const uint32_t* 
     for (uint32_t k = offsets[t] + counts[t]; k < end; k++) sorted[k] = kPadEntry;
 }
 
+// The slot pairs of round r that one launch handles: slots [*s_begin, *s_end) of round 0 (bucket boundaries read from the
+// offsets array on the device; s_begin == nullptr means 0) shrink to pairs [(*s_begin >> r) / 2, (*s_end >> r) / 2).
+// A whole pass is ONE span; with two spans (the lower and the upper half of the buckets) the rounds of the halves are
+// independent pipelines that run on two streams, so the latency-bound inversion of one half overlaps the
+// multiplier-bound forward / backward pass of the other.
+// Storage: the two spans advance through their rounds at their own pace, and the pair indices of a later round of the
+// upper span fall into the range an earlier round of the lower span may still be reading.  So every span addresses
+// its round storage (points, prefix products) by the LOCAL pair / slot index, the lower span upwards from 0 and the
+// upper span (`rev`) downwards from the end of the same arrays: [0, a_r) and (cap - b_r, cap] never meet
+// (a_r + b_r = pairs of the round <= cap), whatever the rounds the two spans are in.
+struct PairSpan {
+    const uint32_t* s_begin;
+    const uint32_t* s_end;
+    int rev;
+    __device__ __forceinline__ size_t at(size_t cap, size_t local) const { return rev ? cap - 1 - local : local; }
+    __device__ __forceinline__ void get(int r, size_t& begin, size_t& count) const {
+        begin = s_begin ? ((size_t)(*s_begin >> r) >> 1) : 0;
+        count = ((size_t)(*s_end >> r) >> 1) - begin;
+    }
+};
+
 // operands of slot pair p in round storage: FIRST reads two (index | sign) entries and gathers from the table
 template <bool FIRST>
 struct PairSource {
@@ -270,29 +291,30 @@ struct PairSource {
         return make_uint2(0u, 0u);
     }
     // x coordinates only; returns false when an operand is padding (FIRST only)
-    __device__ __forceinline__ bool gather_x(size_t p, const uint2& e, Fq& x1, Fq& x2) const {
+    // (later rounds read the previous round's output at the span's LOCAL slots 2 pl, 2 pl + 1: PairSpan::at)
+    __device__ __forceinline__ bool gather_x(const PairSpan& sp, size_t pl, const uint2& e, Fq& x1, Fq& x2) const {
         if (FIRST) {
             if (e.x == kPadEntry || e.y == kPadEntry) return false;
             x1 = load_fq(&table[e.x & 0x7fffffffu].x);
             x2 = load_fq(&table[e.y & 0x7fffffffu].x);
         } else {
-            x1 = in.load_x(2 * p);
-            x2 = in.load_x(2 * p + 1);
+            x1 = in.load_x(sp.at(in.cap, 2 * pl));
+            x2 = in.load_x(sp.at(in.cap, 2 * pl + 1));
         }
         return true;
     }
-    __device__ __forceinline__ void load_y(size_t p, const uint2& e, Fq& y1, Fq& y2) const {
+    __device__ __forceinline__ void load_y(const PairSpan& sp, size_t pl, const uint2& e, Fq& y1, Fq& y2) const {
         if (FIRST) {
             y1 = load_fq(&table[e.x & 0x7fffffffu].y);
             y2 = load_fq(&table[e.y & 0x7fffffffu].y);
             if (e.x >> 31) y1 = y1.neg();
             if (e.y >> 31) y2 = y2.neg();
         } else {
-            y1 = in.load_y(2 * p);
-            y2 = in.load_y(2 * p + 1);
+            y1 = in.load_y(sp.at(in.cap, 2 * pl));
+            y2 = in.load_y(sp.at(in.cap, 2 * pl + 1));
         }
     }
-    __device__ __forceinline__ void load_pair(size_t p, G1Affine& a, G1Affine& b) const {
+    __device__ __forceinline__ void load_pair(const PairSpan& sp, size_t p, size_t pl, G1Affine& a, G1Affine& b) const {
         if (FIRST) {
             uint2 e = *reinterpret_cast<const uint2*>(sorted + 2 * p);
             a = G1Affine::inf();
@@ -306,25 +328,25 @@ struct PairSource {
                 if (e.y >> 31) b.y = b.y.neg();
             }
         } else {
-            a = in.load(2 * p);
-            b = in.load(2 * p + 1);
+            a = in.load(sp.at(in.cap, 2 * pl));
+            b = in.load(sp.at(in.cap, 2 * pl + 1));
         }
     }
 };
 
-// slot pairs of round r: (S_0 >> r) / 2 with S_0 = *slots0
-__device__ __forceinline__ size_t round_pairs(const uint32_t* __restrict__ slots0, int r) { return (size_t)(*slots0 >> r) >> 1; }
 
 // Software-pipelined: the (index | sign) entries are fetched two pairs ahead and the x coordinates one pair ahead of
 // the product chain, so the two dependent memory latencies of the first round (entry -> table gather, random 96-byte
 // records of a multi-GB table) overlap the multiplication of the previous pair instead of serialising with it.
 template <bool FIRST>
-__global__ void __launch_bounds__(128) k_pairs_forward(PairSource<FIRST> src, const uint32_t* __restrict__ slots0, int r, int ppt,
+__global__ void __launch_bounds__(128) k_pairs_forward(PairSource<FIRST> src, PairSpan span, int r, int ppt,
                                                        FqPlanes prefix, Fq* __restrict__ T) {
-    const size_t npairs = round_pairs(slots0, r);
+    size_t first, count;
+    span.get(r, first, count);
     const size_t base = (size_t)blockIdx.x * pair_tile(ppt);
-    if (base >= npairs) return;
-    const size_t p0 = base + threadIdx.x;
+    if (base >= count) return;
+    const size_t npairs = first + count;                 // pairs are addressed globally, [first, npairs)
+    const size_t p0 = first + base + threadIdx.x;
     auto pair_at = [&](int i) { return p0 + (size_t)i * 128; };
     auto live = [&](int i) { return i < ppt && pair_at(i) < npairs; };
     Fq acc = Fq::one();
@@ -333,7 +355,7 @@ __global__ void __launch_bounds__(128) k_pairs_forward(PairSource<FIRST> src, co
     bool has = false;
     if (live(0)) e_cur = src.load_e(pair_at(0));
     if (live(1)) e_nxt = src.load_e(pair_at(1));
-    if (live(0)) has = src.gather_x(pair_at(0), e_cur, x1, x2);
+    if (live(0)) has = src.gather_x(span, pair_at(0) - first, e_cur, x1, x2);
     for (int i = 0; i < ppt; i++) {
         const size_t p = pair_at(i);
         if (p >= npairs) break;
@@ -342,7 +364,7 @@ __global__ void __launch_bounds__(128) k_pairs_forward(PairSource<FIRST> src, co
         if (live(i + 2)) e_nn = src.load_e(pair_at(i + 2));
         Fq nx1, nx2;
         bool nhas = false;
-        if (live(i + 1)) nhas = src.gather_x(pair_at(i + 1), e_nxt, nx1, nx2);
+        if (live(i + 1)) nhas = src.gather_x(span, pair_at(i + 1) - first, e_nxt, nx1, nx2);
         Fq d;
         if (has) {
             d = x2 - x1;
@@ -351,13 +373,13 @@ __global__ void __launch_bounds__(128) k_pairs_forward(PairSource<FIRST> src, co
                 G1Affine a, b;
                 a.x = x1;
                 b.x = x2;
-                src.load_y(p, e_cur, a.y, b.y);
+                src.load_y(span, p - first, e_cur, a.y, b.y);
                 const int kind = pair_kind(a, b);
                 if (kind == kPairDouble) d = a.y.dbl();
                 else if (kind != kPairAdd) has = false;
             }
         }
-        prefix.store(p, acc);
+        prefix.store(span.at(prefix.cap, p - first), acc);
         if (has) acc = fq_mul_call(acc, d);
         e_cur = e_nxt;
         e_nxt = e_nn;
@@ -368,180 +390,73 @@ __global__ void __launch_bounds__(128) k_pairs_forward(PairSource<FIRST> src, co
     store_fq(T + (size_t)blockIdx.x * 128 + threadIdx.x, acc);
 }
 
-// ---- inversion of the thread totals T of round r (all non-zero), Montgomery's trick over block trees ----
-// Level sizes: n_0 = thread totals of k_pairs_forward, n_{l+1} = ceil(n_l / kInvTile).  One CTA owns a tile of
-// kInvTile = 512 threads x 4 elements, held in REGISTERS (loaded up front, so no serial chain of dependent global
-// loads), and multiplies it down to one product through an 8 x 8 x 8 tree in shared memory (exclusive prefixes
-// kept per tree level):  k_inv_up writes the tile products of level l as level l+1,  k_inv_top (one CTA, the last
-// level: <= kInvTile elements) inverts its tile product with ONE binary extended-Euclid inverse and walks its tree
-// back down,  k_inv_down does the same for the tiles of a lower level with the inverse of its tile product taken
-// from the level above.  Serial depth per kernel ~30 / ~85 Fq products instead of five latency-bound kernels of
-// 32-element global-memory chains (420 us per round under ncu, profiles/launches_r1_h_bench_2p20.csv).
-constexpr int kInvThreads = 512;
-constexpr int kInvPer = 4;
-constexpr uint32_t kInvTile = kInvThreads * kInvPer;
-constexpr int kInvMaxLevels = 4;      // 2048^3 tiles of 128 thread totals: far beyond 2^32 slots
-__device__ __forceinline__ size_t invert_level_size(const uint32_t* __restrict__ slots0, int r, int ppt, int level) {
-    size_t n = (round_pairs(slots0, r) + pair_tile(ppt) - 1) / pair_tile(ppt) * 128;
-    for (int l = 0; l < level; l++) n = (n + kInvTile - 1) / kInvTile;
+// ---- inversion of the thread totals T of round r (all non-zero), Montgomery's trick over a small tree ----
+// Level sizes: n_0 = thread totals of k_pairs_forward, n_{l+1} = ceil(n_l / kInvFan).  k_invert_up multiplies
+// kInvFan strided elements of level l into one element of level l+1 (exclusive prefixes kept), k_invert_top
+// takes the binary-Euclid inverse of the few top elements, k_invert_down walks back.  3 products per element and
+// level.  A dependent Fq product costs ~1.4 us in a lone warp (its carry chains serialise ~500 instructions), so the
+// tree is LATENCY-bound: 3 x 32 x 2 product latencies + the inverse = ~0.4 ms per round whatever the size.  Measured
+// and rejected in round 2 (profiles/r2_b_summary.md): block-wide shared-memory trees with the tile held in registers
+// (one launch per level, but 1100 CTAs of 512 threads x 123 us = 0.9 ms).  The latency is hidden instead: the bucket
+// range is cut in two halves whose rounds run on two streams (MsmEngine::run), so one half's inversion overlaps
+// the other half's forward / backward pass.
+constexpr uint32_t kInvFan = 32;
+constexpr int kInvLevels = 2;
+__device__ __forceinline__ size_t invert_level_size(const PairSpan& span, int r, int ppt, int level) {
+    size_t first, count;
+    span.get(r, first, count);
+    size_t n = (count + pair_tile(ppt) - 1) / pair_tile(ppt) * 128;
+    for (int l = 0; l < level; l++) n = (n + kInvFan - 1) / kInvFan;
     return n;
 }
-
-struct InvTree {             // shared memory of one tile: values and exclusive prefixes of the three tree levels
-    Fq v0[kInvThreads], p0[kInvThreads];   // thread products, prefix inside groups of 8
-    Fq v1[64], p1[64];                     // group products, prefix inside groups of 8
-    Fq v2[8], p2[8];                       // 8 top products, prefix
-};
-
-// tile product -> returned in thread 0 (other threads: undefined)
-__device__ __forceinline__ Fq inv_tree_up(InvTree& t, const Fq& mine) {
-    const int tid = threadIdx.x;
-    t.v0[tid] = mine;
-    __syncthreads();
-    if (tid < 64) {
-        Fq acc = Fq::one();
-#pragma unroll 1
-        for (int k = 0; k < 8; k++) {
-            t.p0[tid * 8 + k] = acc;
-            acc = fq_mul_call(acc, t.v0[tid * 8 + k]);
-        }
-        t.v1[tid] = acc;
+__global__ void __launch_bounds__(128) k_invert_up(const Fq* __restrict__ lo, Fq* __restrict__ pre, Fq* __restrict__ hi,
+                                                   PairSpan span, int r, int ppt, int level) {
+    const size_t n = invert_level_size(span, r, ppt, level), m = (n + kInvFan - 1) / kInvFan;
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    Fq acc = Fq::one();
+    for (size_t idx = j; idx < n; idx += m) {
+        store_fq(pre + idx, acc);
+        acc = fq_mul_call(acc, load_fq(lo + idx));
     }
-    __syncthreads();
-    if (tid < 8) {
-        Fq acc = Fq::one();
-#pragma unroll 1
-        for (int k = 0; k < 8; k++) {
-            t.p1[tid * 8 + k] = acc;
-            acc = fq_mul_call(acc, t.v1[tid * 8 + k]);
-        }
-        t.v2[tid] = acc;
-    }
-    __syncthreads();
-    Fq total = Fq::one();
-    if (tid == 0) {
-#pragma unroll 1
-        for (int k = 0; k < 8; k++) {
-            t.p2[k] = total;
-            total = fq_mul_call(total, t.v2[k]);
-        }
-    }
-    return total;
+    store_fq(hi + j, acc);
 }
-// thread 0 passes the inverse of the tile product; every thread gets the inverse of the value it gave to inv_tree_up
-__device__ __forceinline__ Fq inv_tree_down(InvTree& t, Fq inv_total) {
-    const int tid = threadIdx.x;
-    if (tid == 0) {
-#pragma unroll 1
-        for (int k = 8; k-- > 0;) {
-            Fq val = t.v2[k];
-            t.v2[k] = fq_mul_call(inv_total, t.p2[k]);
-            inv_total = fq_mul_call(inv_total, val);
-        }
+__global__ void __launch_bounds__(128) k_invert_top(Fq* __restrict__ top, PairSpan span, int r, int ppt, int level) {
+    const size_t n = invert_level_size(span, r, ppt, level);
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    store_fq(top + j, load_fq(top + j).inv());
+}
+__global__ void __launch_bounds__(128) k_invert_down(Fq* __restrict__ lo, const Fq* __restrict__ pre, const Fq* __restrict__ hi,
+                                                     PairSpan span, int r, int ppt, int level) {
+    const size_t n = invert_level_size(span, r, ppt, level), m = (n + kInvFan - 1) / kInvFan;
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    Fq inv = load_fq(hi + j);
+    const size_t cnt = (n - j + m - 1) / m;
+    for (size_t k = cnt; k-- > 0;) {
+        const size_t idx = j + k * m;
+        Fq t = load_fq(lo + idx);
+        store_fq(lo + idx, fq_mul_call(inv, load_fq(pre + idx)));
+        inv = fq_mul_call(inv, t);
     }
-    __syncthreads();
-    if (tid < 8) {
-        Fq inv = t.v2[tid];
-#pragma unroll 1
-        for (int k = 8; k-- > 0;) {
-            Fq val = t.v1[tid * 8 + k];
-            t.v1[tid * 8 + k] = fq_mul_call(inv, t.p1[tid * 8 + k]);
-            inv = fq_mul_call(inv, val);
-        }
-    }
-    __syncthreads();
-    if (tid < 64) {
-        Fq inv = t.v1[tid];
-#pragma unroll 1
-        for (int k = 8; k-- > 0;) {
-            Fq val = t.v0[tid * 8 + k];
-            t.v0[tid * 8 + k] = fq_mul_call(inv, t.p0[tid * 8 + k]);
-            inv = fq_mul_call(inv, val);
-        }
-    }
-    __syncthreads();
-    return t.v0[tid];
-}
-
-// the tile's elements of this thread (strided by the CTA: coalesced), ones beyond n
-__device__ __forceinline__ void inv_tile_load(const Fq* __restrict__ lo, size_t n, Fq vals[kInvPer]) {
-    const size_t base = (size_t)blockIdx.x * kInvTile + threadIdx.x;
-#pragma unroll
-    for (int k = 0; k < kInvPer; k++) {
-        const size_t idx = base + (size_t)k * kInvThreads;
-        vals[k] = idx < n ? load_fq(lo + idx) : Fq::one();
-    }
-}
-__device__ __forceinline__ Fq inv_thread_product(const Fq vals[kInvPer]) {
-    Fq acc = vals[0];
-#pragma unroll
-    for (int k = 1; k < kInvPer; k++) acc = fq_mul_call(acc, vals[k]);
-    return acc;
-}
-// inverses of the thread's elements from the inverse of their product, stored in place
-__device__ __forceinline__ void inv_tile_store(Fq* __restrict__ lo, size_t n, const Fq vals[kInvPer], Fq inv) {
-    const size_t base = (size_t)blockIdx.x * kInvTile + threadIdx.x;
-    // exclusive prefixes again (cheaper than keeping them live across the tree)
-    Fq pre[kInvPer];
-    pre[0] = Fq::one();
-#pragma unroll
-    for (int k = 1; k < kInvPer; k++) pre[k] = k == 1 ? vals[0] : fq_mul_call(pre[k - 1], vals[k - 1]);
-#pragma unroll
-    for (int k = kInvPer; k-- > 0;) {
-        const size_t idx = base + (size_t)k * kInvThreads;
-        if (idx < n) store_fq(lo + idx, k == 0 ? inv : fq_mul_call(inv, pre[k]));
-        if (k) inv = fq_mul_call(inv, vals[k]);
-    }
-}
-
-__global__ void __launch_bounds__(kInvThreads) k_inv_up(const Fq* __restrict__ lo, Fq* __restrict__ hi,
-                                                        const uint32_t* __restrict__ slots0, int r, int ppt, int level) {
-    extern __shared__ uint4 inv_smem[];
-    InvTree& tree = *reinterpret_cast<InvTree*>(inv_smem);
-    const size_t n = invert_level_size(slots0, r, ppt, level);
-    if ((size_t)blockIdx.x * kInvTile >= n) return;
-    Fq vals[kInvPer];
-    inv_tile_load(lo, n, vals);
-    const Fq total = inv_tree_up(tree, inv_thread_product(vals));
-    if (threadIdx.x == 0) store_fq(hi + blockIdx.x, total);
-}
-__global__ void __launch_bounds__(kInvThreads) k_inv_top(Fq* __restrict__ top, const uint32_t* __restrict__ slots0, int r, int ppt, int level) {
-    extern __shared__ uint4 inv_smem[];
-    InvTree& tree = *reinterpret_cast<InvTree*>(inv_smem);
-    const size_t n = invert_level_size(slots0, r, ppt, level);    // <= kInvTile by construction
-    Fq vals[kInvPer];
-    inv_tile_load(top, n, vals);
-    Fq total = inv_tree_up(tree, inv_thread_product(vals));
-    if (threadIdx.x == 0) total = total.inv();
-    inv_tile_store(top, n, vals, inv_tree_down(tree, total));
-}
-__global__ void __launch_bounds__(kInvThreads) k_inv_down(Fq* __restrict__ lo, const Fq* __restrict__ hi_inv,
-                                                          const uint32_t* __restrict__ slots0, int r, int ppt, int level) {
-    extern __shared__ uint4 inv_smem[];
-    InvTree& tree = *reinterpret_cast<InvTree*>(inv_smem);
-    const size_t n = invert_level_size(slots0, r, ppt, level);
-    if ((size_t)blockIdx.x * kInvTile >= n) return;
-    Fq vals[kInvPer];
-    inv_tile_load(lo, n, vals);
-    inv_tree_up(tree, inv_thread_product(vals));
-    Fq total_inv = Fq::one();
-    if (threadIdx.x == 0) total_inv = load_fq(hi_inv + blockIdx.x);
-    inv_tile_store(lo, n, vals, inv_tree_down(tree, total_inv));
 }
 
 template <bool FIRST>
-__global__ void __launch_bounds__(128, 4) k_pairs_backward(PairSource<FIRST> src, const uint32_t* __restrict__ slots0, int r, int ppt,
+__global__ void __launch_bounds__(128, 4) k_pairs_backward(PairSource<FIRST> src, PairSpan span, int r, int ppt,
                                                            FqPlanes prefix, const Fq* __restrict__ Tinv, PointPlanes next) {
-    const size_t npairs = round_pairs(slots0, r);
-    const size_t base = (size_t)blockIdx.x * pair_tile(ppt);
-    if (base >= npairs) return;
+    size_t first, count;
+    span.get(r, first, count);
+    if ((size_t)blockIdx.x * pair_tile(ppt) >= count) return;
+    const size_t npairs = first + count;
+    const size_t base = first + (size_t)blockIdx.x * pair_tile(ppt);
     // threads of a partial last tile that own no pair hold T = 1
     Fq inv = load_fq(Tinv + (size_t)blockIdx.x * 128 + threadIdx.x);
     for (int i = ppt; i-- > 0;) {
         const size_t p = base + (size_t)i * 128 + threadIdx.x;
         if (p >= npairs) continue;
         G1Affine a, b;
-        src.load_pair(p, a, b);
+        src.load_pair(span, p, p - first, a, b);
         G1Affine res;
         Fq d = b.x - a.x, num;
         int kind = kPairAdd;
@@ -554,7 +469,7 @@ __global__ void __launch_bounds__(128, 4) k_pairs_backward(PairSource<FIRST> src
             num = xx.dbl() + xx;
         }
         if (kind <= kPairDouble) {
-            Fq inv_d = fq_mul_call(inv, prefix.load(p));
+            Fq inv_d = fq_mul_call(inv, prefix.load(span.at(prefix.cap, p - first)));
             inv = fq_mul_call(inv, d);
             Fq lam = fq_mul_call(num, inv_d);
             res.x = fq_mul_call(lam, lam) - a.x - b.x;
@@ -566,7 +481,7 @@ __global__ void __launch_bounds__(128, 4) k_pairs_backward(PairSource<FIRST> src
         } else {
             res = G1Affine::inf();
         }
-        next.store(p, res);
+        next.store(span.at(next.cap, p - first), res);
     }
 }
 
@@ -608,7 +523,21 @@ __global__ void __launch_bounds__(128, MINB) k_accumulate(const G1Affine* __rest
 
 // After R pair rounds: bucket t owns X_R[offsets[t] >> R .. offsets[t+1] >> R); one thread per bucket finishes the
 // few remaining points in XYZZ.  Runs still longer than heavy_thr (hot buckets) go to the chunked path.
-__global__ void __launch_bounds__(128, 4) k_accumulate_rounds(PointPlanes pts, const uint32_t* __restrict__ offsets,
+// Where slot k of X_R lives: the lower span stores its slots upwards from 0, the upper span (slots >= *mid >> R) downwards
+// from the end of the planes (PairSpan).  mid == nullptr: one span, identity.
+struct RoundSlots {
+    PointPlanes pts;
+    const uint32_t* mid;
+    int R;
+    __device__ __forceinline__ G1Affine load(uint32_t k) const {
+        if (mid) {
+            const uint32_t m = *mid >> R;
+            if (k >= m) return pts.load(pts.cap - 1 - (size_t)(k - m));
+        }
+        return pts.load(k);
+    }
+};
+__global__ void __launch_bounds__(128, 4) k_accumulate_rounds(RoundSlots slots, const uint32_t* __restrict__ offsets,
                                                               const uint32_t* __restrict__ order, int R,
                                                               G1XYZZ* __restrict__ buckets, uint32_t total_buckets,
                                                               uint32_t heavy_thr, HeavyLists hl) {
@@ -621,7 +550,7 @@ __global__ void __launch_bounds__(128, 4) k_accumulate_rounds(PointPlanes pts, c
         return;
     }
     G1XYZZ acc = G1XYZZ::inf();
-    for (uint32_t k = beg; k < end; k++) xyzz_madd_t<MulCall>(acc, pts.load(k), false);
+    for (uint32_t k = beg; k < end; k++) xyzz_madd_t<MulCall>(acc, slots.load(k), false);
     buckets[t] = acc;
 }
 
@@ -629,7 +558,7 @@ __global__ void __launch_bounds__(128, 4) k_accumulate_rounds(PointPlanes pts, c
 // ROUNDS: the chunk is a range of X_R (after R pair rounds) instead of the sorted list.
 template <bool ROUNDS>
 __global__ void __launch_bounds__(256) k_accumulate_heavy(const G1Affine* __restrict__ bases, const uint32_t* __restrict__ sorted,
-                                                          PointPlanes pts, int R,
+                                                          RoundSlots slots, int R,
                                                           const uint32_t* __restrict__ offsets, HeavyLists hl) {
     extern __shared__ uint4 smem_raw[];
     G1XYZZ* sh = reinterpret_cast<G1XYZZ*>(smem_raw);
@@ -643,7 +572,7 @@ __global__ void __launch_bounds__(256) k_accumulate_heavy(const G1Affine* __rest
         G1XYZZ acc = G1XYZZ::inf();
         for (uint32_t k = beg + threadIdx.x; k < end; k += blockDim.x) {
             if (ROUNDS) {
-                xyzz_madd_t<MulCall>(acc, pts.load(k), false);
+                xyzz_madd_t<MulCall>(acc, slots.load(k), false);
             } else {
                 uint32_t e = sorted[k];
                 G1Affine p = load_point(bases, e & 0x7fffffffu);
@@ -900,6 +829,9 @@ int MsmEngine::choose_window(size_t n) {
 }
 
 MsmEngine::~MsmEngine() {
+    if (side_stream_) cudaStreamDestroy(side_stream_);
+    if (ev_fork_) cudaEventDestroy(ev_fork_);
+    if (ev_join_) cudaEventDestroy(ev_join_);
     if (ev_acc_begin) cudaEventDestroy(ev_acc_begin);
     if (ev_acc_end) cudaEventDestroy(ev_acc_end);
     if (ev_bwd_begin) cudaEventDestroy(ev_bwd_begin);
@@ -994,11 +926,12 @@ MsmEngine::Shape MsmEngine::run(const G1Affine* bases, const Fr* scalars, size_t
                 // Cost per bucket in ns, constants measured on B200 (profiles/r1_e_summary.md): a slot pair of the padded
                 // run costs 0.205 (backward) + 0.083 / 0.044 (forward: first round gathers, later rounds stream), an XYZZ
                 // addition of what is left 0.38, and every round a fixed ~0.55 ms (inversion tree, launches)
-                // (round 2: block-tree inversion over 16..128 pairs per thread, fixed cost ~0.35 ms instead of 0.55)
+                // (round 2: the two halves of the buckets run their rounds on two streams, which hides most of the ~0.45 ms of
+                // latency-bound inversion per round: ~0.2 ms of launches and tails remain)
                 static double round_fixed_ns = -1;
                 if (round_fixed_ns < 0) {
                     const char* v = getenv("PM_MSM_ROUND_FIXED_NS");
-                    round_fixed_ns = v ? atof(v) : 0.35e6;
+                    round_fixed_ns = v ? atof(v) : 0.2e6;
                 }
                 double best = 1e300;
                 for (int r = 0; r <= 6; r++) {
@@ -1133,77 +1066,104 @@ MsmEngine::Shape MsmEngine::run(const G1Affine* bases, const Fr* scalars, size_t
         PM_LAUNCH_CHECK();
         if (timed) PM_CUDA(cudaEventRecord(ev_acc_begin, stream));
         PointPlanes run_pts{nullptr, 0};
+        const uint32_t* round_mid = nullptr;      // two spans: first slot (round 0) of the upper one
         if (rounds > 0) {
             const size_t cap_a = slots_max / 2 + 2, cap_b = slots_max / 4 + 2;
             PointPlanes ping{pairs_a_.as<uint4>(6 * cap_a), cap_a};
             PointPlanes pong{rounds > 1 ? pairs_b_.as<uint4>(6 * cap_b) : nullptr, cap_b};
             FqPlanes prefix{prefix_.as<uint4>(3 * cap_a), cap_a};
-            // thread totals and the levels of the inversion tree above them: [T_0 | T_1 | ...], T_{l+1} = tile products of T_l
-            size_t lvl[kInvMaxLevels + 1];
-            int nlevels = 0;             // levels above T_0
-            lvl[0] = (slots_max / 2 + pair_tile(kMinPairsPerThread) - 1) / pair_tile(kMinPairsPerThread) * 128 + 128;
-            size_t lvl_total = lvl[0];
-            while (lvl[nlevels] > kInvTile) {
-                if (nlevels == kInvMaxLevels) throw CudaError("msm: inversion tree too deep");
-                lvl[nlevels + 1] = (lvl[nlevels] + kInvTile - 1) / kInvTile + 1;
-                lvl_total += lvl[++nlevels];
+            // Two spans = the lower and the upper half of this pass's buckets (PairSpan): independent pipelines over
+            // disjoint ranges of the same arrays, each with its own thread totals and inversion tree, on two streams.
+            static int halves_env = -1;
+            if (halves_env < 0) {
+                const char* v = getenv("PM_MSM_HALVES");      // tuning hook: 0 = one span on the caller's stream
+                halves_env = v ? atoi(v) : 1;
             }
-            Fq* tlev[kInvMaxLevels + 1];
-            tlev[0] = tvals_.as<Fq>(lvl_total);
-            for (int l = 0; l < nlevels; l++) tlev[l + 1] = tlev[l] + lvl[l];
-            Fq* tvals = tlev[0];
-            const uint32_t* slots0 = offsets + total;
+            const int nspans = (halves_env && total >= 2) ? 2 : 1;
+            // thread totals and the levels of the inversion tree above them: [T_0 | T_1 | T_2], prefixes [pre_0 | pre_1];
+            // sized for the smallest pairs-per-thread; one set per span
+            size_t lvl[kInvLevels + 1];
+            lvl[0] = (slots_max / 2 + pair_tile(kMinPairsPerThread) - 1) / pair_tile(kMinPairsPerThread) * 128 + 256;
+            for (int l = 0; l < kInvLevels; l++) lvl[l + 1] = (lvl[l] + kInvFan - 1) / kInvFan + 1;
+            const size_t t_per_span = lvl[0] + lvl[1] + lvl[2], p_per_span = lvl[0] + lvl[1];
+            Fq* t_all = tvals_.as<Fq>(t_per_span * nspans);
+            Fq* p_all = tpre_.as<Fq>(p_per_span * nspans);
             static int forced_ppt = -1;
             if (forced_ppt < 0) {
                 const char* v = getenv("PM_MSM_PAIRS_PER_THREAD");      // tuning hook
                 forced_ppt = v ? atoi(v) : 0;
             }
-            for (int r = 0; r < rounds; r++) {
-                const size_t pairs_max = (slots_max >> r) >> 1;
-                // pairs per thread: keep >= ~4 waves of 128-thread CTAs (148 SMs x 4 resident) in the round
-                int ppt = kMinPairsPerThread;
-                while (ppt < kMaxPairsPerThread && pairs_max / (pair_tile(ppt) * 2) >= (size_t)sm_count() * 16) ppt *= 2;
-                if (forced_ppt >= kMinPairsPerThread && forced_ppt <= kMaxPairsPerThread) ppt = forced_ppt;
-                const unsigned g = ceil_div(pairs_max, pair_tile(ppt));
-                if (g == 0) break;
-                PointPlanes dst = (r & 1) ? pong : ping;
-                // level sizes for the grids (upper bounds; the kernels derive the exact ones from slots0).  The tree depth
-                // is fixed by the upper bound of the FIRST round, so a later, smaller round may find its top level with
-                // one element: k_inv_top handles any n <= kInvTile.
-                size_t nl[kInvMaxLevels + 1];
-                nl[0] = (size_t)g * 128;
-                int top = 0;
-                while (nl[top] > kInvTile) { nl[top + 1] = (nl[top] + kInvTile - 1) / kInvTile; top++; }
-                constexpr int ism = (int)sizeof(InvTree);
-                static bool inv_attr_set = false;
-                if (!inv_attr_set) {
-                    PM_CUDA(cudaFuncSetAttribute(k_inv_up, cudaFuncAttributeMaxDynamicSharedMemorySize, ism));
-                    PM_CUDA(cudaFuncSetAttribute(k_inv_top, cudaFuncAttributeMaxDynamicSharedMemorySize, ism));
-                    PM_CUDA(cudaFuncSetAttribute(k_inv_down, cudaFuncAttributeMaxDynamicSharedMemorySize, ism));
-                    inv_attr_set = true;
+            if (nspans == 2) {
+                if (!side_stream_) {
+                    PM_CUDA(cudaStreamCreateWithFlags(&side_stream_, cudaStreamNonBlocking));
+                    PM_CUDA(cudaEventCreateWithFlags(&ev_fork_, cudaEventDisableTiming));
+                    PM_CUDA(cudaEventCreateWithFlags(&ev_join_, cudaEventDisableTiming));
                 }
-                auto invert = [&]() {
-                    for (int l = 0; l < top; l++) k_inv_up<<<(unsigned)nl[l + 1], kInvThreads, ism, stream>>>(tlev[l], tlev[l + 1], slots0, r, ppt, l);
-                    k_inv_top<<<1, kInvThreads, ism, stream>>>(tlev[top], slots0, r, ppt, top);
-                    for (int l = top; l-- > 0;) k_inv_down<<<(unsigned)nl[l + 1], kInvThreads, ism, stream>>>(tlev[l], tlev[l + 1], slots0, r, ppt, l);
-                    launches += 1 + 2 * (size_t)top;
-                };
-                if (r == 0) {
-                    PairSource<true> src{bases, sorted, run_pts};
-                    k_pairs_forward<true><<<g, 128, 0, stream>>>(src, slots0, r, ppt, prefix, tvals);
-                    invert();
-                    if (timed) PM_CUDA(cudaEventRecord(ev_bwd_begin, stream));
-                    k_pairs_backward<true><<<g, 128, 0, stream>>>(src, slots0, r, ppt, prefix, tvals, dst);
-                    if (timed) PM_CUDA(cudaEventRecord(ev_bwd_end, stream));
-                } else {
-                    PairSource<false> src{bases, sorted, run_pts};
-                    k_pairs_forward<false><<<g, 128, 0, stream>>>(src, slots0, r, ppt, prefix, tvals);
-                    invert();
-                    k_pairs_backward<false><<<g, 128, 0, stream>>>(src, slots0, r, ppt, prefix, tvals, dst);
+                PM_CUDA(cudaEventRecord(ev_fork_, stream));
+                PM_CUDA(cudaStreamWaitEvent(side_stream_, ev_fork_, 0));
+            }
+            const uint32_t mid = total / 2;
+            for (int sp = 0; sp < nspans; sp++) {
+                cudaStream_t st = sp == 0 ? stream : side_stream_;
+                PairSpan span;
+                span.s_begin = (nspans == 2 && sp == 1) ? offsets + mid : nullptr;
+                span.s_end = (nspans == 2 && sp == 0) ? offsets + mid : offsets + total;
+                span.rev = sp;
+                Fq* tlev[kInvLevels + 1];
+                Fq* plev[kInvLevels];
+                tlev[0] = t_all + (size_t)sp * t_per_span;
+                plev[0] = p_all + (size_t)sp * p_per_span;
+                for (int l = 0; l < kInvLevels; l++) tlev[l + 1] = tlev[l] + lvl[l];
+                plev[1] = plev[0] + lvl[0];
+                Fq* tvals = tlev[0];
+                PointPlanes cur{nullptr, 0};
+                for (int r = 0; r < rounds; r++) {
+                    // upper bound of the span's pairs (the exact count is read on the device): a half cannot hold more
+                    // than the whole, and for uniform digits holds about half — CTAs beyond the exact count exit at once
+                    const size_t pairs_max = (slots_max >> r) >> 1;
+                    // pairs per thread: keep >= ~4 waves of 128-thread CTAs (148 SMs x 4 resident) in the round
+                    int ppt = kMinPairsPerThread;
+                    const size_t pairs_est = pairs_max / (size_t)nspans;
+                    while (ppt < kMaxPairsPerThread && pairs_est / (pair_tile(ppt) * 2) >= (size_t)sm_count() * 16) ppt *= 2;
+                    if (forced_ppt >= kMinPairsPerThread && forced_ppt <= kMaxPairsPerThread) ppt = forced_ppt;
+                    const unsigned g = ceil_div(pairs_max, pair_tile(ppt));
+                    if (g == 0) break;
+                    PointPlanes dst = (r & 1) ? pong : ping;
+                    // level sizes for the grids (upper bounds; the kernels derive the exact ones from the span)
+                    size_t nl[kInvLevels + 1];
+                    nl[0] = (size_t)g * 128;
+                    for (int l = 0; l < kInvLevels; l++) nl[l + 1] = (nl[l] + kInvFan - 1) / kInvFan;
+                    auto invert = [&]() {
+                        for (int l = 0; l < kInvLevels; l++)
+                            k_invert_up<<<ceil_div(nl[l + 1], 128), 128, 0, st>>>(tlev[l], plev[l], tlev[l + 1], span, r, ppt, l);
+                        k_invert_top<<<ceil_div(nl[kInvLevels], 128), 128, 0, st>>>(tlev[kInvLevels], span, r, ppt, kInvLevels);
+                        for (int l = kInvLevels; l-- > 0;)
+                            k_invert_down<<<ceil_div(nl[l + 1], 128), 128, 0, st>>>(tlev[l], plev[l], tlev[l + 1], span, r, ppt, l);
+                    };
+                    const bool time_bwd = timed && sp == 0 && r == 0;
+                    if (r == 0) {
+                        PairSource<true> src{bases, sorted, cur};
+                        k_pairs_forward<true><<<g, 128, 0, st>>>(src, span, r, ppt, prefix, tvals);
+                        invert();
+                        if (time_bwd) PM_CUDA(cudaEventRecord(ev_bwd_begin, st));
+                        k_pairs_backward<true><<<g, 128, 0, st>>>(src, span, r, ppt, prefix, tvals, dst);
+                        if (time_bwd) PM_CUDA(cudaEventRecord(ev_bwd_end, st));
+                    } else {
+                        PairSource<false> src{bases, sorted, cur};
+                        k_pairs_forward<false><<<g, 128, 0, st>>>(src, span, r, ppt, prefix, tvals);
+                        invert();
+                        k_pairs_backward<false><<<g, 128, 0, st>>>(src, span, r, ppt, prefix, tvals, dst);
+                    }
+                    PM_LAUNCH_CHECK();
+                    cur = dst;
+                    launches += 3 + 2 * kInvLevels;
                 }
-                PM_LAUNCH_CHECK();
-                run_pts = dst;
-                launches += 2;
+                run_pts = cur;
+            }
+            if (nspans == 2) {
+                PM_CUDA(cudaEventRecord(ev_join_, side_stream_));
+                PM_CUDA(cudaStreamWaitEvent(stream, ev_join_, 0));
+                round_mid = offsets + mid;
             }
         }
         // runs are cut into chunked tasks only when walking them serially would approach the kernel's duration
@@ -1215,7 +1175,7 @@ MsmEngine::Shape MsmEngine::run(const G1Affine* bases, const Fr* scalars, size_t
                 variant = v ? atoi(v) : 24;
             }
             const unsigned g = ceil_div(total, 128);
-            if (rounds > 0) k_accumulate_rounds<<<g, 128, 0, stream>>>(run_pts, offsets, order, rounds, buckets, total, walk_heavy_thr, hl);
+            if (rounds > 0) k_accumulate_rounds<<<g, 128, 0, stream>>>(RoundSlots{run_pts, round_mid, rounds}, offsets, order, rounds, buckets, total, walk_heavy_thr, hl);
             else if (variant == 3) k_accumulate<3, MulInline><<<g, 128, 0, stream>>>(bases, sorted, offsets, order, buckets, total, heavy_thr, hl);
             else k_accumulate<4, MulCall><<<g, 128, 0, stream>>>(bases, sorted, offsets, order, buckets, total, heavy_thr, hl);
             PM_LAUNCH_CHECK();
@@ -1229,8 +1189,8 @@ MsmEngine::Shape MsmEngine::run(const G1Affine* bases, const Fr* scalars, size_t
                 PM_CUDA(cudaFuncSetAttribute(k_accumulate_heavy<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
                 attr_set = true;
             }
-            if (rounds > 0) k_accumulate_heavy<true><<<4 * sm_count(), 256, smem, stream>>>(bases, sorted, run_pts, rounds, offsets, hl);
-            else k_accumulate_heavy<false><<<4 * sm_count(), 256, smem, stream>>>(bases, sorted, run_pts, 0, offsets, hl);
+            if (rounds > 0) k_accumulate_heavy<true><<<4 * sm_count(), 256, smem, stream>>>(bases, sorted, RoundSlots{run_pts, round_mid, rounds}, rounds, offsets, hl);
+            else k_accumulate_heavy<false><<<4 * sm_count(), 256, smem, stream>>>(bases, sorted, RoundSlots{run_pts, nullptr, 0}, 0, offsets, hl);
             PM_LAUNCH_CHECK();
             k_heavy_finish<<<2 * sm_count(), 128, 0, stream>>>(buckets, hl);
             PM_LAUNCH_CHECK();

@@ -62,7 +62,9 @@ private:
     using PlanKey = std::tuple<size_t, int, int, int, int, int>;
     std::map<PlanKey, std::pair<int, int>> plans_;
     DevBuf counts_, offsets_, cursors_, sorted_, buckets_, segs_, heavy_list_, heavy_count_, order_;
-    DevBuf pairs_a_, pairs_b_, prefix_, tvals_;   // pair rounds
+    DevBuf pairs_a_, pairs_b_, prefix_, tvals_, tpre_;   // pair rounds
+    cudaStream_t side_stream_ = nullptr;                   // second span of the pair rounds
+    cudaEvent_t ev_fork_ = nullptr, ev_join_ = nullptr;   // pair rounds
 };
 
 constexpr int kMaxMsmWindows = 64;

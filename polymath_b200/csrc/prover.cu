@@ -313,11 +313,13 @@ ProverCtx::Phase1Shapes ProverCtx::phase1_enqueue(const uint8_t* ra) {
     // sort / reduction tail hides behind the c-side bucket accumulation.
     PM_CUDA(cudaEventRecord(rt.ev_fork, s));
     PM_CUDA(cudaStreamWaitEvent(rt.stream2, rt.ev_fork, 0));
-    // beside each other on two streams the MSMs hide their latency-bound inversion passes: one more pair round pays
+    // (round 1 gave the phase-1 MSMs one more pair round than the cost model asked for, because running beside each other
+    // hid their inversion latency; since every MSM now overlaps the two halves of its own buckets the model's choice is
+    // the best one: 21.6 ms against 22.1 ms with the extra round, profiles/r2_e_summary.md)
     static int p1_bias = -100;
     if (p1_bias == -100) {
         const char* v = getenv("PM_P1_ROUNDS_BIAS");
-        p1_bias = v ? atoi(v) : 1;
+        p1_bias = v ? atoi(v) : 0;
     }
     // the a-side bases are a prefix of bases_c: its fixed-base table serves both MSMs
     static int a_tables = -1;

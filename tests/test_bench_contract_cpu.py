@@ -36,12 +36,16 @@ def test_recorded_bench_line_has_the_contract_keys():
 
 
 def test_reference_arm_runs_on_the_cpu_and_prints_its_line():
-    env = dict(os.environ, PM_REF_SAMPLE_LOG="10", OMP_NUM_THREADS="1")      # as under torchrun
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
-                         capture_output=True, text=True, env=env, timeout=600)
+    """The reference arm is ONE complete CPU prove per step (oracle/fast.py); here at 2^10 over a key-shaped set of
+    arbitrary points (no GPU in this container to run the setup), on the box at --log-n 20 with the real key."""
+    env = dict(os.environ, PM_REF_SYNTHETIC_KEY="1", OMP_NUM_THREADS="1")      # as under torchrun
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1", "--log-n", "10"]
+    out = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     d = json.loads(out.stdout.strip().splitlines()[-1])
-    assert d["impl"] == "reference" and d["metric"].startswith("prove_ms_2p20") and d["unit"] == "ms"
+    assert d["impl"] == "reference" and d["metric"] == "prove_ms_2p10_sap_constraints" and d["unit"] == "ms"
+    assert "complete prove" in d["cpu_baseline"]["sample"] and set(d["cpu_baseline"]["split_ms_last"]) >= {"ntt", "msm_d"}
+    assert len(d["cpu_baseline"]["proof_hex"]) == 352 and d["config"]["log_n"] == 10
     assert d["higher_is_better"] is False and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert d["e2e"]["value"] == d["value"] == d["cpu_baseline"]["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
@@ -52,6 +56,5 @@ def test_reference_arm_runs_on_the_cpu_and_prints_its_line():
         avail = os.cpu_count() or 1
     assert d["cpu_baseline"]["cores"] == avail
     # other ranks of a torchrun launch print nothing and exit 0
-    out2 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
-                          capture_output=True, text=True, env=dict(env, RANK="1", WORLD_SIZE="2"), timeout=600)
+    out2 = subprocess.run(cmd, capture_output=True, text=True, env=dict(env, RANK="1", WORLD_SIZE="2"), timeout=600)
     assert out2.returncode == 0 and out2.stdout.strip() == ""

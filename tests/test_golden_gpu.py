@@ -83,14 +83,16 @@ class _Challenges:
         return x2, c_at_x1
 
 
-_LARGE = [int(v) for v in os.environ.get("PM_TEST_LARGE", "").split(",") if v]   # e.g. PM_TEST_LARGE=22,24 (minutes)
+_LARGE = [int(v) for v in os.environ.get("PM_TEST_LARGE", "").split(",") if v]   # e.g. PM_TEST_LARGE=24 (minutes)
 
 
-@pytest.mark.parametrize("log_n", [14, 17, 20] + _LARGE)
+@pytest.mark.parametrize("log_n", [14, 17, 22] + _LARGE)
 def test_large_synthetic_circuit_verifies(pmlib, log_n):
     """S-mimc(2^log_n): setup + prove entirely on the device, then the oracle's pairing
     check must accept — the property the reference's own tests assert.  2^17 exercises the fixed-base tables,
-    2^20 is BASELINE.json's headline size (the workload bench.py times)."""
+    2^22 the first domain whose squaring transform (2^23) takes three NTT passes and the size from which a sharded
+    prove runs its transforms through the all-to-all; 2^20, BASELINE.json's headline size, is covered byte for byte by
+    test_bench_check_proof_matches_golden_and_the_oracle_accepts below."""
     from polymath_b200 import circuits
     from polymath_b200.api import Polymath
     n = 1 << log_n
@@ -115,6 +117,32 @@ def test_large_synthetic_circuit_verifies(pmlib, log_n):
     vk_bytes = vk.serialize_compressed()
     assert Polymath.verify(vk_bytes, inst[1:], proof.serialize_compressed())
     assert Polymath.verify(vk_bytes, inst[1:], proof2.serialize_compressed())
+    pk.close()
+
+
+def test_bench_check_proof_matches_golden_and_the_oracle_accepts(pmlib):
+    """The proof bench.py prints as `proof_check` (S-mimc(2^20), setup seed 1, blinding seed CHECK_SEED) is pinned in
+    tests/golden/bench_proofs.json: the one-GPU path must reproduce it byte for byte here, and the ORACLE's pairing
+    check must accept those bytes — so a bench run on N GPUs that matches the golden has matched an oracle-accepted,
+    unsharded proof of the same seed (VERDICT r1, next #1b)."""
+    import bench
+    from polymath_b200 import keydump
+    from polymath_b200.api import Polymath, StdRng
+    golden = json.load(open(os.path.join(GOLDEN, "bench_proofs.json")))["mimc_2p20_seed1_check"]
+    log_n = 20
+    n = 1 << log_n
+    r1cs, inst, wit, rng = keydump.build_workload("mimc", log_n, 1)
+    x, z = rng.fr_rand(), rng.fr_rand()          # sample_element_outside_domain x2 (generator.rs:72,77)
+    assert pow(x, n, R_MOD) != 1 and pow(z, n, R_MOD) != 1
+    pk, x_g2, z_g2 = Polymath.setup_with_trapdoors(r1cs, x, z)
+    vk = opm.VerifyingKey(one_g1=curve.G1_GEN, one_g2=curve.G2_GEN, x_g2=x_g2, z_g2=z_g2, n=n, m0=2, sigma=n + 3,
+                          omega=__import__("oracle.poly", fromlist=["Domain"]).Domain(n).group_gen)
+    got = Polymath.prove(pk, inst, wit, StdRng.seed_from_u64(bench.CHECK_SEED))
+    assert got.hex() == golden
+    proof = opm.Proof(a_g1=curve.g1_decompress(got[:48]), c_g1=curve.g1_decompress(got[48:96]),
+                      a_at_x1=int.from_bytes(got[96:128], "little"), d_g1=curve.g1_decompress(got[128:]))
+    assert opm.verify_proof(vk, proof, inst[1:])
+    assert Polymath.verify(vk.serialize_compressed(), inst[1:], got)
     pk.close()
 
 
