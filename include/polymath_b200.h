@@ -232,6 +232,12 @@ int pm_host_sum_partials(const uint8_t* parts, int count, size_t stride, uint8_t
  * which: 0 u coeffs (n), 1 w coeffs (n), 2 witness-u coeffs (n), 3 u^2 coeffs (2n), 4 [x|w|y] (cols - m0),
  *        5 phase-1 c-side scalars, 6 opening quotient D (10n + 22).  Returns the element count in *len. */
 int pm_ctx_debug_read(pm_ctx* ctx, int which, uint8_t* out, uint64_t capacity_elems, uint64_t* len);
+/* Test hook for the multi-GPU kernels on ONE GPU: on an unsharded context that has just completed a proof, replays the
+ * polynomial work the way `virtual_world` (2, 4 or 8) ranks of the sharded-resident flow would — SAP rows of each residue
+ * class, sharded transforms with the all-to-all emulated by device copies, ring exchange, local scalar assembly, the
+ * (X - x1) division by chunk ranges with its carry exchange — and returns in *mismatches how many elements differ from
+ * what the unsharded path computed (0 = identical).  Needs n >= 8 * virtual_world^2. */
+int pm_ctx_selftest_resident(pm_ctx* ctx, int virtual_world, uint64_t* mismatches);
 /* Milliseconds spent on the device by the last phase-1 / phase-2 / phase-3 call (CUDA events). */
 int pm_ctx_phase_ms(const pm_ctx* ctx, double ms[3]);
 

@@ -109,32 +109,139 @@ __global__ void k_ra_square(Fr* ra) {
     ra[4] = r1.sqr();
 }
 
-__global__ void __launch_bounds__(256) k_assemble_phase1(const Fr* __restrict__ u, const Fr* __restrict__ u2,
-                                                         const Fr* __restrict__ ztail, uint64_t tail,
-                                                         const Fr* __restrict__ ra, uint64_t n, Fr* __restrict__ scal_a,
-                                                         Fr* __restrict__ scal_c) {
-    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const uint64_t len_c = (n + 1) + 3 + 2 + (n - 1) + tail;
-    if (k >= len_c) return;
+// one scalar of the c-side / a-side arrays at global index k of the CLayout, from accessors for u, h = u2[n + .], ztail
+template <class U, class H, class Z>
+__device__ __forceinline__ void phase1_scalar(const CLayout& L, uint64_t k, const Fr* __restrict__ ra, U u_at, H h_at, Z z_at,
+                                              Fr& sc, Fr& sa) {
+    const uint64_t n = L.n;
+    sc = Fr::zero();
+    sa = Fr::zero();
     if (k <= n) {
-        // 2 r_a(X) u(X): coefficient k = 2 (r0 u_k + r1 u_{k-1})
+        // 2 r_a(X) u(X): coefficient k = 2 (r0 u_k + r1 u_{k-1})   (compute_r_g1, prover.rs:340-347)
         Fr acc = Fr::zero();
-        if (k < n) acc = ra[0] * u[k];
-        if (k >= 1) acc = acc + ra[1] * u[k - 1];
-        scal_c[k] = acc.dbl();
-        // a-side scalars share the first n + 4 bases
-        scal_a[k] = (k < n) ? u[k] : Fr::zero();
-    } else if (k < n + 4) {
-        uint64_t j = k - (n + 1);
-        scal_c[k] = ra[2 + j];
-        scal_a[k] = (j < 2) ? ra[j] : Fr::zero();
-    } else if (k < n + 6) {
-        scal_c[k] = ra[k - (n + 4)];
-    } else if (k < n + 6 + (n - 1)) {
-        scal_c[k] = u2[n + (k - (n + 6))];   // h = u2[n .. 2n-1)
-    } else {
-        scal_c[k] = ztail[k - (n + 6 + (n - 1))];
+        if (k < n) { sa = u_at(k); acc = ra[0] * sa; }
+        if (k >= 1) acc = acc + ra[1] * u_at(k - 1);
+        sc = acc.dbl();
+    } else if (k < L.off_ya) {
+    } else if (k < L.off_ya + 3) {
+        const uint64_t j = k - L.off_ya;
+        sc = ra[2 + j];                       // r_a^2 against x_powers_y_alpha
+        if (j < 2) sa = ra[j];                // r_a against x_powers_y_alpha (compute_a_g1, prover.rs:336)
+    } else if (k < L.off_yg) {
+    } else if (k < L.off_yg + 2) {
+        sc = ra[k - L.off_yg];                // r_a against x_powers_y_gamma
+    } else if (k < L.off_zh) {
+    } else if (k < L.off_zh + (n - 1)) {
+        sc = h_at(k - L.off_zh);              // h = u2[n .. 2n-1) against x_powers_zh_by_y_alpha
+    } else if (k < L.off_lcs) {
+    } else if (k < L.len_c) {
+        sc = z_at(k - L.off_lcs);             // [x | w | y] against uj_wj_lcs
     }
+}
+
+__global__ void __launch_bounds__(256) k_assemble_phase1(const Fr* __restrict__ u, const Fr* __restrict__ u2,
+                                                         const Fr* __restrict__ ztail, CLayout L, const Fr* __restrict__ ra,
+                                                         Fr* __restrict__ scal_a, Fr* __restrict__ scal_c) {
+    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= L.len_c) return;
+    Fr sc, sa;
+    phase1_scalar(L, k, ra, [&](uint64_t i) { return u[i]; }, [&](uint64_t j) { return u2[L.n + j]; },
+                  [&](uint64_t j) { return ztail[j]; }, sc, sa);
+    scal_c[k] = sc;
+    if (k < L.len_a) scal_a[k] = sa;
+}
+
+// ---- sharded-resident variants: thread t of rank r works on the global index r + t * G ---------------------------------
+__device__ __forceinline__ void public_row(const SapDims& d, const Fr* __restrict__ z, uint32_t i, Fr& one_plus, Fr& one_minus, Fr& y) {
+    const Fr one = Fr::one();
+    const Fr x = z[i];
+    one_plus = one + x;
+    one_minus = one - x;
+    y = (i == 0) ? Fr::zero() : one_minus.sqr();      // compute_y_vec: y_0 = 0, y_j = (1 - x_j)^2
+}
+
+__global__ void __launch_bounds__(128) k_sap_rows_strided(SapDims d, DevCsr A, DevCsr B, DevCsr C, const Fr* __restrict__ z,
+                                                          uint32_t rank, uint32_t world, Fr* __restrict__ u_loc,
+                                                          Fr* __restrict__ w_loc, Fr* __restrict__ wu_loc) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t k = (uint64_t)rank + t * world;
+    if (k >= d.n) return;
+    Fr u = Fr::zero(), w = Fr::zero(), wu = Fr::zero();
+    const uint64_t m0 = d.m0, nr = d.nr;
+    if (k < 2 * m0) {
+        Fr op, om, y;
+        public_row(d, z, (uint32_t)(k < m0 ? k : k - m0), op, om, y);
+        if (k < m0) { u = op; w = z[k].dbl().dbl() + y; }
+        else { u = om; w = y; }
+    } else if (k < 2 * m0 + 2 * nr) {
+        const bool second = k >= 2 * m0 + nr;
+        const uint32_t r = (uint32_t)(k - 2 * m0 - (second ? nr : 0));
+        const Fr az = csr_row_dot(A, r, z), bz = csr_row_dot(B, r, z);
+        const Fr diff = az - bz;
+        const Fr y = diff.sqr();
+        if (second) { u = diff; w = y; }
+        else { u = az + bz; w = csr_row_dot(C, r, z).dbl().dbl() + y; }
+        wu = u;
+    }
+    u_loc[t] = u;
+    w_loc[t] = w;
+    wu_loc[t] = wu;
+}
+
+__global__ void __launch_bounds__(128) k_ztail_strided(SapDims d, DevCsr A, DevCsr B, const Fr* __restrict__ z, uint32_t rank,
+                                                       uint32_t world, uint64_t count, Fr* __restrict__ zt_loc) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    const uint64_t j = (uint64_t)rank + t * world;
+    const uint64_t zw = (uint64_t)d.m0 + d.mw;
+    Fr v;
+    if (j < zw) {
+        v = z[j];
+    } else if (j - zw < d.m0) {
+        Fr op, om;
+        public_row(d, z, (uint32_t)(j - zw), op, om, v);
+    } else {
+        const uint32_t r = (uint32_t)(j - zw - d.m0);
+        v = (csr_row_dot(A, r, z) - csr_row_dot(B, r, z)).sqr();
+    }
+    zt_loc[t] = v;
+}
+
+__global__ void __launch_bounds__(256) k_quotient_checks_strided(const Fr* __restrict__ u2_loc, const Fr* __restrict__ w_loc,
+                                                                 uint64_t n, uint32_t rank, uint32_t world,
+                                                                 uint32_t* __restrict__ status, uint32_t* __restrict__ h_nonzero) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t per = n / world;
+    if (t >= per) return;
+    const uint64_t k = (uint64_t)rank + t * world;
+    Fr h = u2_loc[per + t];
+    Fr rem = u2_loc[t] - w_loc[t] + h;
+    if (!rem.is_zero()) atomicOr(status, ST_REMAINDER_NONZERO);
+    if (!h.is_zero()) {
+        if (k == n - 1) atomicOr(status, ST_H_DEGREE);
+        else atomicOr(h_nonzero, 1u);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_assemble_phase1_strided(const Fr* __restrict__ u_loc, const Fr* __restrict__ u_prev,
+                                                                 const Fr* __restrict__ u2_loc, const Fr* __restrict__ zt_loc,
+                                                                 CLayout L, const Fr* __restrict__ ra, uint32_t rank, uint32_t world,
+                                                                 uint64_t cnt_a, uint64_t cnt_c, Fr* __restrict__ scal_a_loc,
+                                                                 Fr* __restrict__ scal_c_loc) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= cnt_c) return;
+    const uint64_t k = (uint64_t)rank + t * world;
+    const uint64_t per = L.n / world;
+    Fr sc, sa;
+    // u_i for i = k (own residue class) or i = k - 1 (the class of rank - 1: u_prev; for rank 0 one local index lower)
+    auto u_at = [&](uint64_t i) {
+        if (i % world == rank) return u_loc[i / world];
+        return u_prev[i / world];
+    };
+    phase1_scalar(L, k, ra, u_at, [&](uint64_t j) { return u2_loc[per + j / world]; }, [&](uint64_t j) { return zt_loc[j / world]; },
+                  sc, sa);
+    scal_c_loc[t] = sc;
+    if (t < cnt_a) scal_a_loc[t] = sa;
 }
 
 // ---- virtual polynomial sources ---------------------------------------------------------
@@ -189,10 +296,12 @@ struct NumSrc {
 // chunk value: sum_{k in chunk} p_k x^(k - lo).  Thread t owns kPerThread consecutive
 // coefficients; per-thread Horner, then a weighted block reduction with powers of x^kPerThread.
 template <class Src>
-__global__ void __launch_bounds__(kThreads) k_chunk_eval(Src src, uint64_t len, const Fr* __restrict__ xp, Fr* __restrict__ chunk_vals) {
+__global__ void __launch_bounds__(kThreads) k_chunk_eval(Src src, uint64_t len, const Fr* __restrict__ xp, Fr* __restrict__ chunk_vals,
+                                                         uint64_t chunk0 = 0) {
     __shared__ Fr sh[kThreads];
     const Fr x = xp[0];
-    const uint64_t lo = (uint64_t)blockIdx.x * kChunk + (uint64_t)threadIdx.x * kPerThread;
+    const uint64_t chunk = chunk0 + blockIdx.x;
+    const uint64_t lo = chunk * kChunk + (uint64_t)threadIdx.x * kPerThread;
     Fr acc = Fr::zero();
 #pragma unroll 1
     for (int j = kPerThread - 1; j >= 0; j--) {
@@ -211,7 +320,7 @@ __global__ void __launch_bounds__(kThreads) k_chunk_eval(Src src, uint64_t len, 
         if (threadIdx.x < stride) sh[threadIdx.x] = sh[threadIdx.x] + sh[threadIdx.x + stride];
         __syncthreads();
     }
-    if (threadIdx.x == 0) chunk_vals[blockIdx.x] = sh[0];
+    if (threadIdx.x == 0) chunk_vals[chunk] = sh[0];
 }
 
 __global__ void k_combine_chunks(const Fr* __restrict__ chunk_vals, uint64_t nchunks, const Fr* __restrict__ xp, Fr* __restrict__ out) {
@@ -238,11 +347,12 @@ __global__ void k_chunk_powers(const Fr* __restrict__ xp, Fr* __restrict__ out) 
 
 // carries[c] = q_{(c+1)*kChunk - 1}: the quotient coefficient entering chunk c from above
 // (xcp[0] = the evaluation point raised to the chunk length).  Serial: used on <= a few hundred values.
+// carry_in (nullable): the quotient coefficient entering the topmost chunk (a rank's range of a sharded division).
 __global__ void k_chunk_carries(const Fr* __restrict__ chunk_vals, uint64_t nchunks, const Fr* __restrict__ xcp,
-                                Fr* __restrict__ carries, uint32_t* __restrict__ status) {
+                                Fr* __restrict__ carries, uint32_t* __restrict__ status, const Fr* __restrict__ carry_in = nullptr) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     Fr xc = xcp[0];
-    Fr q = Fr::zero();
+    Fr q = carry_in ? carry_in[0] : Fr::zero();
     for (uint64_t c = nchunks; c-- > 0;) {
         carries[c] = q;
         q = chunk_vals[c] + xc * q;
@@ -252,11 +362,12 @@ __global__ void k_chunk_carries(const Fr* __restrict__ chunk_vals, uint64_t nchu
 
 template <class Src>
 __global__ void __launch_bounds__(kThreads) k_chunk_divide(Src src, uint64_t len, const Fr* __restrict__ xp,
-                                                           const Fr* __restrict__ carries, Fr* __restrict__ q) {
+                                                           const Fr* __restrict__ carries, Fr* __restrict__ q, uint64_t chunk0 = 0) {
     __shared__ Fr sh[kThreads];
     const Fr x = xp[0];
     const int tid = threadIdx.x;
-    const uint64_t lo = (uint64_t)blockIdx.x * kChunk + (uint64_t)tid * kPerThread;
+    const uint64_t chunk = chunk0 + blockIdx.x;
+    const uint64_t lo = chunk * kChunk + (uint64_t)tid * kPerThread;
     Fr coef[kPerThread];
     Fr acc = Fr::zero();
 #pragma unroll 1
@@ -271,7 +382,7 @@ __global__ void __launch_bounds__(kThreads) k_chunk_divide(Src src, uint64_t len
 #pragma unroll 1
     for (int b = 1; b < kPerThread; b <<= 1) xe = xe.sqr();
     // fold the chunk carry into the last thread's value: H'_{T-1} = H_{T-1} + x^E * carry
-    if (tid == kThreads - 1) acc = acc + xe * carries[blockIdx.x];
+    if (tid == kThreads - 1) acc = acc + xe * carries[chunk];
     sh[tid] = acc;
     __syncthreads();
     Fr mult = xe;
@@ -283,13 +394,37 @@ __global__ void __launch_bounds__(kThreads) k_chunk_divide(Src src, uint64_t len
         mult = mult.sqr();
     }
     // sh[t] = sum_{t' >= t} H'_{t'} x^(E (t'-t)); carry into thread t is sh[t+1] (or the chunk carry)
-    Fr carry = (tid + 1 < kThreads) ? sh[tid + 1] : carries[blockIdx.x];
+    Fr carry = (tid + 1 < kThreads) ? sh[tid + 1] : carries[chunk];
 #pragma unroll 1
     for (int j = kPerThread - 1; j >= 0; j--) {
         uint64_t k = lo + j;
         carry = coef[j] + x * carry;
         if (k >= 1 && k < len) q[k - 1] = carry;
     }
+}
+
+// Exchange step of the sharded division: E_s = value of rank s's chunk range at x (relative to its first chunk lo_s).
+// carry into rank r's range = sum_{s > r} E_s X^(lo_s - hi_r), X = x^kChunk; p(x) = sum_s E_s X^lo_s must vanish.
+__global__ void k_range_carry(const Fr* __restrict__ range_vals, const uint64_t* __restrict__ range_lo, uint32_t rank, uint32_t world,
+                              const Fr* __restrict__ xp, Fr* __restrict__ carry_in, uint32_t* __restrict__ status) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const Fr X = xp[0].pow_u64((uint64_t)kChunk);
+    Fr total = Fr::zero(), carry = Fr::zero();
+    const uint64_t hi = range_lo[rank + 1];
+    for (uint32_t s = 0; s < world; s++) {
+        if (range_lo[s + 1] == range_lo[s]) continue;                // empty range
+        total = total + range_vals[s] * X.pow_u64(range_lo[s]);
+        if (s > rank) carry = carry + range_vals[s] * X.pow_u64(range_lo[s] - hi);
+    }
+    carry_in[0] = carry;
+    if (!total.is_zero()) atomicOr(status, ST_OPENING_REMAINDER);
+}
+
+// v[0] += x^kChunk * carry: folds the carry entering a range from above into its top chunk value (see
+// launch_numerator_range_divide)
+__global__ void k_fold_carry(Fr* __restrict__ v, const Fr* __restrict__ xcp, const Fr* __restrict__ carry) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    v[0] = v[0] + xcp[0] * carry[0];
 }
 
 template <class Src>
@@ -334,10 +469,37 @@ void launch_ra_square(Fr* ra_ext, cudaStream_t stream) {
     PM_LAUNCH_CHECK();
 }
 
-void launch_assemble_phase1_scalars(const Fr* u, const Fr* u2, const Fr* ztail, uint64_t tail, const Fr* ra_ext, uint64_t n,
+void launch_assemble_phase1_scalars(const Fr* u, const Fr* u2, const Fr* ztail, const CLayout& L, const Fr* ra_ext,
                                     Fr* scal_a, Fr* scal_c, cudaStream_t stream) {
-    const uint64_t len_c = (n + 1) + 3 + 2 + (n - 1) + tail;
-    k_assemble_phase1<<<ceil_div(len_c, 256), 256, 0, stream>>>(u, u2, ztail, tail, ra_ext, n, scal_a, scal_c);
+    k_assemble_phase1<<<ceil_div(L.len_c, 256), 256, 0, stream>>>(u, u2, ztail, L, ra_ext, scal_a, scal_c);
+    PM_LAUNCH_CHECK();
+}
+
+void launch_sap_evals_strided(const SapDims& d, const DevCsr& A, const DevCsr& B, const DevCsr& C, const Fr* ztail,
+                              uint32_t rank, uint32_t world, Fr* u_loc, Fr* w_loc, Fr* wu_loc, cudaStream_t stream) {
+    const uint64_t per = d.n / world;
+    k_sap_rows_strided<<<ceil_div(per, 128), 128, 0, stream>>>(d, A, B, C, ztail, rank, world, u_loc, w_loc, wu_loc);
+    PM_LAUNCH_CHECK();
+}
+void launch_ztail_strided(const SapDims& d, const DevCsr& A, const DevCsr& B, const Fr* ztail, uint32_t rank, uint32_t world,
+                          uint64_t count, Fr* zt_loc, cudaStream_t stream) {
+    if (!count) return;
+    k_ztail_strided<<<ceil_div(count, 128), 128, 0, stream>>>(d, A, B, ztail, rank, world, count, zt_loc);
+    PM_LAUNCH_CHECK();
+}
+void launch_quotient_checks_strided(const Fr* u2_loc, const Fr* w_loc, uint64_t n, uint32_t rank, uint32_t world,
+                                    uint32_t* status, cudaStream_t stream) {
+    PM_CUDA(cudaMemsetAsync(status + 1, 0, sizeof(uint32_t), stream));
+    k_quotient_checks_strided<<<ceil_div(n / world, 256), 256, 0, stream>>>(u2_loc, w_loc, n, rank, world, status, status + 1);
+    PM_LAUNCH_CHECK();
+    // "h == 0" needs every rank's slice: status[1] travels with the partial sums and is combined on the host
+}
+void launch_assemble_phase1_strided(const Fr* u_loc, const Fr* u_prev, const Fr* u2_loc, const Fr* zt_loc, const CLayout& L,
+                                    const Fr* ra_ext, uint32_t rank, uint32_t world, uint64_t cnt_a, uint64_t cnt_c,
+                                    Fr* scal_a_loc, Fr* scal_c_loc, cudaStream_t stream) {
+    if (!cnt_c) return;
+    k_assemble_phase1_strided<<<ceil_div(cnt_c, 256), 256, 0, stream>>>(u_loc, u_prev, u2_loc, zt_loc, L, ra_ext, rank, world, cnt_a,
+                                                                      cnt_c, scal_a_loc, scal_c_loc);
     PM_LAUNCH_CHECK();
 }
 
@@ -394,6 +556,81 @@ int launch_divide_numerator(const NumeratorSrc& src, const Fr* x, Fr* q, Fr* wor
     PM_LAUNCH_CHECK();
     return launches + 1;
 }
+namespace {
+struct RangeWork {      // the layout launch_divide_numerator uses for `work`, shared by the range functions
+    Fr *vals1, *carr1, *vals2, *carr2, *xpow;
+    RangeWork(Fr* work, uint64_t len) {
+        const uint64_t c1 = (len + kChunk - 1) / kChunk, c2 = (c1 + kChunk - 1) / kChunk;
+        vals1 = work;
+        carr1 = vals1 + c1 + 1;
+        vals2 = carr1 + c1 + 1;
+        carr2 = vals2 + c2 + 1;
+        xpow = carr2 + c2 + 1;
+    }
+};
+}  // namespace
+
+int launch_numerator_range_eval(const NumeratorSrc& src, const Fr* x, uint64_t c_lo, uint64_t cnt, Fr* work, Fr* range_val,
+                                cudaStream_t stream) {
+    NumSrc s{src};
+    RangeWork w(work, src.len);
+    k_chunk_powers<<<1, 32, 0, stream>>>(x, w.xpow);
+    PM_LAUNCH_CHECK();
+    if (cnt == 0) {
+        PM_CUDA(cudaMemsetAsync(range_val, 0, sizeof(Fr), stream));
+        return 1;
+    }
+    k_chunk_eval<NumSrc><<<(unsigned)cnt, kThreads, 0, stream>>>(s, src.len, x, w.vals1, c_lo);
+    PM_LAUNCH_CHECK();
+    if (cnt <= 128) {
+        k_combine_chunks<<<1, 32, 0, stream>>>(w.vals1 + c_lo, cnt, x, range_val);
+        PM_LAUNCH_CHECK();
+        return 3;
+    }
+    PlainSrc ps{w.vals1 + c_lo, cnt};
+    const uint64_t c2 = (cnt + kChunk - 1) / kChunk;
+    k_chunk_eval<PlainSrc><<<(unsigned)c2, kThreads, 0, stream>>>(ps, cnt, w.xpow, w.vals2);
+    k_combine_chunks<<<1, 32, 0, stream>>>(w.vals2, c2, w.xpow, range_val);     // point x^kChunk: raised to kChunk inside
+    PM_LAUNCH_CHECK();
+    return 4;
+}
+
+void launch_numerator_range_carry(const Fr* range_vals, const uint64_t* range_lo, uint32_t rank, uint32_t world, const Fr* x,
+                                  Fr* carry_in, uint32_t* status, cudaStream_t stream) {
+    k_range_carry<<<1, 32, 0, stream>>>(range_vals, range_lo, rank, world, x, carry_in, status);
+    PM_LAUNCH_CHECK();
+}
+
+int launch_numerator_range_divide(const NumeratorSrc& src, const Fr* x, uint64_t c_lo, uint64_t cnt, const Fr* carry_in, Fr* q,
+                                  Fr* work, cudaStream_t stream) {
+    if (cnt == 0) return 0;
+    NumSrc s{src};
+    RangeWork w(work, src.len);
+    int launches = 0;
+    if (cnt <= 128) {
+        k_chunk_carries<<<1, 32, 0, stream>>>(w.vals1 + c_lo, cnt, w.xpow, w.carr1 + c_lo, nullptr, carry_in);
+        launches += 1;
+    } else {
+        // The carry K entering the range from above is the quotient coefficient above its top chunk: q_{top-1} =
+        // p_top + x K, i.e. a zero incoming carry with the top coefficient raised by x K — for the chunk polynomial: the top
+        // chunk value raised by x^kChunk K.  (Feeding K itself into the second-level recurrence would be wrong: its top
+        // chunk is zero-padded, and a carry does not commute with the padding.)  Then the unsharded two-level scheme:
+        // carries of level 1 = quotient of the chunk polynomial by (Y - x^kChunk), shifted by one; the top one is K.
+        PlainSrc ps{w.vals1 + c_lo, cnt};
+        const uint64_t c2 = (cnt + kChunk - 1) / kChunk;
+        k_fold_carry<<<1, 32, 0, stream>>>(w.vals1 + c_lo + (cnt - 1), w.xpow, carry_in);
+        k_chunk_eval<PlainSrc><<<(unsigned)c2, kThreads, 0, stream>>>(ps, cnt, w.xpow, w.vals2);
+        k_chunk_carries<<<1, 32, 0, stream>>>(w.vals2, c2, w.xpow + 1, w.carr2, nullptr, nullptr);
+        PM_CUDA(cudaMemcpyAsync(w.carr1 + c_lo + (cnt - 1), carry_in, sizeof(Fr), cudaMemcpyDeviceToDevice, stream));
+        k_chunk_divide<PlainSrc><<<(unsigned)c2, kThreads, 0, stream>>>(ps, cnt, w.xpow, w.carr2, w.carr1 + c_lo);
+        launches += 4;
+    }
+    PM_LAUNCH_CHECK();
+    k_chunk_divide<NumSrc><<<(unsigned)cnt, kThreads, 0, stream>>>(s, src.len, x, w.carr1, q, c_lo);
+    PM_LAUNCH_CHECK();
+    return launches + 1;
+}
+
 void launch_materialize_numerator(const NumeratorSrc& src, Fr* out, cudaStream_t stream) {
     NumSrc s{src};
     k_materialize<NumSrc><<<ceil_div(src.len, 256), 256, 0, stream>>>(s, src.len, out);

@@ -38,16 +38,28 @@ constexpr size_t kStageWin = (size_t)kMaxMsmSums * sizeof(G1XYZZ);   // one MSM'
 constexpr size_t kStageBytes = 3 * kStageWin + 256;
 constexpr size_t kStageStatus = 3 * kStageWin;
 
-// loc[j] = data[j * G + r]: this rank's interleaved slice of a replicated array
-__global__ void k_take_stride(const Fr* __restrict__ data, Fr* __restrict__ loc, size_t count, uint32_t g, uint32_t r) {
-    size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j < count) loc[j] = data[j * g + r];
+// The all-gathered coefficient slices back in natural order.  gathered = [rank][u_loc (per) | wu_loc (per) | u2_loc (2 per)]
+// (per = n / G): u[k] = block (k % G), element k / G, and likewise wu, u2.
+__global__ void k_interleave_slices(const Fr* __restrict__ gathered, size_t n, uint32_t g, Fr* __restrict__ u, Fr* __restrict__ wu,
+                                    Fr* __restrict__ u2) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t per = n / g;
+    if (i >= 4 * n) return;
+    if (i < n) u[i] = gathered[(i % g) * 4 * per + i / g];
+    else if (i < 2 * n) { const size_t k = i - n; wu[k] = gathered[(k % g) * 4 * per + per + k / g]; }
+    else { const size_t k = i - 2 * n; u2[k] = gathered[(k % g) * 4 * per + 2 * per + k / g]; }
 }
-// data[r + G * i] = gathered[r * per + i]: the all-gathered slices back in natural order
-__global__ void k_interleave(const Fr* __restrict__ gathered, Fr* __restrict__ data, size_t total, size_t per, uint32_t g) {
-    size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < total) data[k] = gathered[(k % g) * per + k / g];
-}
+
+// Self-describing record of one rank's MSM result inside an in-phase all-gather: the Shape its raw sums are to be decoded
+// with (ranks need not agree on it) and the rank's status words.  Followed by kMaxMsmSums XYZZ records.
+struct SumsHeader {
+    int32_t c, nwin, nsum, count;
+    uint8_t shift[32];
+    uint32_t status0, status1;       // filled on the device (ST_* bits; "h has a non-zero coefficient")
+    uint32_t pad[2];
+};
+static_assert(sizeof(SumsHeader) == 64, "header layout");
+constexpr size_t kBlockBytes = sizeof(SumsHeader) + (size_t)kMaxMsmSums * sizeof(G1XYZZ);
 
 // PM_CUDA_PROFILER=phase1|phase3: cudaProfilerStart/Stop around the device work of that phase of the FIRST proof, so
 // that `ncu --profile-from-start off` captures exactly the kernels of one phase (profiles/: the --set full captures).
@@ -88,6 +100,7 @@ ProverCtx::~ProverCtx() {
     if (nccl_comm && nccl_api().CommDestroy) nccl_api().CommDestroy(nccl_comm);
     if (host_gather) cudaFreeHost(host_gather);
     if (host_stage) cudaFreeHost(host_stage);
+    if (host_hdr) cudaFreeHost(host_hdr);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
 }
@@ -195,7 +208,7 @@ void ProverCtx::plan_tables() {
     // the free memory quantised down to 4 GiB steps; attach_nccl() then compares the plans of all ranks and refuses
     // to continue on a mismatch (e.g. another process occupying one of the GPUs) instead of hanging in the collective.
     auto shard = [&](uint64_t total) { return (total + (uint64_t)world - 1) / (uint64_t)world; };
-    const uint64_t cnt_c = shard(len_c()), cnt_d = shard(len_d()), cnt_a = shard(n + 4);
+    const uint64_t cnt_c = shard(len_c()), cnt_d = world == 1 ? len_d() : d_stride(), cnt_a = shard(len_a());
     plan_c = plan_for(cnt_c, "PM_MSM_PRECOMP_C", true);     // tuning hooks: window bits per array
     plan_d = plan_for(cnt_d, "PM_MSM_PRECOMP_D", false);
     size_t free_b = 0, total_b = 0;
@@ -227,7 +240,7 @@ void ProverCtx::plan_tables() {
 void ProverCtx::build_tables() {
     Runtime& rt = runtime();
     launch_build_levels(bases_c.get<G1Affine>(), local_count(len_c()), plan_c.levels, plan_c.stride, plan_c.c, rt.stream);
-    launch_build_levels(bases_d.get<G1Affine>(), local_count(len_d()), plan_d.levels, plan_d.stride, plan_d.c, rt.stream);
+    launch_build_levels(bases_d.get<G1Affine>(), world == 1 ? len_d() : d_count(), plan_d.levels, plan_d.stride, plan_d.c, rt.stream);
     // (the stride is the largest shard; local_count() <= stride on every rank)
 }
 
@@ -239,7 +252,7 @@ void ProverCtx::allocate_work() {
     ztail.as<Fr>(cols - m0);
     u.as<Fr>(n); w.as<Fr>(n); wu.as<Fr>(n);
     u2.as<Fr>(2 * n);
-    scal_a.as<Fr>(n + 4);
+    scal_a.as<Fr>(len_a());
     scal_c.as<Fr>(len_c());
     q.as<Fr>(len_d());
     const uint64_t nchunks = (len_d() + kChunk - 1) / kChunk;
@@ -248,6 +261,7 @@ void ProverCtx::allocate_work() {
     status.as<uint32_t>(4);
     acc.as<G1XYZZ>(3 * kMaxMsmSums);
     PM_CUDA(cudaMallocHost(&host_stage, kStageBytes));
+    PM_CUDA(cudaMallocHost(&host_hdr, 4 * sizeof(SumsHeader)));
     PM_CUDA(cudaEventCreate(&ev0));
     PM_CUDA(cudaEventCreate(&ev1));
 }
@@ -269,48 +283,15 @@ static void check_status(uint32_t st) {
     if (st & ST_OPENING_REMAINDER) throw StatusError(PM_ERR_REMAINDER, "opening numerator does not vanish at x1 (prover.rs:221)");
 }
 
-ProverCtx::Phase1Shapes ProverCtx::phase1_enqueue(const uint8_t* ra) {
+// ---- phase 1 -------------------------------------------------------------------------------------------------------
+// compute_a_g1 (prover.rs:330-338) and c_g1 (prover.rs:116-123) over this rank's share of the bases: scalars
+// scal[i * stride + offset].  The two MSMs are independent: the a-side runs on the side stream with its own workspace so
+// that its sort / reduction tail hides behind the c-side bucket accumulation.
+ProverCtx::Phase1Shapes ProverCtx::phase1_msms(const Fr* sa_ptr, const Fr* sc_ptr, size_t stride, size_t offset, G1XYZZ* sums_a,
+                                               G1XYZZ* sums_c) {
     Runtime& rt = runtime();
     cudaStream_t s = rt.stream;
-    if (!assignment_set) throw StatusError(PM_ERR_STATE, "phase 1 needs an assignment");
-    if (!ra) throw StatusError(PM_ERR_ARG, "null phase-1 argument");
-    phase = 0;
-    Fr* sm = small.get<Fr>();
-    uint32_t* st = status.get<uint32_t>();
-    static const bool dbg = getenv("PM_PHASE_DEBUG") != nullptr;
-    auto now = [] { return std::chrono::steady_clock::now(); };
-    auto ms_since = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
-        return std::chrono::duration<double, std::milli>(b - a).count();
-    };
-    const auto tp0 = now();
-    profiler_begin(1);
-    PM_CUDA(cudaEventRecord(ev0, s));
-    PM_CUDA(cudaMemcpyAsync(sm + S_RA, ra, 2 * sizeof(Fr), cudaMemcpyHostToDevice, s));
-    const auto tp1 = now();
-    PM_CUDA(cudaMemsetAsync(st, 0, 4 * sizeof(uint32_t), s));
-    launch_ra_square(sm + S_RA, s);
-    SapDims d{(uint32_t)m0, (uint32_t)mw, (uint32_t)nr, n};
-    Fr *pu = u.get<Fr>(), *pw = w.get<Fr>(), *pwu = wu.get<Fr>(), *pu2 = u2.get<Fr>();
-    launch_sap_evals(d, A.csr(), B.csr(), C.csr(), ztail.get<Fr>(), pu, pw, pwu, s);
-    // ntt_full: replicated transform, or the sharded one (one NCCL all-to-all + all-gather) for large domains
-    ntt_full(pu, log_n, true, s);    // poly_coeffs, prover.rs:94
-    ntt_full(pw, log_n, true, s);    // prover.rs:96
-    ntt_full(pwu, log_n, true, s);   // prover.rs:161 (witness_w == w: prover.rs:165 is not recomputed)
-    // square_polynomial, prover.rs:315-328
-    PM_CUDA(cudaMemcpyAsync(pu2, pu, n * sizeof(Fr), cudaMemcpyDeviceToDevice, s));
-    PM_CUDA(cudaMemsetAsync(pu2 + n, 0, n * sizeof(Fr), s));
-    ntt_full(pu2, log_n + 1, false, s);
-    launch_square(pu2, 2 * n, s);
-    ntt_full(pu2, log_n + 1, true, s);
-    launch_quotient_checks(pu2, pw, n, st, s);   // prover.rs:104-108
-    launch_assemble_phase1_scalars(pu, pu2, ztail.get<Fr>(), cols - m0, sm + S_RA, n, scal_a.get<Fr>(), scal_c.get<Fr>(), s);
-    rt.extra_launches += 9;
-    const auto tp2 = now();
-    G1XYZZ* ac = acc.get<G1XYZZ>();
     const G1Affine* bc = bases_c.get<G1Affine>();
-    // compute_a_g1 (prover.rs:330-338) and c_g1 (prover.rs:116-123) over this rank's share of the bases.
-    // The two MSMs are independent: the a-side runs on the side stream with its own workspace so that its
-    // sort / reduction tail hides behind the c-side bucket accumulation.
     PM_CUDA(cudaEventRecord(rt.ev_fork, s));
     PM_CUDA(cudaStreamWaitEvent(rt.stream2, rt.ev_fork, 0));
     // (round 1 gave the phase-1 MSMs one more pair round than the cost model asked for, because running beside each other
@@ -331,32 +312,140 @@ ProverCtx::Phase1Shapes ProverCtx::phase1_enqueue(const uint8_t* ra) {
     cfg_a.rounds_bias = p1_bias;
     MsmConfig cfg_cs = cfg_c();
     cfg_cs.rounds_bias = p1_bias;
-    // every rank of a sharded proof must produce the same layout of partial sums (they are gathered and decoded with
-    // one Shape): without a table the window follows the per-rank share of the GLOBAL count, not the local count
-    if (world > 1 && cfg_a.c == 0) cfg_a.c = MsmEngine::choose_window((n + 4) / world);
+    if (world > 1 && cfg_a.c == 0) cfg_a.c = MsmEngine::choose_window(len_a() / world);
     if (world > 1 && cfg_cs.c == 0) cfg_cs.c = MsmEngine::choose_window(len_c() / world);
     Phase1Shapes sh;
-    sh.sa = rt.msm2.run(bc, scal_a.get<Fr>(), local_count(n + 4), ac, rt.stream2, cfg_a, world, rank);
-    const auto tp3 = now();
+    sh.sa = rt.msm2.run(bc, sa_ptr, local_count(len_a()), sums_a, rt.stream2, cfg_a, stride, offset);
     PM_CUDA(cudaEventRecord(rt.ev_join, rt.stream2));
-    sh.sc = rt.msm.run(bc, scal_c.get<Fr>(), local_count(len_c()), ac + kMaxMsmSums, s, cfg_cs, world, rank);
+    sh.sc = rt.msm.run(bc, sc_ptr, local_count(len_c()), sums_c, s, cfg_cs, stride, offset);
     PM_CUDA(cudaStreamWaitEvent(s, rt.ev_join, 0));
-    const auto tp4 = now();
-    if (dbg && ms_since(tp0, tp4) > 5.0)
-        fprintf(stderr, "[phase1-enqueue] ra copy %.3f | poly %.3f | fork+a-side msm %.3f | c-side msm %.3f ms\n", ms_since(tp0, tp1),
-                ms_since(tp1, tp2), ms_since(tp2, tp3), ms_since(tp3, tp4));
     return sh;
+}
+
+// Replicated polynomial work (one GPU, the callback transport, small domains): prover.rs:73-123.
+ProverCtx::Phase1Shapes ProverCtx::phase1_enqueue(const uint8_t* ra, G1XYZZ* sums_a, G1XYZZ* sums_c) {
+    Runtime& rt = runtime();
+    cudaStream_t s = rt.stream;
+    if (!assignment_set) throw StatusError(PM_ERR_STATE, "phase 1 needs an assignment");
+    if (!ra) throw StatusError(PM_ERR_ARG, "null phase-1 argument");
+    phase = 0;
+    last_phase1_resident = false;
+    Fr* sm = small.get<Fr>();
+    uint32_t* st = status.get<uint32_t>();
+    profiler_begin(1);
+    PM_CUDA(cudaEventRecord(ev0, s));
+    PM_CUDA(cudaMemcpyAsync(sm + S_RA, ra, 2 * sizeof(Fr), cudaMemcpyHostToDevice, s));
+    PM_CUDA(cudaMemsetAsync(st, 0, 4 * sizeof(uint32_t), s));
+    launch_ra_square(sm + S_RA, s);
+    SapDims d{(uint32_t)m0, (uint32_t)mw, (uint32_t)nr, n};
+    Fr *pu = u.get<Fr>(), *pw = w.get<Fr>(), *pwu = wu.get<Fr>(), *pu2 = u2.get<Fr>();
+    launch_sap_evals(d, A.csr(), B.csr(), C.csr(), ztail.get<Fr>(), pu, pw, pwu, s);
+    rt.ntt.run(pu, log_n, true, s);    // poly_coeffs, prover.rs:94
+    rt.ntt.run(pw, log_n, true, s);    // prover.rs:96
+    rt.ntt.run(pwu, log_n, true, s);   // prover.rs:161 (witness_w == w: prover.rs:165 is not recomputed)
+    // square_polynomial, prover.rs:315-328
+    PM_CUDA(cudaMemcpyAsync(pu2, pu, n * sizeof(Fr), cudaMemcpyDeviceToDevice, s));
+    PM_CUDA(cudaMemsetAsync(pu2 + n, 0, n * sizeof(Fr), s));
+    rt.ntt.run(pu2, log_n + 1, false, s);
+    launch_square(pu2, 2 * n, s);
+    rt.ntt.run(pu2, log_n + 1, true, s);
+    launch_quotient_checks(pu2, pw, n, st, s);   // prover.rs:104-108
+    launch_assemble_phase1_scalars(pu, pu2, ztail.get<Fr>(), lay(), sm + S_RA, scal_a.get<Fr>(), scal_c.get<Fr>(), s);
+    rt.extra_launches += 9;
+    return phase1_msms(scal_a.get<Fr>(), scal_c.get<Fr>(), world, rank, sums_a, sums_c);
+}
+
+bool ProverCtx::resident() const {
+    int log_g = 0;
+    while ((1 << log_g) < world) log_g++;
+    return nccl_comm && world > 1 && (1 << log_g) == world && log_g <= 3 && log_n >= resident_min_log && log_n >= 2 * log_g + 3;
+}
+
+// In-place transform of this rank's slice (2^lg / G elements, the residue class `rank`) of a 2^lg-point polynomial:
+// local (N/G)-point NTT + twiddle / pack, ONE all-to-all over NCCL / NVLink, G-point combine.  Slice in, slice out.
+void ProverCtx::sharded_ntt(Fr* loc, int lg, bool inverse, cudaStream_t s) {
+    Runtime& rt = runtime();
+    int log_g = 0;
+    while ((1 << log_g) < world) log_g++;
+    const size_t per = ((size_t)1 << lg) >> log_g, blk = per >> log_g;
+    Fr* send = ntt_send.as<Fr>(per);
+    Fr* recv = ntt_recv.as<Fr>(per);
+    rt.ntt.dist_local(loc, send, lg, log_g, (uint32_t)rank, inverse, s);
+    NcclApi& api = nccl_api();
+    api.check(api.GroupStart(), "ncclGroupStart");
+    for (int h = 0; h < world; h++) {
+        api.check(api.Send(send + (size_t)h * blk, blk * sizeof(Fr), NcclApi::kUint8, h, nccl_comm, s), "ncclSend");
+        api.check(api.Recv(recv + (size_t)h * blk, blk * sizeof(Fr), NcclApi::kUint8, h, nccl_comm, s), "ncclRecv");
+    }
+    api.check(api.GroupEnd(), "ncclGroupEnd");
+    rt.ntt.dist_combine(recv, loc, lg, log_g, inverse, s);      // loc[i] = X[rank + G * i]
+}
+
+// Sharded-resident polynomial work: SAP rows of this rank's residue class ("row-range SpMV" over the
+// interleaved split), sharded transforms, local checks and scalar assembly — the slices feed the MSM shards in place.
+ProverCtx::Phase1Shapes ProverCtx::phase1_enqueue_resident(const uint8_t* ra, G1XYZZ* sums_a, G1XYZZ* sums_c) {
+    Runtime& rt = runtime();
+    cudaStream_t s = rt.stream;
+    if (!assignment_set) throw StatusError(PM_ERR_STATE, "phase 1 needs an assignment");
+    if (!ra) throw StatusError(PM_ERR_ARG, "null phase-1 argument");
+    phase = 0;
+    last_phase1_resident = true;
+    NcclApi& api = nccl_api();
+    Fr* sm = small.get<Fr>();
+    uint32_t* st = status.get<uint32_t>();
+    profiler_begin(1);
+    PM_CUDA(cudaEventRecord(ev0, s));
+    PM_CUDA(cudaMemcpyAsync(sm + S_RA, ra, 2 * sizeof(Fr), cudaMemcpyHostToDevice, s));
+    PM_CUDA(cudaMemsetAsync(st, 0, 4 * sizeof(uint32_t), s));
+    launch_ra_square(sm + S_RA, s);
+    const uint32_t G = (uint32_t)world, r = (uint32_t)rank;
+    const size_t per = n / G;
+    // one buffer: [u_loc (per) | wu_loc (per) | u2_loc (2 per) | w_loc (per)] — the first 4 per elements are all-gathered
+    Fr* loc = res_loc.as<Fr>(5 * per);
+    Fr *u_loc = loc, *wu_loc = loc + per, *u2_loc = loc + 2 * per, *w_loc = loc + 4 * per;
+    SapDims d{(uint32_t)m0, (uint32_t)mw, (uint32_t)nr, n};
+    launch_sap_evals_strided(d, A.csr(), B.csr(), C.csr(), ztail.get<Fr>(), r, G, u_loc, w_loc, wu_loc, s);
+    const CLayout L = lay();
+    const uint64_t cnt_a = local_count(L.len_a), cnt_c = local_count(L.len_c);
+    const uint64_t cnt_zt = L.tail > r ? (L.tail - r + G - 1) / G : 0;
+    Fr* zt_loc = res_zt.as<Fr>(cnt_zt + 1);
+    launch_ztail_strided(d, A.csr(), B.csr(), ztail.get<Fr>(), r, G, cnt_zt, zt_loc, s);
+    sharded_ntt(u_loc, log_n, true, s);     // poly_coeffs, prover.rs:94
+    sharded_ntt(w_loc, log_n, true, s);     // prover.rs:96
+    sharded_ntt(wu_loc, log_n, true, s);    // prover.rs:161
+    // the coefficient u_{k-1} next to u_k lives one rank down: ring exchange of the u slices (rank -> rank + 1)
+    Fr* u_prev = res_prev.as<Fr>(per);
+    api.check(api.GroupStart(), "ncclGroupStart");
+    api.check(api.Send(u_loc, per * sizeof(Fr), NcclApi::kUint8, (rank + 1) % world, nccl_comm, s), "ncclSend");
+    api.check(api.Recv(u_prev, per * sizeof(Fr), NcclApi::kUint8, (rank + world - 1) % world, nccl_comm, s), "ncclRecv");
+    api.check(api.GroupEnd(), "ncclGroupEnd");
+    // square_polynomial, prover.rs:315-328: the slice of the zero-padded 2n-array is [u_loc | 0]
+    PM_CUDA(cudaMemcpyAsync(u2_loc, u_loc, per * sizeof(Fr), cudaMemcpyDeviceToDevice, s));
+    PM_CUDA(cudaMemsetAsync(u2_loc + per, 0, per * sizeof(Fr), s));
+    sharded_ntt(u2_loc, log_n + 1, false, s);
+    launch_square(u2_loc, 2 * per, s);
+    sharded_ntt(u2_loc, log_n + 1, true, s);
+    launch_quotient_checks_strided(u2_loc, w_loc, n, r, G, st, s);   // prover.rs:104-108 on the slices
+    Fr* sa_loc = res_scal_a.as<Fr>(cnt_a + 1);
+    Fr* sc_loc = res_scal_c.as<Fr>(cnt_c + 1);
+    launch_assemble_phase1_strided(u_loc, u_prev, u2_loc, zt_loc, L, sm + S_RA, r, G, cnt_a, cnt_c, sa_loc, sc_loc, s);
+    // The opening phase works on contiguous coefficient ranges: ONE all-gather brings the coefficient slices of u, wu,
+    // u^2 to every rank (natural order restored), issued before the MSMs so that it is long done when they end.
+    Fr* gath = ntt_gather.as<Fr>(4 * (size_t)n);
+    api.check(api.AllGather(loc, gath, 4 * per * sizeof(Fr), NcclApi::kUint8, nccl_comm, s), "ncclAllGather");
+    k_interleave_slices<<<ceil_div(4 * (size_t)n, 256), 256, 0, s>>>(gath, n, G, u.get<Fr>(), wu.get<Fr>(), u2.get<Fr>());
+    PM_LAUNCH_CHECK();
+    rt.extra_launches += 10;
+    return phase1_msms(sa_loc, sc_loc, 1, 0, sums_a, sums_c);
 }
 
 void ProverCtx::phase1_partial(const uint8_t* ra, uint8_t* partials_out) {
     Runtime& rt = runtime();
     cudaStream_t s = rt.stream;
     if (!partials_out) throw StatusError(PM_ERR_ARG, "null phase-1 argument");
-    const auto t_host0 = std::chrono::steady_clock::now();
-    Phase1Shapes sh = phase1_enqueue(ra);
-    const auto t_host1 = std::chrono::steady_clock::now();
-    const MsmEngine::Shape &sa = sh.sa, &sc = sh.sc;
     G1XYZZ* ac = acc.get<G1XYZZ>();
+    Phase1Shapes sh = phase1_enqueue(ra, ac, ac + kMaxMsmSums);
+    const MsmEngine::Shape &sa = sh.sa, &sc = sh.sc;
     uint32_t* st = status.get<uint32_t>();
     uint8_t* hs = static_cast<uint8_t*>(host_stage);
     PM_CUDA(cudaMemcpyAsync(hs, ac, sa.count() * sizeof(G1XYZZ), cudaMemcpyDeviceToHost, s));
@@ -368,10 +457,6 @@ void ProverCtx::phase1_partial(const uint8_t* ra, uint8_t* partials_out) {
     float ms = 0;
     PM_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
     phase_ms[0] = ms;
-    if (getenv("PM_PHASE_DEBUG"))
-        fprintf(stderr, "[phase1] device %.3f ms, host enqueue %.3f ms, enqueue+sync %.3f ms\n", ms,
-                std::chrono::duration<double, std::milli>(t_host1 - t_host0).count(),
-                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_host0).count());
     uint32_t stv;
     memcpy(&stv, hs + kStageStatus, 4);
     check_status(stv);
@@ -392,38 +477,6 @@ uint8_t* ProverCtx::gather_stage(size_t bytes) {
     return static_cast<uint8_t*>(host_gather);
 }
 
-void ProverCtx::ntt_full(Fr* data, int lg, bool inverse, cudaStream_t s) {
-    Runtime& rt = runtime();
-    int log_g = 0;
-    while ((1 << log_g) < world) log_g++;
-    const bool pow2 = (1 << log_g) == world;
-    if (world == 1 || !nccl_comm || !pow2 || log_g > 3 || lg < sharded_ntt_min_log || lg < 2 * log_g) {
-        rt.ntt.run(data, lg, inverse, s);
-        return;
-    }
-    const size_t total = (size_t)1 << lg, per = total >> log_g, blk = per >> log_g;
-    Fr* loc = ntt_loc.as<Fr>(per);
-    Fr* send = ntt_send.as<Fr>(per);
-    Fr* recv = ntt_recv.as<Fr>(per);
-    Fr* gath = ntt_gather.as<Fr>(total);
-    k_take_stride<<<ceil_div(per, 256), 256, 0, s>>>(data, loc, per, (uint32_t)world, (uint32_t)rank);
-    PM_LAUNCH_CHECK();
-    rt.ntt.dist_local(loc, send, lg, log_g, (uint32_t)rank, inverse, s);
-    NcclApi& api = nccl_api();
-    // the one exchange of the four-step transform: block h of `send` goes to rank h (NVLink all-to-all)
-    api.check(api.GroupStart(), "ncclGroupStart");
-    for (int h = 0; h < world; h++) {
-        api.check(api.Send(send + (size_t)h * blk, blk * sizeof(Fr), NcclApi::kUint8, h, nccl_comm, s), "ncclSend");
-        api.check(api.Recv(recv + (size_t)h * blk, blk * sizeof(Fr), NcclApi::kUint8, h, nccl_comm, s), "ncclRecv");
-    }
-    api.check(api.GroupEnd(), "ncclGroupEnd");
-    rt.ntt.dist_combine(recv, loc, lg, log_g, inverse, s);      // loc[i] = X[rank + G * i]
-    api.check(api.AllGather(loc, gath, per * sizeof(Fr), NcclApi::kUint8, nccl_comm, s), "ncclAllGather");
-    k_interleave<<<ceil_div(total, 256), 256, 0, s>>>(gath, data, total, per, (uint32_t)world);
-    PM_LAUNCH_CHECK();
-    rt.extra_launches += 2;
-}
-
 void ProverCtx::attach_nccl(const char* libnccl_path, const uint8_t id[128]) {
     if (nccl_comm) throw StatusError(PM_ERR_STATE, "context already has a communicator");
     if (!id) throw StatusError(PM_ERR_ARG, "null NCCL id");
@@ -434,13 +487,13 @@ void ProverCtx::attach_nccl(const char* libnccl_path, const uint8_t id[128]) {
     void* comm = nullptr;
     api.check(api.CommInitRank(&comm, world, uid, rank), "ncclCommInitRank");
     nccl_comm = comm;
-    if (const char* v = getenv("PM_SHARDED_NTT_MIN_LOG")) sharded_ntt_min_log = atoi(v);   // tuning / test hook
-    // All ranks must decode each other's raw per-window sums with one Shape: compare the table plans now, where a
-    // mismatch is an error message, not a hang or a silently wrong proof inside phase{1,3}_collective.
+    if (const char* v = getenv("PM_RESIDENT_MIN_LOG")) resident_min_log = atoi(v);   // tuning / test hook
+    // Settings that select the code path of a collective phase (sharded-resident or replicated polynomial work, the
+    // geometry of the exchanges) must agree on every rank: compare them now, where a mismatch is an error message and not
+    // a hang inside a phase.  (The MSM results themselves travel self-described: see SumsHeader.)
     {
         Runtime& rt = runtime();
-        const uint64_t mine[8] = {(uint64_t)plan_c.c, (uint64_t)plan_c.levels, (uint64_t)plan_d.c, (uint64_t)plan_d.levels,
-                                  n, (uint64_t)world, cols, (uint64_t)sharded_ntt_min_log};
+        const uint64_t mine[8] = {n, (uint64_t)world, cols, (uint64_t)resident_min_log, m0, mw, nr, 0};
         uint64_t* dev = reinterpret_cast<uint64_t*>(gathered.as<uint8_t>((size_t)(world + 1) * sizeof mine + 256));
         std::vector<uint64_t> all((size_t)world * 8);
         PM_CUDA(cudaMemcpyAsync(dev + (size_t)world * 8, mine, sizeof mine, cudaMemcpyHostToDevice, rt.stream));
@@ -448,53 +501,75 @@ void ProverCtx::attach_nccl(const char* libnccl_path, const uint8_t id[128]) {
         PM_CUDA(cudaMemcpyAsync(all.data(), dev, all.size() * sizeof(uint64_t), cudaMemcpyDeviceToHost, rt.stream));
         PM_CUDA(cudaStreamSynchronize(rt.stream));
         for (int r = 0; r < world; r++)
-            if (memcmp(all.data() + (size_t)r * 8, mine, sizeof mine) != 0) {
-                char msg[256];
-                snprintf(msg, sizeof msg,
-                         "rank %d planned (c-side c=%llu levels=%llu, d c=%llu levels=%llu), rank %d planned (c=%llu levels=%llu, c=%llu "
-                         "levels=%llu): the ranks of a sharded context must see the same free device memory and settings",
-                         rank, (unsigned long long)mine[0], (unsigned long long)mine[1], (unsigned long long)mine[2],
-                         (unsigned long long)mine[3], r, (unsigned long long)all[(size_t)r * 8], (unsigned long long)all[(size_t)r * 8 + 1],
-                         (unsigned long long)all[(size_t)r * 8 + 2], (unsigned long long)all[(size_t)r * 8 + 3]);
-                throw StatusError(PM_ERR_STATE, msg);
-            }
+            if (memcmp(all.data() + (size_t)r * 8, mine, sizeof mine) != 0)
+                throw StatusError(PM_ERR_STATE, "rank " + std::to_string(rank) + " and rank " + std::to_string(r) +
+                                                    " disagree on the circuit dimensions or the sharding settings of the context");
     }
 }
+
+namespace {
+
+// host side of an in-phase all-gather: fill this rank's headers, then (after the exchange) decode every rank's block
+void fill_header(SumsHeader& h, const MsmEngine::Shape& sh) {
+    memset(&h, 0, sizeof h);
+    h.c = sh.c; h.nwin = sh.nwin; h.nsum = sh.nsum; h.count = sh.count();
+    memcpy(h.shift, sh.shift, sizeof h.shift);
+}
+host::XyzzH decode_block(const uint8_t* block) {
+    SumsHeader h;
+    memcpy(&h, block, sizeof h);
+    if (h.count < 0 || h.count > kMaxMsmSums || h.nwin * h.nsum != h.count) throw StatusError(PM_ERR_STATE, "corrupt partial-sum block");
+    return host::combine_shifted(block + sizeof(SumsHeader), h.nwin, h.c, h.nsum, h.shift);
+}
+void block_status(const uint8_t* block, uint32_t& st0, uint32_t& st1) {
+    SumsHeader h;
+    memcpy(&h, block, sizeof h);
+    st0 |= h.status0;
+    st1 |= h.status1;
+}
+
+}  // namespace
 
 void ProverCtx::phase1_collective(const uint8_t* ra, uint8_t* a_out, uint8_t* c_out) {
     Runtime& rt = runtime();
     cudaStream_t s = rt.stream;
     if (!nccl_comm) throw StatusError(PM_ERR_STATE, "no communicator attached (pm_ctx_attach_nccl)");
     if (!a_out || !c_out) throw StatusError(PM_ERR_ARG, "null phase-1 argument");
-    Phase1Shapes sh = phase1_enqueue(ra);
-    const MsmEngine::Shape &sa = sh.sa, &sc = sh.sc;
-    const size_t ba = sa.count() * sizeof(G1XYZZ), bc_ = sc.count() * sizeof(G1XYZZ);
-    G1XYZZ* ac = acc.get<G1XYZZ>();
+    // this rank's two blocks: [header | a sums] [header | c sums]
+    uint8_t* mine = xchg.as<uint8_t>(2 * kBlockBytes);
+    G1XYZZ* sums_a = reinterpret_cast<G1XYZZ*>(mine + sizeof(SumsHeader));
+    G1XYZZ* sums_c = reinterpret_cast<G1XYZZ*>(mine + kBlockBytes + sizeof(SumsHeader));
+    const bool res = resident();
+    Phase1Shapes sh = res ? phase1_enqueue_resident(ra, sums_a, sums_c) : phase1_enqueue(ra, sums_a, sums_c);
     uint32_t* st = status.get<uint32_t>();
-    // gathered = [rank][a sums] then [rank][c sums]
-    uint8_t* g = gathered.as<uint8_t>((size_t)world * (ba + bc_) + 256);
+    SumsHeader* hh = static_cast<SumsHeader*>(host_hdr);
+    fill_header(hh[0], sh.sa);
+    fill_header(hh[1], sh.sc);
+    // headers first (their status words are then overwritten from the device), sums are already in place
+    PM_CUDA(cudaMemcpyAsync(mine, &hh[0], sizeof(SumsHeader), cudaMemcpyHostToDevice, s));
+    PM_CUDA(cudaMemcpyAsync(mine + kBlockBytes, &hh[1], sizeof(SumsHeader), cudaMemcpyHostToDevice, s));
+    PM_CUDA(cudaMemcpyAsync(mine + offsetof(SumsHeader, status0), st, 2 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+    uint8_t* g = gathered.as<uint8_t>((size_t)world * 2 * kBlockBytes + 256);
     NcclApi& api = nccl_api();
-    api.check(api.GroupStart(), "ncclGroupStart");
-    api.check(api.AllGather(ac, g, ba, NcclApi::kUint8, nccl_comm, s), "ncclAllGather");
-    api.check(api.AllGather(ac + kMaxMsmSums, g + (size_t)world * ba, bc_, NcclApi::kUint8, nccl_comm, s), "ncclAllGather");
-    api.check(api.GroupEnd(), "ncclGroupEnd");
-    uint8_t* hg = gather_stage((size_t)world * (ba + bc_) + 256);
-    uint8_t* hs = static_cast<uint8_t*>(host_stage);
-    PM_CUDA(cudaMemcpyAsync(hg, g, (size_t)world * (ba + bc_), cudaMemcpyDeviceToHost, s));
-    PM_CUDA(cudaMemcpyAsync(hs + kStageStatus, st, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    api.check(api.AllGather(mine, g, 2 * kBlockBytes, NcclApi::kUint8, nccl_comm, s), "ncclAllGather");
+    uint8_t* hg = gather_stage((size_t)world * 2 * kBlockBytes + 256);
+    PM_CUDA(cudaMemcpyAsync(hg, g, (size_t)world * 2 * kBlockBytes, cudaMemcpyDeviceToHost, s));
     PM_CUDA(cudaEventRecord(ev1, s));
     PM_CUDA(cudaStreamSynchronize(s));
     profiler_end();
     float ms = 0;
     PM_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
     phase_ms[0] = ms;
-    uint32_t stv;
-    memcpy(&stv, hs + kStageStatus, 4);
-    check_status(stv);     // the polynomial work is replicated: every rank sees the same status
+    // status: replicated work -> every rank reports the same bits; resident work -> the union over the slices, and
+    // "h == 0" only if no rank saw a non-zero coefficient
+    uint32_t st0 = 0, st1 = 0;
+    for (int r = 0; r < world; r++) block_status(hg + (size_t)r * 2 * kBlockBytes, st0, st1);
+    if (res && st1 == 0) st0 |= ST_H_ZERO;
+    check_status(st0);
     host::XyzzH sum_a = host::XyzzH::inf(), sum_c = host::XyzzH::inf();
     for (int r = 0; r < world; r++) {
-        host::xyzz_add(sum_a, host::combine_shifted(hg + (size_t)r * ba, sa.nwin, sa.c, sa.nsum, sa.shift));
-        host::xyzz_add(sum_c, host::combine_shifted(hg + (size_t)world * ba + (size_t)r * bc_, sc.nwin, sc.c, sc.nsum, sc.shift));
+        host::xyzz_add(sum_a, decode_block(hg + (size_t)r * 2 * kBlockBytes));
+        host::xyzz_add(sum_c, decode_block(hg + (size_t)r * 2 * kBlockBytes + kBlockBytes));
     }
     host::xyzz_to_affine_wire(sum_a, a_out);
     host::xyzz_to_affine_wire(sum_c, c_out);
@@ -549,7 +624,133 @@ NumeratorSrc ProverCtx::numerator_src() const {
     return src;
 }
 
-MsmEngine::Shape ProverCtx::phase3_enqueue(const uint8_t* x2, const uint8_t* c_at_x1) {
+// ---- self-test of the sharded-resident kernels with VIRTUAL ranks on one GPU ------------------------------------------
+// For a world == 1 context that has just finished a proof: replays the polynomial work of phase 1 and the division of
+// phase 3 the way G ranks would — strided SAP rows, sharded transforms (the all-to-all emulated by copies between the
+// virtual ranks' buffers), ring exchange, local checks and scalar assembly, chunk-range division with the carry exchange —
+// and counts the elements that differ from what the replicated path left in the context (which the tests compare with
+// the oracle).  Covers everything of the multi-GPU flow except the NCCL calls themselves.
+namespace {
+__global__ void k_count_mismatch_strided(const Fr* __restrict__ full, const Fr* __restrict__ loc, uint64_t count, uint32_t g, uint32_t r,
+                                         unsigned long long* __restrict__ bad) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    if (full[(uint64_t)r + t * g] != loc[t]) atomicAdd(bad, 1ull);
+}
+}  // namespace
+
+uint64_t ProverCtx::selftest_resident(int G) {
+    Runtime& rt = runtime();
+    cudaStream_t s = rt.stream;
+    int log_g = 0;
+    while ((1 << log_g) < G) log_g++;
+    if (world != 1 || (1 << log_g) != G || G < 2 || G > 8 || log_n < 2 * log_g + 3)
+        throw StatusError(PM_ERR_ARG, "self-test needs an unsharded context, 2 <= G <= 8 a power of two, n >= 8 G^2");
+    if (phase != 0 || !assignment_set) throw StatusError(PM_ERR_STATE, "self-test must follow a complete proof");
+    const size_t per = n / G;
+    const CLayout L = lay();
+    Fr* sm = small.get<Fr>();
+    DevBuf b_loc, b_zt, b_send, b_recv, b_prev, b_sa, b_sc, b_bad, b_st, b_q2, b_rv, b_rlo, b_work;
+    Fr* loc = b_loc.as<Fr>(5 * per * G);
+    const uint64_t zt_cap = (L.tail + G - 1) / G + 1, sc_cap = (L.len_c + G - 1) / G + 1;
+    Fr* zt = b_zt.as<Fr>(zt_cap * G);
+    Fr* send = b_send.as<Fr>(2 * per * G);
+    Fr* recv = b_recv.as<Fr>(2 * per * G);
+    Fr* prev = b_prev.as<Fr>(per * G);
+    Fr* sa = b_sa.as<Fr>(sc_cap * G);
+    Fr* sc = b_sc.as<Fr>(sc_cap * G);
+    unsigned long long* bad = b_bad.as<unsigned long long>(1);
+    uint32_t* st = b_st.as<uint32_t>(4 * G);
+    PM_CUDA(cudaMemsetAsync(bad, 0, sizeof(unsigned long long), s));
+    PM_CUDA(cudaMemsetAsync(st, 0, 4 * G * sizeof(uint32_t), s));
+    SapDims d{(uint32_t)m0, (uint32_t)mw, (uint32_t)nr, n};
+    auto rloc = [&](int r) { return loc + (size_t)r * 5 * per; };
+    for (int r = 0; r < G; r++) {
+        Fr* l = rloc(r);
+        launch_sap_evals_strided(d, A.csr(), B.csr(), C.csr(), ztail.get<Fr>(), r, G, l, l + 4 * per, l + per, s);
+        const uint64_t cnt_zt = L.tail > (uint64_t)r ? (L.tail - r + G - 1) / G : 0;
+        launch_ztail_strided(d, A.csr(), B.csr(), ztail.get<Fr>(), r, G, cnt_zt, zt + (size_t)r * zt_cap, s);
+    }
+    // sharded transform of the slices at offset `off` of every virtual rank's buffer, 2^lg points in total
+    auto vntt = [&](size_t off, int lg, bool inverse) {
+        const size_t p2 = ((size_t)1 << lg) >> log_g, blk = p2 >> log_g;
+        for (int r = 0; r < G; r++) rt.ntt.dist_local(rloc(r) + off, send + (size_t)r * 2 * per, lg, log_g, (uint32_t)r, inverse, s);
+        for (int h = 0; h < G; h++)
+            for (int r = 0; r < G; r++)
+                PM_CUDA(cudaMemcpyAsync(recv + (size_t)h * 2 * per + (size_t)r * blk, send + (size_t)r * 2 * per + (size_t)h * blk,
+                                        blk * sizeof(Fr), cudaMemcpyDeviceToDevice, s));
+        for (int h = 0; h < G; h++) rt.ntt.dist_combine(recv + (size_t)h * 2 * per, rloc(h) + off, lg, log_g, inverse, s);
+    };
+    vntt(0, log_n, true);
+    vntt(4 * per, log_n, true);
+    vntt(per, log_n, true);
+    for (int r = 0; r < G; r++) {
+        PM_CUDA(cudaMemcpyAsync(prev + (size_t)r * per, rloc((r + G - 1) % G), per * sizeof(Fr), cudaMemcpyDeviceToDevice, s));
+        PM_CUDA(cudaMemcpyAsync(rloc(r) + 2 * per, rloc(r), per * sizeof(Fr), cudaMemcpyDeviceToDevice, s));
+        PM_CUDA(cudaMemsetAsync(rloc(r) + 3 * per, 0, per * sizeof(Fr), s));
+    }
+    vntt(2 * per, log_n + 1, false);
+    for (int r = 0; r < G; r++) launch_square(rloc(r) + 2 * per, 2 * per, s);
+    vntt(2 * per, log_n + 1, true);
+    for (int r = 0; r < G; r++) {
+        Fr* l = rloc(r);
+        launch_quotient_checks_strided(l + 2 * per, l + 4 * per, n, r, G, st + 4 * r, s);
+        const uint64_t cnt_a = L.len_a > (uint64_t)r ? (L.len_a - r + G - 1) / G : 0, cnt_c = L.len_c > (uint64_t)r ? (L.len_c - r + G - 1) / G : 0;
+        launch_assemble_phase1_strided(l, prev + (size_t)r * per, l + 2 * per, zt + (size_t)r * zt_cap, L, sm + S_RA, r, G, cnt_a, cnt_c,
+                                       sa + (size_t)r * sc_cap, sc + (size_t)r * sc_cap, s);
+        auto cmp = [&](const Fr* full, const Fr* part, uint64_t count) {
+            if (count) k_count_mismatch_strided<<<ceil_div(count, 256), 256, 0, s>>>(full, part, count, G, r, bad);
+        };
+        cmp(scal_a.get<Fr>(), sa + (size_t)r * sc_cap, cnt_a);
+        cmp(scal_c.get<Fr>(), sc + (size_t)r * sc_cap, cnt_c);
+        cmp(u.get<Fr>(), l, per);
+        cmp(wu.get<Fr>(), l + per, per);
+        cmp(u2.get<Fr>(), l + 2 * per, 2 * per);
+        cmp(w.get<Fr>(), l + 4 * per, per);
+        PM_LAUNCH_CHECK();
+    }
+    // phase 3: the division by chunk ranges with the carry exchange, against the q of the replicated division
+    NumeratorSrc src = numerator_src();
+    const uint64_t c1 = d_chunks(), per_c = (c1 + G - 1) / G;
+    auto clo = [&](int r) { uint64_t v = (uint64_t)r * per_c; return v < c1 ? v : c1; };
+    Fr* q2 = b_q2.as<Fr>(len_d());
+    PM_CUDA(cudaMemsetAsync(q2, 0xff, (len_d() - 1) * sizeof(Fr), s));
+    Fr* rv = b_rv.as<Fr>((size_t)G + 4);
+    uint64_t* rlo = b_rlo.as<uint64_t>((size_t)G + 1);
+    std::vector<uint64_t> lo((size_t)G + 1);
+    for (int r = 0; r <= G; r++) lo[r] = clo(r);
+    PM_CUDA(cudaMemcpyAsync(rlo, lo.data(), lo.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+    const uint64_t nchunks = (len_d() + kChunk - 1) / kChunk;
+    Fr* work = b_work.as<Fr>(2 * (nchunks + 1) + 2 * (nchunks / kChunk + 2) + 8);
+    for (int r = 0; r < G; r++) launch_numerator_range_eval(src, sm + S_X1, clo(r), clo(r + 1) - clo(r), work, rv + r, s);
+    for (int r = 0; r < G; r++) {
+        // the virtual ranks share one `work` buffer: restore rank r's chunk values (the second-level values of a long
+        // range are indexed from 0 and were overwritten by the other ranks' evaluations)
+        launch_numerator_range_eval(src, sm + S_X1, clo(r), clo(r + 1) - clo(r), work, rv + G + 1, s);
+        launch_numerator_range_carry(rv, rlo, (uint32_t)r, (uint32_t)G, sm + S_X1, rv + G, st + 4 * r, s);
+        launch_numerator_range_divide(src, sm + S_X1, clo(r), clo(r + 1) - clo(r), rv + G, q2, work, s);
+    }
+    k_count_mismatch_strided<<<ceil_div(len_d() - 1, 256), 256, 0, s>>>(q.get<Fr>(), q2, len_d() - 1, 1, 0, bad);
+    PM_LAUNCH_CHECK();
+    unsigned long long hbad = 0;
+    std::vector<uint32_t> hst(4 * (size_t)G);
+    PM_CUDA(cudaMemcpyAsync(&hbad, bad, sizeof hbad, cudaMemcpyDeviceToHost, s));
+    PM_CUDA(cudaMemcpyAsync(hst.data(), st, hst.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    PM_CUDA(cudaStreamSynchronize(s));
+    uint32_t any_h = 0;
+    for (int r = 0; r < G; r++) {
+        if (hst[4 * r] != 0) hbad += 1000000;        // a satisfied witness must raise no status bit on any virtual rank
+        any_h |= hst[4 * r + 1];
+    }
+    if (!any_h) hbad += 1000000;
+    return hbad;
+}
+
+// ---- phase 3 -------------------------------------------------------------------------------------------------------
+// range_division (collective flow): every rank divides only its own chunk range of the numerator — chunk values of the
+// range, ONE all-gather of the G range values ("carry exchange"), the range's quotient coefficients — and feeds them
+// to its contiguous shard of x_powers_y_gamma_z.  Otherwise the whole division runs here (one GPU / callback transport).
+MsmEngine::Shape ProverCtx::phase3_enqueue(const uint8_t* x2, const uint8_t* c_at_x1, G1XYZZ* sums_d, bool range_division) {
     Runtime& rt = runtime();
     cudaStream_t s = rt.stream;
     if (phase != 2) throw StatusError(PM_ERR_STATE, "phase 3 must follow phase 2");
@@ -563,19 +764,38 @@ MsmEngine::Shape ProverCtx::phase3_enqueue(const uint8_t* x2, const uint8_t* c_a
     k_phase3_consts<<<1, 32, 0, s>>>(sm);
     PM_LAUNCH_CHECK();
     NumeratorSrc src = numerator_src();
-    rt.extra_launches += 1 + launch_divide_numerator(src, sm + S_X1, q.get<Fr>(), chunk_vals.get<Fr>(), st, s);   // prover.rs:211-225
-    G1XYZZ* ac = acc.get<G1XYZZ>() + 2 * kMaxMsmSums;
+    Fr* qp = q.get<Fr>();
+    if (range_division && world > 1) {
+        NcclApi& api = nccl_api();
+        const uint64_t c_lo = chunk_lo(rank), cnt = chunk_lo(rank + 1) - c_lo;
+        Fr* rv = range_vals.as<Fr>((size_t)world + 4);          // [0, world): gathered; [world]: mine; [world + 1]: carry in
+        uint64_t* rlo = range_lo_dev.as<uint64_t>((size_t)world + 1);
+        if (!range_lo_uploaded) {
+            std::vector<uint64_t> lo((size_t)world + 1);
+            for (int r = 0; r <= world; r++) lo[r] = chunk_lo(r);
+            PM_CUDA(cudaMemcpyAsync(rlo, lo.data(), lo.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+            PM_CUDA(cudaStreamSynchronize(s));
+            range_lo_uploaded = true;
+        }
+        rt.extra_launches += 1 + launch_numerator_range_eval(src, sm + S_X1, c_lo, cnt, chunk_vals.get<Fr>(), rv + world, s);
+        api.check(api.AllGather(rv + world, rv, sizeof(Fr), NcclApi::kUint8, nccl_comm, s), "ncclAllGather");
+        launch_numerator_range_carry(rv, rlo, (uint32_t)rank, (uint32_t)world, sm + S_X1, rv + world + 1, st, s);
+        rt.extra_launches += 1 + launch_numerator_range_divide(src, sm + S_X1, c_lo, cnt, rv + world + 1, qp, chunk_vals.get<Fr>(), s);
+    } else {
+        rt.extra_launches += 1 + launch_divide_numerator(src, sm + S_X1, qp, chunk_vals.get<Fr>(), st, s);   // prover.rs:211-225
+    }
     MsmConfig cfg = cfg_d();
-    if (world > 1 && cfg.c == 0) cfg.c = MsmEngine::choose_window((src.len - 1) / world);   // same Shape on every rank
-    return rt.msm.run(bases_d.get<G1Affine>(), q.get<Fr>(), local_count(src.len - 1), ac, s, cfg, world, rank);  // prover.rs:229
+    const uint64_t lo = world == 1 ? 0 : d_lo(rank), cnt_d = world == 1 ? src.len - 1 : d_count();
+    if (world > 1 && cfg.c == 0) cfg.c = MsmEngine::choose_window((src.len - 1) / world);
+    return rt.msm.run(bases_d.get<G1Affine>(), qp + lo, cnt_d, sums_d, s, cfg, 1, 0);  // prover.rs:229
 }
 
 void ProverCtx::phase3_partial(const uint8_t* x2, const uint8_t* c_at_x1, uint8_t* partial_out) {
     Runtime& rt = runtime();
     cudaStream_t s = rt.stream;
     if (!partial_out) throw StatusError(PM_ERR_ARG, "null phase-3 argument");
-    MsmEngine::Shape sd = phase3_enqueue(x2, c_at_x1);
     G1XYZZ* ac = acc.get<G1XYZZ>() + 2 * kMaxMsmSums;
+    MsmEngine::Shape sd = phase3_enqueue(x2, c_at_x1, ac, false);
     uint32_t* st = status.get<uint32_t>();
     uint8_t* hs = static_cast<uint8_t*>(host_stage);
     PM_CUDA(cudaMemcpyAsync(hs, ac, sd.count() * sizeof(G1XYZZ), cudaMemcpyDeviceToHost, s));
@@ -598,28 +818,30 @@ void ProverCtx::phase3_collective(const uint8_t* x2, const uint8_t* c_at_x1, uin
     cudaStream_t s = rt.stream;
     if (!nccl_comm) throw StatusError(PM_ERR_STATE, "no communicator attached (pm_ctx_attach_nccl)");
     if (!d_out) throw StatusError(PM_ERR_ARG, "null phase-3 argument");
-    MsmEngine::Shape sd = phase3_enqueue(x2, c_at_x1);
-    const size_t bd = sd.count() * sizeof(G1XYZZ);
-    G1XYZZ* ac = acc.get<G1XYZZ>() + 2 * kMaxMsmSums;
+    uint8_t* mine = xchg.as<uint8_t>(2 * kBlockBytes);
+    G1XYZZ* sums_d = reinterpret_cast<G1XYZZ*>(mine + sizeof(SumsHeader));
+    MsmEngine::Shape sd = phase3_enqueue(x2, c_at_x1, sums_d, true);
     uint32_t* st = status.get<uint32_t>();
-    uint8_t* g = gathered.as<uint8_t>((size_t)world * bd + 256);
+    SumsHeader* hh = static_cast<SumsHeader*>(host_hdr);
+    fill_header(hh[2], sd);
+    PM_CUDA(cudaMemcpyAsync(mine, &hh[2], sizeof(SumsHeader), cudaMemcpyHostToDevice, s));
+    PM_CUDA(cudaMemcpyAsync(mine + offsetof(SumsHeader, status0), st, 2 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+    uint8_t* g = gathered.as<uint8_t>((size_t)world * 2 * kBlockBytes + 256);
     NcclApi& api = nccl_api();
-    api.check(api.AllGather(ac, g, bd, NcclApi::kUint8, nccl_comm, s), "ncclAllGather");
-    uint8_t* hg = gather_stage((size_t)world * bd + 256);
-    uint8_t* hs = static_cast<uint8_t*>(host_stage);
-    PM_CUDA(cudaMemcpyAsync(hg, g, (size_t)world * bd, cudaMemcpyDeviceToHost, s));
-    PM_CUDA(cudaMemcpyAsync(hs + kStageStatus, st, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    api.check(api.AllGather(mine, g, kBlockBytes, NcclApi::kUint8, nccl_comm, s), "ncclAllGather");
+    uint8_t* hg = gather_stage((size_t)world * 2 * kBlockBytes + 256);
+    PM_CUDA(cudaMemcpyAsync(hg, g, (size_t)world * kBlockBytes, cudaMemcpyDeviceToHost, s));
     PM_CUDA(cudaEventRecord(ev1, s));
     PM_CUDA(cudaStreamSynchronize(s));
     profiler_end();
     float ms = 0;
     PM_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
     phase_ms[2] = ms;
-    uint32_t stv;
-    memcpy(&stv, hs + kStageStatus, 4);
-    check_status(stv);
+    uint32_t st0 = 0, st1 = 0;
+    for (int r = 0; r < world; r++) block_status(hg + (size_t)r * kBlockBytes, st0, st1);
+    check_status(st0);
     host::XyzzH sum_d = host::XyzzH::inf();
-    for (int r = 0; r < world; r++) host::xyzz_add(sum_d, host::combine_shifted(hg + (size_t)r * bd, sd.nwin, sd.c, sd.nsum, sd.shift));
+    for (int r = 0; r < world; r++) host::xyzz_add(sum_d, decode_block(hg + (size_t)r * kBlockBytes));
     host::xyzz_to_affine_wire(sum_d, d_out);
     phase = 0;
 }
@@ -656,10 +878,20 @@ void init_dims(ProverCtx& c, const pm_r1cs_view& r) {
 // inside the concatenated base array; the rank keeps global indices g with g % world == rank, stored
 // compactly at local index g / world.
 void upload_points(const ProverCtx& c, G1Affine* dst_base, uint64_t global_off, const uint8_t* src, size_t stride,
-                   uint64_t len, uint64_t expect, const char* name) {
+                   uint64_t len, uint64_t expect, const char* name, bool contiguous = false) {
     if (len != expect) throw StatusError(PM_ERR_ARG, std::string("unexpected length of ") + name);
     if (len && !src) throw StatusError(PM_ERR_ARG, std::string("null ") + name);
     Runtime& rt = runtime();
+    if (contiguous && c.world > 1) {
+        // the d-side vector: this rank's contiguous range [d_lo, d_hi) as an unsharded upload of that sub-vector
+        ProverCtx one;
+        one.world = 1;
+        one.rank = 0;
+        one.validate_key = c.validate_key;
+        const uint64_t lo = c.d_lo(c.rank), cnt = c.d_count();
+        if (cnt) upload_points(one, dst_base, 0, src + lo * stride, stride, cnt, cnt, name, false);
+        return;
+    }
     if (c.world == 1 && stride == PM_G1_BYTES) {
         PM_CUDA(cudaMemcpyAsync(dst_base + global_off, src, len * sizeof(G1Affine), cudaMemcpyHostToDevice, rt.stream));
         PM_CUDA(cudaStreamSynchronize(rt.stream));
@@ -709,13 +941,14 @@ void upload_points(const ProverCtx& c, G1Affine* dst_base, uint64_t global_off, 
 struct KeySlice { uint64_t off, len; bool in_d; };
 KeySlice key_slice(const ProverCtx& c, int which) {
     const uint64_t n = c.n;
+    const CLayout L = c.lay();
     switch (which) {
         case 0: return {0, n + 1, false};
-        case 1: return {n + 1, 3, false};
-        case 2: return {n + 6, n - 1, false};
-        case 3: return {n + 4, 2, false};
+        case 1: return {L.off_ya, 3, false};
+        case 2: return {L.off_zh, n - 1, false};
+        case 3: return {L.off_yg, 2, false};
         case 4: return {0, c.len_d(), true};
-        case 5: return {n + 6 + (n - 1), c.cols - c.m0, false};
+        case 5: return {L.off_lcs, c.cols - c.m0, false};
         default: throw StatusError(PM_ERR_ARG, "bad key vector index");
     }
 }
@@ -752,14 +985,17 @@ static int ctx_create_impl(const pm_pk_view* pk, int rank, int world, bool valid
         c.plan_tables();
         G1Affine* bc = c.bases_c.as<G1Affine>(c.plan_c.levels * c.plan_c.stride);
         G1Affine* bd = c.bases_d.as<G1Affine>(c.plan_d.levels * c.plan_d.stride);
+        // the gaps of the c-side layout (CLayout) are points at infinity
+        PM_CUDA(cudaMemsetAsync(bc, 0, c.plan_c.stride * sizeof(G1Affine), runtime().stream));
         const size_t st = pk->point_stride;
         const uint64_t n = c.n;
+        const CLayout L = c.lay();
         upload_points(c, bc, 0, pk->x_powers_g1, st, pk->x_powers_g1_len, n + 1, "x_powers_g1");
-        upload_points(c, bc, n + 1, pk->x_powers_y_alpha_g1, st, pk->x_powers_y_alpha_g1_len, 3, "x_powers_y_alpha_g1");
-        upload_points(c, bc, n + 4, pk->x_powers_y_gamma_g1, st, pk->x_powers_y_gamma_g1_len, 2, "x_powers_y_gamma_g1");
-        upload_points(c, bc, n + 6, pk->x_powers_zh_by_y_alpha_g1, st, pk->x_powers_zh_by_y_alpha_g1_len, n - 1, "x_powers_zh_by_y_alpha_g1");
-        upload_points(c, bc, n + 6 + (n - 1), pk->uj_wj_lcs_by_y_alpha_g1, st, pk->uj_wj_lcs_by_y_alpha_g1_len, c.cols - c.m0, "uj_wj_lcs_by_y_alpha_g1");
-        upload_points(c, bd, 0, pk->x_powers_y_gamma_z_g1, st, pk->x_powers_y_gamma_z_g1_len, c.len_d(), "x_powers_y_gamma_z_g1");
+        upload_points(c, bc, L.off_ya, pk->x_powers_y_alpha_g1, st, pk->x_powers_y_alpha_g1_len, 3, "x_powers_y_alpha_g1");
+        upload_points(c, bc, L.off_yg, pk->x_powers_y_gamma_g1, st, pk->x_powers_y_gamma_g1_len, 2, "x_powers_y_gamma_g1");
+        upload_points(c, bc, L.off_zh, pk->x_powers_zh_by_y_alpha_g1, st, pk->x_powers_zh_by_y_alpha_g1_len, n - 1, "x_powers_zh_by_y_alpha_g1");
+        upload_points(c, bc, L.off_lcs, pk->uj_wj_lcs_by_y_alpha_g1, st, pk->uj_wj_lcs_by_y_alpha_g1_len, c.cols - c.m0, "uj_wj_lcs_by_y_alpha_g1");
+        upload_points(c, bd, 0, pk->x_powers_y_gamma_z_g1, st, pk->x_powers_y_gamma_z_g1_len, c.len_d(), "x_powers_y_gamma_z_g1", true);
         c.build_tables();
         *out = h.release();
     });
@@ -996,6 +1232,13 @@ int pm_ctx_debug_read(pm_ctx* ctx, int which, uint8_t* out, uint64_t capacity_el
         Runtime& rt = runtime();
         PM_CUDA(cudaMemcpyAsync(out, src, cnt * sizeof(Fr), cudaMemcpyDeviceToHost, rt.stream));
         PM_CUDA(cudaStreamSynchronize(rt.stream));
+    });
+}
+
+int pm_ctx_selftest_resident(pm_ctx* ctx, int virtual_world, uint64_t* mismatches) {
+    return guarded([&] {
+        if (!ctx || !mismatches) throw StatusError(PM_ERR_ARG, "null argument");
+        *mismatches = ctx->impl.selftest_resident(virtual_world);
     });
 }
 

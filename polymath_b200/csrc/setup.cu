@@ -238,11 +238,13 @@ void run_setup(ProverCtx& ctx, const uint8_t* x, const uint8_t* z, uint8_t* x_g2
 
     // c-side scalars, laid out like ProverCtx::bases_c
     const uint64_t len_c = ctx.len_c(), len_d = ctx.len_d();
+    const CLayout lay = ctx.lay();
     Fr* sc = scal_b.as<Fr>(len_c > len_d ? len_c : len_d);
+    PM_CUDA(cudaMemsetAsync(sc, 0, len_c * sizeof(Fr), s));      // the gaps of the layout: [0]G = the point at infinity
     powers(sc, n + 1, C_ONE);
-    powers(sc + n + 1, 3, C_Y_ALPHA);
-    powers(sc + n + 4, 2, C_Y_GAMMA);
-    powers(sc + n + 6, n - 1, C_ZH_Y3);
+    powers(sc + lay.off_ya, 3, C_Y_ALPHA);
+    powers(sc + lay.off_yg, 2, C_Y_GAMMA);
+    powers(sc + lay.off_zh, n - 1, C_ZH_Y3);
     Fr* L = lag_b.as<Fr>(n);
     {
         uint64_t threads = (n + kSeq - 1) / kSeq;
@@ -253,7 +255,7 @@ void run_setup(ProverCtx& ctx, const uint8_t* x, const uint8_t* z, uint8_t* x_g2
         DevCsc C{ctx.C.col_ptr.get<uint32_t>(), ctx.C.row.get<uint32_t>(), ctx.C.cval.get<Fr>()};
         const uint64_t total = ctx.cols - ctx.m0;
         k_lcs_scalars<<<ceil_div(total, 128), 128, 0, s>>>(A, B, C, L, (uint32_t)ctx.m0, (uint32_t)ctx.mw, (uint32_t)ctx.nr, c,
-                                                          sc + n + 6 + (n - 1));
+                                                          sc + lay.off_lcs);
         PM_LAUNCH_CHECK();
         rt.extra_launches += 3;
     }
@@ -271,9 +273,10 @@ void run_setup(ProverCtx& ctx, const uint8_t* x, const uint8_t* z, uint8_t* x_g2
         rt.fixed_base.run(share, cnt, out, s);
     };
     run_share(len_c, ctx.bases_c.get<G1Affine>());
-    // d-side
+    // d-side: contiguous range of this rank (the chunk range of its share of the opening division)
     powers(sc, len_d, C_Y_GAMMA_Z);
-    run_share(len_d, ctx.bases_d.get<G1Affine>());
+    if (ctx.world == 1) rt.fixed_base.run(sc, len_d, ctx.bases_d.get<G1Affine>(), s);
+    else rt.fixed_base.run(sc + ctx.d_lo(ctx.rank), ctx.d_count(), ctx.bases_d.get<G1Affine>(), s);
     // vk: [x]_2, [z]_2
     Fq* g2 = g2_b.as<Fq>(8);
     k_g2_mul<<<1, 32, 0, s>>>(c + C_X, 2, g2);

@@ -138,3 +138,44 @@ def test_collective_phases_with_a_one_rank_communicator(pmlib):
     check(lib.pm_polymath_prove_sharded(h, codec.frs_to_wire(inst), codec.frs_to_wire(wit), 1, drng._h, null_cb, None, got))
     assert got.raw == want.serialize_compressed()
     lib.pm_ctx_destroy(h)
+
+
+@pytest.mark.parametrize("log_n", [10, 14, 20])
+def test_resident_kernels_with_virtual_ranks(pmlib, log_n):
+    """The multi-GPU data path on ONE GPU (`pm_ctx_selftest_resident`): after a proof whose bytes the oracle / the golden
+    file pins, the polynomial work is replayed the way 2, 4 and 8 ranks of the sharded-resident flow run it — strided SAP
+    rows (row-range SpMV), sharded transforms with the all-to-all emulated by copies between the virtual ranks, the
+    ring exchange, local quotient checks and scalar assembly, and the (X - x1) division by chunk ranges with its carry
+    exchange — and every slice / range must equal what the unsharded path computed.  2^20 exercises the two-level carry
+    propagation inside a rank's range; the real NCCL exchange is covered by bench.py --gpus N (golden proof_check)."""
+    from polymath_b200 import circuits
+    from polymath_b200.api import Polymath, StdRng, _lib
+    from polymath_b200.lib import check
+    lib = _lib()
+    lib.pm_ctx_selftest_resident.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint64)]
+    n = 1 << log_n
+    r1cs, inst, wit, rng = circuits.synthetic_mimc(n, seed=3)
+    pk, vk_bytes = Polymath.setup(r1cs, rng)
+    proof = Polymath.prove(pk, inst, wit, rng)
+    assert Polymath.verify(vk_bytes, inst[1:], proof)
+    if log_n <= 10:        # byte-identical to the oracle at the size it can reach
+        from oracle import fast
+        from oracle.poly import Domain
+        import numpy as np
+        # same key (exported), witness and blinding through the CPU prove
+        from polymath_b200 import keydump
+        import bench
+        key = bench._key_from_device(pk)
+        cpu = bench.CpuProver(r1cs, inst, wit, key, "device key")
+        rng2 = StdRng.seed_from_u64(77)
+        ra_rng = StdRng.seed_from_u64(77)
+        ra = [ra_rng.fr_rand(), ra_rng.fr_rand()]
+        assert cpu.prove(ra).serialize_compressed() == Polymath.prove(pk, inst, wit, rng2)
+    for world in (2, 4, 8):
+        if n < 8 * world * world:
+            continue
+        bad = C.c_uint64(123)
+        check(lib.pm_ctx_selftest_resident(pk._h, world, C.byref(bad)))
+        assert bad.value == 0, (log_n, world, bad.value)
+    # an unsharded context only, after a complete proof
+    pk.close()
