@@ -9,6 +9,8 @@
 //! There is no CPU fallback: every compute call fails with [`Error::Cuda`] when no device is visible.
 
 pub mod ffi;
+#[cfg(feature = "arkworks")]
+pub mod ark;
 
 use core::ffi::c_int;
 use std::ffi::CStr;
