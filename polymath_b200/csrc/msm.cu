@@ -624,18 +624,31 @@ __global__ void __launch_bounds__(128) k_heavy_finish(G1XYZZ* __restrict__ bucke
 // The second term is the same problem on the K-times shorter array R with off = 0, so level j
 // contributes 2^(kbits*j) * sum(T_j); the plain sums of the T arrays are tree-reduced and the few
 // level sums are combined on the host (combine_levels).  No data-dependent scalar multiplications.
-constexpr int kRedBits = 4;
-constexpr uint32_t kRedK = 1u << kRedBits;
+// Level radix K = 2^red_bits.  One thread walks a segment with 2 K dependent XYZZ additions, the array shrinks K-fold per
+// level; the first level is throughput-bound (2 additions per bucket = 0.5 ms of Fq products for 2^19 buckets), the later
+// ones latency-bound, so a smaller K shortens the tail (sum_levels 2 K + top additions) at the price of more launches.
+// Measured on S-mimc(2^20), one GPU / as rank 0 of 8 (phase 1 + 3): K = 16: 66.5 / 16.2 ms, K = 8: 66.6 / 15.7 ms,
+// K = 4: 67.1 / 16.1 ms (profiles/r2_summary.md).  The plain sums of the T arrays run on a side stream.
+// PM_RED_BITS overrides (tuning hook).
+inline int red_bits() {
+    static int bits = -1;
+    if (bits < 0) {
+        const char* v = getenv("PM_RED_BITS");
+        bits = v ? atoi(v) : 3;
+        if (bits < 1 || bits > 6) bits = 3;
+    }
+    return bits;
+}
 
 // X: [ngroups][m];  T, R: [ngroups][mseg]
 template <bool FIRST>
 __global__ void __launch_bounds__(128) k_reduce_level(const G1XYZZ* __restrict__ X, uint32_t m, uint32_t mseg, uint32_t ngroups,
-                                                      G1XYZZ* __restrict__ T, G1XYZZ* __restrict__ R) {
+                                                      uint32_t seg_len, G1XYZZ* __restrict__ T, G1XYZZ* __restrict__ R) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= mseg * ngroups) return;
     uint32_t g = t / mseg, sgm = t % mseg;
-    uint32_t lo = sgm * kRedK;
-    uint32_t hi = min(lo + kRedK, m);
+    uint32_t lo = sgm * seg_len;
+    uint32_t hi = min(lo + seg_len, m);
     const G1XYZZ* xs = X + (size_t)g * m;
     G1XYZZ running = G1XYZZ::inf(), acc = G1XYZZ::inf();
     for (uint32_t b = hi; b-- > lo;) {
@@ -669,9 +682,9 @@ __global__ void __launch_bounds__(128) k_sum_slices(const G1XYZZ* __restrict__ i
     if (threadIdx.x == 0) out[(size_t)g * out_stride + sl] = sh[0];
 }
 
-// Top of the reduction (arrays of <= kTopMax elements): sum_i (i + off) X_i = [off] * sum_i X_i +
+// Top of the reduction (arrays of a few thousand elements at most): sum_i (i + off) X_i = [off] * sum_i X_i +
 // sum_bit 2^bit * sum_{i : bit set} X_i.  One CTA per (bucket set, masked sum); the masked sums go to the host.
-constexpr uint32_t kTopMax = 8192;
+constexpr uint32_t kTopTarget = 2048;   // 8 serial + 8 tree additions per thread of k_reduce_top
 __global__ void __launch_bounds__(256) k_reduce_top(const G1XYZZ* __restrict__ X, uint32_t m, uint32_t nsums, int with_ones,
                                                     uint32_t out_stride, G1XYZZ* __restrict__ out) {
     __shared__ uint4 smem_raw[256 * sizeof(G1XYZZ) / sizeof(uint4)];
@@ -838,6 +851,15 @@ MsmEngine::~MsmEngine() {
     if (ev_bwd_end) cudaEventDestroy(ev_bwd_end);
 }
 
+static inline size_t entries_of(size_t n, int nwin) { return n * (size_t)nwin; }
+
+void MsmEngine::ensure_side_stream() {
+    if (side_stream_) return;
+    PM_CUDA(cudaStreamCreateWithFlags(&side_stream_, cudaStreamNonBlocking));
+    PM_CUDA(cudaEventCreateWithFlags(&ev_fork_, cudaEventDisableTiming));
+    PM_CUDA(cudaEventCreateWithFlags(&ev_join_, cudaEventDisableTiming));
+}
+
 MsmEngine::Shape MsmEngine::run(const G1Affine* bases, const Fr* scalars, size_t n, G1XYZZ* winsums, cudaStream_t stream,
                                 MsmConfig cfg, size_t scalar_stride, size_t scalar_offset) {
     if (n == 0) {
@@ -854,20 +876,22 @@ MsmEngine::Shape MsmEngine::run(const G1Affine* bases, const Fr* scalars, size_t
         throw CudaError("msm: bad precomputed-level layout");
     const uint32_t nb = 1u << (c - 1);
     const uint32_t total = (uint32_t)ngroups * nb;
-    // hierarchical reduction geometry: 16-ary levels while the array is longer than kTopMax, then bit sums
-    uint32_t lev_m[16];
+    // hierarchical reduction geometry: K-ary levels (K = 2^red_bits) down to a top of <= kTopTarget elements, then bit sums
+    const int kRedBits = red_bits();
+    const uint32_t kRedK = 1u << kRedBits;
+    uint32_t lev_m[24];
     int nlev = 0;
     uint32_t m_top = nb;
     for (;;) {
         if (m_top <= 512) break;
-        if (m_top <= kTopMax) {
+        if (m_top <= kTopTarget) {
             // The masked sums make log2(m) half-empty passes over the array (~16 k pipe cycles per warp addition on
-            // 592 schedulers), another 16-ary level costs ~0.35 ms of latency: descend while that is cheaper
-            // (many bucket sets of a few thousand buckets: the shards of a multi-GPU prove).
+            // 592 schedulers); with many bucket sets (the shards of a multi-GPU prove, table-less MSMs) another level
+            // (2 K additions of latency, ~17 us each) is cheaper than those passes: descend while it is
             int bits = 0;
             while ((1u << bits) < m_top) bits++;
             const double masked_ms = (double)ngroups * (bits + 1) * (m_top / 32.0 + 12.0) * 16e3 / 592.0 / 1.9e6;
-            if (masked_ms <= 0.35) break;
+            if (masked_ms <= 2.0 * kRedK * 0.017) break;
         }
         lev_m[nlev++] = m_top;
         m_top = (m_top + kRedK - 1) / kRedK;
@@ -891,7 +915,12 @@ MsmEngine::Shape MsmEngine::run(const G1Affine* bases, const Fr* scalars, size_t
     // thread adds a point every ~6.4 us, the whole GPU ~2.8 G points/s, so a run of E / 18000 entries already takes
     // as long as everything else together; split from E / 32768 (skewed witnesses: repeated values).
     size_t share = n * (size_t)nwin / 32768;
-    uint32_t heavy_thr = cfg.heavy ? (uint32_t)cfg.heavy : (uint32_t)(share > 128 ? share : 128);
+    // Small MSMs are latency-bound by their LONGEST run (one thread, ~12-25 us per dependent mixed addition): the floor of
+    // the threshold follows the mean run length (4x, between 24 and 128 entries) — narrow top windows of a 2k-point MSM put
+    // 64 entries into each of 16 buckets, 0.8 ms as serial walks against 0.15 ms as chunk tasks (profiles/r2_summary.md).
+    const size_t mean_run = entries_of(n, nwin) / total;
+    const size_t thr_floor = mean_run * 4 < 24 ? 24 : mean_run * 4 > 128 ? 128 : mean_run * 4;
+    uint32_t heavy_thr = cfg.heavy ? (uint32_t)cfg.heavy : (uint32_t)(share > thr_floor ? share : thr_floor);
     const size_t max_tasks = n * (size_t)nwin / kHeavyChunk + total + 16;
     const size_t entries = n * (size_t)nwin;   // upper bound of the sorted list
 
@@ -1094,11 +1123,7 @@ MsmEngine::Shape MsmEngine::run(const G1Affine* bases, const Fr* scalars, size_t
                 forced_ppt = v ? atoi(v) : 0;
             }
             if (nspans == 2) {
-                if (!side_stream_) {
-                    PM_CUDA(cudaStreamCreateWithFlags(&side_stream_, cudaStreamNonBlocking));
-                    PM_CUDA(cudaEventCreateWithFlags(&ev_fork_, cudaEventDisableTiming));
-                    PM_CUDA(cudaEventCreateWithFlags(&ev_join_, cudaEventDisableTiming));
-                }
+                ensure_side_stream();
                 PM_CUDA(cudaEventRecord(ev_fork_, stream));
                 PM_CUDA(cudaStreamWaitEvent(side_stream_, ev_fork_, 0));
             }
@@ -1203,16 +1228,21 @@ MsmEngine::Shape MsmEngine::run(const G1Affine* bases, const Fr* scalars, size_t
         G1XYZZ* scratch = segs + 2 * seg_total;     // [ngroups][64] slice partials
         const int nsum = shape.nsum;
         uint32_t m_last = nb;
+        // The level kernels form the critical path; the plain sums of the T arrays only feed the host, so they run on
+        // the side stream behind an event per level and rejoin before the caller reads winsums.
+        ensure_side_stream();
         for (int j = 0; j < nlev; j++) {
             const uint32_t m = lev_m[j], mseg = (m + kRedK - 1) / kRedK;
             G1XYZZ* T = cursor;
             G1XYZZ* R = cursor + (size_t)mseg * ngroups;
             cursor = R + (size_t)mseg * ngroups;
             const unsigned grid = ceil_div((size_t)mseg * ngroups, 128);
-            if (j == 0) k_reduce_level<true><<<grid, 128, 0, stream>>>(X, m, mseg, ngroups, T, R);
-            else k_reduce_level<false><<<grid, 128, 0, stream>>>(X, m, mseg, ngroups, T, R);
+            if (j == 0) k_reduce_level<true><<<grid, 128, 0, stream>>>(X, m, mseg, ngroups, kRedK, T, R);
+            else k_reduce_level<false><<<grid, 128, 0, stream>>>(X, m, mseg, ngroups, kRedK, T, R);
             PM_LAUNCH_CHECK();
             launches++;
+            PM_CUDA(cudaEventRecord(ev_fork_, stream));
+            PM_CUDA(cudaStreamWaitEvent(side_stream_, ev_fork_, 0));
             // level sum: winsums[g*nsum + j] = sum_seg T[g][seg]
             if (mseg > 512) {
                 // two stages: slices of <= 512 elements per 128-thread CTA (4 serial + 7 tree additions), then
@@ -1220,11 +1250,11 @@ MsmEngine::Shape MsmEngine::run(const G1Affine* bases, const Fr* scalars, size_t
                 uint32_t slice = (mseg + 255) / 256;
                 if (slice < 256) slice = 256;
                 const uint32_t nsl = (mseg + slice - 1) / slice;
-                k_sum_slices<<<ngroups * nsl, 128, 0, stream>>>(T, mseg, mseg, slice, nsl, 256, scratch);
-                k_sum_slices<<<ngroups, 128, 0, stream>>>(scratch, 256, nsl, nsl, 1, nsum, winsums + j);
+                k_sum_slices<<<ngroups * nsl, 128, 0, side_stream_>>>(T, mseg, mseg, slice, nsl, 256, scratch);
+                k_sum_slices<<<ngroups, 128, 0, side_stream_>>>(scratch, 256, nsl, nsl, 1, nsum, winsums + j);
                 launches += 2;
             } else {
-                k_sum_slices<<<ngroups, 128, 0, stream>>>(T, mseg, mseg, mseg, 1, nsum, winsums + j);
+                k_sum_slices<<<ngroups, 128, 0, side_stream_>>>(T, mseg, mseg, mseg, 1, nsum, winsums + j);
                 launches++;
             }
             PM_LAUNCH_CHECK();
@@ -1234,6 +1264,10 @@ MsmEngine::Shape MsmEngine::run(const G1Affine* bases, const Fr* scalars, size_t
         k_reduce_top<<<ngroups * ntop, 256, 0, stream>>>(X, m_last, (uint32_t)ntop, with_ones, (uint32_t)nsum, winsums + nlev);
         PM_LAUNCH_CHECK();
         launches++;
+        if (nlev > 0) {
+            PM_CUDA(cudaEventRecord(ev_join_, side_stream_));
+            PM_CUDA(cudaStreamWaitEvent(stream, ev_join_, 0));
+        }
     }
     return shape;
 }

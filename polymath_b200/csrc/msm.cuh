@@ -63,7 +63,8 @@ private:
     std::map<PlanKey, std::pair<int, int>> plans_;
     DevBuf counts_, offsets_, cursors_, sorted_, buckets_, segs_, heavy_list_, heavy_count_, order_;
     DevBuf pairs_a_, pairs_b_, prefix_, tvals_, tpre_;   // pair rounds
-    cudaStream_t side_stream_ = nullptr;                   // second span of the pair rounds
+    void ensure_side_stream();
+    cudaStream_t side_stream_ = nullptr;                   // second span of the pair rounds; level sums of the reduction
     cudaEvent_t ev_fork_ = nullptr, ev_join_ = nullptr;   // pair rounds
 };
 

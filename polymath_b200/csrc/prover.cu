@@ -521,6 +521,32 @@ host::XyzzH decode_block(const uint8_t* block) {
     if (h.count < 0 || h.count > kMaxMsmSums || h.nwin * h.nsum != h.count) throw StatusError(PM_ERR_STATE, "corrupt partial-sum block");
     return host::combine_shifted(block + sizeof(SumsHeader), h.nwin, h.c, h.nsum, h.shift);
 }
+// Sum of one MSM over all ranks' blocks (spaced `pitch` bytes).  Ranks that planned the same shape — the normal case —
+// are added element-wise first and decoded ONCE: (G - 1) * count additions instead of G Horner passes with their
+// ~20 doublings each (0.25 ms of host time per proof at eight ranks).
+host::XyzzH decode_blocks(const uint8_t* first, size_t pitch, int world) {
+    SumsHeader h0;
+    memcpy(&h0, first, sizeof h0);
+    bool uniform = h0.count >= 0 && h0.count <= kMaxMsmSums && h0.nwin * h0.nsum == h0.count;
+    for (int r = 1; r < world && uniform; r++) {
+        SumsHeader h;
+        memcpy(&h, first + (size_t)r * pitch, sizeof h);
+        uniform = h.c == h0.c && h.nwin == h0.nwin && h.nsum == h0.nsum && h.count == h0.count && memcmp(h.shift, h0.shift, sizeof h.shift) == 0;
+    }
+    if (!uniform) {
+        host::XyzzH sum = host::XyzzH::inf();
+        for (int r = 0; r < world; r++) host::xyzz_add(sum, decode_block(first + (size_t)r * pitch));
+        return sum;
+    }
+    std::vector<uint8_t> merged((size_t)h0.count * sizeof(G1XYZZ));
+    for (int i = 0; i < h0.count; i++) {
+        host::XyzzH acc = host::XyzzH::inf();
+        for (int r = 0; r < world; r++)
+            host::xyzz_add(acc, host::XyzzH::from_wire(first + (size_t)r * pitch + sizeof(SumsHeader) + (size_t)i * sizeof(G1XYZZ)));
+        acc.to_wire(merged.data() + (size_t)i * sizeof(G1XYZZ));
+    }
+    return host::combine_shifted(merged.data(), h0.nwin, h0.c, h0.nsum, h0.shift);
+}
 void block_status(const uint8_t* block, uint32_t& st0, uint32_t& st1) {
     SumsHeader h;
     memcpy(&h, block, sizeof h);
@@ -566,11 +592,7 @@ void ProverCtx::phase1_collective(const uint8_t* ra, uint8_t* a_out, uint8_t* c_
     for (int r = 0; r < world; r++) block_status(hg + (size_t)r * 2 * kBlockBytes, st0, st1);
     if (res && st1 == 0) st0 |= ST_H_ZERO;
     check_status(st0);
-    host::XyzzH sum_a = host::XyzzH::inf(), sum_c = host::XyzzH::inf();
-    for (int r = 0; r < world; r++) {
-        host::xyzz_add(sum_a, decode_block(hg + (size_t)r * 2 * kBlockBytes));
-        host::xyzz_add(sum_c, decode_block(hg + (size_t)r * 2 * kBlockBytes + kBlockBytes));
-    }
+    host::XyzzH sum_a = decode_blocks(hg, 2 * kBlockBytes, world), sum_c = decode_blocks(hg + kBlockBytes, 2 * kBlockBytes, world);
     host::xyzz_to_affine_wire(sum_a, a_out);
     host::xyzz_to_affine_wire(sum_c, c_out);
     phase = 1;
@@ -840,8 +862,7 @@ void ProverCtx::phase3_collective(const uint8_t* x2, const uint8_t* c_at_x1, uin
     uint32_t st0 = 0, st1 = 0;
     for (int r = 0; r < world; r++) block_status(hg + (size_t)r * kBlockBytes, st0, st1);
     check_status(st0);
-    host::XyzzH sum_d = host::XyzzH::inf();
-    for (int r = 0; r < world; r++) host::xyzz_add(sum_d, decode_block(hg + (size_t)r * kBlockBytes));
+    host::XyzzH sum_d = decode_blocks(hg, kBlockBytes, world);
     host::xyzz_to_affine_wire(sum_d, d_out);
     phase = 0;
 }
