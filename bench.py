@@ -473,24 +473,30 @@ def run_ours(args):
     d = C.c_double()
     if world > 1:
         from polymath_b200 import sharded as _sh
-        ntt_log = 24
-        sn = _sh.ShardedNtt(ntt_log, rank, world)
-        sn.data.random_(0, 256)
-        sn.data.view(-1, 32)[:, 31] &= 0x3F                 # < 2^254 < r: valid Montgomery limbs
-        sn.run()
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(5):
+        for ntt_log in (20, 24, 26):
+            sn = _sh.ShardedNtt(ntt_log, rank, world)
+            sn.data.random_(0, 256)
+            sn.data.view(-1, 32)[:, 31] &= 0x3F                 # < 2^254 < r: valid Montgomery limbs
             sn.run()
-        e1.record()
-        barrier()
-        t_ntt = _max_over_ranks(e0.elapsed_time(e1) / 5, world)
-        sweep_dist["fr_ntt_gelem_per_s_2p%d_sharded" % ntt_log] = (1 << ntt_log) / (t_ntt * 1e-3) / 1e9
-        del sn
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                sn.run()
+            e1.record()
+            barrier()
+            t_ntt = _max_over_ranks(e0.elapsed_time(e1) / 5, world)
+            sweep_dist["fr_ntt_gelem_per_s_2p%d_sharded" % ntt_log] = (1 << ntt_log) / (t_ntt * 1e-3) / 1e9
+            del sn
+            torch.cuda.empty_cache()
         dacc = C.c_double()
+        for msm_log in (20, 24, 26):
+            check(lib.pm_bench_msm((1 << msm_log) // world, 0, 2, C.byref(d), C.byref(dacc)))
+            sweep_dist["g1_msm_mpts_per_s_2p%d_sharded" % msm_log] = (1 << msm_log) / (_max_over_ranks(d.value, world) * 1e-3) / 1e6
+        check(lib.pm_bench_set_msm_skew(1))
         check(lib.pm_bench_msm((1 << 24) // world, 0, 2, C.byref(d), C.byref(dacc)))
-        sweep_dist["g1_msm_mpts_per_s_2p24_sharded"] = (1 << 24) / (_max_over_ranks(d.value, world) * 1e-3) / 1e6
+        check(lib.pm_bench_set_msm_skew(0))
+        sweep_dist["g1_msm_mpts_per_s_2p24_sharded_skewed"] = (1 << 24) / (_max_over_ranks(d.value, world) * 1e-3) / 1e6
 
     # the 2^24 leg (BASELINE.json configs[3]): setup + proves sharded over the N GPUs ------------------------------------
     leg24 = None
@@ -584,6 +590,11 @@ def run_ours(args):
     acc_d = C.c_double()
     check(lib.pm_bench_msm(1 << 22, 0, 2, C.byref(d), C.byref(acc_d)))
     msm_mpts = (1 << 22) / (d.value * 1e-3) / 1e6
+    # the skewed inputs of SURVEY.md 8d (89 % one repeated scalar, 10 % zero, 1 % infinity bases): hot buckets
+    check(lib.pm_bench_set_msm_skew(1))
+    check(lib.pm_bench_msm(1 << 22, 0, 2, C.byref(d), C.byref(acc_d)))
+    check(lib.pm_bench_set_msm_skew(0))
+    sweep_dist["g1_msm_mpts_per_s_2p22_skewed"] = (1 << 22) / (d.value * 1e-3) / 1e6
     # setup (BASELINE.json configs[2]: "prove + setup (fixed-base batch mul)"): the generator's fixed-base batch alone
     fb_n = 1 << 22
     check(lib.pm_bench_fixed_base(fb_n, 2, C.byref(d)))

@@ -339,6 +339,10 @@ int pm_bench_fixed_base(size_t n, int iters, double* ms_avg);
 int pm_bench_msm(size_t n, int window_bits, int iters, double* ms_avg, double* ms_accumulate);
 /* Same with `levels` precomputed multiples 2^(c*l) P per base (fixed-base tables; 0/1 = none). */
 int pm_bench_msm_levels(size_t n, int window_bits, int levels, int iters, double* ms_avg, double* ms_accumulate);
+/* Input distribution of the later pm_bench_msm* calls: 0 = uniform scalars (default), 1 = the skewed case of
+ * SURVEY.md 8d — 89 % of the scalars one repeated value, 10 % zero, 1 % uniform, and 1 % of the bases at infinity
+ * (S-dummy keys, benches/bench.rs:38-61: one hot bucket per window, the chunked heavy-run path). */
+int pm_bench_set_msm_skew(int mode);
 
 /* CUDA-event stopwatch on the library's stream: start records an event, stop records another,
  * synchronises it and returns the elapsed device-timeline milliseconds. */

@@ -412,6 +412,12 @@ int pm_bench_fixed_base(size_t n, int iters, double* ms_avg) {
     });
 }
 
+static int g_bench_msm_skew = 0;
+int pm_bench_set_msm_skew(int mode) {
+    g_bench_msm_skew = mode;
+    return PM_OK;
+}
+
 int pm_bench_msm(size_t n, int window_bits, int iters, double* ms_avg, double* ms_accumulate) {
     return pm_bench_msm_levels(n, window_bits, 1, iters, ms_avg, ms_accumulate);
 }
@@ -428,8 +434,9 @@ int pm_bench_msm_levels(size_t n, int window_bits, int levels, int iters, double
         G1XYZZ* acc = dres.as<G1XYZZ>(kMaxMsmSums);
         launch_fill_fr(ps, n, 0xabcdef, rt.stream);
         rt.fixed_base.run(ps, n, pb, rt.stream);       // bases = [s_i]G for pseudo-random s_i
-        launch_build_levels(pb, n, levels, n, window_bits, rt.stream);
         launch_fill_fr(ps, n, 0x5eed, rt.stream);      // uniform scalars
+        if (g_bench_msm_skew) launch_skew_msm_inputs(ps, pb, n, 0x5ca1ab1e, rt.stream);   // before the levels: infinity stays infinity
+        launch_build_levels(pb, n, levels, n, window_bits, rt.stream);
         MsmConfig cfg;
         cfg.c = window_bits;
         cfg.levels = levels;

@@ -51,18 +51,23 @@ __global__ void __launch_bounds__(256) k_digits(const G1Affine* __restrict__ bas
                                                 int levels, uint32_t level_stride, int set_begin, int set_end,
                                                 uint32_t* __restrict__ counters, uint32_t* __restrict__ sorted) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    Fr s = scalars[i * sc_stride + sc_offset];
-    if (s.is_zero()) return;
+    // every thread of the warp stays to the end (the atomics below are warp-aggregated): `live` marks the ones with work
+    bool live = i < n;
+    Fr s = Fr::zero();
+    if (live) {
+        s = scalars[i * sc_stride + sc_offset];
+        live = !s.is_zero();
+    }
     // infinity bases carry no weight: test the first limbs cheaply, full test only if they vanish
-    {
+    if (live) {
         const uint4* bp = reinterpret_cast<const uint4*>(bases + i);
         uint4 q = __ldg(bp);
         if ((q.x | q.y | q.z | q.w) == 0) {
             G1Affine b = bases[i];
-            if (b.is_inf()) return;
+            if (b.is_inf()) live = false;
         }
     }
+    if (!__any_sync(0xffffffffu, live)) return;
     s = s.from_mont();
     uint32_t limbs[8];
 #pragma unroll
@@ -81,21 +86,28 @@ __global__ void __launch_bounds__(256) k_digits(const G1Affine* __restrict__ bas
                 uint32_t d = window_bits(limbs, w * c, c) + carry;
                 uint32_t neg = 0;
                 if (d > half) { d = (1u << c) - d; neg = 1; carry = 1; } else { carry = 0; }
-                if (d != 0 && w / levels >= set_begin) {
+                if (live && d != 0 && w / levels >= set_begin) {
                     slot[k] = (uint32_t)(w / levels - set_begin) * nb + (d - 1);
                     val[k] = ((uint32_t)(w % levels) * level_stride + (uint32_t)i) | (neg << 31);
                 }
             }
         }
-        if (SCATTER) {
-            uint32_t pos[4];
+        // Warp-aggregated: lanes that target the same bucket (repeated scalars — skewed witnesses, SURVEY.md 8d — put
+        // most of a warp into ONE bucket per window) elect a leader that reserves all their positions with one atomic.
+        // Uniform digits find no peers and pay one MATCH per window.
+        const uint32_t lane = threadIdx.x & 31u;
+        uint32_t pos[4];
 #pragma unroll
-            for (int k = 0; k < 4; k++) if (slot[k] != 0xffffffffu) pos[k] = atomicAdd(&counters[slot[k]], 1u);
+        for (int k = 0; k < 4; k++) {
+            const unsigned peers = __match_any_sync(0xffffffffu, slot[k]);
+            const int leader = __ffs(peers) - 1;
+            uint32_t base = 0;
+            if (slot[k] != 0xffffffffu && lane == (uint32_t)leader) base = atomicAdd(&counters[slot[k]], (uint32_t)__popc(peers));
+            if (SCATTER) pos[k] = __shfl_sync(0xffffffffu, base, leader) + __popc(peers & ((1u << lane) - 1u));
+        }
+        if (SCATTER) {
 #pragma unroll
             for (int k = 0; k < 4; k++) if (slot[k] != 0xffffffffu) sorted[pos[k]] = val[k];
-        } else {
-#pragma unroll
-            for (int k = 0; k < 4; k++) if (slot[k] != 0xffffffffu) atomicAdd(&counters[slot[k]], 1u);
         }
     }
 }

@@ -320,7 +320,7 @@ mod tests {
     #[test]
     fn library_loads() {
         assert_eq!(abi_version(), 1);
-        assert_eq!(ffi::BOUND_SYMBOLS.len(), 79);
+        assert_eq!(ffi::BOUND_SYMBOLS.len(), 80);
     }
 
     /// Without a device every compute entry fails loudly (there is no CPU fallback).

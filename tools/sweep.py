@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--levels", default="1", help="comma list; 0 = as many levels as windows")
     ap.add_argument("--rounds", default="-1", help="comma list of pair-round settings (-1 = automatic, 0 = XYZZ walk only)")
     ap.add_argument("--skip-basics", action="store_true")
+    ap.add_argument("--skew", action="store_true", help="MSM inputs of SURVEY.md 8d: 89 %% one repeated scalar, 10 %% zero, 1 %% infinity bases")
     ap.add_argument("--codec", default="", help="comma list of log2 sizes for the G1 (de)compression kernels")
     a = ap.parse_args()
     lib = require_device()
@@ -44,6 +45,7 @@ def main():
         print(json.dumps({"kernel": "g1_decompress", "log_n": lg, "ms": d.value, "mpts_per_s": (1 << lg) / d.value / 1e3,
                           "compress_ms": acc.value}), flush=True)
     acc = C.c_double()
+    check(lib.pm_bench_set_msm_skew(1 if a.skew else 0))
     for lg in [float(x) for x in a.msm.split(",") if x]:
         for w in [int(x) for x in a.windows.split(",")]:
             n = int(round(2 ** lg))
@@ -55,9 +57,10 @@ def main():
                 for rd in [int(x) for x in a.rounds.split(",")]:
                     check(lib.pm_msm_set_tuning(rd))
                     check(lib.pm_bench_msm_levels(n, w, lv, a.iters, C.byref(d), C.byref(acc)))
-                    print(json.dumps({"kernel": "msm_g1", "log_n": lg, "window": w, "levels": lv, "rounds": rd, "ms": d.value,
+                    print(json.dumps({"kernel": "msm_g1", "log_n": lg, "window": w, "levels": lv, "rounds": rd, "skewed": bool(a.skew), "ms": d.value,
                                       "ms_accumulate": acc.value, "mpts_per_s": n / d.value / 1e3}), flush=True)
                 check(lib.pm_msm_set_tuning(-1))
+    check(lib.pm_bench_set_msm_skew(0))
 
 
 if __name__ == "__main__":
