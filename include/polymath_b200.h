@@ -325,7 +325,8 @@ int pm_polymath_prove_resident(pm_ctx* ctx, const uint8_t* instance, pm_rng* rng
 /* Issue rate of dependency-free IMAD.WIDE.U32 (32x32+64 multiply-adds per second, whole GPU):
  * the INT32 IMAD-pipe roofline denominator for the MSM / field kernels. */
 int pm_bench_imad_peak(double* mads_per_s);
-/* Register-resident Montgomery products per second; field: 0 = Fr, 1 = Fq. */
+/* Register-resident Montgomery products per second; field: 0 = Fr, 1 = Fq; variants of the same dependent chain:
+ * 2 = Fq squaring, 3 = Fq Karatsuba product, 4 = Fr squaring, 5 = Fr Karatsuba product. */
 int pm_bench_field_mul(int field, double* muls_per_s);
 /* Average milliseconds of `iters` size-2^log_n transforms on resident data (after one warm-up). */
 int pm_bench_ntt(unsigned log_n, int inverse, int iters, double* ms_avg);

@@ -35,6 +35,13 @@ Runtime::Runtime() {
     if (e != cudaSuccess || count <= 0)
         throw CudaError(std::string("no CUDA device available (the product path has no CPU fallback): ") +
                         cudaGetErrorString(e));
+    // The bucket accumulation gathers 48- / 96-byte records at random from multi-GB tables: with the default L2 fetch
+    // granularity every miss pulls a whole 128-byte line (measured 160 / 223 bytes of DRAM traffic per gathered x / point,
+    // profiles/r2_summary.md).  PM_L2_FETCH = 32 | 64 | 128 sets the hint (tuning hook).
+    if (const char* v = getenv("PM_L2_FETCH")) {
+        const int g = atoi(v);
+        if (g == 32 || g == 64 || g == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)g);
+    }
     PM_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     PM_CUDA(cudaStreamCreateWithFlags(&stream2, cudaStreamNonBlocking));
     PM_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
@@ -326,7 +333,18 @@ int pm_bench_imad_peak(double* mads_per_s) {
 }
 
 int pm_bench_field_mul(int field, double* muls_per_s) {
-    return guarded([&] { runtime(); *muls_per_s = field ? measure_fq_mul_rate(2000) : measure_fr_mul_rate(4000); });
+    return guarded([&] {
+        runtime();
+        switch (field) {
+            case 0: *muls_per_s = measure_fr_mul_rate(4000); break;
+            case 1: *muls_per_s = measure_fq_mul_rate(2000); break;
+            case 2: *muls_per_s = measure_fq_variant_rate(1, 2000); break;   // Fq squaring
+            case 3: *muls_per_s = measure_fq_variant_rate(2, 2000); break;   // Fq Karatsuba product
+            case 4: *muls_per_s = measure_fr_variant_rate(1, 4000); break;   // Fr squaring
+            case 5: *muls_per_s = measure_fr_variant_rate(2, 4000); break;   // Fr Karatsuba product
+            default: throw StatusError(PM_ERR_ARG, "unknown field / variant");
+        }
+    });
 }
 
 int pm_bench_ntt(unsigned log_n, int inverse, int iters, double* ms_avg) {

@@ -30,10 +30,14 @@ struct alignas(16) G1XYZZ {
 // of the Fq product (keeps the loop body inside the instruction caches).
 struct MulInline {
     static __device__ __forceinline__ Fq mul(const Fq& a, const Fq& b) { return a * b; }
+    static __device__ __forceinline__ Fq sqr(const Fq& a) { return a.sqr_wide(); }
 };
 static __device__ __noinline__ Fq fq_mul_call(Fq a, Fq b) { return a * b; }
+// dedicated squaring (222 instead of 288 wide IMADs, field.cuh): one more out-of-line copy
+static __device__ __noinline__ Fq fq_sqr_call(Fq a) { return a.sqr_wide(); }
 struct MulCall {
     static __device__ __forceinline__ Fq mul(const Fq& a, const Fq& b) { return fq_mul_call(a, b); }
+    static __device__ __forceinline__ Fq sqr(const Fq& a) { return fq_sqr_call(a); }
 };
 
 // The general-purpose group operations below (full addition, doubling) go through the ONE out-of-line product too:
@@ -44,12 +48,12 @@ struct MulCall {
 static __device__ __noinline__ G1XYZZ xyzz_dbl_affine(const G1Affine& p) {
     G1XYZZ r;
     Fq u = p.y.dbl();
-    Fq v = fq_mul_call(u, u);
+    Fq v = fq_sqr_call(u);
     Fq w = fq_mul_call(u, v);
     Fq s = fq_mul_call(p.x, v);
-    Fq xx = fq_mul_call(p.x, p.x);
+    Fq xx = fq_sqr_call(p.x);
     Fq m = xx.dbl() + xx;
-    r.x = fq_mul_call(m, m) - s.dbl();
+    r.x = fq_sqr_call(m) - s.dbl();
     r.y = fq_mul_call(m, s - r.x) - fq_mul_call(w, p.y);
     r.zz = v;
     r.zzz = w;
@@ -60,12 +64,12 @@ static __device__ __noinline__ G1XYZZ xyzz_dbl_affine(const G1Affine& p) {
 static __device__ __noinline__ void xyzz_dbl(G1XYZZ& a) {
     if (a.is_inf()) return;
     Fq u = a.y.dbl();
-    Fq v = fq_mul_call(u, u);
+    Fq v = fq_sqr_call(u);
     Fq w = fq_mul_call(u, v);
     Fq s = fq_mul_call(a.x, v);
-    Fq xx = fq_mul_call(a.x, a.x);
+    Fq xx = fq_sqr_call(a.x);
     Fq m = xx.dbl() + xx;
-    Fq x3 = fq_mul_call(m, m) - s.dbl();
+    Fq x3 = fq_sqr_call(m) - s.dbl();
     a.y = fq_mul_call(m, s - x3) - fq_mul_call(w, a.y);
     a.x = x3;
     a.zz = fq_mul_call(v, a.zz);
@@ -95,10 +99,10 @@ __device__ __forceinline__ void xyzz_madd_t(G1XYZZ& a, const G1Affine& p_in, boo
         }
         return;
     }
-    Fq pp = M::mul(p, p);
+    Fq pp = M::sqr(p);
     Fq ppp = M::mul(p, pp);
     Fq q = M::mul(a.x, pp);
-    Fq x3 = M::mul(r, r) - ppp - q.dbl();
+    Fq x3 = M::sqr(r) - ppp - q.dbl();
     a.y = M::mul(r, q - x3) - M::mul(a.y, ppp);
     a.x = x3;
     a.zz = M::mul(a.zz, pp);
@@ -151,10 +155,10 @@ static __device__ __noinline__ void xyzz_add(G1XYZZ& a, const G1XYZZ& b) {
         else a = G1XYZZ::inf();
         return;
     }
-    Fq pp = fq_mul_call(p, p);
+    Fq pp = fq_sqr_call(p);
     Fq ppp = fq_mul_call(p, pp);
     Fq q = fq_mul_call(u1, pp);
-    Fq x3 = fq_mul_call(r, r) - ppp - q.dbl();
+    Fq x3 = fq_sqr_call(r) - ppp - q.dbl();
     a.y = fq_mul_call(r, q - x3) - fq_mul_call(s1, ppp);
     a.x = x3;
     a.zz = fq_mul_call(fq_mul_call(a.zz, b.zz), pp);
@@ -166,7 +170,7 @@ static __device__ __noinline__ G1Affine xyzz_to_affine(const G1XYZZ& a) {
     if (a.is_inf()) return G1Affine::inf();
     Fq izzz = a.zzz.inv();
     Fq t = fq_mul_call(a.zz, izzz);
-    Fq izz = fq_mul_call(t, t);
+    Fq izz = fq_sqr_call(t);
     return {fq_mul_call(a.x, izz), fq_mul_call(a.y, izzz)};
 }
 

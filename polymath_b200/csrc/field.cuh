@@ -17,6 +17,7 @@ namespace pm {
 // ---------------------------------------------------------------------------------------
 // one PTX instruction per wrapper; `volatile` keeps the implicit carry-flag order
 // ---------------------------------------------------------------------------------------
+#ifndef PM_HOST_EMU   // tests/csrc/field_emu_test.cpp supplies the same functions on the host (explicit carry flag)
 namespace ptx {
 __device__ __forceinline__ uint32_t add_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("add.cc.u32 %0,%1,%2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
 __device__ __forceinline__ uint32_t addc_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("addc.cc.u32 %0,%1,%2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
@@ -33,7 +34,10 @@ __device__ __forceinline__ uint64_t mad_wide(uint32_t a, uint32_t b, uint64_t c)
 __device__ __forceinline__ uint64_t add_cc64(uint64_t a, uint64_t b) { uint64_t r; asm volatile("add.cc.u64 %0,%1,%2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ uint64_t addc_cc64(uint64_t a, uint64_t b) { uint64_t r; asm volatile("addc.cc.u64 %0,%1,%2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ uint64_t addc64(uint64_t a, uint64_t b) { uint64_t r; asm volatile("addc.u64 %0,%1,%2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ uint64_t sub_cc64(uint64_t a, uint64_t b) { uint64_t r; asm volatile("sub.cc.u64 %0,%1,%2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ uint64_t subc_cc64(uint64_t a, uint64_t b) { uint64_t r; asm volatile("subc.cc.u64 %0,%1,%2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 }  // namespace ptx
+#endif
 
 // ---------------------------------------------------------------------------------------
 // field parameters (constant bank: usable directly as IMAD operands)
@@ -207,7 +211,207 @@ struct alignas(16) Fp {
         final_sub(r.v);
         return r;
     }
+    // One reduction word WITHOUT a multiplicand word: step() with b_i = 0, the carried limb t0 folded into the first
+    // product of the A chain (p_0 m + t0 < 2^64), so a word costs N wide IMADs like reduce().
     __device__ __forceinline__ Fp sqr() const { return *this * *this; }
+    __device__ __forceinline__ static void redc_step(uint64_t* A, uint64_t* B) {
+        const uint32_t t0 = (uint32_t)(B[0] >> 32);
+        const uint32_t m = ((uint32_t)A[0] + t0) * P::INV;
+        B[0] = ptx::add_cc64(B[1], ptx::mul_wide(P::mod()[1], m));
+#pragma unroll
+        for (int k = 1; k < H - 1; k++) B[k] = ptx::addc_cc64(B[k + 1], ptx::mul_wide(P::mod()[2 * k + 1], m));
+        B[H - 1] = ptx::addc64(ptx::mul_wide(P::mod()[N - 1], m), 0);
+        A[0] = ptx::add_cc64(A[0], ptx::mad_wide(P::mod()[0], m, t0));
+#pragma unroll
+        for (int k = 1; k < H; k++) A[k] = ptx::addc_cc64(A[k], ptx::mul_wide(P::mod()[2 * k], m));
+        uint32_t c = ptx::addc(0, 0);
+        B[H - 1] += (uint64_t)c << 32;
+    }
+    // Montgomery reduction of a 2N-limb value T < p * 2^(32N) given as N 64-bit columns (T[k] = limbs 2k, 2k+1):
+    // T_hi + (T_lo + M p) / 2^(32N) < 2p, one conditional subtraction.  N^2 wide IMADs.
+    __device__ __forceinline__ static Fp redc_wide(const uint64_t* T) {
+        uint64_t ev[H], od[H];
+#pragma unroll
+        for (int k = 0; k < H; k++) { ev[k] = T[k]; od[k] = 0; }
+        reduce(ev, od);
+#pragma unroll
+        for (int i = 1; i < N; i += 2) {
+            redc_step(od, ev);
+            if (i + 1 < N) redc_step(ev, od);
+        }
+        // low part: ev + (od >> 32), then the high half of T on top
+        Fp r;
+        uint64_t lo[H];
+        uint64_t sft = (od[0] >> 32) | (od[1] << 32);
+        lo[0] = ptx::add_cc64(ev[0], sft);
+#pragma unroll
+        for (int k = 1; k < H; k++) {
+            sft = (k + 1 < H) ? ((od[k] >> 32) | (od[k + 1] << 32)) : (od[k] >> 32);
+            lo[k] = (k + 1 < H) ? ptx::addc_cc64(ev[k], sft) : ptx::addc64(ev[k], sft);
+        }
+        lo[0] = ptx::add_cc64(lo[0], T[H]);
+#pragma unroll
+        for (int k = 1; k < H; k++) lo[k] = (k + 1 < H) ? ptx::addc_cc64(lo[k], T[H + k]) : ptx::addc64(lo[k], T[H + k]);
+#pragma unroll
+        for (int k = 0; k < H; k++) { r.v[2 * k] = (uint32_t)lo[k]; r.v[2 * k + 1] = (uint32_t)(lo[k] >> 32); }
+        final_sub(r.v);
+        return r;
+    }
+    // ---- Karatsuba product (one level) + redc_wide ------------------------------------------------------------
+    // Z (HL 64-bit columns) = x * y for HL-limb operands: rows in increasing i, two carry chains per row (positions
+    // i + j even -> E, odd -> O), the carry-out of a chain absorbed by the column above its top (carries only so far).
+    static constexpr int HL = N / 2;      // limbs of a half operand (even: N is a multiple of 4)
+    static constexpr int HC = N / 4;      // 64-bit columns of a half operand
+    __device__ __forceinline__ static void mul_half(const uint32_t* x, const uint32_t* y, uint64_t* Z) {
+        uint64_t E[HL], O[HL];
+#pragma unroll
+        for (int k = 0; k < HL; k++) { E[k] = 0; O[k] = 0; }
+#pragma unroll
+        for (int j = 0; j < HL; j++) {
+            if (j & 1) O[(j - 1) / 2] = ptx::mul_wide(x[j], y[0]);
+            else E[j / 2] = ptx::mul_wide(x[j], y[0]);
+        }
+#pragma unroll
+        for (int i = 1; i < HL; i++) {
+            {   // even positions: j = i mod 2, +2, ...
+                int last = -1;
+#pragma unroll
+                for (int j = i & 1; j < HL; j += 2) {
+                    const int k = (i + j) / 2;
+                    E[k] = (j == (i & 1)) ? ptx::add_cc64(E[k], ptx::mul_wide(x[j], y[i])) : ptx::addc_cc64(E[k], ptx::mul_wide(x[j], y[i]));
+                    last = k;
+                }
+                if (last + 1 < HL) E[last + 1] = ptx::addc64(E[last + 1], 0);
+            }
+            {   // odd positions
+                int last = -1;
+#pragma unroll
+                for (int j = 1 - (i & 1); j < HL; j += 2) {
+                    const int k = (i + j - 1) / 2;
+                    O[k] = (j == 1 - (i & 1)) ? ptx::add_cc64(O[k], ptx::mul_wide(x[j], y[i])) : ptx::addc_cc64(O[k], ptx::mul_wide(x[j], y[i]));
+                    last = k;
+                }
+                if (last + 1 < HL) O[last + 1] = ptx::addc64(O[last + 1], 0);
+            }
+        }
+        Z[0] = ptx::add_cc64(E[0], O[0] << 32);
+#pragma unroll
+        for (int k = 1; k < HL; k++) {
+            const uint64_t o = (O[k] << 32) | (O[k - 1] >> 32);
+            Z[k] = (k + 1 < HL) ? ptx::addc_cc64(E[k], o) : ptx::addc64(E[k], o);
+        }
+    }
+    // a * b = z0 + (M - z0 - z2) 2^(32 HL) + z2 2^(64 HL) with z0 = a_lo b_lo, z2 = a_hi b_hi, M = (a_lo + a_hi)(b_lo + b_hi):
+    // 3 (N/2)^2 wide IMADs instead of N^2 (Fq: 108 instead of 144; with the reduction 252 instead of 288); the extra
+    // ~110 additions run on the ALU pipe.  MEASURED AND NOT USED (pm_bench_field_mul variants 3 / 5): 28.6 G/s against
+    // 29.4 G/s for the word-serial product in Fq, 60.5 against 65.5 in Fr — the saved multiplier slots are eaten by the
+    // additions and the longer dependency chain.  Kept as the checked alternative (tests/csrc/field_emu_test.cpp).
+    __device__ __forceinline__ static Fp mul_karatsuba(const Fp& a, const Fp& b) {
+        uint64_t T[N];
+        mul_half(a.v, b.v, T);                    // z0 -> T[0, HL)
+        mul_half(a.v + HL, b.v + HL, T + HL);     // z2 -> T[HL, N)
+        uint32_t sa[HL], sb[HL];
+        sa[0] = ptx::add_cc(a.v[0], a.v[HL]);
+#pragma unroll
+        for (int i = 1; i < HL; i++) sa[i] = ptx::addc_cc(a.v[i], a.v[HL + i]);
+        const uint32_t ca = ptx::addc(0, 0);
+        sb[0] = ptx::add_cc(b.v[0], b.v[HL]);
+#pragma unroll
+        for (int i = 1; i < HL; i++) sb[i] = ptx::addc_cc(b.v[i], b.v[HL + i]);
+        const uint32_t cb = ptx::addc(0, 0);
+        uint64_t M[HL];
+        mul_half(sa, sb, M);
+        // the carried bits: + ca * sb * 2^(32 HL) + cb * sa * 2^(32 HL) + ca * cb * 2^(64 HL); top word beyond the HL columns
+        const uint64_t ma = 0 - (uint64_t)ca, mb = 0 - (uint64_t)cb;
+        uint64_t mtop = ca & cb;
+        M[HC] = ptx::add_cc64(M[HC], ma & ((uint64_t)sb[0] | ((uint64_t)sb[1] << 32)));
+#pragma unroll
+        for (int k = 1; k < HC; k++) M[HC + k] = ptx::addc_cc64(M[HC + k], ma & ((uint64_t)sb[2 * k] | ((uint64_t)sb[2 * k + 1] << 32)));
+        mtop = ptx::addc64(mtop, 0);
+        M[HC] = ptx::add_cc64(M[HC], mb & ((uint64_t)sa[0] | ((uint64_t)sa[1] << 32)));
+#pragma unroll
+        for (int k = 1; k < HC; k++) M[HC + k] = ptx::addc_cc64(M[HC + k], mb & ((uint64_t)sa[2 * k] | ((uint64_t)sa[2 * k + 1] << 32)));
+        mtop = ptx::addc64(mtop, 0);
+        // z1 = M - z0 - z2 (non-negative, < 2^(64 HL + 1)): the borrows come out of mtop
+        M[0] = ptx::sub_cc64(M[0], T[0]);
+#pragma unroll
+        for (int k = 1; k < HL; k++) M[k] = ptx::subc_cc64(M[k], T[k]);
+        mtop = ptx::subc_cc64(mtop, 0);
+        M[0] = ptx::sub_cc64(M[0], T[HL]);
+#pragma unroll
+        for (int k = 1; k < HL; k++) M[k] = ptx::subc_cc64(M[k], T[HL + k]);
+        mtop = ptx::subc_cc64(mtop, 0);
+        // T += z1 * 2^(32 HL): columns HC .. HC + HL, then the carry runs to the top
+        T[HC] = ptx::add_cc64(T[HC], M[0]);
+#pragma unroll
+        for (int k = 1; k < HL; k++) T[HC + k] = ptx::addc_cc64(T[HC + k], M[k]);
+#pragma unroll
+        for (int k = HC + HL; k < N; k++) T[k] = (k + 1 < N) ? ptx::addc_cc64(T[k], k == HC + HL ? mtop : 0) : ptx::addc64(T[k], k == HC + HL ? mtop : 0);
+        return redc_wide(T);
+    }
+    // Squaring: the N(N-1)/2 products a_i a_j (i < j) once, doubled, plus the N squares a_i^2 — N(N+1)/2 wide IMADs
+    // instead of N^2 — then redc_wide: 222 instead of 288 for Fq.  Columns as in the product: E[k] = limbs (2k, 2k+1),
+    // O[k] = limbs (2k+1, 2k+2); a_i a_j lands on E[(i+j)/2] or O[(i+j-1)/2].  Rows are added in increasing i, each as
+    // two carry chains (even / odd positions); the column above a chain's top has only seen carries so far, so the
+    // chain's carry-out is absorbed there without further propagation.
+    // Measured on B200 (profiles/r2_summary.md): in a register-resident chain of independent squarings 46 G/s against
+    // 29 G/s for the product, but in the kernels the gain is small — the group operations are bound by the latency of
+    // their dependent carry chains at 25 % occupancy, not by the IMAD count: standalone MSM 2^22 +1.2 %, prove +0 %;
+    // the Fermat / square-root chains of the G1 codec run 6 % SLOWER with it (longer critical path per squaring), so
+    // sqr() below stays the product and only the MSM group operations call sqr_wide().
+    __device__ __forceinline__ Fp sqr_wide() const {
+        const uint32_t* a = v;
+        uint64_t E[N], O[N];
+#pragma unroll
+        for (int k = 0; k < N; k++) { E[k] = 0; O[k] = 0; }
+        // row 0 initialises its columns
+#pragma unroll
+        for (int j = 1; j < N; j++) {
+            if (j & 1) O[(j - 1) / 2] = ptx::mul_wide(a[0], a[j]);
+            else E[j / 2] = ptx::mul_wide(a[0], a[j]);
+        }
+#pragma unroll
+        for (int i = 1; i < N - 1; i++) {
+            // odd positions i + j: j = i+1, i+3, ...
+            {
+                int last = -1;
+#pragma unroll
+                for (int j = i + 1; j < N; j += 2) {
+                    const int k = (i + j - 1) / 2;
+                    O[k] = (j == i + 1) ? ptx::add_cc64(O[k], ptx::mul_wide(a[i], a[j])) : ptx::addc_cc64(O[k], ptx::mul_wide(a[i], a[j]));
+                    last = k;
+                }
+                if (last >= 0) O[last + 1] = ptx::addc64(O[last + 1], 0);
+            }
+            // even positions: j = i+2, i+4, ...
+            {
+                int last = -1;
+#pragma unroll
+                for (int j = i + 2; j < N; j += 2) {
+                    const int k = (i + j) / 2;
+                    E[k] = (j == i + 2) ? ptx::add_cc64(E[k], ptx::mul_wide(a[i], a[j])) : ptx::addc_cc64(E[k], ptx::mul_wide(a[i], a[j]));
+                    last = k;
+                }
+                if (last >= 0) E[last + 1] = ptx::addc64(E[last + 1], 0);
+            }
+        }
+        // S = E + (O << 32) on the E grid, doubled, plus the squares on the diagonal
+        uint64_t S[N];
+        S[0] = ptx::add_cc64(E[0], O[0] << 32);
+#pragma unroll
+        for (int k = 1; k < N; k++) {
+            const uint64_t o = (O[k] << 32) | (O[k - 1] >> 32);
+            S[k] = (k + 1 < N) ? ptx::addc_cc64(E[k], o) : ptx::addc64(E[k], o);
+        }
+        uint64_t T[N];
+        T[0] = ptx::add_cc64(S[0] << 1, ptx::mul_wide(a[0], a[0]));
+#pragma unroll
+        for (int k = 1; k < N; k++) {
+            const uint64_t d = (S[k] << 1) | (S[k - 1] >> 63);
+            T[k] = (k + 1 < N) ? ptx::addc_cc64(d, ptx::mul_wide(a[k], a[k])) : ptx::addc64(d, ptx::mul_wide(a[k], a[k]));
+        }
+        return redc_wide(T);
+    }
 
     __device__ __forceinline__ Fp& operator+=(const Fp& b) { *this = *this + b; return *this; }
     __device__ __forceinline__ Fp& operator-=(const Fp& b) { *this = *this - b; return *this; }

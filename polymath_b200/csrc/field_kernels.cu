@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(256) k_imad_peak(uint64_t* sink, uint32_t a, u
     if (s == 0x1234567812345678ull) sink[0] = s;  // never true in practice; keeps the loop alive
 }
 
-template <class F>
+template <class F, int MODE>
 __global__ void __launch_bounds__(256) k_mul_rate(F* sink, int depth) {
     F x, y;
 #pragma unroll
@@ -61,8 +61,16 @@ __global__ void __launch_bounds__(256) k_mul_rate(F* sink, int depth) {
     x.v[F::N - 1] &= 0x0fffffffu;
     y.v[F::N - 1] &= 0x0fffffffu;
     for (int it = 0; it < depth; it++) {
-        x = x * y;
-        y = y * x;
+        if (MODE == 1) {
+            x = x.sqr_wide();
+            y = y.sqr_wide();
+        } else if (MODE == 2) {
+            x = F::mul_karatsuba(x, y);
+            y = F::mul_karatsuba(y, x);
+        } else {
+            x = x * y;
+            y = y * x;
+        }
     }
     if (x.v[0] == 0xdeadbeefu && y.v[1] == 0x12345u) sink[0] = x;
 }
@@ -112,7 +120,7 @@ double measure_fr_mul_rate(int depth) {
     DevBuf sink;
     Fr* d = sink.as<Fr>(1);
     const int blocks = sm_count() * 8;
-    double ms = time_kernel_ms(k_mul_rate<Fr>, dim3(blocks), dim3(256), d, depth);
+    double ms = time_kernel_ms(k_mul_rate<Fr, 0>, dim3(blocks), dim3(256), d, depth);
     return (double)blocks * 256.0 * 2.0 * depth / (ms * 1e-3);
 }
 
@@ -120,7 +128,25 @@ double measure_fq_mul_rate(int depth) {
     DevBuf sink;
     Fq* d = sink.as<Fq>(1);
     const int blocks = sm_count() * 8;
-    double ms = time_kernel_ms(k_mul_rate<Fq>, dim3(blocks), dim3(256), d, depth);
+    double ms = time_kernel_ms(k_mul_rate<Fq, 0>, dim3(blocks), dim3(256), d, depth);
+    return (double)blocks * 256.0 * 2.0 * depth / (ms * 1e-3);
+}
+
+// mode 1 = dedicated squaring, 2 = Karatsuba product (Fq; same chain shape as measure_fq_mul_rate)
+double measure_fq_variant_rate(int mode, int depth) {
+    DevBuf sink;
+    Fq* d = sink.as<Fq>(1);
+    const int blocks = sm_count() * 8;
+    double ms = mode == 1 ? time_kernel_ms(k_mul_rate<Fq, 1>, dim3(blocks), dim3(256), d, depth)
+                          : time_kernel_ms(k_mul_rate<Fq, 2>, dim3(blocks), dim3(256), d, depth);
+    return (double)blocks * 256.0 * 2.0 * depth / (ms * 1e-3);
+}
+double measure_fr_variant_rate(int mode, int depth) {
+    DevBuf sink;
+    Fr* d = sink.as<Fr>(1);
+    const int blocks = sm_count() * 8;
+    double ms = mode == 1 ? time_kernel_ms(k_mul_rate<Fr, 1>, dim3(blocks), dim3(256), d, depth)
+                          : time_kernel_ms(k_mul_rate<Fr, 2>, dim3(blocks), dim3(256), d, depth);
     return (double)blocks * 256.0 * 2.0 * depth / (ms * 1e-3);
 }
 

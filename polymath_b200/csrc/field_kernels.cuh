@@ -14,5 +14,7 @@ double measure_imad_peak(int iters);
 // Register-resident Montgomery products per second (chains of `depth` dependent products per thread).
 double measure_fr_mul_rate(int depth);
 double measure_fq_mul_rate(int depth);
+double measure_fq_variant_rate(int mode, int depth);   // 1 = squaring, 2 = Karatsuba product
+double measure_fr_variant_rate(int mode, int depth);
 
 }  // namespace pm

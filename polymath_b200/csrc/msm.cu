@@ -350,9 +350,9 @@ struct PairSource {
 // Software-pipelined: the (index | sign) entries are fetched two pairs ahead and the x coordinates one pair ahead of
 // the product chain, so the two dependent memory latencies of the first round (entry -> table gather, random 96-byte
 // records of a multi-GB table) overlap the multiplication of the previous pair instead of serialising with it.
-template <bool FIRST>
-__global__ void __launch_bounds__(128) k_pairs_forward(PairSource<FIRST> src, PairSpan span, int r, int ppt,
-                                                       FqPlanes prefix, Fq* __restrict__ T) {
+template <bool FIRST, int MINB = 4>
+__global__ void __launch_bounds__(128, MINB) k_pairs_forward(PairSource<FIRST> src, PairSpan span, int r, int ppt,
+                                                             FqPlanes prefix, Fq* __restrict__ T) {
     size_t first, count;
     span.get(r, first, count);
     const size_t base = (size_t)blockIdx.x * pair_tile(ppt);
@@ -477,14 +477,14 @@ __global__ void __launch_bounds__(128, 4) k_pairs_backward(PairSource<FIRST> src
             num = b.y - a.y;
         } else if (kind == kPairDouble) {
             d = a.y.dbl();
-            Fq xx = fq_mul_call(a.x, a.x);
+            Fq xx = fq_sqr_call(a.x);
             num = xx.dbl() + xx;
         }
         if (kind <= kPairDouble) {
             Fq inv_d = fq_mul_call(inv, prefix.load(span.at(prefix.cap, p - first)));
             inv = fq_mul_call(inv, d);
             Fq lam = fq_mul_call(num, inv_d);
-            res.x = fq_mul_call(lam, lam) - a.x - b.x;
+            res.x = fq_sqr_call(lam) - a.x - b.x;
             res.y = fq_mul_call(lam, a.x - res.x) - a.y;
         } else if (kind == kPairFirst) {
             res = a;
@@ -1180,7 +1180,15 @@ MsmEngine::Shape MsmEngine::run(const G1Affine* bases, const Fr* scalars, size_t
                     const bool time_bwd = timed && sp == 0 && r == 0;
                     if (r == 0) {
                         PairSource<true> src{bases, sorted, cur};
-                        k_pairs_forward<true><<<g, 128, 0, st>>>(src, span, r, ppt, prefix, tvals);
+                        static int fwd_ctas = -1;
+                        if (fwd_ctas < 0) {
+                            const char* v = getenv("PM_FWD_CTAS");        // tuning hook: resident CTAs of the gather-bound pass
+                            fwd_ctas = v ? atoi(v) : 4;
+                        }
+                        if (fwd_ctas == 6) k_pairs_forward<true, 6><<<g, 128, 0, st>>>(src, span, r, ppt, prefix, tvals);
+                        else if (fwd_ctas == 5) k_pairs_forward<true, 5><<<g, 128, 0, st>>>(src, span, r, ppt, prefix, tvals);
+                        else if (fwd_ctas == 3) k_pairs_forward<true, 3><<<g, 128, 0, st>>>(src, span, r, ppt, prefix, tvals);
+                        else k_pairs_forward<true, 4><<<g, 128, 0, st>>>(src, span, r, ppt, prefix, tvals);
                         invert();
                         if (time_bwd) PM_CUDA(cudaEventRecord(ev_bwd_begin, st));
                         k_pairs_backward<true><<<g, 128, 0, st>>>(src, span, r, ppt, prefix, tvals, dst);
