@@ -92,18 +92,26 @@ __global__ void __launch_bounds__(256) k_digits(const G1Affine* __restrict__ bas
                 }
             }
         }
-        // Warp-aggregated: lanes that target the same bucket (repeated scalars — skewed witnesses, SURVEY.md 8d — put
-        // most of a warp into ONE bucket per window) elect a leader that reserves all their positions with one atomic.
-        // Uniform digits find no peers and pay one MATCH per window.
+        // Lanes that target the same bucket (repeated scalars — skewed witnesses, SURVEY.md 8d — put most of a warp into
+        // ONE bucket per window) elect a leader that reserves all their positions with one atomic.  The MATCH costs
+        // (+0.5 ms per prove on uniform digits when issued for every window), so it only runs when a one-shuffle probe
+        // sees two neighbouring lanes on the same bucket: never for uniform digits (2^-19 per pair), always under skew.
         const uint32_t lane = threadIdx.x & 31u;
         uint32_t pos[4];
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            const unsigned peers = __match_any_sync(0xffffffffu, slot[k]);
-            const int leader = __ffs(peers) - 1;
-            uint32_t base = 0;
-            if (slot[k] != 0xffffffffu && lane == (uint32_t)leader) base = atomicAdd(&counters[slot[k]], (uint32_t)__popc(peers));
-            if (SCATTER) pos[k] = __shfl_sync(0xffffffffu, base, leader) + __popc(peers & ((1u << lane) - 1u));
+            const uint32_t nbr = __shfl_down_sync(0xffffffffu, slot[k], 1);
+            const bool dup = lane < 31u && slot[k] != 0xffffffffu && nbr == slot[k];
+            if (__any_sync(0xffffffffu, dup)) {
+                const unsigned peers = __match_any_sync(0xffffffffu, slot[k]);
+                const int leader = __ffs(peers) - 1;
+                uint32_t base = 0;
+                if (slot[k] != 0xffffffffu && lane == (uint32_t)leader) base = atomicAdd(&counters[slot[k]], (uint32_t)__popc(peers));
+                if (SCATTER) pos[k] = __shfl_sync(0xffffffffu, base, leader) + __popc(peers & ((1u << lane) - 1u));
+            } else if (slot[k] != 0xffffffffu) {
+                const uint32_t old = atomicAdd(&counters[slot[k]], 1u);
+                if (SCATTER) pos[k] = old;
+            }
         }
         if (SCATTER) {
 #pragma unroll
