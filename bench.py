@@ -578,7 +578,7 @@ def run_ours(args):
                     "peak": hbm_peak, "unit": "GB/s", "frac": ntt_gbs / hbm_peak,
                     "traffic": tj.get("ntt_2p21_bytes") if log_n == 20 else None, "traffic_source": tj.get("source") if log_n == 20 else None,
                     "note": "a 255-bit-field NTT is multiplier-bound: 4 % of HBM peak with the fmaheavy pipe ~60 % active "
-                            "(profiles/r2_b_summary.md); ceiling from the measured Fr product rate reported beside it",
+                            "(profiles/r2_summary.md); ceiling from the measured Fr product rate reported beside it",
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
                     "gelem_per_s": (2 * n) / (ntt_ms * 1e-3) / 1e9}
     check(lib.pm_bench_field_mul(0, C.byref(d)))

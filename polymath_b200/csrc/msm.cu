@@ -416,7 +416,7 @@ __global__ void __launch_bounds__(128, MINB) k_pairs_forward(PairSource<FIRST> s
 // takes the binary-Euclid inverse of the few top elements, k_invert_down walks back.  3 products per element and
 // level.  A dependent Fq product costs ~1.4 us in a lone warp (its carry chains serialise ~500 instructions), so the
 // tree is LATENCY-bound: 3 x 32 x 2 product latencies + the inverse = ~0.4 ms per round whatever the size.  Measured
-// and rejected in round 2 (profiles/r2_b_summary.md): block-wide shared-memory trees with the tile held in registers
+// and rejected in round 2 (profiles/r2_summary.md): block-wide shared-memory trees with the tile held in registers
 // (one launch per level, but 1100 CTAs of 512 threads x 123 us = 0.9 ms).  The latency is hidden instead: the bucket
 // range is cut in two halves whose rounds run on two streams (MsmEngine::run), so one half's inversion overlaps
 // the other half's forward / backward pass.

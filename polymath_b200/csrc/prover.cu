@@ -296,7 +296,7 @@ ProverCtx::Phase1Shapes ProverCtx::phase1_msms(const Fr* sa_ptr, const Fr* sc_pt
     PM_CUDA(cudaStreamWaitEvent(rt.stream2, rt.ev_fork, 0));
     // (round 1 gave the phase-1 MSMs one more pair round than the cost model asked for, because running beside each other
     // hid their inversion latency; since every MSM now overlaps the two halves of its own buckets the model's choice is
-    // the best one: 21.6 ms against 22.1 ms with the extra round, profiles/r2_e_summary.md)
+    // the best one: 21.6 ms against 22.1 ms with the extra round, profiles/r2_summary.md)
     static int p1_bias = -100;
     if (p1_bias == -100) {
         const char* v = getenv("PM_P1_ROUNDS_BIAS");
