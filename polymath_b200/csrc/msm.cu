@@ -411,27 +411,35 @@ __global__ void __launch_bounds__(128, MINB) k_pairs_forward(PairSource<FIRST> s
 }
 
 // ---- inversion of the thread totals T of round r (all non-zero), Montgomery's trick over a small tree ----
-// Level sizes: n_0 = thread totals of k_pairs_forward, n_{l+1} = ceil(n_l / kInvFan).  k_invert_up multiplies
-// kInvFan strided elements of level l into one element of level l+1 (exclusive prefixes kept), k_invert_top
-// takes the binary-Euclid inverse of the few top elements, k_invert_down walks back.  3 products per element and
+// Level sizes: n_0 = thread totals of k_pairs_forward, n_{l+1} = ceil(n_l / fan_l).  k_invert_up multiplies
+// fan_l strided elements of level l into one element of level l+1 (exclusive prefixes kept), k_invert_top
+// takes the binary-Euclid inverse of the top elements, k_invert_down walks back.  3 products per element and
 // level.  A dependent Fq product costs ~1.4 us in a lone warp (its carry chains serialise ~500 instructions), so the
-// tree is LATENCY-bound: 3 x 32 x 2 product latencies + the inverse = ~0.4 ms per round whatever the size.  Measured
+// tree is LATENCY-bound: 3 x (fan_0 + fan_1) product latencies + the inverse (~90 us), whatever the size.  Measured
 // and rejected in round 2 (profiles/r2_summary.md): block-wide shared-memory trees with the tile held in registers
 // (one launch per level, but 1100 CTAs of 512 threads x 123 us = 0.9 ms).  The latency is hidden instead: the bucket
 // range is cut in two halves whose rounds run on two streams (MsmEngine::run), so one half's inversion overlaps
 // the other half's forward / backward pass.
-constexpr uint32_t kInvFan = 32;
+constexpr uint32_t kInvFan = 16;       // level 0: many short chains side by side
 constexpr int kInvLevels = 2;
-__device__ __forceinline__ size_t invert_level_size(const PairSpan& span, int r, int ppt, int level) {
+// Fan-in of level l.  Level 1 works on ~1/32 of the totals with a few hundred threads: there a SHORT chain (fan 4) and
+// more elements for the parallel inverses of the top (thousands instead of hundreds, still under one wave) cut the
+// critical path from 32 + 64 dependent products to 4 + 8 (PM_INV_FAN1 overrides; profiles/r2_summary.md).
+// Measured, S-mimc(2^20) phases 1 + 3: fans 32 / 32: 65.38 ms, 32 / 4: 64.83, 16 / 4: 64.74, 8 / 4: 64.80 (as rank 0 of 8: 15.44 / 15.24 / 15.17 / 15.11).
+// fan1 packs both: low 16 bits = fan of level >= 1, high 16 bits = fan of level 0 (0 = kInvFan)
+__host__ __device__ __forceinline__ uint32_t inv_fan(int level, uint32_t fan1) {
+    return level == 0 ? ((fan1 >> 16) ? (fan1 >> 16) : kInvFan) : (fan1 & 0xffffu);
+}
+__device__ __forceinline__ size_t invert_level_size(const PairSpan& span, int r, int ppt, int level, uint32_t fan1) {
     size_t first, count;
     span.get(r, first, count);
     size_t n = (count + pair_tile(ppt) - 1) / pair_tile(ppt) * 128;
-    for (int l = 0; l < level; l++) n = (n + kInvFan - 1) / kInvFan;
+    for (int l = 0; l < level; l++) n = (n + inv_fan(l, fan1) - 1) / inv_fan(l, fan1);
     return n;
 }
 __global__ void __launch_bounds__(128) k_invert_up(const Fq* __restrict__ lo, Fq* __restrict__ pre, Fq* __restrict__ hi,
-                                                   PairSpan span, int r, int ppt, int level) {
-    const size_t n = invert_level_size(span, r, ppt, level), m = (n + kInvFan - 1) / kInvFan;
+                                                   PairSpan span, int r, int ppt, int level, uint32_t fan1) {
+    const size_t n = invert_level_size(span, r, ppt, level, fan1), m = (n + inv_fan(level, fan1) - 1) / inv_fan(level, fan1);
     const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= m) return;
     Fq acc = Fq::one();
@@ -441,15 +449,15 @@ __global__ void __launch_bounds__(128) k_invert_up(const Fq* __restrict__ lo, Fq
     }
     store_fq(hi + j, acc);
 }
-__global__ void __launch_bounds__(128) k_invert_top(Fq* __restrict__ top, PairSpan span, int r, int ppt, int level) {
-    const size_t n = invert_level_size(span, r, ppt, level);
+__global__ void __launch_bounds__(128) k_invert_top(Fq* __restrict__ top, PairSpan span, int r, int ppt, int level, uint32_t fan1) {
+    const size_t n = invert_level_size(span, r, ppt, level, fan1);
     const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
     store_fq(top + j, load_fq(top + j).inv());
 }
 __global__ void __launch_bounds__(128) k_invert_down(Fq* __restrict__ lo, const Fq* __restrict__ pre, const Fq* __restrict__ hi,
-                                                     PairSpan span, int r, int ppt, int level) {
-    const size_t n = invert_level_size(span, r, ppt, level), m = (n + kInvFan - 1) / kInvFan;
+                                                     PairSpan span, int r, int ppt, int level, uint32_t fan1) {
+    const size_t n = invert_level_size(span, r, ppt, level, fan1), m = (n + inv_fan(level, fan1) - 1) / inv_fan(level, fan1);
     const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= m) return;
     Fq inv = load_fq(hi + j);
@@ -1133,7 +1141,16 @@ MsmEngine::Shape MsmEngine::run(const G1Affine* bases, const Fr* scalars, size_t
             // sized for the smallest pairs-per-thread; one set per span
             size_t lvl[kInvLevels + 1];
             lvl[0] = (slots_max / 2 + pair_tile(kMinPairsPerThread) - 1) / pair_tile(kMinPairsPerThread) * 128 + 256;
-            for (int l = 0; l < kInvLevels; l++) lvl[l + 1] = (lvl[l] + kInvFan - 1) / kInvFan + 1;
+            static uint32_t fan1 = 0;
+            if (fan1 == 0) {
+                const char* v = getenv("PM_INV_FAN1");      // tuning hook
+                const int f = v ? atoi(v) : 4;
+                fan1 = (f >= 2 && f <= 64) ? (uint32_t)f : 4;
+                const char* v0 = getenv("PM_INV_FAN0");     // tuning hook
+                const int f0 = v0 ? atoi(v0) : 0;
+                if (f0 >= 2 && f0 <= 64) fan1 |= (uint32_t)f0 << 16;
+            }
+            for (int l = 0; l < kInvLevels; l++) lvl[l + 1] = (lvl[l] + inv_fan(l, fan1) - 1) / inv_fan(l, fan1) + 1;
             const size_t t_per_span = lvl[0] + lvl[1] + lvl[2], p_per_span = lvl[0] + lvl[1];
             Fq* t_all = tvals_.as<Fq>(t_per_span * nspans);
             Fq* p_all = tpre_.as<Fq>(p_per_span * nspans);
@@ -1177,13 +1194,13 @@ MsmEngine::Shape MsmEngine::run(const G1Affine* bases, const Fr* scalars, size_t
                     // level sizes for the grids (upper bounds; the kernels derive the exact ones from the span)
                     size_t nl[kInvLevels + 1];
                     nl[0] = (size_t)g * 128;
-                    for (int l = 0; l < kInvLevels; l++) nl[l + 1] = (nl[l] + kInvFan - 1) / kInvFan;
+                    for (int l = 0; l < kInvLevels; l++) nl[l + 1] = (nl[l] + inv_fan(l, fan1) - 1) / inv_fan(l, fan1);
                     auto invert = [&]() {
                         for (int l = 0; l < kInvLevels; l++)
-                            k_invert_up<<<ceil_div(nl[l + 1], 128), 128, 0, st>>>(tlev[l], plev[l], tlev[l + 1], span, r, ppt, l);
-                        k_invert_top<<<ceil_div(nl[kInvLevels], 128), 128, 0, st>>>(tlev[kInvLevels], span, r, ppt, kInvLevels);
+                            k_invert_up<<<ceil_div(nl[l + 1], 128), 128, 0, st>>>(tlev[l], plev[l], tlev[l + 1], span, r, ppt, l, fan1);
+                        k_invert_top<<<ceil_div(nl[kInvLevels], 128), 128, 0, st>>>(tlev[kInvLevels], span, r, ppt, kInvLevels, fan1);
                         for (int l = kInvLevels; l-- > 0;)
-                            k_invert_down<<<ceil_div(nl[l + 1], 128), 128, 0, st>>>(tlev[l], plev[l], tlev[l + 1], span, r, ppt, l);
+                            k_invert_down<<<ceil_div(nl[l + 1], 128), 128, 0, st>>>(tlev[l], plev[l], tlev[l + 1], span, r, ppt, l, fan1);
                     };
                     const bool time_bwd = timed && sp == 0 && r == 0;
                     if (r == 0) {
