@@ -328,7 +328,8 @@ int pm_bench_imad_peak(double* mads_per_s);
 /* Register-resident Montgomery products per second; field: 0 = Fr, 1 = Fq; variants of the same dependent chain:
  * 2 = Fq squaring, 3 = Fq Karatsuba product, 4 = Fr squaring, 5 = Fr Karatsuba product. */
 int pm_bench_field_mul(int field, double* muls_per_s);
-/* Average milliseconds of `iters` size-2^log_n transforms on resident data (after one warm-up). */
+/* Average milliseconds of `iters` size-2^log_n transforms on resident data (after one warm-up).
+ * inverse: bit 0 = inverse transform, bit 1 = the coset variant of pm_ntt_fr (the g^i / g^-i scaling pass included). */
 int pm_bench_ntt(unsigned log_n, int inverse, int iters, double* ms_avg);
 /* Milliseconds of one device-resident decompression / compression of n synthetic G1 points. */
 int pm_bench_g1_codec(size_t n, double* ms_decompress, double* ms_compress);

@@ -355,13 +355,27 @@ int pm_bench_ntt(unsigned log_n, int inverse, int iters, double* ms_avg) {
         DevBuf d;
         Fr* p = d.as<Fr>(n);
         launch_fill_fr(p, n, 0x1234 + log_n, rt.stream);
-        rt.ntt.run(p, (int)log_n, inverse != 0, rt.stream);  // warm-up (builds twiddle tables)
+        // bit 1 of `inverse`: the coset variant of pm_ntt_fr (scale by g^i before a forward / by g^-i after an inverse transform)
+        const bool inv = (inverse & 1) != 0, coset = (inverse & 2) != 0;
+        DevBuf g;
+        Fr* gd = nullptr;
+        if (coset) {
+            gd = g.as<Fr>(2);
+            launch_fill_fr(gd, 1, 0x7, rt.stream);
+            launch_fr_inverse(gd, gd + 1, rt.stream);
+        }
+        auto once = [&]() {
+            if (coset && !inv) launch_scale_by_powers(p, n, gd, rt.stream);
+            rt.ntt.run(p, (int)log_n, inv, rt.stream);
+            if (coset && inv) launch_scale_by_powers(p, n, gd + 1, rt.stream);
+        };
+        once();  // warm-up (builds twiddle tables)
         cudaEvent_t e0, e1;
         PM_CUDA(cudaEventCreate(&e0));
         PM_CUDA(cudaEventCreate(&e1));
         PM_CUDA(cudaStreamSynchronize(rt.stream));
         PM_CUDA(cudaEventRecord(e0, rt.stream));
-        for (int i = 0; i < iters; i++) rt.ntt.run(p, (int)log_n, inverse != 0, rt.stream);
+        for (int i = 0; i < iters; i++) once();
         PM_CUDA(cudaEventRecord(e1, rt.stream));
         PM_CUDA(cudaEventSynchronize(e1));
         float ms = 0;

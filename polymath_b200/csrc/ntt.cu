@@ -31,7 +31,11 @@ namespace {
 constexpr int kCoreBits = 11;
 constexpr int kMaxTileBits = 11;
 constexpr int kMinTileBits = 9;
-constexpr int kTwBits = 11;
+constexpr int kTwBits = 11;          // inter-pass twiddle tables of transforms up to 2^22: 2048 entries per level
+// Above 2^22 two levels of 2^ceil(log_n / 2) entries (128 KB .. 2 MB per table, L2-resident) keep the inter-pass twiddle at
+// ONE table product: with three 2048-entry levels a 2^24 transform spent 6 of its 18 products per element on rebuilding
+// twiddles (3.25 Gelem/s against 4.15 at 2^22, profiles/r2_summary.md).
+__host__ __device__ constexpr int tw_bits_for(int log_n) { return log_n <= 2 * kTwBits ? kTwBits : (log_n + 1) / 2; }
 
 __host__ __device__ constexpr int skew(int i) { return i + (i >> 3) + (i >> 6) + (i >> 9); }
 __host__ __device__ constexpr int data_plane(int log_tile) { return skew(1 << log_tile) + 8; }
@@ -147,9 +151,10 @@ __device__ __forceinline__ void core_ntt(uint4* lo, uint4* hi, const uint4* tlo,
 }
 
 __device__ __forceinline__ Fr interpass_twiddle(const PassArgs& a, uint64_t e) {
-    Fr t = a.tw0[e & ((1u << kTwBits) - 1)];
-    if (a.log_n > kTwBits) t = t * a.tw1[(e >> kTwBits) & ((1u << kTwBits) - 1)];
-    if (a.log_n > 2 * kTwBits) t = t * a.tw2[e >> (2 * kTwBits)];
+    const int tb = tw_bits_for(a.log_n);
+    Fr t = a.tw0[e & ((1u << tb) - 1)];
+    if (a.log_n > tb) t = t * a.tw1[(e >> tb) & ((1u << tb) - 1)];
+    if (a.log_n > 2 * tb) t = t * a.tw2[e >> (2 * tb)];
     return t;
 }
 
@@ -354,11 +359,12 @@ const NttEngine::Tables& NttEngine::tables(int log_n, cudaStream_t stream) {
     k_build_table<<<ceil_div(core_n, 128), 128, 0, stream>>>(t->core_fwd.as<Fr>(core_n), core_n, kCoreBits, 0, false);
     k_build_table<<<ceil_div(core_n, 128), 128, 0, stream>>>(t->core_inv.as<Fr>(core_n), core_n, kCoreBits, 0, true);
     PM_LAUNCH_CHECK();
-    const int tw_n = 1 << kTwBits;
+    const int tb = tw_bits_for(log_n);
+    const int tw_n = 1 << tb;
     for (int level = 0; level < 3; level++) {
-        if (level * kTwBits >= log_n && level > 0) break;
-        k_build_table<<<ceil_div(tw_n, 128), 128, 0, stream>>>(t->tw_fwd[level].as<Fr>(tw_n), tw_n, log_n, level * kTwBits, false);
-        k_build_table<<<ceil_div(tw_n, 128), 128, 0, stream>>>(t->tw_inv[level].as<Fr>(tw_n), tw_n, log_n, level * kTwBits, true);
+        if (level * tb >= log_n && level > 0) break;
+        k_build_table<<<ceil_div(tw_n, 128), 128, 0, stream>>>(t->tw_fwd[level].as<Fr>(tw_n), tw_n, log_n, level * tb, false);
+        k_build_table<<<ceil_div(tw_n, 128), 128, 0, stream>>>(t->tw_inv[level].as<Fr>(tw_n), tw_n, log_n, level * tb, true);
         PM_LAUNCH_CHECK();
     }
     k_build_ninv<<<1, 32, 0, stream>>>(t->n_inv.as<Fr>(1), log_n);

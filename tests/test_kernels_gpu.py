@@ -198,6 +198,36 @@ def test_msm_edge_cases(pmlib):
     assert kernels.msm_g1(bases, scalars[:100]) == poly.msm_pippenger(scalars[:100], bases[:100])
 
 
+@pytest.mark.parametrize("rounds", [-1, 0, 3])
+def test_msm_skewed_inputs(pmlib, rounds):
+    """SURVEY.md 8d skew: 89 % of the scalars one repeated value, 10 % zero, 1 % uniform, 1 % infinity bases — whole
+    warps land in ONE bucket per window (the warp-aggregated atomics of the sort, gated by the neighbour probe), mixed
+    with lanes that do not (partial groups), through the walk, the heavy-run path and the pair rounds."""
+    from polymath_b200 import kernels
+    rnd = random.Random(8100 + rounds)
+    n = 3000
+    bases = _bases(n, rnd)
+    hot = rnd.randrange(R_MOD)
+    scalars = []
+    for i in range(n):
+        h = rnd.randrange(1000)
+        scalars.append(hot if h < 890 else 0 if h < 990 else rnd.randrange(R_MOD))
+        if rnd.randrange(100) == 0:
+            bases[i] = None
+    # runs of equal scalars shorter and longer than a warp, and an isolated pair of equal neighbours
+    for i in range(64, 64 + 40):
+        scalars[i] = 12345
+    scalars[200] = scalars[201] = R_MOD - 2
+    want = poly.msm_pippenger(scalars, bases)
+    kernels.msm_set_tuning(rounds)
+    try:
+        assert kernels.msm_g1(bases, scalars) == want
+        assert kernels.msm_g1(bases, scalars, window_bits=9, heavy_threshold=16) == want
+        assert kernels.msm_g1(bases, scalars, window_bits=10, levels=4) == want
+    finally:
+        kernels.msm_set_tuning(-1)
+
+
 @pytest.fixture
 def msm_tuning(pmlib):
     from polymath_b200 import kernels

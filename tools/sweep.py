@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--levels", default="1", help="comma list; 0 = as many levels as windows")
     ap.add_argument("--rounds", default="-1", help="comma list of pair-round settings (-1 = automatic, 0 = XYZZ walk only)")
     ap.add_argument("--skip-basics", action="store_true")
+    ap.add_argument("--coset", action="store_true", help="also time the coset variants of the NTT (scaling pass included)")
     ap.add_argument("--skew", action="store_true", help="MSM inputs of SURVEY.md 8d: 89 %% one repeated scalar, 10 %% zero, 1 %% infinity bases")
     ap.add_argument("--codec", default="", help="comma list of log2 sizes for the G1 (de)compression kernels")
     a = ap.parse_args()
@@ -34,10 +35,10 @@ def main():
         print(json.dumps({"kernel": name, "muls_per_s": d.value, "imad_equiv_per_s": d.value * cost,
                           "frac_of_imad_peak": d.value * cost / imad}), flush=True)
     for lg in [int(x) for x in a.ntt.split(",") if x]:
-        for inv in (0, 1):
+        for inv in ((0, 1, 2, 3) if a.coset else (0, 1)):
             check(lib.pm_bench_ntt(lg, inv, a.iters, C.byref(d)))
             n = 1 << lg
-            print(json.dumps({"kernel": "ntt_fr", "log_n": lg, "inverse": inv, "ms": d.value,
+            print(json.dumps({"kernel": "ntt_fr", "log_n": lg, "inverse": inv & 1, "coset": bool(inv & 2), "ms": d.value,
                               "gelem_per_s": n / d.value / 1e6, "algo_gb_per_s": 64 * n / d.value / 1e6,
                               "butterfly_muls_per_s": (n / 2) * lg / (d.value * 1e-3)}), flush=True)
     for lg in [int(x) for x in a.codec.split(",") if x]:
