@@ -28,8 +28,9 @@ namespace pm {
 
 namespace {
 
-constexpr int kCoreBits = 11;
-constexpr int kMaxTileBits = 11;
+constexpr int kCoreBits = 12;        // largest digit: one CTA transforms up to 4096 points in shared memory
+constexpr int kMaxTileBits = 12;     // 4096-element tiles (220 KB, one CTA of 512 threads per SM): PM_NTT_BIG_TILE, off by default
+constexpr int kStdTileBits = 11;     // 2048-element tiles (110 KB, two CTAs of 256 threads per SM) everywhere else
 constexpr int kMinTileBits = 9;
 constexpr int kTwBits = 11;          // inter-pass twiddle tables of transforms up to 2^22: 2048 entries per level
 // Above 2^22 two levels of 2^ceil(log_n / 2) entries (128 KB .. 2 MB per table, L2-resident) keep the inter-pass twiddle at
@@ -169,7 +170,8 @@ __device__ __forceinline__ void load_core_twiddles(uint4* tlo, uint4* thi, const
 }
 
 // ---- column pass ----------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 2) k_ntt_columns(PassArgs a) {
+template <int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) k_ntt_columns(PassArgs a) {
     extern __shared__ uint4 smem[];
     const int lt = a.log_tile, tile = 1 << lt;
     uint4* lo = smem;
@@ -213,7 +215,8 @@ __global__ void __launch_bounds__(256, 2) k_ntt_columns(PassArgs a) {
 }
 
 // ---- row pass (final; digit-reversal transpose on store) --------------------------------
-__global__ void __launch_bounds__(256, 2) k_ntt_rows(PassArgs a) {
+template <int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) k_ntt_rows(PassArgs a) {
     extern __shared__ uint4 smem[];
     const int lt = a.log_tile;
     uint4* lo = smem;
@@ -386,15 +389,26 @@ void NttEngine::run(Fr* data, int log_n, bool inverse, cudaStream_t stream) {
     }
     static bool attr_set = false;
     if (!attr_set) {
-        PM_CUDA(cudaFuncSetAttribute(k_ntt_columns, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(kMaxTileBits)));
-        PM_CUDA(cudaFuncSetAttribute(k_ntt_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(kMaxTileBits)));
+        PM_CUDA(cudaFuncSetAttribute(k_ntt_columns<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(kStdTileBits)));
+        PM_CUDA(cudaFuncSetAttribute(k_ntt_rows<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(kStdTileBits)));
+        PM_CUDA(cudaFuncSetAttribute(k_ntt_columns<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(kMaxTileBits)));
+        PM_CUDA(cudaFuncSetAttribute(k_ntt_rows<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(kMaxTileBits)));
         attr_set = true;
     }
     const Tables& t = tables(log_n, stream);
     const size_t n = (size_t)1 << log_n;
 
-    // digit split: 1 pass up to 2^11, 2 passes up to 2^22, else 3; most significant digit first
-    int npass = log_n <= kCoreBits ? 1 : (log_n <= 2 * kCoreBits ? 2 : 3);
+    // digit split: 1 pass up to 2^11, 2 passes up to 2^22 (digits <= 11, 2048-element tiles), else 3; most significant first.
+    // PM_NTT_BIG_TILE=1: 2^23 / 2^24 as TWO passes of 12-bit digits on 4096-element tiles (220 KB, one CTA of 512 threads
+    // per SM).  Measured slower than three passes — 2^23: 3.70 vs 3.79, 2^24: 3.55 vs 3.68 Gelem/s — because a lone CTA
+    // cannot overlap its global loads / stores with another CTA's butterflies; kept as a checked alternative.
+    static int big_tile = -1;
+    if (big_tile < 0) {
+        const char* v = getenv("PM_NTT_BIG_TILE");          // tuning hook (see above)
+        big_tile = v ? atoi(v) : 0;
+    }
+    const bool two_big = big_tile && log_n > 2 * kStdTileBits && log_n <= 2 * kMaxTileBits;
+    int npass = log_n <= kStdTileBits ? 1 : (log_n <= 2 * kStdTileBits || two_big ? 2 : 3);
     int digits[3] = {0, 0, 0};
     {
         int rem = log_n;
@@ -405,14 +419,14 @@ void NttEngine::run(Fr* data, int log_n, bool inverse, cudaStream_t stream) {
     }
     // Tile: 2048 elements per CTA from 2^20 on; below, the smallest tile that holds the largest digit (>= 512), so that
     // 2^16 launches 128 CTAs instead of 32 on the 148 SMs
-    int log_tile = kMaxTileBits;
+    int log_tile = two_big ? kMaxTileBits : kStdTileBits;
     if (log_n < 20) {
         log_tile = digits[0] > kMinTileBits ? digits[0] : kMinTileBits;
-        if (log_tile > kMaxTileBits) log_tile = kMaxTileBits;
+        if (log_tile > kStdTileBits) log_tile = kStdTileBits;
     }
     if (const char* v = getenv("PM_NTT_TILE_BITS")) {       // tuning hook
         const int f = atoi(v);
-        if (f >= digits[0] && f >= kMinTileBits && f <= kMaxTileBits) log_tile = f;
+        if (f >= digits[0] && f >= kMinTileBits && f <= kStdTileBits && !two_big) log_tile = f;
     }
     const int smem = smem_bytes(log_tile);
     PassArgs a{};
@@ -437,7 +451,8 @@ void NttEngine::run(Fr* data, int log_n, bool inverse, cudaStream_t stream) {
         a.m = digits[p];
         a.log_s = log_n - consumed - digits[p];
         a.scale = nullptr;
-        k_ntt_columns<<<(unsigned)(n >> log_tile), (1 << log_tile) / 8, smem, stream>>>(a);
+        if (log_tile > kStdTileBits) k_ntt_columns<512, 1><<<(unsigned)(n >> log_tile), (1 << log_tile) / 8, smem, stream>>>(a);
+        else k_ntt_columns<256, 2><<<(unsigned)(n >> log_tile), (1 << log_tile) / 8, smem, stream>>>(a);
         PM_LAUNCH_CHECK();
         launches++;
         consumed += digits[p];
@@ -456,7 +471,8 @@ void NttEngine::run(Fr* data, int log_n, bool inverse, cudaStream_t stream) {
         const unsigned ctas = (unsigned)((size_t)1 << (log_rows - log_b));
         int threads = ((1 << log_b) << a.m) / 8;
         if (threads < 1) threads = 1;
-        k_ntt_rows<<<ctas, threads, smem, stream>>>(a);
+        if (log_tile > kStdTileBits) k_ntt_rows<512, 1><<<ctas, threads, smem, stream>>>(a);
+        else k_ntt_rows<256, 2><<<ctas, threads, smem, stream>>>(a);
         PM_LAUNCH_CHECK();
         launches++;
     }

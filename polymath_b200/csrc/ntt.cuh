@@ -27,7 +27,7 @@ public:
     ~NttEngine();
 
     struct Tables {
-        DevBuf core_fwd, core_inv;     // w_{2^11}^k and its inverse, k < 2^10
+        DevBuf core_fwd, core_inv;     // w_{2^12}^k and its inverse, k < 2^11
         DevBuf tw_fwd[3], tw_inv[3];   // w_N^(k * 2^(b*level)), k < 2^b per level; b = 11 up to 2^22, ceil(log_n / 2) above
         DevBuf n_inv;                  // n^-1
     };
