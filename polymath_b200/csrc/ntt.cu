@@ -417,9 +417,13 @@ void NttEngine::run(Fr* data, int log_n, bool inverse, cudaStream_t stream) {
             rem -= digits[p];
         }
     }
-    // Tile: 2048 elements per CTA from 2^20 on; below, the smallest tile that holds the largest digit (>= 512), so that
-    // 2^16 launches 128 CTAs instead of 32 on the 148 SMs
-    int log_tile = two_big ? kMaxTileBits : kStdTileBits;
+    // Tile: the smallest one that holds the largest digit (>= 512 elements): 2^16 launches 128 CTAs instead of 32 on the
+    // 148 SMs, and up to 2^20 (digits of 10 bits) four 1024-element CTAs share an SM instead of two of 2048 — one CTA's
+    // global loads / stores overlap the others' butterflies (2^20: 3.85 -> 4.24 Gelem/s).  2^21 / 2^22 need 2048.
+    // From 2^20 on every pass takes max(its digit, 10) bits: the 10-bit row pass of 2^21 and the 8-bit passes of 2^24 run on
+    // 1024-element tiles as well (2^21: 4.23 -> 4.29, 2^24: 3.69 -> 3.80 Gelem/s; 512-element tiles lose the coalescing
+    // of the column passes: 2.9 Gelem/s at 2^24).
+    int log_tile = two_big ? kMaxTileBits : 10;
     if (log_n < 20) {
         log_tile = digits[0] > kMinTileBits ? digits[0] : kMinTileBits;
         if (log_tile > kStdTileBits) log_tile = kStdTileBits;
@@ -428,10 +432,20 @@ void NttEngine::run(Fr* data, int log_n, bool inverse, cudaStream_t stream) {
         const int f = atoi(v);
         if (f >= digits[0] && f >= kMinTileBits && f <= kStdTileBits && !two_big) log_tile = f;
     }
-    const int smem = smem_bytes(log_tile);
+    // Per-pass tiles (PM_NTT_COL_TILE / PM_NTT_ROW_TILE: tile bits of the column passes / the row pass, each at least its
+    // digit): a smaller tile puts more independent CTAs on an SM, a larger one makes the column pass read longer
+    // contiguous chunks (B = tile / M adjacent columns of 32 bytes).
+    auto pass_tile = [&](int digit, const char* env, int dflt) {
+        int lt = dflt;
+        if (const char* v = getenv(env)) {
+            const int f = atoi(v);
+            if (f >= kMinTileBits && f <= kStdTileBits && !two_big) lt = f;
+        }
+        if (lt < digit) lt = digit;
+        return lt;
+    };
     PassArgs a{};
     a.log_n = log_n;
-    a.log_tile = log_tile;
     a.core = (inverse ? t.core_inv : t.core_fwd).get<Fr>();
     a.tw0 = (inverse ? t.tw_inv[0] : t.tw_fwd[0]).get<Fr>();
     a.tw1 = (inverse ? t.tw_inv[1] : t.tw_fwd[1]).get<Fr>();
@@ -451,8 +465,11 @@ void NttEngine::run(Fr* data, int log_n, bool inverse, cudaStream_t stream) {
         a.m = digits[p];
         a.log_s = log_n - consumed - digits[p];
         a.scale = nullptr;
-        if (log_tile > kStdTileBits) k_ntt_columns<512, 1><<<(unsigned)(n >> log_tile), (1 << log_tile) / 8, smem, stream>>>(a);
-        else k_ntt_columns<256, 2><<<(unsigned)(n >> log_tile), (1 << log_tile) / 8, smem, stream>>>(a);
+        int lt = pass_tile(digits[p], "PM_NTT_COL_TILE", log_tile);
+        if (lt - a.m > a.log_s) lt = a.m + a.log_s;          // no more adjacent columns than exist
+        a.log_tile = lt;
+        if (lt > kStdTileBits) k_ntt_columns<512, 1><<<(unsigned)(n >> lt), (1 << lt) / 8, smem_bytes(lt), stream>>>(a);
+        else k_ntt_columns<256, 2><<<(unsigned)(n >> lt), (1 << lt) / 8, smem_bytes(lt), stream>>>(a);
         PM_LAUNCH_CHECK();
         launches++;
         consumed += digits[p];
@@ -464,15 +481,17 @@ void NttEngine::run(Fr* data, int log_n, bool inverse, cudaStream_t stream) {
     a.log_n1 = npass == 1 ? 0 : digits[0];
     a.scale = inverse ? t.n_inv.get<Fr>() : nullptr;
     {
+        const int lt = pass_tile(a.m, "PM_NTT_ROW_TILE", log_tile);
+        a.log_tile = lt;
         const int log_rows = log_n - a.m;
-        int log_b = log_tile - a.m;
+        int log_b = lt - a.m;
         if (log_b < 0) throw CudaError("ntt: tile smaller than the row digit");
         if (log_b > log_rows) log_b = log_rows;
         const unsigned ctas = (unsigned)((size_t)1 << (log_rows - log_b));
         int threads = ((1 << log_b) << a.m) / 8;
         if (threads < 1) threads = 1;
-        if (log_tile > kStdTileBits) k_ntt_rows<512, 1><<<ctas, threads, smem, stream>>>(a);
-        else k_ntt_rows<256, 2><<<ctas, threads, smem, stream>>>(a);
+        if (lt > kStdTileBits) k_ntt_rows<512, 1><<<ctas, threads, smem_bytes(lt), stream>>>(a);
+        else k_ntt_rows<256, 2><<<ctas, threads, smem_bytes(lt), stream>>>(a);
         PM_LAUNCH_CHECK();
         launches++;
     }
