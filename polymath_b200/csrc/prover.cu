@@ -162,7 +162,10 @@ static ProverCtx::MsmPlan plan_for(uint64_t count, const char* env_name, bool se
     if (!env) env = getenv("PM_MSM_PRECOMP");
     const bool enabled = !(env && atoi(env) == 0);
     const char* envmin = getenv("PM_MSM_PRECOMP_MIN");             // test hook: minimum size that gets tables
-    const uint64_t min_count = envmin ? (uint64_t)atoll(envmin) : ((uint64_t)1 << 14);
+    // From 1024 points on: below 2^14 points the table's value is not the additions it saves but its SINGLE bucket set —
+    // a table-less 2k-point MSM leaves 26 bucket sets x 10 partial sums to the host (1.07 ms of Horner per phase 1 at
+    // n = 2^11, against 1.2 ms of device time): MiMC-322-sized proofs 3.6 -> 2.6 ms (profiles/r2_summary.md).
+    const uint64_t min_count = envmin ? (uint64_t)atoll(envmin) : ((uint64_t)1 << 10);
     if (!enabled || count < min_count) return p;                   // small MSMs: plain windows (c chosen per call)
     // All windows of a table share ONE bucket set: the host combines a single group of partial sums instead of
     // 16-22 (7 ms -> 0.1 ms of host time per proof at n = 2^16, profiles/r1_h_summary.md), and the window can be
