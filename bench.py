@@ -114,16 +114,6 @@ def _check_ra():
     return [fr_rand(rng), fr_rand(rng)]
 
 
-def _cpu_field_mul():
-    """Which Montgomery-product formulation the CPU port picked on this host (oracle/cpu_ref.cpp: orc_calibrate)."""
-    try:
-        from oracle import cpp
-        mode, sos, cios = cpp.field_mul_calibration()
-        return {"used": "cios" if mode == 2 else "sos", "fq_ns_sos": sos, "fq_ns_cios": cios}
-    except Exception:
-        return None
-
-
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -178,7 +168,7 @@ def run_reference(args):
               "slower per core than arkworks' assembly-free Montgomery code by an estimated 1.5-2x), transcript in Python; %s"
               % (args.steps, "S-" + args.workload, log_n, key_kind))
     cpu_line = {"value": value, "unit": "ms", "cores": cpu.cores, "kind": "port", "sample": sample,
-                "split_ms_last": {k: v * 1e3 / args.steps for k, v in tm.items()}, "field_mul": _cpu_field_mul(),
+                "split_ms_last": {k: v * 1e3 / args.steps for k, v in tm.items()},
                 "proof_hex": proof_hex,
                 "proof_matches_golden": (proof_hex == golden) if (golden and vk_bytes is not None) else None}
     out = {
@@ -635,7 +625,7 @@ def run_ours(args):
                              "`proof_check`: oracle/fast.py — the five MSMs, four iFFTs, fft/square/ifft(2n), Horner, assembly and "
                              "division of prover.rs:66-237 in oracle/cpu_ref.cpp (C++/OpenMP on all host cores, portable u128 "
                              "arithmetic; arkworks' own field code is an estimated 1.5-2x faster per core)",
-                   "split_ms": {k: v * 1e3 for k, v in tm.items()}, "field_mul": _cpu_field_mul(), "proof_hex": chex,
+                   "split_ms": {k: v * 1e3 for k, v in tm.items()}, "proof_hex": chex,
                    "proof_matches_device": chex == proof_check["proof_hex"]}
             if not cpu["proof_matches_device"]:
                 raise SystemExit("CPU oracle proof differs from the device proof:\n cpu    %s\n device %s" % (chex, proof_check["proof_hex"]))

@@ -19,9 +19,6 @@ def load():
         lib.orc_fr_mul.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
         lib.orc_fq_mul.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
         lib.orc_make_bases.argtypes = [C.c_size_t, C.c_void_p]
-        # the faster of the two Montgomery-product formulations on THIS host (timed once, ~0.1 s)
-        lib.orc_calibrate.argtypes = [C.POINTER(C.c_double)]
-        lib.orc_calibrate(None)
         _lib = lib
     return _lib
 
@@ -36,13 +33,6 @@ def msm_wire(bases: bytes, scalars: bytes, n: int) -> bytes:
     out = C.create_string_buffer(96)
     load().orc_msm(bases, scalars, n, out)
     return out.raw
-
-
-def field_mul_calibration():
-    """(mode, ns per Fq product in SOS form, in CIOS form); mode 1 = SOS, 2 = CIOS is what the library uses."""
-    ns = (C.c_double * 2)()
-    mode = load().orc_calibrate(ns)
-    return mode, ns[0], ns[1]
 
 
 def num_threads() -> int:

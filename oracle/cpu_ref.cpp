@@ -36,8 +36,6 @@ static const Mod<6> FQ = {
     {0x760900000002fffdull, 0xebf4000bc40c0002ull, 0x5f48985753c758baull, 0x77ce585370525745ull, 0x5c071a97a256ec6dull, 0x15f65ec3fa80e493ull},
     0x89f3fffcfffcfffdull};
 
-static int g_mul_mode = 1;   // 1 = SOS, 2 = CIOS (orc_calibrate)
-
 template <int N, const Mod<N>& M>
 struct El {
     uint64_t l[N];
@@ -67,12 +65,10 @@ struct El {
     }
     El neg() const { return zero().sub(*this); }
     El dbl() const { return add(*this); }
-    // Two formulations of the Montgomery product; which one is faster depends on the host CPU and compiler (build host:
-    // CIOS 47 / 96 ns against SOS 76 / 112 ns for Fr / Fq; the GPU boxes' hosts run the SOS form ~10 % faster), so
-    // orc_calibrate() times both once per process and mul() uses the winner: the CPU baseline is the better of the two.
-    El mul(const El& b) const { return g_mul_mode == 2 ? mul_cios(b) : mul_sos(b); }
-    // separated product + Montgomery reduction (SOS form)
-    El mul_sos(const El& b) const {
+    // separated product + Montgomery reduction (SOS form).  A word-serial CIOS product ("no-carry" variant, as in ark-ff)
+    // was measured in round 2: faster as a lone dependent chain (39 vs 49 ns per Fq product on the GPU boxes' host) but
+    // SLOWER inside the 16-thread MSM (one 2^20 prove 16.8-17.8 s against 14.7-15.2 s), so the baseline keeps this form.
+    El mul(const El& b) const {
         uint64_t t[2 * N + 1];
         memset(t, 0, sizeof t);
         for (int i = 0; i < N; i++) {
@@ -87,62 +83,6 @@ struct El {
         }
         El r; memcpy(r.l, t + N, sizeof r.l);
         if (t[2 * N] || ge_p(r.l)) sub_p(r.l);
-        return r;
-    }
-    // Word-serial Montgomery product (CIOS) with the "no-carry" shortcut ark-ff uses for moduli whose top limb leaves a
-    // spare bit (both BLS12-381 fields): the running value stays below 2p, so N + 1 limbs suffice and no carry loop is
-    // data-dependent.  Measured on the 2.0 GHz build host (dependent chain): Fr 76 -> 47 ns, Fq 112 -> 96 ns per product
-    // against the separated form it replaces.
-    El mul_cios(const El& b) const {
-        if constexpr (N == 6) return mul6(b);
-        uint64_t t[N + 1];
-        for (int j = 0; j <= N; j++) t[j] = 0;
-#pragma GCC unroll 8
-        for (int i = 0; i < N; i++) {
-            uint64_t c = 0;
-#pragma GCC unroll 8
-            for (int j = 0; j < N; j++) { u128 s = (u128)l[i] * b.l[j] + t[j] + c; t[j] = (uint64_t)s; c = (uint64_t)(s >> 64); }
-            const uint64_t top = t[N] + c;            // < 2^64: value < 2p * 2^64
-            const uint64_t m = t[0] * M.ninv;
-            u128 s = (u128)m * M.p[0] + t[0];
-            c = (uint64_t)(s >> 64);
-#pragma GCC unroll 8
-            for (int j = 1; j < N; j++) { s = (u128)m * M.p[j] + t[j] + c; t[j - 1] = (uint64_t)s; c = (uint64_t)(s >> 64); }
-            s = (u128)top + c;
-            t[N - 1] = (uint64_t)s;
-            t[N] = (uint64_t)(s >> 64);
-        }
-        El r; memcpy(r.l, t, sizeof r.l);
-        if (t[N] || ge_p(r.l)) sub_p(r.l);
-        return r;
-    }
-    // the same for six limbs with the running value in named scalars (gcc keeps the array form in memory: 111 -> 79 ns)
-    El mul6(const El& b) const {
-        uint64_t t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0, t5 = 0, t6 = 0;
-#pragma GCC unroll 8
-        for (int i = 0; i < 6; i++) {
-            const uint64_t ai = l[i];
-            uint64_t c;
-            u128 s;
-            s = (u128)ai * b.l[0] + t0; t0 = (uint64_t)s; c = (uint64_t)(s >> 64);
-            s = (u128)ai * b.l[1] + t1 + c; t1 = (uint64_t)s; c = (uint64_t)(s >> 64);
-            s = (u128)ai * b.l[2] + t2 + c; t2 = (uint64_t)s; c = (uint64_t)(s >> 64);
-            s = (u128)ai * b.l[3] + t3 + c; t3 = (uint64_t)s; c = (uint64_t)(s >> 64);
-            s = (u128)ai * b.l[4] + t4 + c; t4 = (uint64_t)s; c = (uint64_t)(s >> 64);
-            s = (u128)ai * b.l[5] + t5 + c; t5 = (uint64_t)s; c = (uint64_t)(s >> 64);
-            t6 += c;
-            const uint64_t m = t0 * M.ninv;
-            s = (u128)m * M.p[0] + t0; c = (uint64_t)(s >> 64);
-            s = (u128)m * M.p[1] + t1 + c; t0 = (uint64_t)s; c = (uint64_t)(s >> 64);
-            s = (u128)m * M.p[2] + t2 + c; t1 = (uint64_t)s; c = (uint64_t)(s >> 64);
-            s = (u128)m * M.p[3] + t3 + c; t2 = (uint64_t)s; c = (uint64_t)(s >> 64);
-            s = (u128)m * M.p[4] + t4 + c; t3 = (uint64_t)s; c = (uint64_t)(s >> 64);
-            s = (u128)m * M.p[5] + t5 + c; t4 = (uint64_t)s; c = (uint64_t)(s >> 64);
-            s = (u128)t6 + c; t5 = (uint64_t)s; t6 = (uint64_t)(s >> 64);
-        }
-        El r;
-        r.l[0] = t0; r.l[1] = t1; r.l[2] = t2; r.l[3] = t3; r.l[4] = t4; r.l[5] = t5;
-        if (t6 || ge_p(r.l)) sub_p(r.l);
         return r;
     }
     El sqr() const { return mul(*this); }
@@ -163,30 +103,6 @@ struct El {
 };
 typedef El<4, FR> Fr;
 typedef El<6, FQ> Fq;
-
-// Times a dependent chain of Fq products in both formulations and keeps the faster one for the whole process.
-// Returns the chosen mode; ns[0], ns[1] (nullable) receive the nanoseconds per product of SOS and CIOS.
-extern "C" int orc_calibrate(double* ns) {
-    static int done = 0;
-    static double cached[2] = {0, 0};
-    if (!done) {
-        for (int mode = 1; mode <= 2; mode++) {
-            Fq a = Fq::one(), b = Fq::one();
-            a.l[0] = 12345; b.l[1] = 999;
-            const int iters = 400000;
-            const double t0 = omp_get_wtime();
-            for (int i = 0; i < iters; i++) {
-                a = mode == 2 ? a.mul_cios(b) : a.mul_sos(b);
-                b = mode == 2 ? b.mul_cios(a) : b.mul_sos(a);
-            }
-            cached[mode - 1] = (omp_get_wtime() - t0) * 1e9 / (2.0 * iters) + (a.l[0] == 1 ? 1e-9 : 0);
-        }
-        g_mul_mode = cached[1] < cached[0] ? 2 : 1;
-        done = 1;
-    }
-    if (ns) { ns[0] = cached[0]; ns[1] = cached[1]; }
-    return g_mul_mode;
-}
 
 // ------------------------------------------------------------------------------------------
 // NTT
