@@ -13,7 +13,7 @@ def _num(v):
 
 
 def test_recorded_bench_line_has_the_contract_keys():
-    d = json.load(open(os.path.join(ROOT, "profiles", "bench_r1_l.json")))
+    d = json.load(open(os.path.join(ROOT, "profiles", "bench_r2_ak.json")))      # the round's final capture (tools/gpu_ak.sh)
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
               "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
         assert k in d, k
@@ -33,6 +33,15 @@ def test_recorded_bench_line_has_the_contract_keys():
     k = d["clocks"]
     assert k["sm_mhz"] and k["sm_max_mhz"] and not set(k["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
     assert d["proof_verified"] is True and len(d["proof_hex"]) == 352
+    # round 2: stage-level roofline with the executed fraction beside it, measured traffic with its source, the golden
+    # proof check, a complete CPU prove whose bytes equal the device's, the NTT view, the sweep incl. skewed inputs
+    assert 0 < r["executed_frac"] < r["frac"] and r["traffic_source"] and r["kernel_share_of_step"] > 0.5
+    assert d["proof_check"]["matches_golden"] is True and d["proof_check"]["verified"] is True
+    assert c["proof_matches_device"] is True and set(c["split_ms"]) >= {"sap", "ntt", "msm_phase1", "opening", "msm_d"}
+    h = d["roofline_hbm"]
+    assert h["bound"] == "hbm" and 0 < h["frac"] < 1 and h["traffic"] >= 64 * (1 << 21) and 0 < h["fr_mul_view"]["frac"] < 1
+    assert {"g1_msm_mpts_per_s_2p22", "fr_ntt_gelem_per_s_2p21", "g1_msm_mpts_per_s_2p22_skewed"} <= set(d["kernel_sweep"])
+    assert d["setup"]["fixed_base_roofline"]["bound"] == "imad"
 
 
 def test_reference_arm_runs_on_the_cpu_and_prints_its_line():
