@@ -1,22 +1,24 @@
 // K4 — G1 Pippenger MSM for sm_100a.
 //
 // Replaces `VariableBaseMSM::msm_unchecked` as called from /root/reference/src/prover.rs:380-384
-// (callers :114-121, :229, :330-357).  Pipeline (all on one stream, no host sync):
+// (callers :114-121, :229, :330-357).  Pipeline (no host sync; the pair rounds of the two bucket halves and the level
+// sums of the reduction use a second stream):
 //   1. k_digits<COUNT>   scalar -> canonical -> signed c-bit digits; histogram of (window, bucket)
 //   2. k_scan            exclusive prefix of the histogram -> bucket offsets
 //   3. k_digits<SCATTER> counting-sort scatter of (point index | sign) by (window, bucket)
-//                        (order inside a bucket is irrelevant: group addition commutes)
+//                        (order inside a bucket is irrelevant: group addition commutes); lanes of a warp that hit the
+//                        same bucket share one atomic (repeated scalars: SURVEY.md 8d)
 //   4a. pair rounds      (large MSMs) batched-AFFINE tree reduction of every bucket's run: round r adds the
 //                        entries of a run pairwise (2i, 2i+1) -> half as many affine points, with ONE shared
 //                        inversion per round (Montgomery's trick: k_pairs_forward prefix products,
-//                        k_batch_invert, k_pairs_backward) = 6 Fq products per addition instead of the 10 of
+//                        k_invert_up / top / down, k_pairs_backward) = 6 Fq products per addition instead of the 10 of
 //                        an XYZZ mixed addition
 //   4. k_accumulate      one thread per bucket, XYZZ mixed additions over its (remaining) run;
 //                        buckets longer than a threshold are deferred to
 //      k_accumulate_heavy / k_heavy_finish (4096-entry chunks, one CTA each, then a per-bucket
 //                        sum of the chunk partials) so narrow top windows and skewed scalar
 //                        distributions (SURVEY.md §7 "hard parts") spread over the whole GPU
-//   5. k_reduce_level    hierarchical running sums over 16-bucket segments (see below), k_sum_slices
+//   5. k_reduce_level    hierarchical running sums over K-bucket segments (K = 8, see below), k_sum_slices
 //                        tree-sums each level: a handful of partial sums per bucket set
 //   6. host: Horner over the <= 32 window sums (c doublings each) and the affine normalisation
 //      (host/g1_host.hpp) — a serial chain of ~255 doublings that costs a GPU thread milliseconds
